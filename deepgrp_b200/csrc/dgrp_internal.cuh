@@ -1,0 +1,146 @@
+// Internal declarations shared by the translation units of libdeepgrp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/deepgrp_b200.h"
+
+namespace dgrp {
+
+void set_error(const char *fmt, ...);
+
+#define DGRP_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      dgrp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return DGRP_E_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define DGRP_CHECK(call)          \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ != DGRP_OK) return rc__; \
+  } while (0)
+
+#define DGRP_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      dgrp::set_error(__VA_ARGS__);  \
+      return DGRP_E_ARG;             \
+    }                                \
+  } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Grow-only pinned host buffer.
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace dgrp
+
+struct dgrp_model {
+  int device = 0;
+  int rnn = 0;
+  int T = 0, U = 0, C = 0, UP = 0;  // UP: units padded to a multiple of 16
+  bool attention = false;
+  // device arrays
+  float *d_kernel = nullptr;     // [5, 3U]     raw Keras kernel
+  float *d_bias = nullptr;       // [2, 3U]
+  float *d_recurrent = nullptr;  // [U, 3U]     raw Keras recurrent kernel
+  float *d_P = nullptr;          // [5, 3, UP]  kernel[c, g*U+u] + bias[0, g*U+u], zero padded
+  float *d_Rp = nullptr;         // [UP, 3, UP] recurrent[k, g*U+u], zero padded
+  float *d_b1 = nullptr;         // [3, UP]     bias[1, g*U+u], zero padded
+  float *d_scale = nullptr;      // [U] or null
+  float *d_ffk = nullptr;        // [F, C]
+  float *d_ffb = nullptr;        // [C]
+};
+
+struct dgrp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  int64_t launches = 0;
+  dgrp_timings_t timings = {};
+  // workspaces (grow-only)
+  dgrp::DevBuf raw, codes, onehot, avg, pred, labels, labels2, scores32, scores64, classes64,
+      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, scan;
+  dgrp::PinBuf pin_small, pin_a, pin_b;
+  // staged one-hot state (dgrp_one_hot_stage -> dgrp_one_hot_fetch)
+  int64_t staged_n = 0, staged_start = 0, staged_len = -1;
+};
+
+namespace dgrp {
+
+struct Use {  // RAII: make the context's device current
+  int prev = -1;
+  explicit Use(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~Use() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- kernel launchers (device pointers, enqueue on ctx->stream) ------------------------------
+// encode.cu
+int launch_trim(dgrp_ctx *c, const uint8_t *d_seq, int64_t n, int fold_case, int64_t *d_first_last);
+int launch_onehot(dgrp_ctx *c, const uint8_t *d_seq, int64_t start, int64_t len, int8_t *d_fwd);
+int launch_codes(dgrp_ctx *c, const uint8_t *d_seq, int64_t start, int64_t len, uint8_t *d_codes);
+int launch_onehot_to_codes(dgrp_ctx *c, const int8_t *d_fwd, int64_t len, uint8_t *d_codes);
+// vote.cu
+int launch_get_max(dgrp_ctx *c, float *d_out, const float *d_in, int64_t batch, int64_t dim0,
+                   int64_t dim1, int64_t stride);
+int launch_score(dgrp_ctx *c, const float *d_pred, int64_t n, int C, uint8_t *d_label,
+                 float *d_score32, double *d_score64, int64_t *d_class64);
+int launch_softmax_global(dgrp_ctx *c, const float *d_in, int64_t n, int C, float *d_out);
+// forward.cu
+struct Placement {  // where window w is max-merged (prediction.py:105 compatibility)
+  int64_t n_windows;    // W
+  int64_t full_windows; // windows in complete batches (= W when compat is FIXED)
+  int64_t tail_base;    // row offset of the first window of the short last batch
+  int step;
+};
+Placement make_placement(int64_t length, int T, int step, int batch_size, int compat);
+// Run GRU + attention + FF + softmax for windows [w_begin, w_end) of the code array and
+// max-merge into d_pred (rows relative to pred_row0; rows outside [0, pred_rows) are dropped).
+int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
+                     int64_t w_begin, int64_t w_end, const Placement &pl, float *d_pred,
+                     int64_t pred_row0, int64_t pred_rows);
+// dense float windows [B, T, 5] -> probs [B, T, C] (predict_on_batch semantics)
+int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t nbatch,
+                      float *d_probs);
+// mss.cu
+int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
+                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg);
+int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t *d_label_in,
+                 const int64_t *d_label64_in, int n, int nof_labels, uint8_t *d_label_out);
+int launch_labels_to_onehot(dgrp_ctx *c, const uint8_t *d_label, int64_t n, int C, double *d_out);
+// segments.cu
+int run_segments(dgrp_ctx *c, const uint8_t *d_label, const int64_t *d_label64, int64_t n,
+                 int64_t offset, bool keep_zero, int64_t **d_triples, int64_t *n_out);
+int launch_get_segments(dgrp_ctx *c, const int64_t *d_classes, int64_t size, int64_t startpos,
+                        int64_t *d_out3);
+
+}  // namespace dgrp

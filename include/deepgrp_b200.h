@@ -1,0 +1,195 @@
+/* deepgrp_b200.h -- C ABI of libdeepgrp_b200.so, the B200-native replacement for DeepGRP's
+ * prediction hot path.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repo fhausmann/deepgrp).
+ * INTEGRATION.md shows the ctypes / Cython stubs a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative DGRP_E_* code; dgrp_last_error() gives
+ *    the message of the last failure on the calling thread;
+ *  - "host" entry points take HOST pointers and do their own H2D/D2H copies on the context's
+ *    stream (they are what the Python shims of deepgrp.sequence / deepgrp.mss call);
+ *  - "_dev" entry points take DEVICE pointers resident on the context's GPU and only enqueue
+ *    kernels on the context's stream (no implicit synchronisation);
+ *  - there is NO CPU fallback: without a usable sm_100 GPU dgrp_ctx_create fails.
+ */
+#ifndef DEEPGRP_B200_H_
+#define DEEPGRP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGRP_OK 0
+#define DGRP_E_CUDA (-1)        /* a CUDA runtime call failed */
+#define DGRP_E_ARG (-2)         /* invalid argument */
+#define DGRP_E_NOGPU (-3)       /* no CUDA device / wrong architecture */
+#define DGRP_E_ALLN (-4)        /* all-'N' sequence: the reference raises ValueError (sequence.pyx:32) */
+#define DGRP_E_CAPACITY (-5)    /* caller-provided output too small; required size is reported */
+#define DGRP_E_UNSUPPORTED (-6) /* model variant not implemented by the CUDA path */
+#define DGRP_E_FASTA (-7)       /* malformed FASTA (blank line: the reference raises IndexError) */
+
+/* Window-placement compatibility:
+ * DGRP_COMPAT_REFERENCE reproduces deepgrp/prediction.py:105, where the final short batch is
+ * max-merged at offset i*len(batch)*step; DGRP_COMPAT_FIXED places every window at w*step. */
+#define DGRP_COMPAT_REFERENCE 0
+#define DGRP_COMPAT_FIXED 1
+
+typedef struct dgrp_ctx dgrp_ctx;     /* one GPU: device id, stream, workspace */
+typedef struct dgrp_model dgrp_model; /* device-resident weights of one model */
+
+/* Same layout as msseg_t, deepgrp/_mss/mss.h:11-14 */
+typedef struct {
+  int st, en;
+  double sc;
+} dgrp_seg_t;
+
+/* One output row of `deepgrp predict` before formatting (deepgrp/__main__.py:288-292):
+ * 0-based half-open [start, end) in ORIGINAL (untrimmed) record coordinates, label in 1..C-1. */
+typedef struct {
+  int64_t start, end;
+  int32_t label;
+  int32_t record; /* index of the FASTA record (dgrp_predict_fasta only; else 0) */
+} dgrp_row_t;
+
+/* Per-stage device times of the last dgrp_predict_* call, milliseconds (CUDA events). */
+typedef struct {
+  float encode_ms, forward_ms, attend_ms, score_ms, mss_ms, segments_ms, total_ms;
+  int64_t windows, bases;
+  int64_t kernel_launches;
+} dgrp_timings_t;
+
+/* ---- library / context ---------------------------------------------------------------- */
+int dgrp_version(void);
+const char *dgrp_last_error(void);
+int dgrp_device_count(int *count);
+int dgrp_ctx_create(int device, dgrp_ctx **out);
+int dgrp_ctx_destroy(dgrp_ctx *ctx);
+int dgrp_ctx_synchronize(dgrp_ctx *ctx);
+/* CUDA stream of the context as a void* (cudaStream_t), for callers that enqueue their own work */
+void *dgrp_ctx_stream(dgrp_ctx *ctx);
+int dgrp_ctx_timings(dgrp_ctx *ctx, dgrp_timings_t *out);
+/* number of kernels this library has launched on the context since creation */
+int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
+
+/* ---- deepgrp.sequence (deepgrp/sequence.pyx + deepgrp/maxcalc.c) --------------------- */
+
+/* one_hot_encode_dna_sequence, sequence.pyx:55-58 / :21-36.  Two steps so the caller can size
+ * the int8[5, L] array: _stage uploads the bytes and finds the edge-'N' trim on the GPU;
+ * _fetch writes the one-hot matrix (C order [5, out_len]) into `fwd`.
+ * fold_case != 0 treats 'n' like 'N' for trimming (the CLI upper-cases first, __main__.py:41).
+ * Returns DGRP_E_ALLN when the trimmed length is negative (all-'N' input). */
+int dgrp_one_hot_stage(dgrp_ctx *ctx, const uint8_t *seq, int64_t n, int fold_case,
+                       int64_t *startpos, int64_t *out_len);
+int dgrp_one_hot_fetch(dgrp_ctx *ctx, int8_t *fwd);
+
+/* _get_max, maxcalc.c:10-24 / get_max, sequence.pyx:67-76: window b (dim0 x dim1 floats) is
+ * max-merged into `output` at row b*stride.  `out_rows` is the number of rows of `output`
+ * (the reference does not know it and never checks; rows beyond it are an error here). */
+int dgrp_get_max(dgrp_ctx *ctx, float *output, int64_t out_rows, const float *inputs,
+                 int64_t batchsize, int64_t dim0, int64_t dim1, int64_t stride);
+int dgrp_get_max_dev(dgrp_ctx *ctx, float *d_output, int64_t out_rows, const float *d_inputs,
+                     int64_t batchsize, int64_t dim0, int64_t dim1, int64_t stride);
+
+/* get_segments, sequence.pyx:40-53 (including its size-1 loop bounds). out3 = start,end,label */
+int dgrp_get_segments(dgrp_ctx *ctx, const int64_t *classes, int64_t size, int64_t startpos,
+                      int64_t out3[3]);
+/* yield_segments, sequence.pyx:79-85, materialised: all (start+off, end+off, label) triples in
+ * order, label 0 included.  `out` holds cap triples; *n_out is the true count (DGRP_E_CAPACITY
+ * if cap is too small; call again with a larger buffer). */
+int dgrp_yield_segments(dgrp_ctx *ctx, const int64_t *classes, int64_t size, int64_t start_offset,
+                        int64_t *out, int64_t cap, int64_t *n_out);
+
+/* ---- deepgrp.mss (deepgrp/_mss/pymss.pyx + deepgrp/_mss/mss.c) ---------------------- */
+
+/* mss_find_all, mss.c:50-101 (min_sc is truncated to int as at the reference call site,
+ * mss.c:35).  Writes at most cap segments sorted by start; *n_seg is the true count. */
+int dgrp_mss_find_all(dgrp_ctx *ctx, int n, const double *S, double min_sc, double xdrop,
+                      dgrp_seg_t *out, int64_t cap, int *n_seg);
+/* find_mss_labels, pymss.pyx:16-27: one_hot is double[n, nof_labels], written completely. */
+int dgrp_find_mss_labels(dgrp_ctx *ctx, const double *scores, const int64_t *label, int n,
+                         int nof_labels, int min_mss_len, int xdrop_len, double *one_hot);
+
+/* ---- model (deepgrp/model.py:293-336; weights as stored by Keras) ---------------------- */
+
+/* rnn: 0 = GRU (reset_after, gate order z,r,h).  kernel[5,3U], recurrent[U,3U], bias[2,3U],
+ * att_scale[U] or NULL (no attention), ff_kernel[F,C] (F = 2U with attention else U), ff_bias[C]. */
+int dgrp_model_create(dgrp_ctx *ctx, int rnn, int vecsize, int units, int n_classes,
+                      const float *kernel, const float *recurrent, const float *bias,
+                      const float *att_scale, const float *ff_kernel, const float *ff_bias,
+                      dgrp_model **out);
+int dgrp_model_destroy(dgrp_model *model);
+
+/* keras.Model.predict_on_batch as used in deepgrp/prediction.py:106:
+ * batch float32[B, T, 5] (host) -> probs float32[B, T, C] (host). */
+int dgrp_forward_windows(dgrp_ctx *ctx, dgrp_model *model, const float *batch, int64_t nbatch,
+                         float *probs);
+
+/* ---- deepgrp.prediction ---------------------------------------------------------------- */
+
+/* fetch_validation_batch + predict (prediction.py:14-37, 89-111) on a one-hot int8[5, L] matrix:
+ * windows start at range(0, L-T, step); every window's softmax output is max-merged into the
+ * zero-initialised predictions float32[L, C].  batch_size only matters for
+ * DGRP_COMPAT_REFERENCE placement. */
+int dgrp_predict_onehot(dgrp_ctx *ctx, dgrp_model *model, const int8_t *fwd, int64_t length,
+                        int step, int batch_size, int compat, float *predictions);
+
+/* apply_mss (prediction.py:40-59): probs float32[n, C] -> one-hot float64[n, C]. */
+int dgrp_apply_mss(dgrp_ctx *ctx, const float *probs, int n, int n_classes, int min_mss_len,
+                   int xdrop_len, double *one_hot);
+/* The score transform alone (prediction.py:51-57): float64 scores + int64 classes. */
+int dgrp_mss_scores(dgrp_ctx *ctx, const float *probs, int64_t n, int n_classes, double *scores,
+                    int64_t *classes);
+/* softmax (prediction.py:62-65): exp(x - global max) / row sum, float32[n, C]. */
+int dgrp_softmax(dgrp_ctx *ctx, const float *array, int64_t n, int n_classes, float *out);
+
+/* ---- deepgrp.__main__ ------------------------------------------------------------------ */
+
+/* _predict (__main__.py:46-83) for one record given as raw sequence bytes (no header, no
+ * newlines): encode (fold_case as the CLI), forward, vote, then MSS (use_mss) or plain argmax.
+ * labels (uint8[n]) receives labels for the trimmed record, *length its length. labels may be
+ * NULL.  Rows (yield_segments + label>0 filter, __main__.py:288-290) are written to `rows`
+ * (cap entries; DGRP_E_CAPACITY with *n_rows = required if too small). */
+int dgrp_predict_sequence(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *seq, int64_t n,
+                          int fold_case, int step, int batch_size, int use_mss, int min_mss_len,
+                          int xdrop_len, int compat, int64_t *startpos, int64_t *length,
+                          uint8_t *labels, dgrp_row_t *rows, int64_t cap, int64_t *n_rows);
+
+/* The same on a window range of one record, for multi-GPU sharding:
+ * computes label (uint8) and float32 score for positions [pos0, pos1) of the TRIMMED record of
+ * length `length` whose codes (0..4, 5 = non-ACGTN) are given for the whole record or at least
+ * for [pos0 - T, pos1 + T) via `codes_base` (position of codes[0]). Outputs are host arrays. */
+int dgrp_predict_range(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *codes, int64_t codes_base,
+                       int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                       int batch_size, int compat, uint8_t *labels, float *scores);
+/* MSS gap fill + segment rows from gathered (label, score) of a whole record. */
+int dgrp_finish_record(dgrp_ctx *ctx, const uint8_t *labels, const float *scores, int64_t length,
+                       int n_classes, int use_mss, int min_mss_len, int xdrop_len,
+                       int64_t startpos, uint8_t *labels_out, dgrp_row_t *rows, int64_t cap,
+                       int64_t *n_rows);
+
+/* Whole-file driver (__main__.py:275-292 for one FASTA): raw FASTA text in, rows out.  The FASTA
+ * is decoded on the GPU (line stripping, '>' records, case folding, edge-'N' trim).  Record
+ * header offsets (into `fasta`) are returned so the caller can format the TSV:
+ * hdr_off[r], hdr_len[r] for r < *n_records (cap_records entries each). */
+int dgrp_predict_fasta(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
+                       int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len,
+                       int compat, dgrp_row_t *rows, int64_t cap_rows, int64_t *n_rows,
+                       int64_t *hdr_off, int64_t *hdr_len, int64_t cap_records,
+                       int64_t *n_records);
+
+/* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),
+ * runs forward + vote + score + MSS + segment extraction entirely on the device and leaves the
+ * row count in *n_rows (rows stay on the device).  No host copies except the 8-byte count. */
+int dgrp_predict_codes_dev(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *d_codes,
+                           int64_t length, int step, int batch_size, int use_mss,
+                           int min_mss_len, int xdrop_len, int compat, int64_t *n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPGRP_B200_H_ */
