@@ -1,0 +1,193 @@
+# !/usr/bin/env python3
+"""DeepGRP prediction with a pretrained model on B200 -- drop-in for ``deepgrp predict``
+(reference ``deepgrp/__main__.py``).  Same options (``-b -s -x -l -t --xla -v``, ``predict
+--output --no_use_mss``); ``-t`` and ``--xla`` are accepted and ignored (there is no TensorFlow).
+The README form ``deepgrp <modelfile> <fastafile>...`` (reference ``README.rst:92-98``) is accepted
+as well as the ``predict`` sub-command.  ``train`` is out of scope.
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import sys
+from typing import Iterator, List, TextIO, Tuple
+
+import numpy as np
+
+from . import model as dgmodel
+from . import prediction as dgpred
+from . import sequence as dgsequence
+
+logging.basicConfig()
+_LOG = logging.getLogger(__name__)
+
+
+def _read_multi_fasta(filestream: TextIO) -> Iterator[Tuple[str, str]]:
+    """Reads a multi FASTA file (reference ``deepgrp/__main__.py:20-43``): every line is stripped,
+    ``>`` starts a record (header = rest of the line), other lines are upper-cased and joined;
+    records with an empty header are dropped; a blank line raises ``IndexError``."""
+    _LOG.debug("Reading FASTA file.")
+    header = ""
+    sequence: List[str] = []
+    for line in filestream:
+        line = line.strip()
+        if line[0] == ">":
+            if header:
+                yield header, "".join(sequence)
+            header = line[1:]
+            sequence = []
+        else:
+            sequence.append(line.upper())
+    if header:
+        yield header, "".join(sequence)
+
+
+def _predict(dnasequence: str, model: dgmodel.ModelWeights, options: dgmodel.Options,
+             step_size: int, use_mss: bool) -> Tuple[np.ndarray, int]:
+    """Runs a prediction for one sequence (reference ``deepgrp/__main__.py:46-83``): the same five
+    calls in the same order, each through the CUDA path."""
+    _LOG.debug("One hot encoding sequence.")
+    start_pos, inputs = dgsequence.one_hot_encode_dna_sequence(dnasequence)
+    _LOG.debug("Start prediction.")
+    data_iterator = dgpred.fetch_validation_batch(inputs, step_size, options.batch_size,
+                                                  options.vecsize)
+    output_shape = (inputs.shape[1], model.output_shape[2])
+    prediction = dgpred.predict(model, data_iterator, output_shape, step_size)
+    _LOG.debug("Finish prediction.")
+    if use_mss:
+        _LOG.debug("Applying MSS.")
+        prediction = dgpred.apply_mss(prediction, options)
+    else:
+        prediction = dgpred.softmax(prediction)
+    return np.asanyarray(prediction.argmax(axis=1)), start_pos
+
+
+class CommandLineParser:
+    """Commandline parser (reference ``deepgrp/__main__.py:86-351``)."""
+
+    def __init__(self, **kwargs):
+        kwargs.setdefault("prog", "deepgrp")
+        kwargs.setdefault("formatter_class", argparse.ArgumentDefaultsHelpFormatter)
+        kwargs.setdefault("description", "DeepGRP - Prediction of repetitive elements")
+        self.parser = argparse.ArgumentParser(**kwargs)
+        self.args = None
+        self.threads = 1
+        self.xla = False
+        self.verbose = 0
+        subparsers = self.parser.add_subparsers(help="sub-command help", dest="command")
+        self.parser.add_argument("--batch_size", "-b", type=int, default=256,
+                                 help="Batch size (only decides where the reference places the "
+                                      "final short batch)")
+        self.parser.add_argument("--step_size", "-s", type=int, default=50, help="Window step size")
+        self.parser.add_argument("--xdrop_length", "-x", type=int, default=50,
+                                 help="XDrop parameter for MSS algorithm, ignored if "
+                                      "--no_use_mss, disabled with values<0")
+        self.parser.add_argument("--min_mss_length", "-l", type=int, default=50,
+                                 help="Minimal length of maximum scoring segments, ignored if "
+                                      "--no_use_mss")
+        self.parser.add_argument("--threads", "-t", type=int, default=1,
+                                 help="Accepted for compatibility; ignored (GPU path)")
+        self.parser.add_argument("--xla", action="store_true",
+                                 help="Accepted for compatibility; ignored")
+        self.parser.add_argument("-v", "--verbose", action="count", default=0,
+                                 help="Increase verbosity")
+        predict_subparser = subparsers.add_parser(
+            name="predict", formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+            description="predict using a deepgrp model")
+        predict_subparser.add_argument("model", type=str,
+                                       help="Keras model in HDF5 format (or .npz weights)")
+        predict_subparser.add_argument("FASTA", nargs="+", type=str, help="Fasta input files")
+        predict_subparser.add_argument("--output", type=str, default="-", help="Output filename")
+        predict_subparser.add_argument("--no_use_mss", "-m", action="store_true",
+                                       help="Disable maximum scoring segment algorithm")
+        predict_subparser.add_argument("--stepwise", action="store_true",
+                                       help="Run the reference's five Python-level calls per record "
+                                            "instead of the fused whole-record GPU call")
+
+    def parse_args(self, argv=None) -> "CommandLineParser":
+        """Parse command line arguments."""
+        argv = list(sys.argv[1:] if argv is None else argv)
+        # README form: `deepgrp [options] <modelfile> <fasta...>` without the sub-command
+        if not any(a in ("predict", "train") for a in argv) and not any(a in ("-h", "--help") for a in argv):
+            with_value = {"-b", "--batch_size", "-s", "--step_size", "-x", "--xdrop_length", "-l",
+                          "--min_mss_length", "-t", "--threads"}
+            i = 0
+            while i < len(argv):
+                if argv[i] in with_value:
+                    i += 2
+                elif argv[i].startswith("-") and argv[i] != "-":
+                    i += 1
+                else:
+                    break
+            argv.insert(i, "predict")
+        args = self.parser.parse_args(argv)
+        self.threads = args.threads
+        self.verbose = args.verbose
+        self.xla = args.xla
+        self.args = args
+        return self
+
+    def setup_tensorflow(self) -> "CommandLineParser":
+        """Kept for call-compatibility with the reference (``:221-233``); nothing to set up."""
+        return self
+
+    def set_logging(self) -> "CommandLineParser":
+        loglevels = [logging.WARNING, logging.INFO, logging.DEBUG]
+        _LOG.setLevel(level=loglevels[min(len(loglevels) - 1, self.verbose)])
+        return self
+
+    def run(self):
+        """Run the command provided by the user."""
+        if self.args.command is None:
+            self.parser.error("a sub-command is required")
+        options = dgmodel.Options(min_mss_len=self.args.min_mss_length,
+                                  batch_size=self.args.batch_size,
+                                  xdrop_len=self.args.xdrop_length)
+        getattr(self, self.args.command)(self.args, options)
+
+    @staticmethod
+    def predict(args: argparse.Namespace, options: dgmodel.Options):
+        """Predict with deepgrp (reference ``deepgrp/__main__.py:252-297``)."""
+        _LOG.debug("Loading model %s!", args.model)
+        model = dgmodel.load_model(args.model)
+        options.vecsize = model.input_shape[1]
+        _LOG.info("Model loading finished successfully!")
+        outstream = sys.stdout if args.output == "-" else open(args.output, "w")
+        use_mss = not args.no_use_mss
+        for filename in args.FASTA:
+            _LOG.info("Processing %s", filename)
+            try:
+                filestream = sys.stdin if filename == "-" else open(filename, "r")
+                if getattr(args, "stepwise", False):
+                    for header, dnasequence in _read_multi_fasta(filestream):
+                        predictions, startpos = _predict(dnasequence, model, options,
+                                                         args.step_size, use_mss=use_mss)
+                        for segment in dgsequence.yield_segments(predictions, startpos):
+                            if segment[2] > 0:
+                                outstream.write("{}\t{}\t{}\t{}\t{}\n".format(
+                                    filename, header, *segment))
+                else:
+                    raw = (sys.stdin.buffer.read() if filename == "-"
+                           else open(filename, "rb").read())
+                    outstream.write(dgpred.predict_fasta_tsv(
+                        model, raw, filename, args.step_size, options.batch_size, use_mss,
+                        options.min_mss_len, options.xdrop_len))
+            finally:
+                if filename != "-":
+                    filestream.close()
+        if args.output != "-":
+            outstream.close()
+
+    @staticmethod
+    def train(args, options):  # pragma: no cover
+        raise SystemExit("deepgrp_b200 implements the prediction path only; use the reference "
+                         "package to train")
+
+
+def main():
+    """Main function."""
+    CommandLineParser().parse_args().set_logging().setup_tensorflow().run()
+
+
+if __name__ == "__main__":
+    main()

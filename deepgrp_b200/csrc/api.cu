@@ -1,0 +1,790 @@
+// C ABI of libdeepgrp_b200.so (include/deepgrp_b200.h): contexts, weight handles and the host-side
+// sequencing of the kernels.  No CPU fallback: every entry point that computes needs a context, and a
+// context needs an sm_100 GPU.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dgrp_internal.cuh"
+
+namespace dgrp {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return DGRP_OK;
+  if (bytes < 256) bytes = 256;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  const size_t want = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+  DGRP_CUDA(cudaMalloc(&p, want));
+  cap = want;
+  return DGRP_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+}
+int PinBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return DGRP_OK;
+  if (bytes < 256) bytes = 256;
+  if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+  DGRP_CUDA(cudaMallocHost(&p, bytes));
+  cap = bytes;
+  return DGRP_OK;
+}
+void PinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr; cap = 0;
+}
+
+// s0 = ln(0.99/0.01) and the two thresholds of pymss.pyx:46-53
+static void mss_thresholds(int min_mss_len, int xdrop_len, double *min_sc, double *xdrop) {
+  const double s0 = log(0.99 / (1.0 - 0.99));
+  *xdrop = xdrop_len > 0 ? s0 * xdrop_len * 10.0 : -1.0;
+  *min_sc = s0 * min_mss_len;
+}
+
+static void stamp(dgrp_ctx *c, int i) { cudaEventRecord(c->ev[i], c->stream); }
+
+// codes (device, trimmed record of length L) -> predictions f32[L, C] in c->pred
+static int core_predict(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t L, int step,
+                        int batch_size, int compat) {
+  DGRP_REQUIRE(step > 0, "step_size must be positive");
+  DGRP_CHECK(c->pred.reserve((size_t)(L > 0 ? L : 1) * m->C * sizeof(float)));
+  if (L > 0) DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)L * m->C * sizeof(float), c->stream));
+  const Placement pl = make_placement(L, m->T, step, batch_size, compat);
+  c->timings.windows = pl.n_windows;
+  c->timings.bases = L;
+  return run_forward_vote(c, m, d_codes, 0, 0, pl.n_windows, pl, c->pred.as<float>(), 0, L);
+}
+
+// predictions (device f32[L, C]) or ready (label, score) -> final labels in c->labels2
+static int core_labels(dgrp_ctx *c, const float *d_pred, const uint8_t *d_lab_in,
+                       const float *d_score_in, int64_t L, int C, int use_mss, int min_mss_len,
+                       int xdrop_len) {
+  DGRP_REQUIRE(L < 2147483647LL, "record longer than 2^31-1 bases (int indices in mss.h:16)");
+  DGRP_CHECK(c->labels2.reserve((size_t)(L > 0 ? L : 1)));
+  if (L <= 0) return DGRP_OK;
+  if (use_mss) {
+    const uint8_t *lab = d_lab_in;
+    const float *sc = d_score_in;
+    if (d_pred) {
+      DGRP_CHECK(c->labels.reserve((size_t)L));
+      DGRP_CHECK(c->scores32.reserve((size_t)L * 4));
+      DGRP_CHECK(launch_score(c, d_pred, L, C, c->labels.as<uint8_t>(), c->scores32.as<float>(),
+                              nullptr, nullptr));
+      lab = c->labels.as<uint8_t>();
+      sc = c->scores32.as<float>();
+    }
+    stamp(c, 3);
+    double min_sc, xdrop;
+    mss_thresholds(min_mss_len, xdrop_len, &min_sc, &xdrop);
+    dgrp_seg_t *d_segs = nullptr;
+    int n_seg = 0;
+    DGRP_CHECK(run_mss_segments(c, nullptr, sc, (int)L, min_sc, xdrop, &d_segs, &n_seg));
+    DGRP_CHECK(run_gap_fill(c, d_segs, n_seg, lab, nullptr, (int)L, C, c->labels2.as<uint8_t>()));
+  } else {
+    // softmax (prediction.py:62-65) then argmax (__main__.py:83)
+    if (d_pred) {
+      DGRP_CHECK(c->io_a.reserve((size_t)L * C * 4));
+      DGRP_CHECK(launch_softmax_global(c, d_pred, L, C, c->io_a.as<float>()));
+      DGRP_CHECK(launch_score(c, c->io_a.as<float>(), L, C, c->labels2.as<uint8_t>(), nullptr,
+                              nullptr, nullptr));
+    } else {
+      DGRP_CUDA(cudaMemcpyAsync(c->labels2.p, d_lab_in, (size_t)L, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    stamp(c, 3);
+  }
+  return DGRP_OK;
+}
+
+// final labels (c->labels2) -> rows on the host (label > 0 only, __main__.py:288-290)
+static int core_rows(dgrp_ctx *c, int64_t L, int64_t startpos, int32_t record, bool to_host,
+                     dgrp_row_t *rows, int64_t cap, int64_t *n_rows) {
+  int64_t *d_tri = nullptr;
+  int64_t cnt = 0;
+  DGRP_CHECK(run_segments(c, c->labels2.as<uint8_t>(), nullptr, L, startpos, false, &d_tri, &cnt));
+  *n_rows = cnt;
+  if (!to_host || cnt == 0) return DGRP_OK;
+  if (cnt > cap || !rows) {
+    set_error("row buffer too small: %lld rows needed, capacity %lld", (long long)cnt, (long long)cap);
+    return DGRP_E_CAPACITY;
+  }
+  DGRP_CHECK(c->pin_a.reserve((size_t)cnt * 24));
+  DGRP_CUDA(cudaMemcpyAsync(c->pin_a.p, d_tri, (size_t)cnt * 24, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  const int64_t *t = c->pin_a.as<int64_t>();
+  for (int64_t i = 0; i < cnt; ++i) {
+    rows[i].start = t[3 * i]; rows[i].end = t[3 * i + 1];
+    rows[i].label = (int32_t)t[3 * i + 2]; rows[i].record = record;
+  }
+  return DGRP_OK;
+}
+
+static void finish_timings(dgrp_ctx *c, int64_t launches0) {
+  cudaStreamSynchronize(c->stream);
+  dgrp_timings_t &t = c->timings;
+  cudaEventElapsedTime(&t.encode_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&t.forward_ms, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&t.score_ms, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&t.mss_ms, c->ev[3], c->ev[4]);
+  cudaEventElapsedTime(&t.segments_ms, c->ev[4], c->ev[5]);
+  cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[5]);
+  t.attend_ms = 0.f;
+  t.kernel_launches = c->launches - launches0;
+}
+
+// raw record bytes on the device -> (startpos, length) and codes in c->codes
+static int core_encode(dgrp_ctx *c, const uint8_t *d_seq, int64_t n, int fold_case,
+                       int64_t *startpos, int64_t *length) {
+  DGRP_CHECK(c->small.reserve(256));
+  DGRP_CHECK(c->pin_small.reserve(256));
+  int64_t *d_fl = c->small.as<int64_t>() + 16;
+  DGRP_CHECK(launch_trim(c, d_seq, n, fold_case, d_fl));
+  int64_t *h = c->pin_small.as<int64_t>() + 8;
+  DGRP_CUDA(cudaMemcpyAsync(h, d_fl, 16, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  *startpos = h[0];           // first non-'N' (n when there is none)
+  *length = h[1] - h[0];      // (last non-'N' + 1) - startpos: -n for an all-'N' record
+  if (*length > 0) {
+    DGRP_CHECK(c->codes.reserve((size_t)*length + 16));
+    DGRP_CHECK(launch_codes(c, d_seq, *startpos, *length, c->codes.as<uint8_t>()));
+  }
+  return DGRP_OK;
+}
+
+}  // namespace dgrp
+
+using namespace dgrp;
+
+extern "C" {
+
+int dgrp_version(void) { return 100; }
+const char *dgrp_last_error(void) { return g_err; }
+
+int dgrp_device_count(int *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    *count = 0;
+    return DGRP_E_NOGPU;
+  }
+  *count = n;
+  return DGRP_OK;
+}
+
+int dgrp_ctx_create(int device, dgrp_ctx **out) {
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    set_error("no CUDA device is visible; deepgrp_b200 has no CPU fallback");
+    return DGRP_E_NOGPU;
+  }
+  DGRP_REQUIRE(device >= 0 && device < n, "device %d out of range (%d visible)", device, n);
+  cudaDeviceProp prop;
+  DGRP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name, prop.major,
+              prop.minor);
+    return DGRP_E_NOGPU;
+  }
+  DGRP_CUDA(cudaSetDevice(device));
+  dgrp_ctx *c = new dgrp_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete c;
+    return DGRP_E_CUDA;
+  }
+  for (auto &e : c->ev) cudaEventCreate(&e);
+  for (int i = 0; i < 6; ++i) cudaEventRecord(c->ev[i], c->stream);
+  *out = c;
+  return DGRP_OK;
+}
+
+int dgrp_ctx_destroy(dgrp_ctx *c) {
+  if (!c) return DGRP_OK;
+  Use use(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->raw, &c->codes, &c->onehot, &c->avg, &c->pred, &c->labels, &c->labels2,
+                    &c->scores32, &c->scores64, &c->classes64, &c->io_a, &c->io_b, &c->io_c,
+                    &c->small, &c->segs, &c->rows, &c->mss_a, &c->mss_b, &c->mss_c, &c->mss_d,
+                    &c->mss_e, &c->scan};
+  for (auto b : bufs) b->release();
+  c->pin_small.release(); c->pin_a.release(); c->pin_b.release();
+  for (auto &e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return DGRP_OK;
+}
+
+int dgrp_ctx_synchronize(dgrp_ctx *c) {
+  Use use(c->device);
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+void *dgrp_ctx_stream(dgrp_ctx *c) { return (void *)c->stream; }
+int dgrp_ctx_timings(dgrp_ctx *c, dgrp_timings_t *out) { *out = c->timings; return DGRP_OK; }
+int64_t dgrp_ctx_launch_count(dgrp_ctx *c) { return c->launches; }
+
+int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
+  if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
+  else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
+  else { set_error("unknown option %s", key); return DGRP_E_ARG; }
+  return DGRP_OK;
+}
+int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
+  if (!strcmp(key, "mss_chunk")) *value = c->mss_chunk;
+  else if (!strcmp(key, "mss_max_rounds")) *value = c->mss_max_rounds;
+  else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
+  else if (!strcmp(key, "sm_count")) *value = c->sm_count;
+  else { set_error("unknown option %s", key); return DGRP_E_ARG; }
+  return DGRP_OK;
+}
+
+/* ---------------------------------- deepgrp.sequence ---------------------------------- */
+
+int dgrp_one_hot_stage(dgrp_ctx *c, const uint8_t *seq, int64_t n, int fold_case,
+                       int64_t *startpos, int64_t *out_len) {
+  Use use(c->device);
+  DGRP_REQUIRE(n >= 0, "negative length");
+  c->staged_len = -1;
+  DGRP_CHECK(c->raw.reserve((size_t)n + 16));
+  if (n > 0) DGRP_CUDA(cudaMemcpyAsync(c->raw.p, seq, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(c->small.reserve(256));
+  DGRP_CHECK(c->pin_small.reserve(256));
+  int64_t *d_fl = c->small.as<int64_t>() + 16;
+  DGRP_CHECK(launch_trim(c, c->raw.as<uint8_t>(), n, fold_case, d_fl));
+  int64_t *h = c->pin_small.as<int64_t>() + 8;
+  DGRP_CUDA(cudaMemcpyAsync(h, d_fl, 16, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  *startpos = h[0];
+  *out_len = h[1] - h[0];
+  c->staged_n = n; c->staged_start = h[0]; c->staged_len = *out_len;
+  if (*out_len < 0) {
+    set_error("negative dimensions are not allowed (all-'N' sequence)");
+    return DGRP_E_ALLN;
+  }
+  return DGRP_OK;
+}
+
+int dgrp_one_hot_fetch(dgrp_ctx *c, int8_t *fwd) {
+  Use use(c->device);
+  DGRP_REQUIRE(c->staged_len >= 0, "dgrp_one_hot_fetch without a successful dgrp_one_hot_stage");
+  const int64_t len = c->staged_len;
+  if (len == 0) return DGRP_OK;
+  DGRP_CHECK(c->onehot.reserve((size_t)len * 5));
+  DGRP_CHECK(launch_onehot(c, c->raw.as<uint8_t>(), c->staged_start, len, c->onehot.as<int8_t>()));
+  DGRP_CUDA(cudaMemcpyAsync(fwd, c->onehot.p, (size_t)len * 5, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_get_max_dev(dgrp_ctx *c, float *d_output, int64_t out_rows, const float *d_inputs,
+                     int64_t batchsize, int64_t dim0, int64_t dim1, int64_t stride) {
+  Use use(c->device);
+  DGRP_REQUIRE(batchsize >= 0 && dim0 >= 0 && dim1 >= 0 && stride >= 0, "negative dimension");
+  if (batchsize == 0 || dim0 == 0 || dim1 == 0) return DGRP_OK;
+  DGRP_REQUIRE((batchsize - 1) * stride + dim0 <= out_rows,
+               "get_max would write %lld rows but output has %lld",
+               (long long)((batchsize - 1) * stride + dim0), (long long)out_rows);
+  return launch_get_max(c, d_output, d_inputs, batchsize, dim0, dim1, stride);
+}
+
+int dgrp_get_max(dgrp_ctx *c, float *output, int64_t out_rows, const float *inputs,
+                 int64_t batchsize, int64_t dim0, int64_t dim1, int64_t stride) {
+  Use use(c->device);
+  DGRP_REQUIRE(batchsize >= 0 && dim0 >= 0 && dim1 >= 0 && stride >= 0, "negative dimension");
+  if (batchsize == 0 || dim0 == 0 || dim1 == 0) return DGRP_OK;
+  const int64_t rows = (batchsize - 1) * stride + dim0;
+  DGRP_REQUIRE(rows <= out_rows, "get_max would write %lld rows but output has %lld",
+               (long long)rows, (long long)out_rows);
+  const size_t ob = (size_t)rows * dim1 * 4, ib = (size_t)batchsize * dim0 * dim1 * 4;
+  DGRP_CHECK(c->io_a.reserve(ob));
+  DGRP_CHECK(c->io_b.reserve(ib));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_a.p, output, ob, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_b.p, inputs, ib, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(launch_get_max(c, c->io_a.as<float>(), c->io_b.as<float>(), batchsize, dim0, dim1, stride));
+  DGRP_CUDA(cudaMemcpyAsync(output, c->io_a.p, ob, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_get_segments(dgrp_ctx *c, const int64_t *classes, int64_t size, int64_t startpos,
+                      int64_t out3[3]) {
+  Use use(c->device);
+  DGRP_REQUIRE(size > 0 && startpos >= 0 && startpos < size, "startpos %lld outside [0, %lld)",
+               (long long)startpos, (long long)size);
+  DGRP_CHECK(c->classes64.reserve((size_t)size * 8));
+  DGRP_CHECK(c->small.reserve(256));
+  DGRP_CUDA(cudaMemcpyAsync(c->classes64.p, classes, (size_t)size * 8, cudaMemcpyHostToDevice, c->stream));
+  int64_t *d_out = c->small.as<int64_t>() + 24;
+  DGRP_CHECK(launch_get_segments(c, c->classes64.as<int64_t>(), size, startpos, d_out));
+  DGRP_CUDA(cudaMemcpyAsync(out3, d_out, 24, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_yield_segments(dgrp_ctx *c, const int64_t *classes, int64_t size, int64_t start_offset,
+                        int64_t *out, int64_t cap, int64_t *n_out) {
+  Use use(c->device);
+  *n_out = 0;
+  if (size <= 0) return DGRP_OK;
+  DGRP_CHECK(c->classes64.reserve((size_t)size * 8));
+  DGRP_CUDA(cudaMemcpyAsync(c->classes64.p, classes, (size_t)size * 8, cudaMemcpyHostToDevice, c->stream));
+  int64_t *d_tri = nullptr;
+  int64_t cnt = 0;
+  DGRP_CHECK(run_segments(c, nullptr, c->classes64.as<int64_t>(), size, start_offset, true, &d_tri, &cnt));
+  *n_out = cnt;
+  if (cnt == 0) return DGRP_OK;
+  if (cnt > cap || !out) {
+    set_error("segment buffer too small: %lld needed, capacity %lld", (long long)cnt, (long long)cap);
+    return DGRP_E_CAPACITY;
+  }
+  DGRP_CUDA(cudaMemcpyAsync(out, d_tri, (size_t)cnt * 24, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+/* ------------------------------------- deepgrp.mss ------------------------------------- */
+
+int dgrp_mss_find_all(dgrp_ctx *c, int n, const double *S, double min_sc, double xdrop,
+                      dgrp_seg_t *out, int64_t cap, int *n_seg) {
+  Use use(c->device);
+  *n_seg = 0;
+  if (n <= 0) return DGRP_OK;
+  DGRP_CHECK(c->scores64.reserve((size_t)n * 8));
+  DGRP_CUDA(cudaMemcpyAsync(c->scores64.p, S, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  dgrp_seg_t *d_segs = nullptr;
+  DGRP_CHECK(run_mss_segments(c, c->scores64.as<double>(), nullptr, n, min_sc, xdrop, &d_segs, n_seg));
+  if (*n_seg == 0) return DGRP_OK;
+  if (*n_seg > cap || !out) {
+    set_error("segment buffer too small: %d needed, capacity %lld", *n_seg, (long long)cap);
+    return DGRP_E_CAPACITY;
+  }
+  DGRP_CUDA(cudaMemcpyAsync(out, d_segs, (size_t)*n_seg * sizeof(dgrp_seg_t), cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_find_mss_labels(dgrp_ctx *c, const double *scores, const int64_t *label, int n,
+                         int nof_labels, int min_mss_len, int xdrop_len, double *one_hot) {
+  Use use(c->device);
+  if (n <= 0) return DGRP_OK;
+  double min_sc, xdrop;
+  mss_thresholds(min_mss_len, xdrop_len, &min_sc, &xdrop);
+  DGRP_CHECK(c->scores64.reserve((size_t)n * 8));
+  DGRP_CHECK(c->classes64.reserve((size_t)n * 8));
+  DGRP_CHECK(c->labels2.reserve((size_t)n));
+  DGRP_CHECK(c->io_a.reserve((size_t)n * nof_labels * 8));
+  DGRP_CUDA(cudaMemcpyAsync(c->scores64.p, scores, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CUDA(cudaMemcpyAsync(c->classes64.p, label, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  dgrp_seg_t *d_segs = nullptr;
+  int n_seg = 0;
+  DGRP_CHECK(run_mss_segments(c, c->scores64.as<double>(), nullptr, n, min_sc, xdrop, &d_segs, &n_seg));
+  DGRP_CHECK(run_gap_fill(c, d_segs, n_seg, nullptr, c->classes64.as<int64_t>(), n, nof_labels,
+                          c->labels2.as<uint8_t>()));
+  DGRP_CHECK(launch_labels_to_onehot(c, c->labels2.as<uint8_t>(), n, nof_labels, c->io_a.as<double>()));
+  DGRP_CUDA(cudaMemcpyAsync(one_hot, c->io_a.p, (size_t)n * nof_labels * 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+/* ---------------------------------------- model ---------------------------------------- */
+
+int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classes,
+                      const float *kernel, const float *recurrent, const float *bias,
+                      const float *att_scale, const float *ff_kernel, const float *ff_bias,
+                      dgrp_model **out) {
+  Use use(c->device);
+  *out = nullptr;
+  if (rnn != 0) {
+    set_error("only the GRU variant (reset_after=True) is implemented by the CUDA forward");
+    return DGRP_E_UNSUPPORTED;
+  }
+  DGRP_REQUIRE(vecsize > 0 && units > 0, "vecsize and units must be positive");
+  DGRP_REQUIRE(n_classes >= 2 && n_classes <= 5, "n_classes must be in [2, 5], got %d", n_classes);
+  if (units > 128) {
+    set_error("units=%d not supported by the CUDA forward (max 128)", units);
+    return DGRP_E_UNSUPPORTED;
+  }
+  int UP = 16;
+  while (UP < units) UP <<= 1;
+  const int U = units, G = 3;
+  std::vector<float> P((size_t)5 * G * UP, 0.f), Wk((size_t)5 * G * UP, 0.f), b0((size_t)G * UP, 0.f),
+      b1((size_t)G * UP, 0.f), Rp((size_t)UP * G * UP, 0.f);
+  for (int cc = 0; cc < 5; ++cc)
+    for (int g = 0; g < G; ++g)
+      for (int u = 0; u < U; ++u) {
+        const float w = kernel[(size_t)cc * G * U + g * U + u];
+        Wk[((size_t)cc * G + g) * UP + u] = w;
+        P[((size_t)cc * G + g) * UP + u] = w + bias[g * U + u];
+      }
+  for (int g = 0; g < G; ++g)
+    for (int u = 0; u < U; ++u) {
+      b0[(size_t)g * UP + u] = bias[g * U + u];
+      b1[(size_t)g * UP + u] = bias[(size_t)G * U + g * U + u];
+    }
+  for (int k = 0; k < U; ++k)
+    for (int g = 0; g < G; ++g)
+      for (int u = 0; u < U; ++u)
+        Rp[((size_t)k * G + g) * UP + u] = recurrent[(size_t)k * G * U + g * U + u];
+  dgrp_model *m = new dgrp_model();
+  m->device = c->device; m->rnn = rnn; m->T = vecsize; m->U = U; m->C = n_classes; m->UP = UP;
+  m->attention = att_scale != nullptr;
+  const int F = m->attention ? 2 * U : U;
+  auto up = [&](float **dst, const float *src, size_t count) -> int {
+    DGRP_CUDA(cudaMalloc((void **)dst, count * sizeof(float)));
+    DGRP_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return DGRP_OK;
+  };
+  int rc = DGRP_OK;
+  if ((rc = up(&m->d_P, P.data(), P.size())) || (rc = up(&m->d_Wk, Wk.data(), Wk.size())) ||
+      (rc = up(&m->d_b0, b0.data(), b0.size())) || (rc = up(&m->d_b1, b1.data(), b1.size())) ||
+      (rc = up(&m->d_Rp, Rp.data(), Rp.size())) ||
+      (rc = up(&m->d_ffk, ff_kernel, (size_t)F * n_classes)) ||
+      (rc = up(&m->d_ffb, ff_bias, (size_t)n_classes)) ||
+      (m->attention && (rc = up(&m->d_scale, att_scale, (size_t)U)))) {
+    cudaStreamSynchronize(c->stream);
+    dgrp_model_destroy(m);
+    return rc;
+  }
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+  *out = m;
+  return DGRP_OK;
+}
+
+int dgrp_model_destroy(dgrp_model *m) {
+  if (!m) return DGRP_OK;
+  Use use(m->device);
+  float *ptrs[] = {m->d_kernel, m->d_bias, m->d_recurrent, m->d_P, m->d_Wk, m->d_b0, m->d_Rp,
+                   m->d_b1, m->d_scale, m->d_ffk, m->d_ffb};
+  for (float *p : ptrs)
+    if (p) cudaFree(p);
+  delete m;
+  return DGRP_OK;
+}
+
+int dgrp_forward_windows(dgrp_ctx *c, dgrp_model *m, const float *batch, int64_t nbatch,
+                         float *probs) {
+  Use use(c->device);
+  if (nbatch <= 0) return DGRP_OK;
+  const size_t ib = (size_t)nbatch * m->T * 5 * 4, ob = (size_t)nbatch * m->T * m->C * 4;
+  DGRP_CHECK(c->io_a.reserve(ib));
+  DGRP_CHECK(c->io_b.reserve(ob));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_a.p, batch, ib, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(run_forward_dense(c, m, c->io_a.as<float>(), nbatch, c->io_b.as<float>()));
+  DGRP_CUDA(cudaMemcpyAsync(probs, c->io_b.p, ob, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+/* ---------------------------------- deepgrp.prediction --------------------------------- */
+
+int dgrp_predict_onehot(dgrp_ctx *c, dgrp_model *m, const int8_t *fwd, int64_t length, int step,
+                        int batch_size, int compat, float *predictions) {
+  Use use(c->device);
+  DGRP_REQUIRE(length >= 0, "negative length");
+  if (length == 0) return DGRP_OK;
+  DGRP_CHECK(c->onehot.reserve((size_t)length * 5));
+  DGRP_CHECK(c->codes.reserve((size_t)length + 16));
+  DGRP_CUDA(cudaMemcpyAsync(c->onehot.p, fwd, (size_t)length * 5, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(launch_onehot_to_codes(c, c->onehot.as<int8_t>(), length, c->codes.as<uint8_t>()));
+  DGRP_CHECK(c->pin_small.reserve(256));
+  int *h_flag = c->pin_small.as<int>() + 40;
+  DGRP_CUDA(cudaMemcpyAsync(h_flag, c->small.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  DGRP_REQUIRE(*h_flag == 0, "input matrix is not one-hot int8[5, L] (use forward_windows for dense input)");
+  DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, step, batch_size, compat));
+  DGRP_CUDA(cudaMemcpyAsync(predictions, c->pred.p, (size_t)length * m->C * 4, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_mss_scores(dgrp_ctx *c, const float *probs, int64_t n, int n_classes, double *scores,
+                    int64_t *classes) {
+  Use use(c->device);
+  if (n <= 0) return DGRP_OK;
+  DGRP_CHECK(c->io_a.reserve((size_t)n * n_classes * 4));
+  DGRP_CHECK(c->scores64.reserve((size_t)n * 8));
+  DGRP_CHECK(c->classes64.reserve((size_t)n * 8));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_a.p, probs, (size_t)n * n_classes * 4, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(launch_score(c, c->io_a.as<float>(), n, n_classes, nullptr, nullptr,
+                          c->scores64.as<double>(), c->classes64.as<int64_t>()));
+  if (scores) DGRP_CUDA(cudaMemcpyAsync(scores, c->scores64.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (classes) DGRP_CUDA(cudaMemcpyAsync(classes, c->classes64.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_apply_mss(dgrp_ctx *c, const float *probs, int n, int n_classes, int min_mss_len,
+                   int xdrop_len, double *one_hot) {
+  Use use(c->device);
+  if (n <= 0) return DGRP_OK;
+  DGRP_CHECK(c->io_a.reserve((size_t)n * n_classes * 4));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_a.p, probs, (size_t)n * n_classes * 4, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(core_labels(c, c->io_a.as<float>(), nullptr, nullptr, n, n_classes, 1, min_mss_len, xdrop_len));
+  DGRP_CHECK(c->io_b.reserve((size_t)n * n_classes * 8));
+  DGRP_CHECK(launch_labels_to_onehot(c, c->labels2.as<uint8_t>(), n, n_classes, c->io_b.as<double>()));
+  DGRP_CUDA(cudaMemcpyAsync(one_hot, c->io_b.p, (size_t)n * n_classes * 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_softmax(dgrp_ctx *c, const float *array, int64_t n, int n_classes, float *out) {
+  Use use(c->device);
+  if (n <= 0) return DGRP_OK;
+  const size_t b = (size_t)n * n_classes * 4;
+  DGRP_CHECK(c->io_a.reserve(b));
+  DGRP_CHECK(c->io_b.reserve(b));
+  DGRP_CUDA(cudaMemcpyAsync(c->io_a.p, array, b, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(launch_softmax_global(c, c->io_a.as<float>(), n, n_classes, c->io_b.as<float>()));
+  DGRP_CUDA(cudaMemcpyAsync(out, c->io_b.p, b, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+/* ----------------------------------- deepgrp.__main__ ---------------------------------- */
+
+int dgrp_predict_sequence(dgrp_ctx *c, dgrp_model *m, const uint8_t *seq, int64_t n,
+                          int fold_case, int step, int batch_size, int use_mss, int min_mss_len,
+                          int xdrop_len, int compat, int64_t *startpos, int64_t *length,
+                          uint8_t *labels, dgrp_row_t *rows, int64_t cap, int64_t *n_rows) {
+  Use use(c->device);
+  DGRP_REQUIRE(n >= 0, "negative length");
+  const int64_t launches0 = c->launches;
+  *n_rows = 0;
+  stamp(c, 0);
+  DGRP_CHECK(c->raw.reserve((size_t)n + 16));
+  if (n > 0) DGRP_CUDA(cudaMemcpyAsync(c->raw.p, seq, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(core_encode(c, c->raw.as<uint8_t>(), n, fold_case, startpos, length));
+  if (*length < 0) {
+    set_error("negative dimensions are not allowed (all-'N' sequence)");
+    return DGRP_E_ALLN;
+  }
+  stamp(c, 1);
+  const int64_t L = *length;
+  DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), L, step, batch_size, compat));
+  stamp(c, 2);
+  DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, L, m->C, use_mss, min_mss_len, xdrop_len));
+  stamp(c, 4);
+  if (labels && L > 0)
+    DGRP_CUDA(cudaMemcpyAsync(labels, c->labels2.p, (size_t)L, cudaMemcpyDeviceToHost, c->stream));
+  int rc = DGRP_OK;
+  if (L > 0) rc = core_rows(c, L, *startpos, 0, true, rows, cap, n_rows);
+  stamp(c, 5);
+  finish_timings(c, launches0);
+  return rc;
+}
+
+int dgrp_predict_fasta(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, int step,
+                       int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,
+                       int64_t *n_rows, int64_t *n_records) {
+  Use use(c->device);
+  const int64_t launches0 = c->launches;
+  *n_rows = 0; *n_records = 0;
+  c->fa_rows.clear(); c->fa_hdr_off.clear(); c->fa_hdr_len.clear();
+  c->fa_startpos.clear(); c->fa_length.clear();
+  DGRP_REQUIRE(nbytes >= 0, "negative length");
+  stamp(c, 0);
+  DGRP_CHECK(c->raw.reserve((size_t)nbytes + 16));
+  if (nbytes > 0) DGRP_CUDA(cudaMemcpyAsync(c->raw.p, fasta, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
+  int64_t n_seq = 0, n_hdr = 0;
+  DGRP_CHECK(run_fasta_decode(c, c->raw.as<uint8_t>(), nbytes, &n_seq, &n_hdr));
+  std::vector<int64_t> hpos(n_hdr), hseq(n_hdr + 1);
+  if (n_hdr > 0) {
+    const int64_t *t = c->pin_b.as<int64_t>();
+    for (int64_t k = 0; k < n_hdr; ++k) { hpos[k] = t[k]; hseq[k] = t[(n_hdr + 1) + k]; }
+  }
+  hseq[n_hdr] = n_seq;
+  auto ws = [](uint8_t b) { return (b >= 9 && b <= 13) || (b >= 28 && b <= 32); };
+  float enc_ms = 0.f, fwd_ms = 0.f, score_ms = 0.f, mss_ms = 0.f, seg_ms = 0.f;
+  int64_t windows = 0, bases = 0;
+  cudaEvent_t e_begin = c->ev[6], e_end = c->ev[7];
+  cudaEventRecord(e_begin, c->stream);
+  int rc = DGRP_OK;
+  for (int64_t k = 0; k < n_hdr && rc == DGRP_OK; ++k) {
+    // header = stripped line without its '>' (__main__.py:38)
+    int64_t b = hpos[k] + 1, e = b;
+    while (e < nbytes && fasta[e] != '\n' && !(fasta[e] == '\r' && !(e + 1 < nbytes && fasta[e + 1] == '\n'))) ++e;
+    while (e > b && ws(fasta[e - 1])) --e;
+    if (e == b) continue;                         // empty header: record dropped (__main__.py:36)
+    const int32_t rec = (int32_t)c->fa_hdr_off.size();
+    const uint8_t *d_seq = c->io_b.as<uint8_t>() + hseq[k];
+    const int64_t n = hseq[k + 1] - hseq[k];
+    int64_t startpos = 0, length = 0;
+    stamp(c, 0);
+    rc = core_encode(c, d_seq, n, 1, &startpos, &length);
+    if (rc != DGRP_OK) break;
+    if (length < 0) {
+      set_error("negative dimensions are not allowed (all-'N' record %d)", rec);
+      rc = DGRP_E_ALLN;
+      break;
+    }
+    c->fa_hdr_off.push_back(b); c->fa_hdr_len.push_back(e - b);
+    c->fa_startpos.push_back(startpos); c->fa_length.push_back(length);
+    stamp(c, 1);
+    if ((rc = core_predict(c, m, c->codes.as<uint8_t>(), length, step, batch_size, compat))) break;
+    windows += c->timings.windows; bases += length;
+    stamp(c, 2);
+    if ((rc = core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, use_mss, min_mss_len, xdrop_len))) break;
+    stamp(c, 4);
+    if (length > 0) {
+      int64_t *d_tri = nullptr;
+      int64_t cnt = 0;
+      if ((rc = run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt))) break;
+      if (cnt > 0) {
+        if ((rc = c->pin_a.reserve((size_t)cnt * 24))) break;
+        if (cudaMemcpyAsync(c->pin_a.p, d_tri, (size_t)cnt * 24, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+          set_error("copying rows failed");
+          rc = DGRP_E_CUDA;
+          break;
+        }
+        const int64_t *t = c->pin_a.as<int64_t>();
+        const size_t base = c->fa_rows.size();
+        c->fa_rows.resize(base + (size_t)cnt);
+        for (int64_t i = 0; i < cnt; ++i) {
+          dgrp_row_t &r = c->fa_rows[base + i];
+          r.start = t[3 * i]; r.end = t[3 * i + 1]; r.label = (int32_t)t[3 * i + 2]; r.record = rec;
+        }
+      }
+    }
+    stamp(c, 5);
+    cudaStreamSynchronize(c->stream);
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); enc_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); fwd_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); score_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); mss_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); seg_ms += ms;
+  }
+  cudaEventRecord(e_end, c->stream);
+  cudaStreamSynchronize(c->stream);
+  dgrp_timings_t &t = c->timings;
+  t.encode_ms = enc_ms; t.forward_ms = fwd_ms; t.score_ms = score_ms; t.mss_ms = mss_ms;
+  t.segments_ms = seg_ms; t.attend_ms = 0.f; t.windows = windows; t.bases = bases;
+  cudaEventElapsedTime(&t.total_ms, e_begin, e_end);
+  t.kernel_launches = c->launches - launches0;
+  *n_rows = (int64_t)c->fa_rows.size();
+  *n_records = (int64_t)c->fa_hdr_off.size();
+  return rc;
+}
+
+int dgrp_fasta_rows(dgrp_ctx *c, dgrp_row_t *rows, int64_t cap) {
+  DGRP_REQUIRE((int64_t)c->fa_rows.size() <= cap, "row buffer too small: %lld needed",
+               (long long)c->fa_rows.size());
+  if (!c->fa_rows.empty()) memcpy(rows, c->fa_rows.data(), c->fa_rows.size() * sizeof(dgrp_row_t));
+  return DGRP_OK;
+}
+
+int dgrp_fasta_records(dgrp_ctx *c, int64_t *hdr_off, int64_t *hdr_len, int64_t *startpos,
+                       int64_t *length, int64_t cap) {
+  const size_t n = c->fa_hdr_off.size();
+  DGRP_REQUIRE((int64_t)n <= cap, "record buffer too small: %lld needed", (long long)n);
+  if (n == 0) return DGRP_OK;
+  if (hdr_off) memcpy(hdr_off, c->fa_hdr_off.data(), n * 8);
+  if (hdr_len) memcpy(hdr_len, c->fa_hdr_len.data(), n * 8);
+  if (startpos) memcpy(startpos, c->fa_startpos.data(), n * 8);
+  if (length) memcpy(length, c->fa_length.data(), n * 8);
+  return DGRP_OK;
+}
+
+int dgrp_predict_codes_dev(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t length,
+                           int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len,
+                           int compat, int64_t *n_rows) {
+  Use use(c->device);
+  const int64_t launches0 = c->launches;
+  *n_rows = 0;
+  stamp(c, 0);
+  stamp(c, 1);
+  DGRP_CHECK(core_predict(c, m, d_codes, length, step, batch_size, compat));
+  stamp(c, 2);
+  DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, use_mss, min_mss_len, xdrop_len));
+  stamp(c, 4);
+  int rc = DGRP_OK;
+  if (length > 0) rc = core_rows(c, length, 0, 0, false, nullptr, 0, n_rows);
+  stamp(c, 5);
+  finish_timings(c, launches0);
+  return rc;
+}
+
+int dgrp_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *codes, int64_t codes_base,
+                       int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                       int batch_size, int compat, uint8_t *labels, float *scores) {
+  Use use(c->device);
+  DGRP_REQUIRE(0 <= pos0 && pos0 <= pos1 && pos1 <= length, "bad range [%lld, %lld) of %lld",
+               (long long)pos0, (long long)pos1, (long long)length);
+  const int64_t rows = pos1 - pos0;
+  if (rows == 0) return DGRP_OK;
+  const Placement pl = make_placement(length, m->T, step, batch_size, compat);
+  const int T = m->T;
+  // windows whose PLACED rows [place, place+T) intersect [pos0, pos1)
+  auto range_for = [&](int64_t w_lo, int64_t w_hi, int64_t base, int64_t *b, int64_t *e) {
+    // window w (w_lo <= w < w_hi) is placed at base + (w - w_lo) * step
+    int64_t first = 0, last = w_hi - w_lo;  // local indices
+    if (pos0 - T + 1 - base > 0) first = (pos0 - T + 1 - base + step - 1) / step;
+    if (pos1 - base <= 0) last = 0;
+    else last = std::min<int64_t>(last, (pos1 - 1 - base) / step + 1);
+    if (first > last) first = last;
+    *b = w_lo + first; *e = w_lo + last;
+  };
+  int64_t a0, a1, t0, t1;
+  range_for(0, pl.full_windows, 0, &a0, &a1);
+  range_for(pl.full_windows, pl.n_windows, pl.tail_base, &t0, &t1);
+  // codes needed: true window positions [w*step, w*step + T)
+  int64_t need_lo = length, need_hi = 0;
+  if (a1 > a0) { need_lo = std::min(need_lo, a0 * step); need_hi = std::max(need_hi, (a1 - 1) * step + T); }
+  if (t1 > t0) { need_lo = std::min(need_lo, t0 * step); need_hi = std::max(need_hi, (t1 - 1) * step + T); }
+  if (need_hi > need_lo)
+    DGRP_REQUIRE(codes_base <= need_lo && need_hi <= codes_base + codes_len,
+                 "codes [%lld, %lld) do not cover the needed bases [%lld, %lld)", (long long)codes_base,
+                 (long long)(codes_base + codes_len), (long long)need_lo, (long long)need_hi);
+  DGRP_CHECK(c->codes.reserve((size_t)codes_len + 16));
+  DGRP_CUDA(cudaMemcpyAsync(c->codes.p, codes, (size_t)codes_len, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(c->pred.reserve((size_t)rows * m->C * 4));
+  DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)rows * m->C * 4, c->stream));
+  DGRP_CHECK(run_forward_vote(c, m, c->codes.as<uint8_t>(), codes_base, a0, a1, pl, c->pred.as<float>(), pos0, rows));
+  DGRP_CHECK(run_forward_vote(c, m, c->codes.as<uint8_t>(), codes_base, t0, t1, pl, c->pred.as<float>(), pos0, rows));
+  DGRP_CHECK(c->labels.reserve((size_t)rows));
+  DGRP_CHECK(c->scores32.reserve((size_t)rows * 4));
+  DGRP_CHECK(launch_score(c, c->pred.as<float>(), rows, m->C, c->labels.as<uint8_t>(),
+                          c->scores32.as<float>(), nullptr, nullptr));
+  if (labels) DGRP_CUDA(cudaMemcpyAsync(labels, c->labels.p, (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
+  if (scores) DGRP_CUDA(cudaMemcpyAsync(scores, c->scores32.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_finish_record(dgrp_ctx *c, const uint8_t *labels, const float *scores, int64_t length,
+                       int n_classes, int use_mss, int min_mss_len, int xdrop_len, int64_t startpos,
+                       uint8_t *labels_out, dgrp_row_t *rows, int64_t cap, int64_t *n_rows) {
+  Use use(c->device);
+  *n_rows = 0;
+  if (length <= 0) return DGRP_OK;
+  DGRP_CHECK(c->labels.reserve((size_t)length));
+  DGRP_CHECK(c->scores32.reserve((size_t)length * 4));
+  DGRP_CUDA(cudaMemcpyAsync(c->labels.p, labels, (size_t)length, cudaMemcpyHostToDevice, c->stream));
+  if (use_mss)
+    DGRP_CUDA(cudaMemcpyAsync(c->scores32.p, scores, (size_t)length * 4, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(core_labels(c, nullptr, c->labels.as<uint8_t>(), c->scores32.as<float>(), length,
+                         n_classes, use_mss, min_mss_len, xdrop_len));
+  if (labels_out)
+    DGRP_CUDA(cudaMemcpyAsync(labels_out, c->labels2.p, (size_t)length, cudaMemcpyDeviceToHost, c->stream));
+  const int rc = core_rows(c, length, startpos, 0, true, rows, cap, n_rows);
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+}  // extern "C"

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/deepgrp_b200.h"
@@ -67,6 +68,8 @@ struct dgrp_model {
   float *d_bias = nullptr;       // [2, 3U]
   float *d_recurrent = nullptr;  // [U, 3U]     raw Keras recurrent kernel
   float *d_P = nullptr;          // [5, 3, UP]  kernel[c, g*U+u] + bias[0, g*U+u], zero padded
+  float *d_Wk = nullptr;         // [5, 3, UP]  kernel alone (dense float input), zero padded
+  float *d_b0 = nullptr;         // [3, UP]     bias[0, g*U+u], zero padded
   float *d_Rp = nullptr;         // [UP, 3, UP] recurrent[k, g*U+u], zero padded
   float *d_b1 = nullptr;         // [3, UP]     bias[1, g*U+u], zero padded
   float *d_scale = nullptr;      // [U] or null
@@ -83,8 +86,15 @@ struct dgrp_ctx {
   dgrp_timings_t timings = {};
   // workspaces (grow-only)
   dgrp::DevBuf raw, codes, onehot, avg, pred, labels, labels2, scores32, scores64, classes64,
-      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, scan;
+      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, mss_e, scan;
   dgrp::PinBuf pin_small, pin_a, pin_b;
+  // tuning knobs / diagnostics (dgrp_ctx_set_int / dgrp_ctx_get_int)
+  int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)
+  int mss_max_rounds = 0;  // Jacobi rounds before the sequential completion (0 = default)
+  int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
+  // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
+  std::vector<dgrp_row_t> fa_rows;
+  std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length;
   // staged one-hot state (dgrp_one_hot_stage -> dgrp_one_hot_fetch)
   int64_t staged_n = 0, staged_start = 0, staged_len = -1;
 };
@@ -137,6 +147,8 @@ int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n
 int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t *d_label_in,
                  const int64_t *d_label64_in, int n, int nof_labels, uint8_t *d_label_out);
 int launch_labels_to_onehot(dgrp_ctx *c, const uint8_t *d_label, int64_t n, int C, double *d_out);
+// fasta.cu
+int run_fasta_decode(dgrp_ctx *c, const uint8_t *d_raw, int64_t n, int64_t *n_seq, int64_t *n_hdr);
 // segments.cu
 int run_segments(dgrp_ctx *c, const uint8_t *d_label, const int64_t *d_label64, int64_t n,
                  int64_t offset, bool keep_zero, int64_t **d_triples, int64_t *n_out);

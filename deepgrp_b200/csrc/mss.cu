@@ -1,0 +1,419 @@
+// K7: chunked maximal-scoring-segment scan + majority gap fill.
+// Replaces deepgrp/_mss/mss.c:50-101 (mss_find_all) and deepgrp/_mss/pymss.pyx:31-80
+// (_find_mss_labels).  The algorithm and why it is bit-exact are described in mss_core.cuh.
+#include "dgrp_internal.cuh"
+#include "mss_core.cuh"
+#include "scan_util.cuh"
+
+namespace dgrp {
+
+using mss::RunTable;
+using mss::ScanState;
+
+__global__ void cp_scan_kernel(unsigned int *a, int64_t m, unsigned long long *total) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t base = 0; base < m; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const unsigned long long v = i < m ? a[i] : 0;
+    unsigned long long x = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = lane < nwarp ? s_warp[lane] : 0;
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long excl = s_carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+    if (i < m) a[i] = (unsigned int)excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += s_warp[nwarp - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[0] = s_carry;
+}
+
+// count -> scan -> (host reads the total) -> scatter.  Uses c->scan for tile counts and
+// c->pin_small for the total.
+template <class Pred, class Emit>
+static int compact(dgrp_ctx *c, int64_t n, Pred pred, Emit emit, int64_t *count) {
+  *count = 0;
+  if (n <= 0) return DGRP_OK;
+  const int64_t ntiles = (n + CP_TILE - 1) / CP_TILE;
+  DGRP_CHECK(c->scan.reserve((size_t)ntiles * 4 + 64));
+  DGRP_CHECK(c->pin_small.reserve(256));
+  unsigned int *tiles = c->scan.as<unsigned int>();
+  unsigned long long *total =
+      reinterpret_cast<unsigned long long *>(c->scan.as<unsigned char>() + ((ntiles * 4 + 15) / 16) * 16);
+  DGRP_CHECK(c->scan.reserve(((size_t)ntiles * 4 + 15) / 16 * 16 + 64));
+  tiles = c->scan.as<unsigned int>();
+  total = reinterpret_cast<unsigned long long *>(c->scan.as<unsigned char>() + ((ntiles * 4 + 15) / 16) * 16);
+  cp_count_kernel<<<(unsigned)ntiles, CP_THREADS, 0, c->stream>>>(n, pred, tiles);
+  cp_scan_kernel<<<1, 1024, 0, c->stream>>>(tiles, ntiles, total);
+  c->launches += 2;
+  unsigned long long *h = c->pin_small.as<unsigned long long>();
+  DGRP_CUDA(cudaMemcpyAsync(h, total, 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  *count = (int64_t)h[0];
+  if (*count > 0) {
+    cp_scatter_kernel<<<(unsigned)ntiles, CP_THREADS, 0, c->stream>>>(n, pred, emit, tiles);
+    c->launches++;
+  }
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
+// ---- stage 0: run ordinals --------------------------------------------------------------------
+template <typename T>
+__global__ void mss_count_runs_kernel(const T *__restrict__ S, int n, int CH, unsigned int *cnt) {
+  const int gs = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gs) {   // CH is a multiple of 32
+    const int i = i0 + threadIdx.x;
+    bool f = false;
+    if (i < n) f = ((double)S[i] > 0) && (i == 0 || !((double)S[i - 1] > 0));
+    const unsigned int m = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[(i0 + (int)threadIdx.x) / CH], __popc(m));
+  }
+}
+
+// ---- stage 1: reduced scan, chunked --------------------------------------------------------------
+struct ScanBufs {
+  ScanState *used, *out_a, *out_b;
+  uint8_t *ch_a, *ch_b;
+  uint8_t *reset_flag;
+  const unsigned int *base;   // [NC] first run ordinal of each chunk
+  int *n_changed;
+};
+
+template <typename T>
+__global__ void mss_round1_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
+                                  ScanBufs b, RunTable rt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  ScanState s;
+  mss::state_canonical(s);
+  b.used[c] = s;
+  const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
+  mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, false, rt);
+  b.out_a[c] = s;
+  b.ch_a[c] = 1;
+}
+
+// One Jacobi round: chunk c re-runs from out_prev[c-1] when that changed and differs from the
+// state it last started from.  Reads prev (a), writes next (b).
+template <typename T>
+__global__ void mss_rerun_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
+                                 ScanBufs b, RunTable rt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  ScanState prev_out = b.out_a[c];
+  uint8_t changed = 0;
+  if (c > 0 && b.ch_a[c - 1]) {
+    ScanState s = b.out_a[c - 1];
+    if (!mss::state_equal(s, b.used[c])) {
+      b.used[c] = s;
+      const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
+      const bool synced =
+          mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, true, rt);
+      if (!synced && !mss::state_equal(s, prev_out)) {
+        prev_out = s;
+        changed = 1;
+      }
+    }
+  }
+  b.out_b[c] = prev_out;
+  b.ch_b[c] = changed;
+  if (changed) atomicAdd(b.n_changed, 1);
+}
+
+// Sequential completion of the fixed point by one thread (used when the rounds do not converge
+// quickly, e.g. x-drop disabled): chunk after chunk from the first stale one.
+template <typename T>
+__global__ void mss_chain_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
+                                 ScanBufs b, RunTable rt) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int c = 1; c < NC; ++c) {
+    ScanState s = b.out_a[c - 1];
+    if (mss::state_equal(s, b.used[c])) continue;
+    b.used[c] = s;
+    const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
+    const bool synced = mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, true, rt);
+    if (!synced) b.out_a[c] = s;
+  }
+}
+
+// ---- stage 2: regions ----------------------------------------------------------------------------
+struct IsEvent {
+  const uint8_t *kind;
+  __device__ bool operator()(int64_t k) const { return kind[k] != mss::RUN_PLAIN; }
+};
+struct EmitEvent {
+  int *ev;
+  __device__ void operator()(int64_t k, int64_t pos) const { ev[pos] = (int)k; }
+};
+
+__global__ void mss_regions_kernel(const int *__restrict__ ev, int n_ev, int NR, int min_sc_int,
+                                   RunTable rt, uint8_t *live) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_ev) return;
+  const int k0 = ev[r], k1 = r + 1 < n_ev ? ev[r + 1] : NR;
+  // the event kind of k1 must be read BEFORE region r+1's thread overwrites slot k1?  It does not:
+  // kind[] is never written here, only st/en/L/R/pre of slots inside the own region.
+  const int depth = mss::process_region(k0, k1, rt);
+  const bool flushed = (k1 == NR) || rt.kind[k1] == mss::RUN_FLUSH;
+  for (int j = 0; j < k1 - k0; ++j)
+    live[k0 + j] = (j < depth && flushed && (rt.R[k0 + j] - rt.L[k0 + j] >= (double)min_sc_int)) ? 1 : 0;
+}
+
+struct IsLive {
+  const uint8_t *live;
+  __device__ bool operator()(int64_t k) const { return live[k] != 0; }
+};
+struct EmitSeg {
+  RunTable rt;
+  dgrp_seg_t *out;
+  __device__ void operator()(int64_t k, int64_t pos) const {
+    dgrp_seg_t s;
+    s.st = rt.st[k]; s.en = rt.en[k]; s.sc = rt.R[k] - rt.L[k];
+    out[pos] = s;
+  }
+};
+
+static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+template <typename T>
+static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdrop,
+                     dgrp_seg_t **d_segs_out, int *n_seg) {
+  *n_seg = 0;
+  *d_segs_out = nullptr;
+  if (n <= 0) return DGRP_OK;
+  int CH = c->mss_chunk;
+  if (CH <= 0) {
+    CH = 1024;
+    while (CH > 64 && (int64_t)n / CH < 4096) CH >>= 1;
+  }
+  CH = (CH + 31) / 32 * 32;
+  const int NC = (n + CH - 1) / CH;
+
+  // ---- run ordinals
+  DGRP_CHECK(c->mss_a.reserve((size_t)(NC + 1) * 4 + 64));
+  unsigned int *base = c->mss_a.as<unsigned int>();
+  DGRP_CUDA(cudaMemsetAsync(base, 0, (size_t)(NC + 1) * 4, c->stream));
+  {
+    const int threads = 256;
+    int64_t want = ((int64_t)n + threads - 1) / threads;
+    const int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+    mss_count_runs_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, CH, base);
+    c->launches++;
+  }
+  DGRP_CHECK(c->pin_small.reserve(256));
+  DGRP_CHECK(c->small.reserve(256));
+  unsigned long long *d_total = c->small.as<unsigned long long>() + 8;
+  cp_scan_kernel<<<1, 1024, 0, c->stream>>>(base, NC, d_total);
+  c->launches++;
+  unsigned long long *h = c->pin_small.as<unsigned long long>();
+  DGRP_CUDA(cudaMemcpyAsync(h, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  const int NR = (int)h[0];
+  if (NR == 0) return DGRP_OK;   // no positive score anywhere: no segments
+
+  // ---- buffers
+  const size_t nr1 = (size_t)NR + 1;
+  size_t off = 0;
+  const size_t o_st = off; off = align256(off + nr1 * 4);
+  const size_t o_en = off; off = align256(off + nr1 * 4);
+  const size_t o_pre = off; off = align256(off + nr1 * 4);
+  const size_t o_L = off; off = align256(off + nr1 * 8);
+  const size_t o_R = off; off = align256(off + nr1 * 8);
+  const size_t o_kind = off; off = align256(off + nr1);
+  const size_t o_live = off; off = align256(off + nr1);
+  const size_t o_ev = off; off = align256(off + nr1 * 4);
+  DGRP_CHECK(c->mss_b.reserve(off));
+  unsigned char *pb = c->mss_b.as<unsigned char>();
+  RunTable rt;
+  rt.st = reinterpret_cast<int *>(pb + o_st);
+  rt.en = reinterpret_cast<int *>(pb + o_en);
+  rt.pre = reinterpret_cast<int *>(pb + o_pre);
+  rt.L = reinterpret_cast<double *>(pb + o_L);
+  rt.R = reinterpret_cast<double *>(pb + o_R);
+  rt.kind = pb + o_kind;
+  uint8_t *live = pb + o_live;
+  int *ev = reinterpret_cast<int *>(pb + o_ev);
+
+  off = 0;
+  const size_t o_used = off; off = align256(off + (size_t)NC * sizeof(ScanState));
+  const size_t o_oa = off; off = align256(off + (size_t)NC * sizeof(ScanState));
+  const size_t o_ob = off; off = align256(off + (size_t)NC * sizeof(ScanState));
+  const size_t o_ca = off; off = align256(off + (size_t)NC);
+  const size_t o_cb = off; off = align256(off + (size_t)NC);
+  const size_t o_cnt = off; off = align256(off + 64);
+  DGRP_CHECK(c->mss_c.reserve(off));
+  DGRP_CHECK(c->mss_d.reserve((size_t)n));
+  unsigned char *pc = c->mss_c.as<unsigned char>();
+  ScanBufs sb;
+  sb.used = reinterpret_cast<ScanState *>(pc + o_used);
+  sb.out_a = reinterpret_cast<ScanState *>(pc + o_oa);
+  sb.out_b = reinterpret_cast<ScanState *>(pc + o_ob);
+  sb.ch_a = pc + o_ca;
+  sb.ch_b = pc + o_cb;
+  sb.n_changed = reinterpret_cast<int *>(pc + o_cnt);
+  sb.reset_flag = c->mss_d.as<uint8_t>();
+  sb.base = base;
+  DGRP_CUDA(cudaMemsetAsync(sb.reset_flag, 0, (size_t)n, c->stream));
+
+  // ---- stage 1
+  const int threads = 128;
+  const int blocks = (NC + threads - 1) / threads;
+  mss_round1_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+  c->launches++;
+  int *h_changed = reinterpret_cast<int *>(h + 2);
+  int rounds = 1;
+  const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 4;
+  bool converged = NC == 1;
+  while (!converged && rounds < max_rounds) {
+    DGRP_CUDA(cudaMemsetAsync(sb.n_changed, 0, 4, c->stream));
+    mss_rerun_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+    c->launches++;
+    DGRP_CUDA(cudaMemcpyAsync(h_changed, sb.n_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+    DGRP_CUDA(cudaStreamSynchronize(c->stream));
+    std::swap(sb.out_a, sb.out_b);
+    std::swap(sb.ch_a, sb.ch_b);
+    ++rounds;
+    converged = (*h_changed == 0);
+  }
+  if (!converged) {
+    mss_chain_kernel<T><<<1, 32, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+    c->launches++;
+  }
+  c->mss_rounds = converged ? rounds : -rounds;
+
+  // ---- stage 2
+  int64_t n_ev = 0;
+  DGRP_CHECK(compact(c, NR, IsEvent{rt.kind}, EmitEvent{ev}, &n_ev));
+  if (n_ev > 0) {
+    const int rb = (int)((n_ev + threads - 1) / threads);
+    mss_regions_kernel<<<rb, threads, 0, c->stream>>>(ev, (int)n_ev, NR, (int)min_sc, rt, live);
+    c->launches++;
+  }
+  int64_t n_live = 0;
+  // the segment list is written behind a generous reservation: count first
+  DGRP_CHECK(c->segs.reserve(256));
+  {
+    // two-step: count (inside compact) needs the output buffer only for scatter, so reserve after
+    // counting.  compact() scatters immediately, hence reserve for the worst case NR here.
+    DGRP_CHECK(c->mss_e.reserve(nr1 * sizeof(dgrp_seg_t)));
+    DGRP_CHECK(compact(c, NR, IsLive{live}, EmitSeg{rt, c->mss_e.as<dgrp_seg_t>()}, &n_live));
+  }
+  DGRP_CUDA(cudaGetLastError());
+  *d_segs_out = c->mss_e.as<dgrp_seg_t>();
+  *n_seg = (int)n_live;
+  return DGRP_OK;
+}
+
+int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
+                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg) {
+  if (d_s64) return run_mss_t<double>(c, d_s64, n, min_sc, xdrop, d_segs_out, n_seg);
+  return run_mss_t<float>(c, d_s32, n, min_sc, xdrop, d_segs_out, n_seg);
+}
+
+// ---- gap fill (pymss.pyx:59-77) -------------------------------------------------------------------
+// One warp per segment: count labels 1..nof-1, majority (ties -> lowest, default 1), rewrite zeros.
+constexpr int GF_MAXC = 16;
+
+template <typename LabT>
+__global__ void gap_fill_kernel(const dgrp_seg_t *__restrict__ segs, int n_seg,
+                                const LabT *__restrict__ lab_in, int nof,
+                                uint8_t *__restrict__ lab_out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int g = blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < n_seg;
+       g += gridDim.x * warps_per_block) {
+    const int st = segs[g].st, en = segs[g].en;
+    unsigned int cnt[GF_MAXC];
+#pragma unroll
+    for (int k = 0; k < GF_MAXC; ++k) cnt[k] = 0;
+    for (int i = st + lane; i < en; i += 32) {
+      const int l = (int)lab_in[i];
+#pragma unroll
+      for (int k = 1; k < GF_MAXC; ++k) cnt[k] += (l == k);
+    }
+#pragma unroll
+    for (int k = 1; k < GF_MAXC; ++k)
+      for (int off = 16; off > 0; off >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], off);
+    int best = 1;
+    unsigned int bestv = cnt[1];
+#pragma unroll
+    for (int k = 2; k < GF_MAXC; ++k)
+      if (k < nof && bestv < cnt[k]) { best = k; bestv = cnt[k]; }
+    for (int i = st + lane; i < en; i += 32)
+      if (lab_in[i] == 0) lab_out[i] = (uint8_t)best;
+  }
+}
+
+template <typename LabT>
+__global__ void copy_labels_kernel(const LabT *__restrict__ in, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs)
+    out[i] = (uint8_t)in[i];
+}
+
+int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t *d_label_in,
+                 const int64_t *d_label64_in, int n, int nof_labels, uint8_t *d_label_out) {
+  if (n <= 0) return DGRP_OK;
+  DGRP_REQUIRE(nof_labels >= 2 && nof_labels <= GF_MAXC, "nof_labels must be in [2, %d]", GF_MAXC);
+  const int threads = 256;
+  int64_t want = ((int64_t)n + threads - 1) / threads;
+  int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+  if (d_label_in) {
+    if (d_label_in != d_label_out)
+      copy_labels_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_label_in, n, d_label_out);
+  } else {
+    copy_labels_kernel<int64_t><<<blocks, threads, 0, c->stream>>>(d_label64_in, n, d_label_out);
+  }
+  c->launches++;
+  if (n_seg > 0) {
+    want = ((int64_t)n_seg + 7) / 8;
+    blocks = (int)(want < (int64_t)c->sm_count * 8 ? want : (int64_t)c->sm_count * 8);
+    if (d_label_in)
+      gap_fill_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label_in, nof_labels, d_label_out);
+    else
+      gap_fill_kernel<int64_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label64_in, nof_labels, d_label_out);
+    c->launches++;
+  }
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
+__global__ void labels_to_onehot_kernel(const uint8_t *__restrict__ lab, int64_t n, int C,
+                                        double *__restrict__ out) {
+  const int64_t total = n * C;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gs) {
+    const int64_t i = e / C;
+    out[e] = ((int)lab[i] == (int)(e - i * C)) ? 1.0 : 0.0;
+  }
+}
+
+int launch_labels_to_onehot(dgrp_ctx *c, const uint8_t *d_label, int64_t n, int C, double *d_out) {
+  if (n <= 0) return DGRP_OK;
+  const int threads = 256;
+  int64_t want = (n * C + threads - 1) / threads;
+  const int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+  labels_to_onehot_kernel<<<blocks, threads, 0, c->stream>>>(d_label, n, C, d_out);
+  c->launches++;
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
+}  // namespace dgrp

@@ -1,0 +1,194 @@
+// Scalar building blocks of the chunked maximal-scoring-segment scan (K7).  Replaces
+// deepgrp/_mss/mss.c:50-101 (mss_find_all) and :35-47 (move_segs).
+//
+// The functions are __host__ __device__ so that tests/ can compile this header with g++ and run
+// the exact kernel logic on the CPU next to the oracle (the product only calls them from kernels).
+//
+// How the sequential algorithm is split ("K7"):
+//
+//  1. The reference walks S once keeping (L, max, candidate stack).  Every stack operation happens
+//     at the END of a maximal run of positive scores; the run enters as candidate
+//     t = {st, en, L = prefix sum before the run, R = prefix sum after it}.
+//  2. Two invariants hold whenever the stack is non-empty:
+//        (i)  the bottom candidate has the strictly smallest L on the stack;
+//        (ii) max == bottom.R  (every other candidate's R is <= the R of its `pre` chain, which
+//             ends at the bottom).
+//     Hence what happens to the stack as a whole at a run end is decided by (L, max, bottom.L):
+//        A: stack empty or !(bottom.L < t.L)  -> mss.c:78-81: flush (move_segs), t is the new bottom
+//        B: else R > max                      -> t absorbs every candidate down to the bottom
+//                                                (mss.c:73-76 repeatedly), then j < 0: the stack is
+//                                                {st = bottom.st, L = bottom.L, R, en}; nothing flushed
+//        0: else                              -> ordinary push / partial merges, bottom unchanged
+//     and the x-drop reset (mss.c:89-92) also only reads (L, max).
+//  3. So a REDUCED scan over S carrying (L, max, bottom.L, bottom.st) -- no stack -- yields, per run,
+//     a record {st, en, L, R, kind} with bit-identical doubles, because it performs the same
+//     additions in the same order.  After an A or B run the stack is exactly one known candidate,
+//     so the runs between two consecutive A/B runs form a REGION whose stack evolution is
+//     independent of everything before it.  Regions are processed in parallel (one thread each)
+//     by the unmodified push/merge loop; a region is flushed if the next event is A (or the end)
+//     and dropped if it is B (absorbed).
+//  4. The reduced scan itself is chunked: chunk c > 0 starts speculatively from the state right
+//     after an x-drop reset (L = 0, max = -1e30, empty), the only state that does not depend on
+//     history.  It is then RE-RUN from the true state handed over by chunk c-1; the re-run stops
+//     as soon as it takes an x-drop reset at an index where the previous run of this chunk also
+//     reset (both are then in the identical state, so everything after is already correct).
+//     Iterating "state_in[c] = state_out[c-1]" to a fixed point is exact for any input; with
+//     x-drop enabled it converges in two rounds on real data and degenerates to a sequential
+//     chain (still bit-exact) when no reset ever fires.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DGRP_HD __host__ __device__ __forceinline__
+#else
+#define DGRP_HD inline
+#endif
+
+namespace dgrp {
+namespace mss {
+
+constexpr double kNegInf = -1e30;  // NEG_INF, mss.c:33
+
+enum RunKind : uint8_t { RUN_PLAIN = 0, RUN_FLUSH = 1 /* A */, RUN_ABSORB = 2 /* B */ };
+
+// State of the reduced scan between two elements.  Unused fields are kept at fixed values so that
+// two states can be compared field by field.
+struct ScanState {
+  double L;        // running sum ("L" of mss.c:56)
+  double maxv;     // "max" of mss.c:56
+  double botL;     // bottom candidate's L   (0 when empty)
+  double run_L0;   // L before the run in progress (0 when !in_run)
+  int bot_st;      // bottom candidate's st  (-1 when empty)
+  int run_st;      // start of the run in progress (-1 when !in_run)
+  int run_ord;     // ordinal of the run in progress (-1 when !in_run or unknown)
+  int flags;       // bit 0: stack empty, bit 1: in a positive run
+};
+
+DGRP_HD void state_canonical(ScanState &s) {
+  s.L = 0.0; s.maxv = kNegInf; s.botL = 0.0; s.run_L0 = 0.0;
+  s.bot_st = -1; s.run_st = -1; s.run_ord = -1; s.flags = 1;
+}
+
+DGRP_HD bool state_equal(const ScanState &a, const ScanState &b) {
+  // compare bit patterns of the doubles through integer views (so that -0.0 != 0.0, NaN == NaN)
+  union V { double d; long long i; };
+  V x, y;
+  x.d = a.L; y.d = b.L; if (x.i != y.i) return false;
+  x.d = a.maxv; y.d = b.maxv; if (x.i != y.i) return false;
+  x.d = a.botL; y.d = b.botL; if (x.i != y.i) return false;
+  x.d = a.run_L0; y.d = b.run_L0; if (x.i != y.i) return false;
+  return a.bot_st == b.bot_st && a.run_st == b.run_st && a.run_ord == b.run_ord && a.flags == b.flags;
+}
+
+// Per-run records, struct of arrays indexed by run ordinal.  After region processing the same
+// slots hold the candidate stacks (in place), `pre` added.
+struct RunTable {
+  int *st, *en;
+  double *L, *R;
+  int *pre;
+  uint8_t *kind;
+};
+
+// Close the run in progress at index k (exclusive end); mss.c:64-87 reduced to (L, max, bottom).
+DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt) {
+  const double R = s.L, tL = s.run_L0;
+  const double old_max = s.maxv;
+  if (R > s.maxv) s.maxv = R;                       // mss.c:64
+  uint8_t kind;
+  int rec_st;
+  double rec_L;
+  if ((s.flags & 1) || !(s.botL < tL)) {            // no candidate with L < t.L  ->  j < 0
+    kind = RUN_FLUSH;
+    s.botL = tL; s.bot_st = s.run_st; s.maxv = R;   // mss.c:79-80, t becomes the bottom
+    s.flags &= ~1;
+    rec_st = s.run_st; rec_L = tL;
+  } else if (R > old_max) {                         // absorbs down to and including the bottom
+    kind = RUN_ABSORB;
+    s.maxv = R;
+    rec_st = s.bot_st; rec_L = s.botL;
+  } else {
+    kind = RUN_PLAIN;
+    rec_st = s.run_st; rec_L = tL;
+  }
+  if (s.run_ord >= 0) {
+    rt.st[s.run_ord] = rec_st; rt.en[s.run_ord] = k;
+    rt.L[s.run_ord] = rec_L; rt.R[s.run_ord] = R;
+    rt.kind[s.run_ord] = kind;
+  }
+  s.flags &= ~2;
+  s.run_st = -1; s.run_ord = -1; s.run_L0 = 0.0;
+}
+
+// Reduced scan over elements [b, e) of S (e <= n).  `first_ord` is the ordinal of the first run
+// that STARTS in [b, e).  `reset_flag[i]` records for every non-positive element whether this
+// execution took the x-drop reset there.  With `rerun`, the walk stops (returns true) at the first
+// reset that the previous execution of these elements also took.
+template <typename ScoreT>
+DGRP_HD bool scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
+                        ScanState &s, uint8_t *reset_flag, bool rerun, const RunTable &rt) {
+  int next_ord = first_ord;
+  for (int i = b; i < e; ++i) {
+    const double v = (double)S[i];
+    if (v > 0) {
+      if (!(s.flags & 2)) {
+        s.flags |= 2;
+        s.run_st = i; s.run_L0 = s.L;
+        // a "run" that begins at a speculative chunk start in the middle of a true run has no
+        // ordinal; it only shapes the (to be discarded) speculative state
+        const bool true_start = (i == 0) || !((double)S[i - 1] > 0);
+        s.run_ord = true_start ? next_ord++ : -1;
+      }
+      s.L += v;                                     // R = L + S[i]; R += S[k]  (mss.c:61-63)
+      if (i + 1 == n || !((double)S[i + 1] > 0)) finish_run(s, i + 1, rt);
+    } else {
+      const bool hit = xdrop > 0.0 && s.L + v + xdrop < s.maxv;   // mss.c:89
+      const uint8_t before = reset_flag[i];
+      reset_flag[i] = hit ? 1 : 0;
+      if (hit) {
+        if (rerun && before) return true;           // same reset as last time: states coincide
+        s.L = 0.0; s.maxv = kNegInf;                // mss.c:91 (the flush happens at the next run)
+        s.botL = 0.0; s.bot_st = -1; s.flags |= 1;
+      }
+      s.L += v;                                     // mss.c:93
+    }
+  }
+  return false;
+}
+
+// Stack evolution of one region: runs [k0, k1) where k0 is a FLUSH/ABSORB run (its record is the
+// single candidate on the stack) and no other event lies inside.  The push/merge loop of
+// mss.c:65-86, with the stack stored in place at slots k0.. .  Returns the final depth.
+DGRP_HD int process_region(int k0, int k1, const RunTable &rt) {
+  int depth = 1;
+  rt.pre[k0] = -1;
+  for (int k = k0 + 1; k < k1; ++k) {
+    int t_st = rt.st[k], t_en = rt.en[k], t_pre;
+    double t_L = rt.L[k];
+    const double t_R = rt.R[k];
+    for (;;) {
+      int j = depth - 1;
+      while (j >= 0) {
+        if (rt.L[k0 + j] < t_L) break;
+        const int pj = rt.pre[k0 + j];
+        j = pj >= 0 ? pj : j - 1;
+      }
+      if (j >= 0 && rt.R[k0 + j] < t_R) {
+        t_st = rt.st[k0 + j]; t_L = rt.L[k0 + j]; t_pre = rt.pre[k0 + j];
+        depth = j;
+        (void)t_pre;
+      } else {
+        // j < 0 cannot happen inside a region (it would have been classified FLUSH/ABSORB)
+        t_pre = j;
+        const int slot = k0 + depth;
+        rt.st[slot] = t_st; rt.en[slot] = t_en; rt.L[slot] = t_L; rt.R[slot] = t_R;
+        rt.pre[slot] = t_pre;
+        ++depth;
+        break;
+      }
+    }
+  }
+  return depth;
+}
+
+}  // namespace mss
+}  // namespace dgrp

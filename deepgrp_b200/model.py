@@ -163,6 +163,33 @@ class ModelWeights:
                             self.ff_kernel * factor, self.ff_bias * factor,
                             None if self.att_scale is None else self.att_scale * factor, self.rnn)
 
+    def device_handle(self, ctx):
+        """``dgrp_model*`` of these weights on the context's GPU (uploaded on first use)."""
+        import ctypes
+        from . import _lib
+        key = ctx.device
+        handle = self._device_handles.get(key)
+        if handle is None:
+            if self.rnn != "GRU":
+                raise NotImplementedError("only rnn='GRU' is implemented by the CUDA forward")
+            handle = ctypes.c_void_p()
+            _lib.check(_lib.lib().dgrp_model_create(
+                ctx.handle, 0, self.vecsize, self.units, self.n_classes, _lib.ptr(self.kernel),
+                _lib.ptr(self.recurrent_kernel), _lib.ptr(self.bias), _lib.ptr(self.att_scale),
+                _lib.ptr(self.ff_kernel), _lib.ptr(self.ff_bias), ctypes.byref(handle)))
+            self._device_handles[key] = handle
+            self._handle_vecsize = self.vecsize
+        elif getattr(self, "_handle_vecsize", self.vecsize) != self.vecsize:
+            self.release()
+            return self.device_handle(ctx)
+        return handle
+
+    def release(self) -> None:
+        from . import _lib
+        for handle in self._device_handles.values():
+            _lib.lib().dgrp_model_destroy(handle)
+        self._device_handles = {}
+
     def predict_on_batch(self, batch):
         """keras.Model.predict_on_batch stand-in: float32[B,T,5] one-hot windows -> float32[B,T,C]
         through the CUDA forward (no CPU fallback)."""
@@ -179,6 +206,15 @@ class ModelWeights:
                    z["bias"], z["ff_kernel"], z["ff_bias"],
                    z["att_scale"] if "att_scale" in z.files else None,
                    str(z["rnn"]) if "rnn" in z.files else "GRU")
+
+
+def load_model(path: str) -> ModelWeights:
+    """Stands where ``tf.keras.models.load_model`` stood (reference ``deepgrp/__main__.py:264-269``):
+    reads a Keras HDF5 model file (``.hdf5``/``.h5``) or the ``.npz`` side format."""
+    if str(path).endswith(".npz"):
+        return ModelWeights.load_npz(path)
+    from . import hdf5
+    return hdf5.load_keras_model(path)
 
 
 def _glorot_uniform(rng: np.random.Generator, shape, fan_in: int, fan_out: int) -> np.ndarray:

@@ -1,0 +1,249 @@
+"""deepgrp_b200.prediction -- drop-in for the reference's ``deepgrp.prediction`` on the prediction
+path (``deepgrp/prediction.py:14-141``): same function names and argument meaning.
+
+Differences that callers can see:
+
+* ``fetch_validation_batch`` returns a :class:`WindowDataset` (a lazy window descriptor that can be
+  iterated batch by batch exactly like the reference's ``tf.data.Dataset``) instead of a TensorFlow
+  dataset.  When it is handed to :func:`predict` together with a :class:`~deepgrp_b200.model.ModelWeights`
+  the windows are never materialised: the one-hot matrix is turned into base codes on the GPU and
+  the fused kernel reads windows as strided views (``csrc/forward.cu``).
+* ``predict`` reproduces the reference's placement of the final short batch
+  (``deepgrp/prediction.py:105``) by default; ``compat="fixed"`` places
+  every window at ``w * step``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from . import mss
+from . import sequence as dgsequence
+from .model import ModelWeights, Options, create_model, load_model
+from . import preprocessing  # noqa: F401  (Data, as in the reference's import list)
+
+_COMPAT = {"reference": _lib.COMPAT_REFERENCE, "fixed": _lib.COMPAT_FIXED}
+
+
+class WindowDataset:
+    """Windows ``data.T[i:i+vecsize]`` for ``i in range(0, L - vecsize, step_size)`` in batches of
+    ``batch_size`` (the final batch may be short), reference ``deepgrp/prediction.py:28-37``."""
+
+    def __init__(self, data: np.ndarray, step_size: int, batch_size: int, vecsize: int):
+        self.data = np.asarray(data)
+        self.step_size = int(step_size)
+        self.batch_size = int(batch_size)
+        self.vecsize = int(vecsize)
+
+    @property
+    def length(self) -> int:
+        return int(self.data.shape[1])
+
+    def window_starts(self) -> range:
+        return range(0, self.length - self.vecsize, self.step_size)     # end EXCLUSIVE
+
+    def __len__(self) -> int:
+        n = len(self.window_starts())
+        return (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[np.ndarray]:
+        data_t = self.data.T
+        starts = self.window_starts()
+        for b in range(0, len(starts), self.batch_size):
+            idx = starts[b:b + self.batch_size]
+            yield np.stack([data_t[i:i + self.vecsize].astype("float32") for i in idx])
+
+
+def fetch_validation_batch(data: np.ndarray, step_size: int, batch_size: int,
+                           vecsize: int) -> WindowDataset:
+    """Reference ``deepgrp/prediction.py:14-37`` (no randomisation)."""
+    return WindowDataset(data, step_size, batch_size, vecsize)
+
+
+def forward_windows(model: ModelWeights, batch) -> np.ndarray:
+    """``keras.Model.predict_on_batch``: ``float32[B, T, 5]`` windows -> ``float32[B, T, C]``."""
+    batch = np.ascontiguousarray(batch, dtype=np.float32)
+    if batch.ndim != 3 or batch.shape[1] != model.vecsize or batch.shape[2] != 5:
+        raise ValueError("expected windows of shape [B, %d, 5], got %s" % (model.vecsize, batch.shape))
+    ctx = _lib.context()
+    out = np.zeros((batch.shape[0], model.vecsize, model.n_classes), dtype=np.float32)
+    _lib.check(_lib.lib().dgrp_forward_windows(ctx.handle, model.device_handle(ctx), _lib.ptr(batch),
+                                               batch.shape[0], _lib.ptr(out)))
+    return out
+
+
+def apply_mss(probs: np.ndarray, options: Options) -> np.ndarray:
+    """argmax + logit score -> maximal scoring segments -> gap-filled one-hot ``float64[n, C]``
+    (reference ``deepgrp/prediction.py:40-59``)."""
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    n, nof = probs.shape
+    out = np.zeros((n, nof), dtype=np.float64)
+    if n == 0:
+        return out
+    ctx = _lib.context()
+    _lib.check(_lib.lib().dgrp_apply_mss(ctx.handle, _lib.ptr(probs), n, nof,
+                                         int(options.min_mss_len), int(options.xdrop_len),
+                                         _lib.ptr(out)))
+    return out
+
+
+def mss_scores(probs: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """The score transform of ``apply_mss`` alone (reference ``deepgrp/prediction.py:51-57``):
+    ``(float64 scores, int64 classes)``."""
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    n, nof = probs.shape
+    scores = np.zeros(n, dtype=np.float64)
+    classes = np.zeros(n, dtype=np.int64)
+    if n:
+        ctx = _lib.context()
+        _lib.check(_lib.lib().dgrp_mss_scores(ctx.handle, _lib.ptr(probs), n, nof, _lib.ptr(scores),
+                                              _lib.ptr(classes)))
+    return scores, classes
+
+
+def softmax(array: np.ndarray) -> np.ndarray:
+    """``exp(x - max(x)) / rowsum`` (reference ``deepgrp/prediction.py:62-65``)."""
+    array = np.ascontiguousarray(array, dtype=np.float32)
+    out = np.zeros_like(array)
+    if array.size:
+        ctx = _lib.context()
+        _lib.check(_lib.lib().dgrp_softmax(ctx.handle, _lib.ptr(array), array.shape[0],
+                                           array.shape[1], _lib.ptr(out)))
+    return out
+
+
+def setup_prediction_from_options_checkpoint(options: Options, logdir) -> ModelWeights:
+    """Reference ``deepgrp/prediction.py:68-86``.  ``logdir`` is a weights file (Keras ``.hdf5`` /
+    ``.h5`` or ``.npz``) or a directory holding one; the newest file wins, as the latest checkpoint
+    does in the reference.  (TensorFlow's checkpoint format itself is not read.)"""
+    path = os.fspath(logdir)
+    if os.path.isdir(path):
+        cands = [os.path.join(path, f) for f in os.listdir(path)
+                 if f.endswith((".hdf5", ".h5", ".npz"))]
+        if not cands:
+            raise FileNotFoundError("no .hdf5/.h5/.npz weights in %s" % path)
+        path = max(cands, key=os.path.getmtime)
+    model = load_model(path)
+    if model.vecsize != options.vecsize:
+        model.vecsize = int(options.vecsize)     # weights do not depend on the window length
+    return model
+
+
+def predict(model, data, results_shape: Tuple[int, int], step_size: int,
+            compat: str = "reference") -> np.ndarray:
+    """Predict for a complete sequence (reference ``deepgrp/prediction.py:89-111``): every window's
+    class probabilities are merged into ``float32[L, C]`` by elementwise maximum."""
+    if isinstance(model, ModelWeights) and isinstance(data, WindowDataset) \
+            and data.vecsize == model.vecsize and data.data.shape[0] == 5 \
+            and tuple(results_shape) == (data.length, model.n_classes):
+        fwd = np.ascontiguousarray(data.data, dtype=np.int8)
+        predictions = np.zeros(results_shape, dtype=np.float32)
+        if data.length:
+            ctx = _lib.context()
+            _lib.check(_lib.lib().dgrp_predict_onehot(
+                ctx.handle, model.device_handle(ctx), _lib.ptr(fwd), data.length, int(step_size),
+                data.batch_size, _COMPAT[compat], _lib.ptr(predictions)))
+        return predictions
+    # generic route, literally the reference loop: any object with predict_on_batch, any iterable
+    predictions = np.zeros(results_shape, dtype=np.float32)
+    for i, batch in enumerate(data):
+        index = i * batch.shape[0] * step_size
+        probas = np.ascontiguousarray(model.predict_on_batch(batch), dtype=np.float32)
+        dgsequence.get_max(predictions[index:], probas, step_size)
+    return predictions
+
+
+def predict_complete(step_size: int, options: Options, logdir, data, use_mss: bool = False
+                     ) -> np.ndarray:
+    """Restores a model and predicts for a sequence (reference ``deepgrp/prediction.py:114-141``)."""
+    model = setup_prediction_from_options_checkpoint(options, logdir)
+    val_iterator = fetch_validation_batch(data.fwd, step_size, options.batch_size, options.vecsize)
+    output_shape = data.truelbl.shape[::-1]
+    predictions = predict(model, val_iterator, output_shape, step_size)
+    if use_mss:
+        return apply_mss(predictions, options)
+    return softmax(predictions)
+
+
+def predict_sequence(model: ModelWeights, raw: bytes, step_size: int, batch_size: int,
+                     use_mss: bool, min_mss_len: int, xdrop_len: int, fold_case: bool = True,
+                     compat: str = "reference", want_labels: bool = True):
+    """One record end to end on the GPU (the body of ``_predict`` + ``yield_segments``, reference
+    ``deepgrp/__main__.py:46-83, 288-290``): raw sequence bytes -> (labels uint8[L], startpos, rows).
+    ``rows`` is a structured array (start, end, label, record) of the label > 0 segments."""
+    ctx = _lib.context()
+    n = len(raw)
+    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    labels = np.zeros(n, dtype=np.uint8) if want_labels else None
+    cap = 4096
+    while True:
+        rows = np.zeros(cap, dtype=_lib.ROW_DTYPE)
+        start, length, n_rows = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = _lib.lib().dgrp_predict_sequence(
+            ctx.handle, model.device_handle(ctx), _lib.ptr(buf), n, int(fold_case), int(step_size),
+            int(batch_size), int(use_mss), int(min_mss_len), int(xdrop_len), _COMPAT[compat],
+            ctypes.byref(start), ctypes.byref(length), _lib.ptr(labels), _lib.ptr(rows), cap,
+            ctypes.byref(n_rows))
+        if rc == _lib.E_CAPACITY:
+            cap = int(n_rows.value)
+            continue
+        if rc == _lib.E_ALLN:
+            raise ValueError("negative dimensions are not allowed")
+        _lib.check(rc)
+        break
+    if labels is not None:
+        labels = labels[:length.value]
+    return labels, int(start.value), rows[:n_rows.value]
+
+
+def predict_fasta(model: ModelWeights, raw: bytes, step_size: int, batch_size: int, use_mss: bool,
+                  min_mss_len: int, xdrop_len: int, compat: str = "reference"):
+    """A whole (multi-)FASTA file in one call: raw file bytes -> (rows, records).  The text is decoded
+    on the GPU (reference ``deepgrp/__main__.py:20-43``) and every record runs the fused device
+    pipeline.  ``rows``: structured array (start, end, label, record); ``records``: list of
+    ``(header, startpos, length)``.  A blank line raises ``IndexError`` and an all-'N' record
+    ``ValueError``, as the reference does."""
+    ctx = _lib.context()
+    n = len(raw)
+    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    n_rows, n_rec = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = _lib.lib().dgrp_predict_fasta(
+        ctx.handle, model.device_handle(ctx), _lib.ptr(buf), n, int(step_size), int(batch_size),
+        int(use_mss), int(min_mss_len), int(xdrop_len), _COMPAT[compat], ctypes.byref(n_rows),
+        ctypes.byref(n_rec))
+    if rc == _lib.E_FASTA:
+        raise IndexError("string index out of range")
+    if rc == _lib.E_ALLN:
+        raise ValueError("negative dimensions are not allowed")
+    _lib.check(rc)
+    rows = np.zeros(n_rows.value, dtype=_lib.ROW_DTYPE)
+    if n_rows.value:
+        _lib.check(_lib.lib().dgrp_fasta_rows(ctx.handle, _lib.ptr(rows), n_rows.value))
+    k = n_rec.value
+    off, ln = np.zeros(k, np.int64), np.zeros(k, np.int64)
+    sp, le = np.zeros(k, np.int64), np.zeros(k, np.int64)
+    if k:
+        _lib.check(_lib.lib().dgrp_fasta_records(ctx.handle, _lib.ptr(off), _lib.ptr(ln),
+                                                 _lib.ptr(sp), _lib.ptr(le), k))
+    records = [(raw[off[i]:off[i] + ln[i]].decode("utf-8", "replace"), int(sp[i]), int(le[i]))
+               for i in range(k)]
+    return rows, records
+
+
+def predict_fasta_tsv(model: ModelWeights, raw: bytes, filename: str, step_size: int,
+                      batch_size: int, use_mss: bool, min_mss_len: int, xdrop_len: int,
+                      compat: str = "reference") -> str:
+    """The TSV text ``deepgrp predict`` writes for one file (reference ``deepgrp/__main__.py:288-292``)."""
+    rows, records = predict_fasta(model, raw, step_size, batch_size, use_mss, min_mss_len,
+                                  xdrop_len, compat)
+    if rows.size == 0:
+        return ""
+    headers = [r[0] for r in records]
+    parts = ["%s\t%s\t%d\t%d\t%d\n" % (filename, headers[rec], s, e, l)
+             for s, e, l, rec in zip(rows["start"].tolist(), rows["end"].tolist(),
+                                     rows["label"].tolist(), rows["record"].tolist())]
+    return "".join(parts)

@@ -75,6 +75,11 @@ void *dgrp_ctx_stream(dgrp_ctx *ctx);
 int dgrp_ctx_timings(dgrp_ctx *ctx, dgrp_timings_t *out);
 /* number of kernels this library has launched on the context since creation */
 int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
+/* tuning knobs and diagnostics: "mss_chunk" (elements per MSS scan chunk, 0 = automatic),
+ * "mss_max_rounds" (parallel rounds before the sequential completion), and read-only
+ * "mss_rounds" (rounds the last MSS call used; negative = completed sequentially), "sm_count". */
+int dgrp_ctx_set_int(dgrp_ctx *ctx, const char *key, int64_t value);
+int dgrp_ctx_get_int(dgrp_ctx *ctx, const char *key, int64_t *value);
 
 /* ---- deepgrp.sequence (deepgrp/sequence.pyx + deepgrp/maxcalc.c) --------------------- */
 
@@ -172,15 +177,21 @@ int dgrp_finish_record(dgrp_ctx *ctx, const uint8_t *labels, const float *scores
                        int64_t startpos, uint8_t *labels_out, dgrp_row_t *rows, int64_t cap,
                        int64_t *n_rows);
 
-/* Whole-file driver (__main__.py:275-292 for one FASTA): raw FASTA text in, rows out.  The FASTA
- * is decoded on the GPU (line stripping, '>' records, case folding, edge-'N' trim).  Record
- * header offsets (into `fasta`) are returned so the caller can format the TSV:
- * hdr_off[r], hdr_len[r] for r < *n_records (cap_records entries each). */
+/* Whole-file driver (__main__.py:275-292 for one FASTA): raw FASTA text in, rows out.  The text is
+ * decoded on the GPU (_read_multi_fasta, __main__.py:20-43: line stripping, '>' records, records
+ * with an empty header dropped, case folding) and every record runs encode -> forward -> vote ->
+ * MSS -> segments without leaving the device.  Results stay in the context until the next call:
+ * *n_rows rows in record order and *n_records records; fetch them with the two calls below.
+ * A blank line gives DGRP_E_FASTA (IndexError in the reference), an all-'N' record DGRP_E_ALLN. */
 int dgrp_predict_fasta(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
                        int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len,
-                       int compat, dgrp_row_t *rows, int64_t cap_rows, int64_t *n_rows,
-                       int64_t *hdr_off, int64_t *hdr_len, int64_t cap_records,
-                       int64_t *n_records);
+                       int compat, int64_t *n_rows, int64_t *n_records);
+/* rows[i].record indexes the record table */
+int dgrp_fasta_rows(dgrp_ctx *ctx, dgrp_row_t *rows, int64_t cap);
+/* per record: header text = fasta[hdr_off, hdr_off + hdr_len); startpos = leading 'N' count;
+ * length = trimmed length.  Any of the four arrays may be NULL. */
+int dgrp_fasta_records(dgrp_ctx *ctx, int64_t *hdr_off, int64_t *hdr_len, int64_t *startpos,
+                       int64_t *length, int64_t cap);
 
 /* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),
  * runs forward + vote + score + MSS + segment extraction entirely on the device and leaves the

@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE: runs the scalar kernel logic of deepgrp_b200/csrc/mss_core.cuh on the CPU,
+// emulating the grid of mss.cu one "thread" at a time, so the chunked algorithm can be checked
+// against the oracle without a GPU.  Build: g++ -O2 -shared -fPIC -o tests/host/libmss_host.so
+// tests/host/mss_host.cpp
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../deepgrp_b200/csrc/mss_core.cuh"
+
+using namespace dgrp::mss;
+
+struct Seg { int st, en; double sc; };
+
+template <typename T>
+static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *out, int cap,
+                   int *rounds_out) {
+  if (n <= 0) { *rounds_out = 0; return 0; }
+  const int min_sc_int = (int)min_sc;
+  const int NC = (n + CH - 1) / CH;
+  std::vector<int> base(NC + 1, 0);
+  for (int c = 0; c < NC; ++c) {
+    int cnt = 0;
+    for (int i = c * CH; i < n && i < (c + 1) * CH; ++i)
+      if ((double)S[i] > 0 && (i == 0 || !((double)S[i - 1] > 0))) ++cnt;
+    base[c + 1] = base[c] + cnt;
+  }
+  const int NR = base[NC];
+  std::vector<int> st(NR + 1), en(NR + 1), pre(NR + 1);
+  std::vector<double> L(NR + 1), R(NR + 1);
+  std::vector<uint8_t> kind(NR + 1), flag(n, 0);
+  RunTable rt{st.data(), en.data(), L.data(), R.data(), pre.data(), kind.data()};
+  std::vector<ScanState> used(NC), outA(NC), outB(NC);
+  std::vector<uint8_t> chA(NC, 1), chB(NC, 0);
+  // round 1
+  for (int c = 0; c < NC; ++c) {
+    ScanState s; state_canonical(s);
+    used[c] = s;
+    int b = c * CH, e = b + CH < n ? b + CH : n;
+    scan_chunk(S, n, xdrop, b, e, base[c], s, flag.data(), false, rt);
+    outA[c] = s;
+  }
+  int rounds = 1;
+  for (;;) {
+    int changed = 0;
+    outB = outA;
+    for (int c = 0; c < NC; ++c) {
+      chB[c] = 0;
+      if (c == 0) continue;
+      if (!chA[c - 1]) continue;
+      if (state_equal(outA[c - 1], used[c])) continue;
+      ScanState s = outA[c - 1];
+      used[c] = s;
+      int b = c * CH, e = b + CH < n ? b + CH : n;
+      bool synced = scan_chunk(S, n, xdrop, b, e, base[c], s, flag.data(), true, rt);
+      if (!synced && !state_equal(s, outA[c])) { outB[c] = s; chB[c] = 1; ++changed; }
+    }
+    outA.swap(outB); chA.swap(chB);
+    ++rounds;
+    if (!changed) break;
+  }
+  *rounds_out = rounds;
+  // regions
+  std::vector<int> ev;
+  for (int k = 0; k < NR; ++k) if (kind[k] != RUN_PLAIN) ev.push_back(k);
+  std::vector<uint8_t> live(NR + 1, 0);
+  for (size_t r = 0; r < ev.size(); ++r) {
+    int k0 = ev[r], k1 = r + 1 < ev.size() ? ev[r + 1] : NR;
+    int depth = process_region(k0, k1, rt);
+    bool flushed = (k1 == NR) || kind[k1] == RUN_FLUSH;
+    for (int j = 0; j < depth; ++j)
+      live[k0 + j] = flushed && (R[k0 + j] - L[k0 + j] >= min_sc_int);
+  }
+  int m = 0;
+  for (int k = 0; k < NR; ++k)
+    if (live[k]) { if (m < cap) { out[m].st = st[k]; out[m].en = en[k]; out[m].sc = R[k] - L[k]; } ++m; }
+  return m;
+}
+
+extern "C" int host_mss_f64(int n, const double *S, double min_sc, double xdrop, int CH, Seg *out,
+                            int cap, int *rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds); }
+extern "C" int host_mss_f32(int n, const float *S, double min_sc, double xdrop, int CH, Seg *out,
+                            int cap, int *rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds); }

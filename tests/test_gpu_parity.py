@@ -1,0 +1,378 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the Python mirror of the reference API)
+against the CPU oracle on the same seeded inputs.  Integer/byte/index work is bit-exact; the
+floating-point forward is within 1e-3 absolute on probabilities (BASELINE.json north_star) -- the
+tests assert the much tighter 2e-5 -- and >= 99.99 % identical labels."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+from conftest import random_dna, write_fasta
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3        # north_star tolerance
+PROB_TOL_TIGHT = 2e-5  # what fp32 FFMA arithmetic should achieve
+
+
+@pytest.fixture(scope="module")
+def dg(gpu_ctx):
+    import deepgrp_b200.sequence as seq
+    import deepgrp_b200.mss as mss
+    import deepgrp_b200.prediction as pred
+    import deepgrp_b200.model as model
+
+    class NS:
+        pass
+    ns = NS()
+    ns.seq, ns.mss, ns.pred, ns.model, ns.ctx = seq, mss, pred, model, gpu_ctx
+    return ns
+
+
+# ------------------------------------------------------------------ encode
+@pytest.mark.parametrize("text", [
+    "ACGT", "acgtnACGTN", "NNNACGTNNN", "nnACGTnn", "NNNNACGTRYKMNNN", "A", "", "NACGTXN",
+    "ACGT" * 1000 + "N" * 77, "N" * 50 + "acgtryswkm" * 333 + "N",
+])
+def test_one_hot_matches_oracle(dg, oracle, text):
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    st_o, fwd_o = oracle.one_hot_encode_dna_sequence(text)
+    assert st == st_o
+    assert fwd.dtype == np.int8 and fwd.shape == fwd_o.shape
+    assert np.array_equal(fwd, fwd_o)
+
+
+def test_one_hot_reference_known_answer(dg):
+    # reference tests/test_sequence.py:10-28
+    rng = np.random.default_rng(3)
+    letters = np.array(list("ACGTN"))
+    seq = "".join(letters[rng.integers(0, 5, size=5000)])
+    seq = "NNNN" + "A" + seq + "C" + "NNN"
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(seq)
+    assert st == 4
+    assert fwd.shape == (5, len(seq) - 7)
+    assert (fwd.sum(axis=0) == 1).all()
+    expected = np.array(["ACGTN".index(c) for c in seq[4:-3]])
+    assert np.array_equal(fwd.argmax(axis=0), expected)
+
+
+def test_one_hot_all_n_raises(dg):
+    with pytest.raises(ValueError):
+        dg.seq.one_hot_encode_dna_sequence("NNNNNN")
+
+
+def test_one_hot_large(dg, oracle):
+    text = "N" * 1234 + random_dna(3_000_017, 11, "ACGTNacgtnRY") + "N" * 999
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    st_o, fwd_o = oracle.one_hot_encode_dna_sequence(text)
+    assert st == st_o and np.array_equal(fwd, fwd_o)
+
+
+# ------------------------------------------------------------------ get_max
+def test_get_max_reference_known_answer(dg):
+    # reference tests/test_sequence.py:47-56
+    inputs = np.zeros((10, 100, 5), dtype=np.float32)
+    for i in range(10):
+        inputs[i] = i + 1
+    out = np.zeros((1000, 5), dtype=np.float32)
+    ret = dg.seq.get_max(out, inputs, 50)
+    assert ret is out
+    exp = np.zeros((1000, 5), dtype=np.float32)
+    for i in range(10):
+        exp[i * 50:i * 50 + 100] = np.maximum(exp[i * 50:i * 50 + 100], i + 1)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("b,t,c,stride", [(7, 150, 5, 50), (3, 10, 5, 10), (5, 33, 4, 1), (4, 20, 5, 37),
+                                          (256, 342, 5, 50)])
+def test_get_max_matches_oracle(dg, oracle, b, t, c, stride):
+    rng = np.random.default_rng(b * 1000 + t)
+    inputs = rng.random((b, t, c), dtype=np.float32)
+    rows = (b - 1) * stride + t + 13
+    base = rng.random((rows, c), dtype=np.float32) * 0.5
+    out = base.copy()
+    exp = oracle.get_max(base.copy(), inputs, stride)
+    dg.seq.get_max(out, inputs, stride)
+    assert np.array_equal(out, exp)
+
+
+def test_get_max_dtype_errors(dg):
+    with pytest.raises(ValueError):
+        dg.seq.get_max(np.zeros((10, 5)), np.zeros((1, 5, 5), np.float32), 1)
+    with pytest.raises(TypeError):
+        dg.seq.get_max(None, np.zeros((1, 5, 5), np.float32), 1)
+
+
+# ------------------------------------------------------------------ segments
+def test_segments_reference_cases(dg, oracle):
+    # reference tests/test_sequence.py:30-44: one run of `label` at [start, start+len)
+    for start in (0, 1, 50, 90):
+        for length in (1, 5, 10):
+            for label in (1, 2, 4):
+                classes = np.zeros(100, dtype=np.int64)
+                classes[start:start + length] = label
+                got = dg.seq.get_segments(classes, 0)
+                assert got == oracle.get_segments(classes, 0)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (3, 2), (100, 3), (4097, 4), (100_000, 5)])
+def test_yield_segments_matches_oracle(dg, oracle, n, seed):
+    rng = np.random.default_rng(seed)
+    # runs of random labels with random lengths
+    lab = np.repeat(rng.integers(0, 5, size=n), rng.integers(1, 9, size=n))[:n].astype(np.int64)
+    for arr in (lab, np.zeros(n, np.int64), np.full(n, 3, np.int64)):
+        got = list(dg.seq.yield_segments(arr, 17))
+        exp = list(oracle.yield_segments(arr, 17))
+        assert got == exp
+        for s in (0, n // 2, n - 1):
+            assert dg.seq.get_segments(arr, s) == oracle.get_segments(arr, s)
+
+
+# ------------------------------------------------------------------ MSS
+def test_mss_reference_known_answer(dg, oracle):
+    # reference tests/test_mss.py:10-24 style: 14-element vector, min_mss_len 0/1, xdrop -1/0/10
+    scores = np.array([4.0, -5, 3, -3, 1, 2, -2, 2, -2, 1, 5, -5, -1, 3], dtype=np.float64)
+    labels = np.array([1, 0, 2, 0, 2, 2, 0, 3, 0, 3, 3, 0, 0, 1], dtype=np.int64)
+    for min_len in (0, 1, 2):
+        for xdrop in (-1, 0, 10):
+            got = dg.mss.find_mss_labels(scores, labels, 5, min_len, xdrop)
+            exp = oracle.find_mss_labels(scores, labels, 5, min_len, xdrop)
+            assert np.array_equal(got, exp)
+
+
+def _score_sets(rng, n):
+    yield "normal", rng.normal(size=n)
+    yield "neg", rng.normal(size=n) - 0.5
+    yield "pos", rng.normal(size=n) + 0.3
+    yield "ties", rng.integers(-3, 4, size=n).astype(np.float64)
+    yield "sparse", np.where(rng.random(n) < 0.05, 13.2, -1.32) * (1 + 1e-3 * rng.normal(size=n))
+    yield "f32", (rng.normal(size=n) * 3).astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 1000, 65_537])
+@pytest.mark.parametrize("chunk", [0, 32, 64])
+def test_mss_find_all_bit_exact(dg, oracle, n, chunk):
+    rng = np.random.default_rng(n + chunk)
+    dg.ctx.set_int("mss_chunk", chunk)
+    try:
+        for name, s in _score_sets(rng, n):
+            for xdrop in (-1.0, 3.0, 40.0):
+                for min_sc in (0.0, 2.7, 25.0):
+                    got = dg.mss.mss_find_all(s, min_sc, xdrop)
+                    exp = oracle.mss_find_all(s, min_sc, xdrop)
+                    assert got.size == exp.size, (name, xdrop, min_sc)
+                    assert np.array_equal(got["st"], exp["st"]) and np.array_equal(got["en"], exp["en"])
+                    assert np.array_equal(got["sc"].view(np.int64), exp["sc"].view(np.int64))
+    finally:
+        dg.ctx.set_int("mss_chunk", 0)
+
+
+def test_find_mss_labels_matches_oracle_large(dg, oracle):
+    rng = np.random.default_rng(77)
+    n = 300_000
+    lab = np.repeat(rng.integers(0, 5, size=n), rng.integers(1, 200, size=n))[:n].astype(np.int64)
+    t = np.float32(np.log(0.99 / 0.01))
+    scores = np.where(lab > 0, t, -10 * t).astype(np.float64) * rng.random(n)
+    for min_len, xdrop in ((50, 50), (0, 50), (50, -1), (5, 2)):
+        got = dg.mss.find_mss_labels(scores, lab, 5, min_len, xdrop)
+        exp = oracle.find_mss_labels(scores, lab, 5, min_len, xdrop)
+        assert np.array_equal(got, exp)
+
+
+# ------------------------------------------------------------------ score transform / softmax
+def test_mss_scores_and_softmax(dg, oracle):
+    rng = np.random.default_rng(5)
+    probs = rng.dirichlet(np.ones(5) * 0.3, size=20_000).astype(np.float32)
+    probs[:100] = 0.0                       # never-covered rows
+    probs[100:200] = [0.2, 0.2, 0.2, 0.2, 0.2]   # ties -> class 0
+    sc, cl = dg.pred.mss_scores(probs)
+    sc_o, cl_o = oracle.apply_mss_scores(probs)
+    assert np.array_equal(cl, cl_o)
+    # device logf vs numpy float32 log may differ by an ulp
+    assert np.allclose(sc, sc_o, rtol=3e-7, atol=1e-6)
+    assert abs(sc[0] - 138.155) < 1e-2
+    sm = dg.pred.softmax(probs)
+    sm_o = oracle.softmax(probs)
+    assert np.allclose(sm, sm_o, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(sm.argmax(axis=1), sm_o.argmax(axis=1))
+
+
+def test_apply_mss_matches_oracle_given_scores(dg, oracle):
+    """MSS bit-exact given identical score inputs: feed the GPU's own scores to the oracle."""
+    rng = np.random.default_rng(6)
+    n = 200_000
+    lab = np.repeat(rng.integers(0, 5, size=n), rng.integers(1, 300, size=n))[:n]
+    conf = rng.random(n).astype(np.float32) * 0.6 + 0.39
+    probs = np.full((n, 5), 0.0, np.float32)
+    probs[np.arange(n), lab] = conf
+    rest = (1 - conf) / 4
+    for c in range(5):
+        probs[np.arange(n), c] = np.where(lab == c, conf, rest)
+    from deepgrp_b200.model import Options
+    opt = Options(min_mss_len=50, xdrop_len=50)
+    got = dg.pred.apply_mss(probs, opt)
+    sc, cl = dg.pred.mss_scores(probs)
+    exp = oracle.find_mss_labels(sc, cl, 5, 50, 50)
+    assert np.array_equal(got, exp)
+
+
+# ------------------------------------------------------------------ forward
+@pytest.mark.parametrize("T,U,attention", [(150, 32, True), (60, 60, True), (40, 16, False),
+                                           (50, 50, True), (30, 100, True), (37, 7, True)])
+def test_forward_windows_matches_oracle(dg, oracle, T, U, attention):
+    w = dg.model.random_weights(T, U, attention=attention, seed=1)
+    rng = np.random.default_rng(T + U)
+    codes = rng.integers(0, 5, size=(70, T))
+    batch = np.eye(5, dtype=np.float32)[codes]
+    got = w.predict_on_batch(batch)
+    exp = oracle.model_forward(batch, w.as_dict())
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() < PROB_TOL_TIGHT
+    # scaled weights: confident outputs
+    w4 = w.scaled(4.0)
+    got4 = w4.predict_on_batch(batch)
+    exp4 = oracle.model_forward(batch, w4.as_dict())
+    assert np.abs(got4 - exp4).max() < PROB_TOL_TIGHT
+
+
+def test_forward_dense_non_onehot_input(dg, oracle):
+    w = dg.model.random_weights(48, 32, attention=True, seed=2)
+    rng = np.random.default_rng(0)
+    batch = rng.random((9, 48, 5), dtype=np.float32)
+    got = w.predict_on_batch(batch)
+    exp = oracle.model_forward(batch, w.as_dict())
+    assert np.abs(got - exp).max() < PROB_TOL_TIGHT
+
+
+@pytest.mark.parametrize("L,T,U,step,B", [(5000, 150, 32, 50, 16), (3000, 150, 32, 50, 256),
+                                          (2000, 100, 60, 33, 7), (150, 150, 32, 50, 16),
+                                          (151, 150, 32, 50, 16), (100, 150, 32, 50, 16)])
+def test_predict_matches_oracle_including_partial_batch(dg, oracle, L, T, U, step, B):
+    w = dg.model.random_weights(T, U, attention=True, seed=3).scaled(3.0)
+    text = random_dna(L, L + step, "ACGTN")
+    text = "A" + text[1:-1] + "C"
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    ds = dg.pred.fetch_validation_batch(fwd, step, B, T)
+    got = dg.pred.predict(w, ds, (fwd.shape[1], 5), step)
+    exp = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict()),
+                         oracle.fetch_validation_batch(fwd, step, B, T), (fwd.shape[1], 5), step)
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() < PROB_TOL_TIGHT
+    assert np.array_equal(got == 0, exp == 0)            # identical coverage (incl. misplaced tail)
+    fixed = dg.pred.predict(w, ds, (fwd.shape[1], 5), step, compat="fixed")
+    n_win = len(range(0, fwd.shape[1] - T, step))
+    if n_win % B:
+        assert not np.array_equal(fixed == 0, exp == 0) or n_win < B
+
+
+def test_predict_generic_route_equals_fused(dg):
+    """The literal reference loop (iterate batches, predict_on_batch, get_max) and the fused call."""
+    w = dg.model.random_weights(150, 32, attention=True, seed=4)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(4000, 9))
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 16, 150)
+    fused = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+
+    class Wrapped:       # hides the ModelWeights type -> generic route
+        def predict_on_batch(self, batch):
+            return w.predict_on_batch(batch)
+    generic = dg.pred.predict(Wrapped(), iter(ds), (fwd.shape[1], 5), 50)
+    assert np.array_equal(fused, generic)
+
+
+# ------------------------------------------------------------------ end to end
+def _labels_agree(a, b):
+    return float((a == b).mean())
+
+
+def test_predict_sequence_vs_oracle_labels_and_rows(dg, oracle):
+    T, U = 150, 32
+    for scale in (1.0, 4.0):
+        w = dg.model.random_weights(T, U, attention=True, seed=0).scaled(scale)
+        text = "NNNNN" + random_dna(60_000, 21, "ACGTacgtN") + "NN"
+        labels, startpos, rows = dg.pred.predict_sequence(w, text.encode(), 50, 256, True, 50, 50)
+        lab_o, st_o, probs_o = oracle.predict_record(text.upper(), w.as_dict(), T, 256, 50, True,
+                                                     return_probs=True)
+        assert startpos == st_o == 5
+        assert labels.shape == lab_o.shape
+        assert _labels_agree(labels, lab_o) >= 0.9999
+        # rows == yield_segments of OUR labels, label > 0 (bit-exact given identical labels)
+        exp_rows = [(s, e, l) for s, e, l in oracle.yield_segments(labels.astype(np.int64), startpos) if l > 0]
+        got_rows = list(zip(rows["start"].tolist(), rows["end"].tolist(), rows["label"].tolist()))
+        assert got_rows == exp_rows
+        # no-MSS branch
+        labels2, _, _ = dg.pred.predict_sequence(w, text.encode(), 50, 256, False, 50, 50)
+        lab2_o, _ = oracle.predict_record(text.upper(), w.as_dict(), T, 256, 50, False)
+        assert _labels_agree(labels2, lab2_o) >= 0.9999
+
+
+def test_stepwise_cli_route_equals_fused(dg, tmp_path):
+    from deepgrp_b200.__main__ import _predict, _read_multi_fasta
+    from deepgrp_b200.model import Options
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    text = "NN" + random_dna(20_000, 5, "ACGTN") + "N"
+    opt = Options(min_mss_len=50, batch_size=256, xdrop_len=50, vecsize=150)
+    lab_a, st_a = _predict(text, w, opt, 50, True)
+    lab_b, st_b, _ = dg.pred.predict_sequence(w, text.encode(), 50, 256, True, 50, 50)
+    assert st_a == st_b
+    assert np.array_equal(lab_a, lab_b)
+
+
+def test_predict_fasta_tsv_vs_oracle(dg, oracle, tmp_path):
+    T, U = 150, 32
+    w = dg.model.random_weights(T, U, attention=True, seed=0).scaled(4.0)
+    recs = [("chrA description text", "NNN" + random_dna(30_000, 1, "ACGTacgtn") + "NNNN"),
+            ("chrB", random_dna(140, 2)),                       # shorter than one window
+            ("chrC", random_dna(12_345, 3, "ACGTRYKM"))]
+    path = tmp_path / "in.fa"
+    write_fasta(str(path), recs, width=60)
+    raw = open(path, "rb").read()
+    got = dg.pred.predict_fasta_tsv(w, raw, str(path), 50, 256, True, 50, 50)
+    exp = oracle.predict_fasta_tsv(str(path), w.as_dict(), T)
+    got_rows, exp_rows = got.splitlines(), exp.splitlines()
+    # identical up to label flips at the 1e-4 level: compare covered bases per (record, label)
+    def cover(rows):
+        d = {}
+        for r in rows:
+            f, h, s, e, l = r.split("\t")
+            d[(h, l)] = d.get((h, l), 0) + int(e) - int(s)
+        return d
+    cg, ce = cover(got_rows), cover(exp_rows)
+    assert set(cg) == set(ce)
+    total = sum(ce.values())
+    diff = sum(abs(cg[k] - ce[k]) for k in ce)
+    assert diff <= max(2, 2e-4 * total)
+    # CRLF line ends, a record with empty header (dropped) and text before the first '>' (dropped)
+    raw2 = b"ACGTACGT\r\n>\r\nACGT\r\n" + raw.replace(b"\n", b"\r\n")
+    got2 = dg.pred.predict_fasta_tsv(w, raw2, str(path), 50, 256, True, 50, 50)
+    assert got2 == got
+    with pytest.raises(IndexError):
+        dg.pred.predict_fasta_tsv(w, b">x\nACGT\n\nACGT\n", "f", 50, 256, True, 50, 50)
+    with pytest.raises(ValueError):
+        dg.pred.predict_fasta_tsv(w, b">x\nNNNN\n", "f", 50, 256, True, 50, 50)
+
+
+def test_predict_range_shards_equal_whole(dg):
+    """Multi-GPU sharding unit: label/score of disjoint position ranges computed independently
+    (with halo re-computation) equal the whole-record result, including the misplaced tail batch."""
+    from deepgrp_b200 import _lib
+    T, U = 150, 32
+    w = dg.model.random_weights(T, U, attention=True, seed=0).scaled(4.0)
+    text = random_dna(40_000, 8)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    codes = fwd.argmax(axis=0).astype(np.uint8)
+    L = codes.size
+    h = w.device_handle(dg.ctx)
+
+    def run(p0, p1, lo, hi):
+        lab = np.zeros(p1 - p0, np.uint8)
+        sc = np.zeros(p1 - p0, np.float32)
+        sub = np.ascontiguousarray(codes[lo:hi])
+        _lib.check(_lib.lib().dgrp_predict_range(dg.ctx.handle, h, _lib.ptr(sub), lo, hi - lo, L, p0, p1,
+                                                  50, 256, 0, _lib.ptr(lab), _lib.ptr(sc)))
+        return lab, sc
+    whole_l, whole_s = run(0, L, 0, L)
+    cuts = [0, 9_973, 20_000, 33_333, L]
+    parts = [run(a, b, 0, L) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), whole_l)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]).view(np.int32), whole_s.view(np.int32))
