@@ -134,11 +134,11 @@ static int run_segments_t(dgrp_ctx *c, const L *d_lab, int64_t n, int64_t offset
   *d_triples = nullptr;
   if (n <= 0) return DGRP_OK;
   const int64_t nblk = (n + SEG_TILE - 1) / SEG_TILE;
-  DGRP_CHECK(c->scan.reserve((size_t)nblk * 8 + 64));
+  DGRP_CHECK(c->scan.reserve((size_t)nblk * 8 + 64));  // bstart | bend | totals[2]
   DGRP_CHECK(c->pin_small.reserve(256));
   unsigned int *bs = c->scan.as<unsigned int>();
   unsigned int *be = bs + nblk;
-  unsigned long long *totals = reinterpret_cast<unsigned long long *>(be + nblk + ((nblk & 1) ? 1 : 0));
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(be + nblk);  // 2*nblk uints: 8-byte aligned
   seg_count_kernel<L><<<(unsigned)nblk, SEG_THREADS, 0, c->stream>>>(d_lab, n, bs, be);
   seg_scan_kernel<<<1, 1024, 0, c->stream>>>(bs, be, nblk, totals);
   c->launches += 2;

@@ -1,0 +1,190 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares
+(no compute without a GPU), the chunked MSS kernel logic (compiled for the host from the product
+header) is bit-exact against the oracle, Options / weights / CLI parsing / window descriptors."""
+import ctypes
+import io
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_every_declared_symbol():
+    from deepgrp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "deepgrp_b200.h")).read()
+    declared = set(re.findall(r"\b(dgrp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dgrp_ctx", "dgrp_model"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name)
+    assert handle.dgrp_version() >= 100
+
+
+def test_no_gpu_is_an_error_not_a_fallback():
+    from deepgrp_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_lib.DeepgrpError) as e:
+        _lib.Context(0)
+    assert e.value.code == _lib.E_NOGPU
+    import deepgrp_b200.sequence as seq
+    with pytest.raises(_lib.DeepgrpError):
+        seq.one_hot_encode_dna_sequence("ACGT")
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "deepgrp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "liboracle" not in text and "oracle_c" not in text, f
+
+
+# ---- chunked MSS kernel logic on the host ---------------------------------------------------------
+class _Seg(ctypes.Structure):
+    _fields_ = [("st", ctypes.c_int), ("en", ctypes.c_int), ("sc", ctypes.c_double)]
+
+
+@pytest.fixture(scope="module")
+def host_mss():
+    so = os.path.join(HERE, "host", "libmss_host.so")
+    src = os.path.join(HERE, "host", "mss_host.cpp")
+    core = os.path.join(ROOT, "deepgrp_b200", "csrc", "mss_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    lib = ctypes.CDLL(so)
+
+    def run(S, min_sc, xdrop, CH):
+        S = np.ascontiguousarray(S)
+        cap = S.size // 2 + 2
+        out = (_Seg * cap)()
+        rounds = ctypes.c_int(0)
+        fn = lib.host_mss_f64 if S.dtype == np.float64 else lib.host_mss_f32
+        fn.restype = ctypes.c_int
+        m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
+               CH, out, cap, ctypes.byref(rounds))
+        return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value
+    return run
+
+
+def test_chunked_mss_logic_bit_exact(host_mss, oracle):
+    rng = np.random.default_rng(5)
+    for trial in range(120):
+        n = int(rng.integers(1, 400))
+        kind = trial % 6
+        if kind == 0:
+            S = rng.normal(size=n)
+        elif kind == 1:
+            S = rng.normal(size=n) - 0.5
+        elif kind == 2:
+            S = rng.normal(size=n) + 0.3
+        elif kind == 3:
+            S = rng.integers(-3, 4, size=n).astype(float)
+        elif kind == 4:
+            S = np.where(rng.random(n) < 0.05, 13.2, -1.32) * (1 + 1e-3 * rng.normal(size=n))
+        else:
+            S = rng.choice([-4.59, 4.59, -45.9, 0.0, 1e-7, -1e-7], size=n)
+        if trial % 2:
+            S = S.astype(np.float32)
+        for xdrop in (-1.0, 0.0, 3.0, 20.0):
+            for min_sc in (0.0, 2.7, 10.0):
+                ref = [(int(a), int(b), float(c)) for a, b, c in
+                       oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+                for CH in (1, 3, 16, 64, 1000):
+                    got, _ = host_mss(S, min_sc, xdrop, CH)
+                    assert got == ref, (trial, xdrop, min_sc, CH)
+
+
+def test_chunked_mss_converges_fast_with_resets(host_mss, oracle):
+    rng = np.random.default_rng(1)
+    n = 300_000
+    S = (np.where(np.repeat(rng.random(n // 100) < 0.4, 100), 4.59, -45.9) * rng.random(n)).astype(np.float32)
+    xdrop, min_sc = np.log(99) * 500, np.log(99) * 50
+    got, rounds = host_mss(S, min_sc, xdrop, 1024)
+    ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+    assert got == ref and rounds <= 4
+
+
+# ---- Options / weights / CLI ---------------------------------------------------------------------
+def test_options_defaults_aliases_and_toml_roundtrip():
+    from deepgrp_b200.model import Options
+    o = Options()
+    assert (o.vecsize, o.units, o.batch_size, o.min_mss_len, o.xdrop_len, o.attention) == (150, 32, 256, 50, 50, False)
+    o = Options(gru_units=60, gru_dropout=0.1, attention=True)
+    assert o.units == 60 and o.dropout == 0.1 and o["gru_units"] == 60
+    buf = io.StringIO()
+    o.to_toml(buf)
+    o2 = Options.from_toml(io.StringIO(buf.getvalue()))
+    assert o2.todict() == o.todict()
+    with pytest.raises(TypeError):
+        Options.from_toml("not a file")
+
+
+def test_reference_defaults_toml_parses():
+    from deepgrp_b200.model import Options
+    text = ('vecsize = 342\nunits = 60\nattention = true\nrnn = "GRU"\nbatch_size = 256\n'
+            'min_mss_len = 50\nxdrop_len = 50\nrepeats_to_search = [ 1, 2, 3, 4,]\n')
+    o = Options.from_toml(io.StringIO(text))
+    assert (o.vecsize, o.units, o.attention) == (342, 60, True)
+
+
+def test_random_weights_shapes_and_npz_roundtrip(tmp_path):
+    from deepgrp_b200.model import ModelWeights, create_model, Options
+    w = create_model(Options(vecsize=342, units=60, attention=True))
+    assert w.kernel.shape == (5, 180) and w.recurrent_kernel.shape == (60, 180)
+    assert w.bias.shape == (2, 180) and w.att_scale.shape == (60,) and w.ff_kernel.shape == (120, 5)
+    assert w.input_shape == (None, 342, 5) and w.output_shape == (None, 342, 5)
+    r = w.recurrent_kernel
+    assert np.allclose(r @ r.T, np.eye(60), atol=1e-5)          # Keras Orthogonal
+    p = str(tmp_path / "w.npz")
+    w.save_npz(p)
+    w2 = ModelWeights.load_npz(p)
+    for k, v in w.as_dict().items():
+        assert np.array_equal(v, w2.as_dict()[k])
+    w3 = create_model(Options(vecsize=150, units=32, attention=False))
+    assert w3.att_scale is None and w3.ff_kernel.shape == (32, 5)
+
+
+def test_window_dataset_matches_reference_enumeration(oracle):
+    from deepgrp_b200.prediction import fetch_validation_batch
+    rng = np.random.default_rng(0)
+    for L, T, step, B in ((1000, 150, 50, 16), (150, 150, 50, 4), (151, 150, 50, 4), (777, 100, 33, 5)):
+        fwd = np.eye(5, dtype=np.int8)[rng.integers(0, 5, size=L)].T.copy()
+        ours = list(fetch_validation_batch(fwd, step, B, T))
+        ref = list(oracle.fetch_validation_batch(fwd, step, B, T))
+        assert len(ours) == len(ref)
+        for a, b in zip(ours, ref):
+            assert a.dtype == np.float32 and np.array_equal(a, b)
+
+
+def test_cli_argument_mapping(monkeypatch):
+    from deepgrp_b200 import __main__ as cli
+    seen = {}
+    monkeypatch.setattr(cli.CommandLineParser, "predict",
+                        staticmethod(lambda args, options: seen.update(args=args, options=options)))
+    p = cli.CommandLineParser().parse_args(["-b", "64", "-s", "25", "-x", "7", "-l", "9", "-vv",
+                                            "predict", "m.hdf5", "a.fa", "b.fa", "--no_use_mss",
+                                            "--output", "o.tsv"])
+    p.set_logging().setup_tensorflow().run()
+    a, o = seen["args"], seen["options"]
+    assert (a.model, a.FASTA, a.output, a.no_use_mss, a.step_size) == ("m.hdf5", ["a.fa", "b.fa"], "o.tsv", True, 25)
+    assert (o.batch_size, o.min_mss_len, o.xdrop_len) == (64, 9, 7)
+    # README form without the sub-command (reference README.rst:92-98)
+    p = cli.CommandLineParser().parse_args(["-s", "10", "model.npz", "x.fa"])
+    p.run()
+    assert seen["args"].command == "predict" and seen["args"].model == "model.npz" and seen["args"].FASTA == ["x.fa"]
+
+
+def test_cli_fasta_reader_matches_oracle(oracle):
+    from deepgrp_b200.__main__ import _read_multi_fasta
+    text = "ACGT\n>h1 desc\nacgt\n NNAC \n>\nGGGG\n>h3\nTT"
+    assert list(_read_multi_fasta(io.StringIO(text))) == list(oracle.read_multi_fasta(io.StringIO(text)))
+    with pytest.raises(IndexError):
+        list(_read_multi_fasta(io.StringIO(">a\nAC\n\nGT\n")))
