@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- bases classified per second (Mbp/s) on the DeepGRP prediction hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbp M]
+
+One "step" = one pass of the whole hot path (forward + vote + score + MSS + segment extraction)
+over one synthetic record.  Workload at N=1: BASELINE.json configs[1] -- defaults.toml architecture
+(vecsize 342, units 60, attention), random-init weights (seed 0), one 46.7 Mbp iid-ACGT record.
+With N ranks every rank processes its own record of that size (contig sharding, no collective on
+the data path), so `scaling` is "weak" and `value` = N * bases / max-over-ranks time.
+
+Keys beyond the base contract:
+  value      device-resident: base codes already in HBM, timed with CUDA events on the library's
+             stream (exposed as a torch ExternalStream), L2 flushed between steps;
+  e2e        the same metric through the public API `deepgrp_b200.prediction.predict_fasta_tsv`
+             with the FASTA text in pinned HOST memory: H2D of the text, GPU decode, forward,
+             MSS, D2H of the rows and TSV formatting all inside the timed region;
+  roofline   the dominant kernel (the fused GRU/attention/vote kernel): algorithmic FLOPs
+             (12TU^2 + 85TU + 3T per window) / its CUDA-event time, against the
+             measured bf16 tensor peak of MEASURED_PEAKS.json;
+  cpu_baseline  the oracle port (reference restated on CPU, TF absent) on a bounded prefix.
+`--impl reference` times the CPU restatement of the reference path only (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_DEFAULT, U_DEFAULT = 342, 60          # defaults.toml
+STEP, BATCH, MIN_MSS, XDROP = 50, 256, 50, 50
+CONFIG2_BASES = 46_700_000
+
+
+def synth_codes(n, seed):
+    """iid uniform ACGT codes (default_rng([1, k]))."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 4, size=n, dtype=np.uint8)
+
+
+def fasta_text(codes, header, width=60):
+    """FASTA text (bytes) of one record, `width` columns per line."""
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    n = letters.size
+    full = n // width
+    body = np.empty((full, width + 1), dtype=np.uint8)
+    body[:, :width] = letters[:full * width].reshape(full, width)
+    body[:, width] = ord("\n")
+    tail = letters[full * width:].tobytes()
+    return b">" + header.encode() + b"\n" + body.tobytes() + (tail + b"\n" if tail else b"")
+
+
+def flops_per_window(T, U):
+    return 12 * T * U * U + 85 * T * U + 3 * T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples in the upper half of the observed range
+        load = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured"
+    except (OSError, KeyError, ValueError):
+        return 1400.0, 6650.0, "fallback"
+
+
+def cpu_reference_step(codes_prefix, weights, T, threads):
+    """The reference path restated on CPU (oracle port; TF absent): encode, windows, forward
+    (torch.nn.GRU engine), max-vote incl. the partial-batch placement, MSS, segments, TSV."""
+    from oracle import oracle as orc
+    import torch
+    torch.set_num_threads(threads)
+    text = fasta_text(codes_prefix, "synthetic_prefix")
+    with tempfile.NamedTemporaryFile("wb", suffix=".fa", delete=False) as fh:
+        fh.write(text)
+        path = fh.name
+    try:
+        t0 = time.perf_counter()
+        tsv = orc.predict_fasta_tsv(path, weights.as_dict(), T, BATCH, STEP, True, MIN_MSS, XDROP,
+                                    engine="torch")
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    return dt, len(tsv)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from deepgrp_b200 import model
+    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    threads = os.cpu_count() or 1
+    sample = args.ref_bases
+    codes = synth_codes(sample, [1, 0])
+    for _ in range(args.warmup):
+        cpu_reference_step(codes[:max(args.vecsize * 4, sample // 10)], weights, args.vecsize, threads)
+    times = [cpu_reference_step(codes, weights, args.vecsize, threads)[0] for _ in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total / 1e6
+    line = {
+        "impl": "reference", "metric": "bases classified/sec end-to-end", "value": value,
+        "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": threads, "kind": "port",
+                         "sample": "%d-base prefix of the workload per step; reference restated on CPU "
+                                   "(TF absent): oracle port with torch.nn.GRU engine" % sample},
+        "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, bases):
+    return {"workload": "BASELINE.json configs[1]: defaults.toml architecture (vecsize %d, units %d, "
+                        "attention), random-init weights seed 0, synthetic iid-ACGT single-record FASTA"
+                        % (args.vecsize, args.units),
+            "bases_per_record": int(bases), "step_size": STEP, "batch_size": BATCH,
+            "min_mss_len": MIN_MSS, "xdrop_len": XDROP, "compat": "reference",
+            "l2": "flushed between steps (256 MiB memset); per-step working set (predictions + "
+                  "scratch, >1.5 GB) also exceeds L2",
+            "sharding": "one record per rank, no collective"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from deepgrp_b200 import _lib, model, prediction
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.context(local_rank)
+    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    handle = weights.device_handle(ctx)
+    L = args.bases
+    codes = synth_codes(L, [1, rank])
+    d_codes = torch.from_numpy(codes).cuda()
+    text = fasta_text(codes, "synthetic_%dbp_rank%d" % (L, rank))
+    pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
+    raw_view = pinned.numpy()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    n_rows = ctypes.c_int64(0)
+
+    def device_step():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        _lib.check(_lib.lib().dgrp_predict_codes_dev(
+            ctx.handle, handle, ctypes.c_void_p(d_codes.data_ptr()), L, STEP, BATCH, 1, MIN_MSS, XDROP,
+            _lib.COMPAT_REFERENCE, ctypes.byref(n_rows)))
+        return ctx.timings()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    devnull = open(os.devnull, "wb")
+
+    def e2e_step():
+        view = prediction.predict_fasta_tsv_view(weights, raw_view, "synthetic.fa", STEP, BATCH, True,
+                                                 MIN_MSS, XDROP)
+        devnull.write(view)
+        return len(view)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fwd_ms, stage_ms = [], []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        t = device_step()
+        fwd_ms.append(t["forward_ms"])
+        stage_ms.append(t)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    rows_per_step = int(n_rows.value)
+
+    # end to end through the public API with host buffers
+    e2e_warm = max(1, min(args.warmup, 2))
+    for _ in range(e2e_warm):
+        tsv_len = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tsv_len = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = (float(x) for x in times.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * L * args.steps / (elapsed_ms / 1e3) / 1e6
+    e2e_value = world * L * args.steps / (e2e_ms / 1e3) / 1e6
+    tflops_peak, hbm_peak, peak_kind = peaks()
+    n_windows = len(range(0, L - args.vecsize, STEP))
+    kernel_ms = float(np.mean(fwd_ms))
+    achieved = flops_per_window(args.vecsize, args.units) * n_windows / (kernel_ms / 1e3) / 1e12
+    mean_stage = {k: float(np.mean([s[k] for s in stage_ms]))
+                  for k in ("forward_ms", "score_ms", "mss_ms", "segments_ms", "total_ms")}
+    line = {
+        "metric": "bases classified/sec end-to-end", "value": value, "unit": "Mbp/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, L),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": len(text),
+                "d2h_bytes_per_step": tsv_len + 64, "tsv_bytes_per_step": tsv_len,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gru_attention_vote_kernel (fp32 FFMA form)",
+                     "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
+                     "frac": achieved / tflops_peak, "traffic": None, "peak_kind": peak_kind,
+                     "kernel_ms": kernel_ms, "share_of_step": kernel_ms / (elapsed_ms / args.steps)},
+        "stages_ms": mean_stage, "rows_per_step": rows_per_step,
+        "mss_rounds": ctx.get_int("mss_rounds"),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = args.ref_bases
+        dt, _ = cpu_reference_step(codes[:sample], weights, args.vecsize, threads)
+        line["cpu_baseline"] = {
+            "value": sample / dt / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
+            "sample": "first %d bases of the workload, once; reference restated on CPU (TF absent): "
+                      "oracle port with torch.nn.GRU engine" % sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bases", type=int, default=CONFIG2_BASES)
+    ap.add_argument("--vecsize", type=int, default=T_DEFAULT)
+    ap.add_argument("--units", type=int, default=U_DEFAULT)
+    ap.add_argument("--ref-bases", type=int, default=100_000,
+                    help="bases per CPU-reference step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

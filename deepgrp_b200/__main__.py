@@ -169,9 +169,11 @@ class CommandLineParser:
                 else:
                     raw = (sys.stdin.buffer.read() if filename == "-"
                            else open(filename, "rb").read())
-                    outstream.write(dgpred.predict_fasta_tsv(
+                    view = dgpred.predict_fasta_tsv_view(
                         model, raw, filename, args.step_size, options.batch_size, use_mss,
-                        options.min_mss_len, options.xdrop_len))
+                        options.min_mss_len, options.xdrop_len)
+                    outstream.flush()
+                    getattr(outstream, "buffer", outstream).write(view)
             finally:
                 if filename != "-":
                     filestream.close()

@@ -87,6 +87,8 @@ SIGNATURES = {
     "dgrp_predict_range": (_I, [_P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
     "dgrp_finish_record": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _L, _P, _P, _L, _PL]),
     "dgrp_predict_fasta": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _PL, _PL]),
+    "dgrp_predict_fasta_tsv": (_I, [_P, _P, _P, _L, ctypes.c_char_p, _I, _I, _I, _I, _I, _I,
+                                    ctypes.POINTER(_P), _PL, _PL, _PL]),
     "dgrp_fasta_rows": (_I, [_P, _P, _L]),
     "dgrp_fasta_records": (_I, [_P, _P, _P, _P, _P, _L]),
     "dgrp_predict_codes_dev": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _PL]),

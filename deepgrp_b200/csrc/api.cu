@@ -222,7 +222,8 @@ int dgrp_ctx_destroy(dgrp_ctx *c) {
                     &c->small, &c->segs, &c->rows, &c->mss_a, &c->mss_b, &c->mss_c, &c->mss_d,
                     &c->mss_e, &c->scan};
   for (auto b : bufs) b->release();
-  c->pin_small.release(); c->pin_a.release(); c->pin_b.release();
+  c->pin_small.release(); c->pin_a.release(); c->pin_b.release(); c->tsv_host.release();
+  c->tsv_dev.release(); c->tsv_prefix.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -588,10 +589,16 @@ int dgrp_predict_sequence(dgrp_ctx *c, dgrp_model *m, const uint8_t *seq, int64_
   return rc;
 }
 
-int dgrp_predict_fasta(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, int step,
-                       int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,
-                       int64_t *n_rows, int64_t *n_records) {
+// filename == nullptr: rows are copied to the host (c->fa_rows); else the TSV text is produced on
+// the device and lands in c->tsv_host.
+static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes,
+                              const char *filename, int step, int batch_size, int use_mss,
+                              int min_mss_len, int xdrop_len, int compat, int64_t *n_rows,
+                              int64_t *n_records) {
   Use use(c->device);
+  c->tsv_len = 0;
+  int64_t total_rows = 0;
+  const size_t fn_len = filename ? strlen(filename) : 0;
   const int64_t launches0 = c->launches;
   *n_rows = 0; *n_records = 0;
   c->fa_rows.clear(); c->fa_hdr_off.clear(); c->fa_hdr_len.clear();
@@ -644,7 +651,37 @@ int dgrp_predict_fasta(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t
       int64_t *d_tri = nullptr;
       int64_t cnt = 0;
       if ((rc = run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt))) break;
-      if (cnt > 0) {
+      total_rows += cnt;
+      if (cnt > 0 && filename) {
+        // prefix = "<filename>\t<header>\t"
+        std::string prefix(filename, fn_len);
+        prefix.push_back('\t');
+        prefix.append(reinterpret_cast<const char *>(fasta + b), (size_t)(e - b));
+        prefix.push_back('\t');
+        int64_t need = 0;
+        if ((rc = c->tsv_prefix.reserve(prefix.size() + 16))) break;
+        if (cudaMemcpyAsync(c->tsv_prefix.p, prefix.data(), prefix.size(), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+          set_error("uploading the TSV prefix failed"); rc = DGRP_E_CUDA; break;
+        }
+        if ((rc = run_tsv_measure(c, d_tri, cnt, (int)prefix.size(), &need))) break;   // syncs
+        if ((rc = c->tsv_dev.reserve((size_t)need + 16))) break;
+        if ((size_t)(c->tsv_len + need) > c->tsv_host.cap) {
+          // grow the pinned text buffer, keeping what earlier records wrote
+          PinBuf bigger;
+          size_t want = std::max<size_t>((size_t)(c->tsv_len + need), c->tsv_host.cap * 2);
+          if ((rc = bigger.reserve(want + 4096))) break;
+          if (c->tsv_len > 0) memcpy(bigger.p, c->tsv_host.p, (size_t)c->tsv_len);
+          c->tsv_host.release();
+          c->tsv_host = bigger;
+        }
+        if ((rc = run_tsv_write(c, d_tri, cnt, c->tsv_prefix.as<uint8_t>(), (int)prefix.size(),
+                                c->tsv_dev.as<uint8_t>()))) break;
+        if (cudaMemcpyAsync(c->tsv_host.as<uint8_t>() + c->tsv_len, c->tsv_dev.p, (size_t)need,
+                            cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+          set_error("copying the TSV text failed"); rc = DGRP_E_CUDA; break;
+        }
+        c->tsv_len += need;
+      } else if (cnt > 0) {
         if ((rc = c->pin_a.reserve((size_t)cnt * 24))) break;
         if (cudaMemcpyAsync(c->pin_a.p, d_tri, (size_t)cnt * 24, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -677,8 +714,27 @@ int dgrp_predict_fasta(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t
   t.segments_ms = seg_ms; t.attend_ms = 0.f; t.windows = windows; t.bases = bases;
   cudaEventElapsedTime(&t.total_ms, e_begin, e_end);
   t.kernel_launches = c->launches - launches0;
-  *n_rows = (int64_t)c->fa_rows.size();
+  *n_rows = total_rows;
   *n_records = (int64_t)c->fa_hdr_off.size();
+  return rc;
+}
+
+int dgrp_predict_fasta(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, int step,
+                       int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,
+                       int64_t *n_rows, int64_t *n_records) {
+  return predict_fasta_impl(c, m, fasta, nbytes, nullptr, step, batch_size, use_mss, min_mss_len,
+                            xdrop_len, compat, n_rows, n_records);
+}
+
+int dgrp_predict_fasta_tsv(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes,
+                           const char *filename, int step, int batch_size, int use_mss,
+                           int min_mss_len, int xdrop_len, int compat, const uint8_t **tsv,
+                           int64_t *tsv_len, int64_t *n_rows, int64_t *n_records) {
+  *tsv = nullptr; *tsv_len = 0;
+  DGRP_REQUIRE(filename != nullptr, "filename is required");
+  const int rc = predict_fasta_impl(c, m, fasta, nbytes, filename, step, batch_size, use_mss,
+                                    min_mss_len, xdrop_len, compat, n_rows, n_records);
+  if (rc == DGRP_OK) { *tsv = c->tsv_host.as<uint8_t>(); *tsv_len = c->tsv_len; }
   return rc;
 }
 

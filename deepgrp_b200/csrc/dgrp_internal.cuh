@@ -95,6 +95,9 @@ struct dgrp_ctx {
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
   std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length;
+  dgrp::PinBuf tsv_host;     // finished TSV text of the last dgrp_predict_fasta_tsv
+  int64_t tsv_len = 0;
+  dgrp::DevBuf tsv_dev, tsv_prefix;
   // staged one-hot state (dgrp_one_hot_stage -> dgrp_one_hot_fetch)
   int64_t staged_n = 0, staged_start = 0, staged_len = -1;
 };
@@ -149,6 +152,10 @@ int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t
 int launch_labels_to_onehot(dgrp_ctx *c, const uint8_t *d_label, int64_t n, int C, double *d_out);
 // fasta.cu
 int run_fasta_decode(dgrp_ctx *c, const uint8_t *d_raw, int64_t n, int64_t *n_seq, int64_t *n_hdr);
+// tsv.cu
+int run_tsv_measure(dgrp_ctx *c, const int64_t *d_tri, int64_t n, int prefix_len, int64_t *need);
+int run_tsv_write(dgrp_ctx *c, const int64_t *d_tri, int64_t n, const uint8_t *d_prefix,
+                  int prefix_len, uint8_t *d_out);
 // segments.cu
 int run_segments(dgrp_ctx *c, const uint8_t *d_label, const int64_t *d_label64, int64_t n,
                  int64_t offset, bool keep_zero, int64_t **d_triples, int64_t *n_out);

@@ -87,69 +87,83 @@ __global__ void mss_count_runs_kernel(const T *__restrict__ S, int n, int CH, un
   }
 }
 
-// ---- stage 1: reduced scan, chunked --------------------------------------------------------------
+// ---- stage 1: reduced scan, chunked (see mss_core.cuh item 4) --------------------------------------
+using mss::ChunkSummary;
+
 struct ScanBufs {
-  ScanState *used, *out_a, *out_b;
-  uint8_t *ch_a, *ch_b;
-  uint8_t *reset_flag;
+  ScanState *used, *out, *pred;
+  ChunkSummary *sum;
+  uint8_t *dirty;
   const unsigned int *base;   // [NC] first run ordinal of each chunk
-  int *n_changed;
+  int *n_dirty;
 };
 
+// mode 0: every chunk from the canonical state; mode 1: stale chunks from their predicted state.
 template <typename T>
-__global__ void mss_round1_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
-                                  ScanBufs b, RunTable rt) {
+__global__ void mss_scan_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
+                                int mode, ScanBufs b, RunTable rt) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
   ScanState s;
-  mss::state_canonical(s);
+  if (mode == 0) mss::state_canonical(s);
+  else {
+    if (!b.dirty[c]) return;
+    s = b.pred[c];
+  }
   b.used[c] = s;
   const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
-  mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, false, rt);
-  b.out_a[c] = s;
-  b.ch_a[c] = 1;
+  ChunkSummary sum;
+  mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, rt, sum);
+  b.out[c] = s;
+  b.sum[c] = sum;
 }
 
-// One Jacobi round: chunk c re-runs from out_prev[c-1] when that changed and differs from the
-// state it last started from.  Reads prev (a), writes next (b).
-template <typename T>
-__global__ void mss_rerun_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
-                                 ScanBufs b, RunTable rt) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= NC) return;
-  ScanState prev_out = b.out_a[c];
-  uint8_t changed = 0;
-  if (c > 0 && b.ch_a[c - 1]) {
-    ScanState s = b.out_a[c - 1];
-    if (!mss::state_equal(s, b.used[c])) {
-      b.used[c] = s;
-      const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
-      const bool synced =
-          mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, true, rt);
-      if (!synced && !mss::state_equal(s, prev_out)) {
-        prev_out = s;
-        changed = 1;
+// One warp walks the chunk summaries: predicts every chunk's start state and marks the chunks whose
+// last execution started from something else.  Lanes stage 32 chunks at a time in shared memory,
+// lane 0 does the (inherently sequential, O(1) per chunk) chain.
+__global__ void mss_chain_kernel(int NC, ScanBufs b) {
+  __shared__ ScanState s_used[32], s_out[32], s_pred[32];
+  __shared__ ChunkSummary s_sum[32];
+  __shared__ uint8_t s_dirty[32];
+  const int lane = threadIdx.x;
+  ScanState s;
+  mss::state_canonical(s);
+  int n_dirty = 0;
+  for (int base = 0; base < NC; base += 32) {
+    const int c = base + lane;
+    if (c < NC) { s_used[lane] = b.used[c]; s_out[lane] = b.out[c]; s_sum[lane] = b.sum[c]; }
+    __syncwarp();
+    if (lane == 0) {
+      const int m = NC - base < 32 ? NC - base : 32;
+      for (int k = 0; k < m; ++k) {
+        s_pred[k] = s;
+        if (mss::state_equal(s_used[k], s)) { s_dirty[k] = 0; s = s_out[k]; }
+        else { s_dirty[k] = 1; ++n_dirty; s = mss::apply_summary(s_sum[k], s_used[k], s_out[k], s); }
       }
     }
+    __syncwarp();
+    if (c < NC) { b.pred[c] = s_pred[lane]; b.dirty[c] = s_dirty[lane]; }
+    __syncwarp();
   }
-  b.out_b[c] = prev_out;
-  b.ch_b[c] = changed;
-  if (changed) atomicAdd(b.n_changed, 1);
+  if (lane == 0) *b.n_dirty = n_dirty;
 }
 
-// Sequential completion of the fixed point by one thread (used when the rounds do not converge
-// quickly, e.g. x-drop disabled): chunk after chunk from the first stale one.
+// Sequential completion by one thread (when predictions keep missing, e.g. arbitrary doubles whose
+// sums round in every chunk): walk the chain, re-running every chunk that is stale.
 template <typename T>
-__global__ void mss_chain_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
-                                 ScanBufs b, RunTable rt) {
+__global__ void mss_complete_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
+                                    ScanBufs b, RunTable rt) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  for (int c = 1; c < NC; ++c) {
-    ScanState s = b.out_a[c - 1];
-    if (mss::state_equal(s, b.used[c])) continue;
+  ScanState s;
+  mss::state_canonical(s);
+  for (int c = 0; c < NC; ++c) {
+    if (mss::state_equal(b.used[c], s)) { s = b.out[c]; continue; }
     b.used[c] = s;
     const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
-    const bool synced = mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, b.reset_flag, true, rt);
-    if (!synced) b.out_a[c] = s;
+    ChunkSummary sum;
+    mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, rt, sum);
+    b.out[c] = s;
+    b.sum[c] = sum;
   }
 }
 
@@ -200,7 +214,7 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   if (n <= 0) return DGRP_OK;
   int CH = c->mss_chunk;
   if (CH <= 0) {
-    CH = 1024;
+    CH = 2048;
     while (CH > 64 && (int64_t)n / CH < 4096) CH >>= 1;
   }
   CH = (CH + 31) / 32 * 32;
@@ -253,47 +267,44 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
 
   off = 0;
   const size_t o_used = off; off = align256(off + (size_t)NC * sizeof(ScanState));
-  const size_t o_oa = off; off = align256(off + (size_t)NC * sizeof(ScanState));
-  const size_t o_ob = off; off = align256(off + (size_t)NC * sizeof(ScanState));
-  const size_t o_ca = off; off = align256(off + (size_t)NC);
-  const size_t o_cb = off; off = align256(off + (size_t)NC);
+  const size_t o_out = off; off = align256(off + (size_t)NC * sizeof(ScanState));
+  const size_t o_pred = off; off = align256(off + (size_t)NC * sizeof(ScanState));
+  const size_t o_sum = off; off = align256(off + (size_t)NC * sizeof(ChunkSummary));
+  const size_t o_dirty = off; off = align256(off + (size_t)NC);
   const size_t o_cnt = off; off = align256(off + 64);
   DGRP_CHECK(c->mss_c.reserve(off));
-  DGRP_CHECK(c->mss_d.reserve((size_t)n));
   unsigned char *pc = c->mss_c.as<unsigned char>();
   ScanBufs sb;
   sb.used = reinterpret_cast<ScanState *>(pc + o_used);
-  sb.out_a = reinterpret_cast<ScanState *>(pc + o_oa);
-  sb.out_b = reinterpret_cast<ScanState *>(pc + o_ob);
-  sb.ch_a = pc + o_ca;
-  sb.ch_b = pc + o_cb;
-  sb.n_changed = reinterpret_cast<int *>(pc + o_cnt);
-  sb.reset_flag = c->mss_d.as<uint8_t>();
+  sb.out = reinterpret_cast<ScanState *>(pc + o_out);
+  sb.pred = reinterpret_cast<ScanState *>(pc + o_pred);
+  sb.sum = reinterpret_cast<ChunkSummary *>(pc + o_sum);
+  sb.dirty = pc + o_dirty;
+  sb.n_dirty = reinterpret_cast<int *>(pc + o_cnt);
   sb.base = base;
-  DGRP_CUDA(cudaMemsetAsync(sb.reset_flag, 0, (size_t)n, c->stream));
 
   // ---- stage 1
   const int threads = 128;
   const int blocks = (NC + threads - 1) / threads;
-  mss_round1_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+  mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, 0, sb, rt);
   c->launches++;
-  int *h_changed = reinterpret_cast<int *>(h + 2);
+  int *h_dirty = reinterpret_cast<int *>(h + 2);
   int rounds = 1;
-  const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 4;
+  const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 8;
   bool converged = NC == 1;
-  while (!converged && rounds < max_rounds) {
-    DGRP_CUDA(cudaMemsetAsync(sb.n_changed, 0, 4, c->stream));
-    mss_rerun_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+  while (!converged) {
+    mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);
     c->launches++;
-    DGRP_CUDA(cudaMemcpyAsync(h_changed, sb.n_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+    DGRP_CUDA(cudaMemcpyAsync(h_dirty, sb.n_dirty, 4, cudaMemcpyDeviceToHost, c->stream));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
-    std::swap(sb.out_a, sb.out_b);
-    std::swap(sb.ch_a, sb.ch_b);
+    if (*h_dirty == 0) { converged = true; break; }
+    if (rounds >= max_rounds) break;
+    mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, 1, sb, rt);
+    c->launches++;
     ++rounds;
-    converged = (*h_changed == 0);
   }
   if (!converged) {
-    mss_chain_kernel<T><<<1, 32, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+    mss_complete_kernel<T><<<1, 32, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
     c->launches++;
   }
   c->mss_rounds = converged ? rounds : -rounds;

@@ -27,14 +27,20 @@
 //     independent of everything before it.  Regions are processed in parallel (one thread each)
 //     by the unmodified push/merge loop; a region is flushed if the next event is A (or the end)
 //     and dropped if it is B (absorbed).
-//  4. The reduced scan itself is chunked: chunk c > 0 starts speculatively from the state right
-//     after an x-drop reset (L = 0, max = -1e30, empty), the only state that does not depend on
-//     history.  It is then RE-RUN from the true state handed over by chunk c-1; the re-run stops
-//     as soon as it takes an x-drop reset at an index where the previous run of this chunk also
-//     reset (both are then in the identical state, so everything after is already correct).
-//     Iterating "state_in[c] = state_out[c-1]" to a fixed point is exact for any input; with
-//     x-drop enabled it converges in two rounds on real data and degenerates to a sequential
-//     chain (still bit-exact) when no reset ever fires.
+//  4. The reduced scan itself is chunked, one thread per chunk.  A chunk's execution is an exact,
+//     deterministic function of the state it starts from, so the scan is correct as soon as every
+//     chunk has been executed from exactly the state its predecessor ended in (chunk 0 starts from
+//     the true initial state): a fixed point of  state_in[c] = state_out[c-1],  verified by bitwise
+//     comparison.  To reach it in O(1) parallel rounds instead of walking the chain, the start states
+//     are PREDICTED: in exact arithmetic the machine is shift-invariant in L, so the effect of a chunk
+//     on (L, max, bottom) is summarised by a few numbers (ChunkSummary) and can be applied to any
+//     start state in O(1) (apply_summary).  A cheap sequential pass over the chunk summaries predicts
+//     all start states, every chunk whose prediction differs from what it last ran from is re-run
+//     in parallel, and the pass repeats until nothing is stale.  Scores that are float32 values
+//     (the fused path) add exactly in double, so predictions are exact and two rounds suffice;
+//     where double rounding does occur a prediction can miss by an ulp, the bitwise check catches
+//     it and the affected chunks simply run again (in the worst case the chain is walked
+//     sequentially -- always bit-exact, never approximate).
 #pragma once
 #include <stdint.h>
 
@@ -119,14 +125,25 @@ DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt) {
   s.run_st = -1; s.run_ord = -1; s.run_L0 = 0.0;
 }
 
-// Reduced scan over elements [b, e) of S (e <= n).  `first_ord` is the ordinal of the first run
-// that STARTS in [b, e).  `reset_flag[i]` records for every non-positive element whether this
-// execution took the x-drop reset there.  With `rerun`, the walk stops (returns true) at the first
-// reset that the previous execution of these elements also took.
+// What a chunk did to (max, bottom) after its last x-drop reset, in shift-invariant form.
+struct ChunkSummary {
+  double carryR;    // R of the run carried in from the previous chunk, if it ended in this chunk
+  double minT;      // min t.L over runs that started AND ended in the chunk (latest on ties)
+  double maxAfter;  // max R from that run on
+  double maxIn;     // max R over runs that started and ended in the chunk
+  int min_st;       // st of the minT run
+  int flags;        // 1: a reset happened, 2: carried run ended here, 4: minT.. valid,
+                    // 8: the run in progress at the chunk end started inside the chunk
+};
+
+// Reduced scan over elements [b, e) of S (e <= n) from state `s`.  `first_ord` is the ordinal of
+// the first run that STARTS in [b, e).  Writes the run records and the chunk summary.
 template <typename ScoreT>
-DGRP_HD bool scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
-                        ScanState &s, uint8_t *reset_flag, bool rerun, const RunTable &rt) {
+DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
+                        ScanState &s, const RunTable &rt, ChunkSummary &sum) {
   int next_ord = first_ord;
+  sum.carryR = 0.0; sum.minT = 0.0; sum.maxAfter = 0.0; sum.maxIn = 0.0; sum.min_st = -1; sum.flags = 0;
+  bool carried = (s.flags & 2) != 0;       // the run in progress came from before the chunk
   for (int i = b; i < e; ++i) {
     const double v = (double)S[i];
     if (v > 0) {
@@ -137,22 +154,70 @@ DGRP_HD bool scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
         // ordinal; it only shapes the (to be discarded) speculative state
         const bool true_start = (i == 0) || !((double)S[i - 1] > 0);
         s.run_ord = true_start ? next_ord++ : -1;
+        carried = !true_start;
       }
       s.L += v;                                     // R = L + S[i]; R += S[k]  (mss.c:61-63)
-      if (i + 1 == n || !((double)S[i + 1] > 0)) finish_run(s, i + 1, rt);
+      if (i + 1 == n || !((double)S[i + 1] > 0)) {
+        const double tL = s.run_L0;
+        const int st = s.run_st;
+        finish_run(s, i + 1, rt);
+        const double R = s.L;
+        if (carried) {
+          sum.flags |= 2; sum.carryR = R;
+        } else {
+          if (!(sum.flags & 4) || !(sum.minT < tL)) { sum.minT = tL; sum.min_st = st; sum.maxAfter = R; }
+          else if (R > sum.maxAfter) sum.maxAfter = R;
+          if (!(sum.flags & 4) || R > sum.maxIn) sum.maxIn = R;
+          sum.flags |= 4;
+        }
+        carried = false;
+      }
     } else {
-      const bool hit = xdrop > 0.0 && s.L + v + xdrop < s.maxv;   // mss.c:89
-      const uint8_t before = reset_flag[i];
-      reset_flag[i] = hit ? 1 : 0;
-      if (hit) {
-        if (rerun && before) return true;           // same reset as last time: states coincide
+      if (xdrop > 0.0 && s.L + v + xdrop < s.maxv) {  // mss.c:89
         s.L = 0.0; s.maxv = kNegInf;                // mss.c:91 (the flush happens at the next run)
         s.botL = 0.0; s.bot_st = -1; s.flags |= 1;
+        sum.flags = 1;                              // summary restarts after a reset
       }
       s.L += v;                                     // mss.c:93
     }
   }
-  return false;
+  if ((s.flags & 2) && !carried) sum.flags |= 8;
+}
+
+// Predict the end state of a chunk for start state `y` from one known execution x_in -> x_out with
+// summary `sum`.  Exact when all additions involved are exact; otherwise only a guess that the
+// bitwise verification will reject.
+DGRP_HD ScanState apply_summary(const ChunkSummary &sum, const ScanState &x_in,
+                                const ScanState &x_out, const ScanState &y) {
+  if (sum.flags & 1) return x_out;                  // after a reset the frame is absolute
+  const double d = y.L - x_in.L;
+  ScanState o = x_out;
+  o.L = x_out.L + d;
+  if (x_out.flags & 2) {
+    if (sum.flags & 8) o.run_L0 = x_out.run_L0 + d;
+    else if (y.flags & 2) { o.run_L0 = y.run_L0; o.run_st = y.run_st; o.run_ord = y.run_ord; }
+    else o.run_L0 = x_out.run_L0 + d;
+  }
+  double bot = y.botL, mx = y.maxv;
+  int bst = y.bot_st;
+  bool empty = (y.flags & 1) != 0;
+  if (sum.flags & 2) {                              // the carried run ended here
+    const double tL = (y.flags & 2) ? y.run_L0 : x_in.run_L0 + d;
+    const int st = (y.flags & 2) ? y.run_st : x_in.run_st;
+    const double R = sum.carryR + d;
+    if (empty || !(bot < tL)) { bot = tL; bst = st; mx = R; empty = false; }
+    else if (R > mx) mx = R;
+  }
+  if (sum.flags & 4) {
+    const double mT = sum.minT + d;
+    if (empty || !(bot < mT)) { bot = mT; bst = sum.min_st; mx = sum.maxAfter + d; empty = false; }
+    else if (sum.maxIn + d > mx) mx = sum.maxIn + d;
+  }
+  o.botL = empty ? 0.0 : bot;
+  o.bot_st = empty ? -1 : bst;
+  o.maxv = mx;
+  o.flags = (x_out.flags & 2) | (empty ? 1 : 0);
+  return o;
 }
 
 // Stack evolution of one region: runs [k0, k1) where k0 is a FLUSH/ABSORB run (its record is the

@@ -229,21 +229,40 @@ def predict_fasta(model: ModelWeights, raw: bytes, step_size: int, batch_size: i
     if k:
         _lib.check(_lib.lib().dgrp_fasta_records(ctx.handle, _lib.ptr(off), _lib.ptr(ln),
                                                  _lib.ptr(sp), _lib.ptr(le), k))
-    records = [(raw[off[i]:off[i] + ln[i]].decode("utf-8", "replace"), int(sp[i]), int(le[i]))
+    records = [(bytes(raw[off[i]:off[i] + ln[i]]).decode("utf-8", "replace"), int(sp[i]), int(le[i]))
                for i in range(k)]
     return rows, records
 
 
-def predict_fasta_tsv(model: ModelWeights, raw: bytes, filename: str, step_size: int,
-                      batch_size: int, use_mss: bool, min_mss_len: int, xdrop_len: int,
+def predict_fasta_tsv_view(model: ModelWeights, raw, filename: str, step_size: int,
+                           batch_size: int, use_mss: bool, min_mss_len: int, xdrop_len: int,
+                           compat: str = "reference") -> memoryview:
+    """The TSV text ``deepgrp predict`` writes for one file (reference ``deepgrp/__main__.py:288-292``),
+    formatted on the GPU.  Returns a read-only view of pinned host memory owned by the context: it is
+    valid until the next prediction call, so write it out (or copy it) first."""
+    ctx = _lib.context()
+    n = len(raw)
+    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    tsv, tsv_len = ctypes.c_void_p(), ctypes.c_int64(0)
+    n_rows, n_rec = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = _lib.lib().dgrp_predict_fasta_tsv(
+        ctx.handle, model.device_handle(ctx), _lib.ptr(buf), n, os.fsencode(filename),
+        int(step_size), int(batch_size), int(use_mss), int(min_mss_len), int(xdrop_len),
+        _COMPAT[compat], ctypes.byref(tsv), ctypes.byref(tsv_len), ctypes.byref(n_rows),
+        ctypes.byref(n_rec))
+    if rc == _lib.E_FASTA:
+        raise IndexError("string index out of range")
+    if rc == _lib.E_ALLN:
+        raise ValueError("negative dimensions are not allowed")
+    _lib.check(rc)
+    if tsv_len.value == 0:
+        return memoryview(b"")
+    return memoryview((ctypes.c_ubyte * tsv_len.value).from_address(tsv.value)).cast("B").toreadonly()
+
+
+def predict_fasta_tsv(model: ModelWeights, raw, filename: str, step_size: int, batch_size: int,
+                      use_mss: bool, min_mss_len: int, xdrop_len: int,
                       compat: str = "reference") -> str:
-    """The TSV text ``deepgrp predict`` writes for one file (reference ``deepgrp/__main__.py:288-292``)."""
-    rows, records = predict_fasta(model, raw, step_size, batch_size, use_mss, min_mss_len,
-                                  xdrop_len, compat)
-    if rows.size == 0:
-        return ""
-    headers = [r[0] for r in records]
-    parts = ["%s\t%s\t%d\t%d\t%d\n" % (filename, headers[rec], s, e, l)
-             for s, e, l, rec in zip(rows["start"].tolist(), rows["end"].tolist(),
-                                     rows["label"].tolist(), rows["record"].tolist())]
-    return "".join(parts)
+    """``predict_fasta_tsv_view`` copied into a ``str``."""
+    return bytes(predict_fasta_tsv_view(model, raw, filename, step_size, batch_size, use_mss,
+                                        min_mss_len, xdrop_len, compat)).decode("utf-8", "replace")

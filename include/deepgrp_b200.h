@@ -186,6 +186,14 @@ int dgrp_finish_record(dgrp_ctx *ctx, const uint8_t *labels, const float *scores
 int dgrp_predict_fasta(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
                        int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len,
                        int compat, int64_t *n_rows, int64_t *n_records);
+/* The same, but the rows are formatted on the GPU exactly as __main__.py:288-292 writes them
+ * ("{filename}\t{header}\t{start}\t{end}\t{label}\n", label > 0 only): *tsv points at *tsv_len
+ * bytes of finished text in pinned host memory owned by the context (valid until the next call).
+ * The record table is available through dgrp_fasta_records; rows are NOT copied to the host. */
+int dgrp_predict_fasta_tsv(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
+                           const char *filename, int step, int batch_size, int use_mss,
+                           int min_mss_len, int xdrop_len, int compat, const uint8_t **tsv,
+                           int64_t *tsv_len, int64_t *n_rows, int64_t *n_records);
 /* rows[i].record indexes the record table */
 int dgrp_fasta_rows(dgrp_ctx *ctx, dgrp_row_t *rows, int64_t cap);
 /* per record: header text = fasta[hdr_off, hdr_off + hdr_len); startpos = leading 'N' count;

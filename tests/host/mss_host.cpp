@@ -12,8 +12,8 @@ using namespace dgrp::mss;
 struct Seg { int st, en; double sc; };
 
 template <typename T>
-static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *out, int cap,
-                   int *rounds_out) {
+static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *segs_out, int cap,
+                   int *rounds_out, int max_rounds) {
   if (n <= 0) { *rounds_out = 0; return 0; }
   const int min_sc_int = (int)min_sc;
   const int NC = (n + CH - 1) / CH;
@@ -27,36 +27,53 @@ static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *
   const int NR = base[NC];
   std::vector<int> st(NR + 1), en(NR + 1), pre(NR + 1);
   std::vector<double> L(NR + 1), R(NR + 1);
-  std::vector<uint8_t> kind(NR + 1), flag(n, 0);
+  std::vector<uint8_t> kind(NR + 1);
   RunTable rt{st.data(), en.data(), L.data(), R.data(), pre.data(), kind.data()};
-  std::vector<ScanState> used(NC), outA(NC), outB(NC);
-  std::vector<uint8_t> chA(NC, 1), chB(NC, 0);
-  // round 1
+  std::vector<ScanState> used(NC), out(NC), pred(NC);
+  std::vector<ChunkSummary> sum(NC);
+  std::vector<uint8_t> dirty(NC, 0);
+  // round 1: every chunk from the canonical state (emulates mss_scan_kernel, one thread per chunk)
   for (int c = 0; c < NC; ++c) {
     ScanState s; state_canonical(s);
     used[c] = s;
     int b = c * CH, e = b + CH < n ? b + CH : n;
-    scan_chunk(S, n, xdrop, b, e, base[c], s, flag.data(), false, rt);
-    outA[c] = s;
+    scan_chunk(S, n, xdrop, b, e, base[c], s, rt, sum[c]);
+    out[c] = s;
   }
   int rounds = 1;
   for (;;) {
-    int changed = 0;
-    outB = outA;
+    // chain pass (emulates mss_chain_kernel): predict every start state, mark stale chunks
+    int n_dirty = 0;
+    ScanState s; state_canonical(s);
     for (int c = 0; c < NC; ++c) {
-      chB[c] = 0;
-      if (c == 0) continue;
-      if (!chA[c - 1]) continue;
-      if (state_equal(outA[c - 1], used[c])) continue;
-      ScanState s = outA[c - 1];
-      used[c] = s;
-      int b = c * CH, e = b + CH < n ? b + CH : n;
-      bool synced = scan_chunk(S, n, xdrop, b, e, base[c], s, flag.data(), true, rt);
-      if (!synced && !state_equal(s, outA[c])) { outB[c] = s; chB[c] = 1; ++changed; }
+      pred[c] = s;
+      if (state_equal(used[c], s)) { dirty[c] = 0; s = out[c]; }
+      else { dirty[c] = 1; ++n_dirty; s = apply_summary(sum[c], used[c], out[c], s); }
     }
-    outA.swap(outB); chA.swap(chB);
+    if (!n_dirty) break;
+    if (max_rounds > 0 && rounds >= max_rounds) {
+      // sequential completion (emulates mss_complete_kernel)
+      ScanState t; state_canonical(t);
+      for (int c = 0; c < NC; ++c) {
+        if (!state_equal(used[c], t)) {
+          used[c] = t;
+          int b = c * CH, e = b + CH < n ? b + CH : n;
+          scan_chunk(S, n, xdrop, b, e, base[c], t, rt, sum[c]);
+          out[c] = t;
+        } else t = out[c];
+      }
+      rounds = -rounds;
+      break;
+    }
+    for (int c = 0; c < NC; ++c) {
+      if (!dirty[c]) continue;
+      ScanState t = pred[c];
+      used[c] = t;
+      int b = c * CH, e = b + CH < n ? b + CH : n;
+      scan_chunk(S, n, xdrop, b, e, base[c], t, rt, sum[c]);
+      out[c] = t;
+    }
     ++rounds;
-    if (!changed) break;
   }
   *rounds_out = rounds;
   // regions
@@ -72,11 +89,11 @@ static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *
   }
   int m = 0;
   for (int k = 0; k < NR; ++k)
-    if (live[k]) { if (m < cap) { out[m].st = st[k]; out[m].en = en[k]; out[m].sc = R[k] - L[k]; } ++m; }
+    if (live[k]) { if (m < cap) { segs_out[m].st = st[k]; segs_out[m].en = en[k]; segs_out[m].sc = R[k] - L[k]; } ++m; }
   return m;
 }
 
 extern "C" int host_mss_f64(int n, const double *S, double min_sc, double xdrop, int CH, Seg *out,
-                            int cap, int *rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds); }
+                            int cap, int *rounds, int max_rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds, max_rounds); }
 extern "C" int host_mss_f32(int n, const float *S, double min_sc, double xdrop, int CH, Seg *out,
-                            int cap, int *rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds); }
+                            int cap, int *rounds, int max_rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds, max_rounds); }

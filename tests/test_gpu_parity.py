@@ -342,6 +342,14 @@ def test_predict_fasta_tsv_vs_oracle(dg, oracle, tmp_path):
     total = sum(ce.values())
     diff = sum(abs(cg[k] - ce[k]) for k in ce)
     assert diff <= max(2, 2e-4 * total)
+    # the GPU-formatted text equals Python formatting of the rows, byte for byte
+    rows, records = dg.pred.predict_fasta(w, raw, 50, 256, True, 50, 50)
+    assert [r[0] for r in records] == [h for h, _ in recs]
+    assert [r[1] for r in records] == [3, 0, 0]
+    text = "".join("%s\t%s\t%d\t%d\t%d\n" % (str(path), records[r][0], s, e, l) for s, e, l, r in
+                   zip(rows["start"].tolist(), rows["end"].tolist(), rows["label"].tolist(),
+                       rows["record"].tolist()))
+    assert text == got
     # CRLF line ends, a record with empty header (dropped) and text before the first '>' (dropped)
     raw2 = b"ACGTACGT\r\n>\r\nACGT\r\n" + raw.replace(b"\n", b"\r\n")
     got2 = dg.pred.predict_fasta_tsv(w, raw2, str(path), 50, 256, True, 50, 50)

@@ -61,7 +61,7 @@ def host_mss():
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
 
-    def run(S, min_sc, xdrop, CH):
+    def run(S, min_sc, xdrop, CH, max_rounds=0):
         S = np.ascontiguousarray(S)
         cap = S.size // 2 + 2
         out = (_Seg * cap)()
@@ -69,7 +69,7 @@ def host_mss():
         fn = lib.host_mss_f64 if S.dtype == np.float64 else lib.host_mss_f32
         fn.restype = ctypes.c_int
         m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
-               CH, out, cap, ctypes.byref(rounds))
+               CH, out, cap, ctypes.byref(rounds), max_rounds)
         return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value
     return run
 
@@ -98,18 +98,29 @@ def test_chunked_mss_logic_bit_exact(host_mss, oracle):
                 ref = [(int(a), int(b), float(c)) for a, b, c in
                        oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
                 for CH in (1, 3, 16, 64, 1000):
-                    got, _ = host_mss(S, min_sc, xdrop, CH)
-                    assert got == ref, (trial, xdrop, min_sc, CH)
+                    for max_rounds in (0, 2):      # 2: forces the sequential completion path
+                        got, _ = host_mss(S, min_sc, xdrop, CH, max_rounds)
+                        assert got == ref, (trial, xdrop, min_sc, CH, max_rounds)
 
 
-def test_chunked_mss_converges_fast_with_resets(host_mss, oracle):
+def test_chunked_mss_converges_in_few_rounds(host_mss, oracle):
+    """float32-valued scores (what the fused path produces) add exactly in double, so the predicted
+    chunk start states are right and the scan needs O(1) parallel rounds in every drift regime --
+    including the benchmark's random-weight regime where no x-drop reset ever fires."""
     rng = np.random.default_rng(1)
     n = 300_000
-    S = (np.where(np.repeat(rng.random(n // 100) < 0.4, 100), 4.59, -45.9) * rng.random(n)).astype(np.float32)
     xdrop, min_sc = np.log(99) * 500, np.log(99) * 50
-    got, rounds = host_mss(S, min_sc, xdrop, 1024)
-    ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
-    assert got == ref and rounds <= 4
+    cases = {
+        "trained-like": np.where(np.repeat(rng.random(n // 100) < 0.4, 100), 4.59, -45.9) * rng.random(n),
+        "negative drift": np.where(rng.random(n) < 0.02, 13.2, -1.32) * (1 + 1e-3 * rng.normal(size=n)),
+        "positive drift": np.where(rng.random(n) < 0.3, 13.2, -1.32),
+    }
+    for name, S in cases.items():
+        S = S.astype(np.float32)
+        got, rounds = host_mss(S, min_sc, xdrop, 1024, 12)
+        ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+        assert got == ref, name
+        assert 0 < rounds <= 4, (name, rounds)
 
 
 # ---- Options / weights / CLI ---------------------------------------------------------------------
