@@ -242,6 +242,7 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *c) { return c->launches; }
 int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
+  else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
   return DGRP_OK;
 }
@@ -249,6 +250,8 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   if (!strcmp(key, "mss_chunk")) *value = c->mss_chunk;
   else if (!strcmp(key, "mss_max_rounds")) *value = c->mss_max_rounds;
   else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
+  else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
+  else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
   return DGRP_OK;
@@ -441,6 +444,39 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
     for (int g = 0; g < G; ++g)
       for (int u = 0; u < U; ++u)
         Rp[((size_t)k * G + g) * UP + u] = recurrent[(size_t)k * G * U + g * U + u];
+  // bf16 hi|mid|lo pieces of recurrent^T in the tcgen05 operand layout (forward_tc.cu)
+  std::vector<uint16_t> Bs;
+  if (UP <= 64) {
+    const int N = 3 * UP, SBO = (UP / 8) * 128;
+    Bs.assign((size_t)3 * N * UP, 0);
+    auto f2bf = [](float f) -> uint16_t {
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+      const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+      return (uint16_t)((u + r) >> 16);
+    };
+    auto bf2f = [](uint16_t b) -> float {
+      const uint32_t u = (uint32_t)b << 16;
+      float f;
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < UP; ++k) {
+        const int g = n / UP, u = n % UP;
+        const float x = Rp[((size_t)k * G + g) * UP + u];
+        const uint16_t hi = f2bf(x);
+        const float r1 = x - bf2f(hi);
+        const uint16_t mid = f2bf(r1);
+        const float r2 = r1 - bf2f(mid);
+        const uint16_t lo = f2bf(r2);
+        const size_t off = ((size_t)(n / 8) * SBO + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2;
+        Bs[off] = hi;
+        Bs[(size_t)N * UP + off] = mid;
+        Bs[(size_t)2 * N * UP + off] = lo;
+      }
+  }
   dgrp_model *m = new dgrp_model();
   m->device = c->device; m->rnn = rnn; m->T = vecsize; m->U = U; m->C = n_classes; m->UP = UP;
   m->attention = att_scale != nullptr;
@@ -456,7 +492,9 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       (rc = up(&m->d_Rp, Rp.data(), Rp.size())) ||
       (rc = up(&m->d_ffk, ff_kernel, (size_t)F * n_classes)) ||
       (rc = up(&m->d_ffb, ff_bias, (size_t)n_classes)) ||
-      (m->attention && (rc = up(&m->d_scale, att_scale, (size_t)U)))) {
+      (m->attention && (rc = up(&m->d_scale, att_scale, (size_t)U))) ||
+      (!Bs.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit),
+                               reinterpret_cast<const float *>(Bs.data()), Bs.size() / 2)))) {
     cudaStreamSynchronize(c->stream);
     dgrp_model_destroy(m);
     return rc;
@@ -473,6 +511,7 @@ int dgrp_model_destroy(dgrp_model *m) {
                    m->d_b1, m->d_scale, m->d_ffk, m->d_ffb};
   for (float *p : ptrs)
     if (p) cudaFree(p);
+  if (m->d_Bsplit) cudaFree(m->d_Bsplit);
   delete m;
   return DGRP_OK;
 }

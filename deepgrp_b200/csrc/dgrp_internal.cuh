@@ -72,6 +72,7 @@ struct dgrp_model {
   float *d_b0 = nullptr;         // [3, UP]     bias[0, g*U+u], zero padded
   float *d_Rp = nullptr;         // [UP, 3, UP] recurrent[k, g*U+u], zero padded
   float *d_b1 = nullptr;         // [3, UP]     bias[1, g*U+u], zero padded
+  uint16_t *d_Bsplit = nullptr;  // [3][3UP x UP] bf16 hi|mid|lo of recurrent^T, UMMA K-major core matrices
   float *d_scale = nullptr;      // [U] or null
   float *d_ffk = nullptr;        // [F, C]
   float *d_ffb = nullptr;        // [C]
@@ -92,6 +93,8 @@ struct dgrp_ctx {
   int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)
   int mss_max_rounds = 0;  // Jacobi rounds before the sequential completion (0 = default)
   int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
+  int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
+  int forward_used_tc = 0; // what the last forward launch used
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
   std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length;

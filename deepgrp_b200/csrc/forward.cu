@@ -16,7 +16,7 @@
 // This file is the fp32 CUDA-core form (the correctness anchor of SURVEY.md section 7 step 5):
 // every product of the recurrence is an FFMA in fp32, so results differ from a float32 CPU run
 // only by summation order and the last-ulp behaviour of expf/tanhf.
-#include "dgrp_internal.cuh"
+#include "forward_common.cuh"
 
 namespace dgrp {
 
@@ -36,7 +36,8 @@ Placement make_placement(int64_t length, int T, int step, int batch_size, int co
   return p;
 }
 
-constexpr int FWD_THREADS = 256;
+
+int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p);   // forward_tc.cu
 
 template <int UP>
 struct Cfg {
@@ -48,20 +49,6 @@ struct Cfg {
   static constexpr int WT = ROWS / 2;                 // windows per tile
   static constexpr int HS = UP + 4;                   // h row stride (floats)
   static constexpr bool R_SMEM = UP <= 64;            // recurrent weights resident in smem
-};
-
-struct FwdParams {
-  const uint8_t *codes;   // code mode
-  int64_t codes_base;     // record position of codes[0]
-  const float *dense;     // dense mode: [n][T][5] windows (predict_on_batch semantics)
-  float *probs_out;       // dense mode: [n][T][C]
-  int64_t w_begin, w_end; // window index range
-  int T, U, C, step, attention;
-  int64_t full_windows, tail_base;
-  const float *P, *Wk, *b0, *Rp, *b1, *scale, *ffk, *ffb;
-  float *scratch, *ff2;
-  float *pred;
-  int64_t pred_row0, pred_rows;
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -81,7 +68,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
 
   const int tid = threadIdx.x;
   const int tu = tid % K::UG, tr = tid / K::UG;
-  const int T = p.T, U = p.U, C = p.C;
+  const int T = p.T, U = p.U;
   const int KU = (U + 3) & ~3;
 
   // ---- one-time: stage weights ----
@@ -89,20 +76,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
     for (int i = tid; i < UP * 3 * UP; i += FWD_THREADS) s_R[i] = p.Rp[i];
   for (int i = tid; i < 5 * 3 * UP; i += FWD_THREADS) s_P[i] = DENSE ? p.Wk[i] : p.P[i];
   for (int i = tid; i < 3 * UP; i += FWD_THREADS) { s_b0[i] = p.b0[i]; s_b1[i] = p.b1[i]; }
-  for (int i = tid; i < UP * 12; i += FWD_THREADS) {
-    const int u = i / 12, j = i % 12;
-    float v = 0.f;
-    if (u < U) {
-      if (p.attention) {
-        if (j < 5) v = j < C ? p.ffk[(size_t)u * C + j] : 0.f;                  // ctx half (first)
-        else if (j < 10) v = (j - 5) < C ? p.ffk[(size_t)(U + u) * C + (j - 5)] : 0.f;  // avg half
-        else if (j == 10) v = p.scale[u];
-      } else if (j >= 5 && j < 10) {
-        v = (j - 5) < C ? p.ffk[(size_t)u * C + (j - 5)] : 0.f;
-      }
-    }
-    s_att[i] = v;
-  }
+  stage_attention_table<UP>(p, s_att, tid);
   __syncthreads();
 
   float *scratch = p.scratch + (size_t)blockIdx.x * K::WT * T * UP;
@@ -260,106 +234,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
     __threadfence_block();
     __syncthreads();
 
-    // ---------------- phase 2: attention + FF + softmax + vote, one warp per window --------
-    const int warp = tid >> 5, lane = tid & 31;
-    float *qv = s_q + warp * UP;
-    float *sc = s_score + (size_t)warp * T;
-    for (int wl = warp; wl < K::WT; wl += FWD_THREADS / 32) {
-      const int64_t w = w_tile0 + wl;
-      if (w >= p.w_end) break;
-      const float *av = scratch + (size_t)wl * T * UP;
-      float *f2 = ff2 + (size_t)wl * T * 5;
-      // query = (h_fwd[T-1] + h_rc[T-1]) / 2 = avg[T-1]   (model.py:311)
-      for (int u = lane; u < UP; u += 32) qv[u] = av[(size_t)(T - 1) * UP + u];
-      __syncwarp();
-      float m_run = -INFINITY, l_run = 0.f, cacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int t = lane; t < T; t += 32) {
-        const float *row = av + (size_t)t * UP;
-        float s = 0.f, k1[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, k2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int u = 0; u < KU; u += 4) {
-          const float4 v4 = *reinterpret_cast<const float4 *>(row + u);
-          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float *a = s_att + (u + j) * 12;
-            const float4 a0 = *reinterpret_cast<const float4 *>(a);
-            const float4 a1 = *reinterpret_cast<const float4 *>(a + 4);
-            const float4 a2 = *reinterpret_cast<const float4 *>(a + 8);
-            const float v = vv[j];
-            if (p.attention) {
-              s = fmaf(a2.z, tanhf(qv[u + j] + v), s);
-              k1[0] = fmaf(v, a0.x, k1[0]); k1[1] = fmaf(v, a0.y, k1[1]);
-              k1[2] = fmaf(v, a0.z, k1[2]); k1[3] = fmaf(v, a0.w, k1[3]);
-              k1[4] = fmaf(v, a1.x, k1[4]);
-            }
-            k2[0] = fmaf(v, a1.y, k2[0]); k2[1] = fmaf(v, a1.z, k2[1]);
-            k2[2] = fmaf(v, a1.w, k2[2]); k2[3] = fmaf(v, a2.x, k2[3]);
-            k2[4] = fmaf(v, a2.y, k2[4]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) f2[(size_t)t * 5 + c] = k2[c];
-        if (p.attention) {
-          sc[t] = s;
-          // online softmax over t of (score, avg[t].K1)
-          const float m_new = fmaxf(m_run, s);
-          const float corr = __expf(m_run - m_new);   // exp(-inf) = 0 on the first element
-          const float e = expf(s - m_new);
-          l_run = l_run * corr + e;
-#pragma unroll
-          for (int c = 0; c < 5; ++c) cacc[c] = cacc[c] * corr + e * k1[c];
-          m_run = m_new;
-        }
-      }
-      float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      if (p.attention) {
-        float m_all = m_run;
-        for (int off = 16; off > 0; off >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, off));
-        const float f = (m_run == -INFINITY) ? 0.f : expf(m_run - m_all);
-        float l = l_run * f;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) cacc[c] *= f;
-        for (int off = 16; off > 0; off >>= 1) {
-          l += __shfl_xor_sync(0xffffffffu, l, off);
-#pragma unroll
-          for (int c = 0; c < 5; ++c) cacc[c] += __shfl_xor_sync(0xffffffffu, cacc[c], off);
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) ctxk[c] = cacc[c] / l;
-      }
-      __syncwarp();
-      // logits[t] = ctx.K1 + avg[t].K2 + b ; softmax over classes ; vote
-      int64_t place;
-      if (DENSE) place = 0;
-      else place = (w < p.full_windows ? w * (int64_t)p.step
-                                       : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
-                   p.pred_row0;
-      for (int t = lane; t < T; t += 32) {
-        float lg[5], mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          lg[c] = c < C ? (ctxk[c] + f2[(size_t)t * 5 + c]) + p.ffb[c] : -INFINITY;
-          mx = fmaxf(mx, lg[c]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { lg[c] = c < C ? expf(lg[c] - mx) : 0.f; sum += lg[c]; }
-        if (DENSE) {
-          float *dst = p.probs_out + ((size_t)w * T + t) * C;
-#pragma unroll
-          for (int c = 0; c < 5; ++c) if (c < C) dst[c] = lg[c] / sum;
-        } else {
-          const int64_t r = place + t;
-          if (r >= 0 && r < p.pred_rows) {
-            int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
-#pragma unroll
-            for (int c = 0; c < 5; ++c)
-              if (c < C) atomicMax(dst + c, __float_as_int(lg[c] / sum));   // probs > 0
-          }
-        }
-      }
-      __syncwarp();
-    }
+    attention_vote_tile<UP, DENSE, K::WT>(p, scratch, ff2, w_tile0, s_att, s_q, s_score);
     __syncthreads();
   }
 }
@@ -424,6 +299,14 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
   p.w_begin = w_begin; p.w_end = w_end;
   p.step = pl.step; p.full_windows = pl.full_windows; p.tail_base = pl.tail_base;
   p.pred = d_pred; p.pred_row0 = pred_row0; p.pred_rows = pred_rows;
+  c->forward_used_tc = 0;
+  if (c->forward_tc) {
+    const int rc = launch_forward_tc(c, m, p);
+    if (rc != DGRP_E_UNSUPPORTED) {
+      c->forward_used_tc = 1;
+      return rc;
+    }
+  }
   return launch_fwd<false>(c, m, p);
 }
 

@@ -1,0 +1,383 @@
+// K2-K6, tcgen05 form: the recurrent product h.R of both GRU passes on the 5th-generation tensor
+// cores, everything else as in forward.cu.
+//
+// Why not plain bf16: the parity bar (>= 99.99 % identical labels against a float32 CPU run, on
+// random-init weights whose class margins are ~1e-4) needs fp32-faithful pre-activations through
+// a 150..512 step recurrence.  Both operands are therefore split into three bf16
+// pieces, x = hi + mid + lo (8+8+8 mantissa bits = the full fp32 significand), and the product is
+// formed from the six piece products whose weight is >= 2^-16:
+//     h.R ~= hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi      (dropped terms <= 2^-24 |h||R|)
+// each a kind::f16 (bf16 x bf16 -> fp32) tcgen05.mma accumulating into the same TMEM tile, smallest
+// terms first.  The gates, sigmoid/tanh and the state update stay in fp32 registers.
+//
+// One CTA = 256 threads = 8 warps, persistent, two tiles of 64 windows x 2 directions (M = 128 rows)
+// in flight: while the tensor core multiplies tile X's new state by R, the CUDA cores compute the
+// gates of tile Y from its finished accumulator, and vice versa.
+//   TMEM   2 x [128 lanes x 3*UP columns] fp32 accumulators (z | r | h gate blocks)
+//   smem   B = R^T pieces, [3][3*UP x UP] bf16, K-major core matrices, resident for the whole kernel
+//          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate threads
+//   warp w: TMEM lane quadrant w % 4 (rows 32*(w%4) ..+31, one row per lane), unit half w / 4
+//   row r of a tile = window r/2, direction r%2, so avg[t] = (fwd + rc)/2 is one lane shuffle.
+// Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 B each; core matrices
+// adjacent along K are 128 B apart (leading byte offset), along M/N they are UP/8 * 128 B apart
+// (stride byte offset); one MMA consumes K = 16 = two core matrices.
+#include <cuda_bf16.h>
+
+#include "forward_common.cuh"
+
+namespace dgrp {
+
+template <int UP>
+struct TCfg {
+  static constexpr int N = 3 * UP;             // accumulator columns per tile
+  static constexpr int ROWS = 128, WT = 64;
+  static constexpr int UPT = UP / 2;           // units per thread
+  static constexpr int KC = UP / 8;            // core matrices along K
+  static constexpr int SBO = KC * 128;         // bytes between 8-row groups
+  static constexpr int A_BYTES = ROWS * UP * 2;  // one piece of one tile
+  static constexpr int B_BYTES = N * UP * 2;     // one piece
+  static constexpr int PSTRIDE = 3 * UP + 4;     // floats per code row of the input table
+  static constexpr int TCOLS = N <= 64 ? 64 : (N <= 128 ? 128 : 256);  // TMEM columns per tile
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= 1ull << 46;  // descriptor version (sm_100)
+  return d;         // layout_type = 0: no swizzle
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// x = hi + mid + lo in bf16 pieces, packed two values per 32-bit word (low half = first value)
+__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+  const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
+  const float ar2 = ar - __bfloat162float(am), br2 = br - __bfloat162float(bm);
+  const __nv_bfloat16 al = __float2bfloat16_rn(ar2), bl = __float2bfloat16_rn(br2);
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+// 1 / (1 + e^-x) for two gates with one reciprocal: z = b/(ab), r = a/(ab)
+__device__ __forceinline__ void sigmoid2(float xz, float xr, float &z, float &r) {
+  const float a = 1.0f + __expf(-xz), b = 1.0f + __expf(-xr);
+  // a*b can overflow only when both arguments are below -44; clamp keeps the product finite
+  const float inv = __fdividef(1.0f, fminf(a, 1e18f) * fminf(b, 1e18f));
+  z = inv * fminf(b, 1e18f);
+  r = inv * fminf(a, 1e18f);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  // 1 - 2/(e^{2x}+1): absolute error ~1e-7 (fp32 rounding of the quotient), exact limits +-1
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+template <int UP>
+__global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
+  using K = TCfg<UP>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
+  unsigned char *s_A = s_B + 3 * K::B_BYTES;                   // [2][3][A_BYTES]
+  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [5][PSTRIDE]
+  float *s_b1 = s_P + 5 * K::PSTRIDE;                          // [3][UP]
+  float *s_att = s_b1 + 3 * UP;                                // [UP][12]
+  float *s_q = s_att + UP * 12;                                // [8][UP]
+  float *s_score = s_q + 8 * UP;                               // [8][T]
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;        // row of the tile = TMEM lane
+  const int wl = row >> 1, dir = row & 1;  // window in tile, direction
+  const int T = p.T, U = p.U;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.Bsplit);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_B);
+    for (int i = tid; i < 3 * K::B_BYTES / 16; i += FWD_THREADS) dst[i] = src[i];
+    for (int i = tid; i < 5 * K::PSTRIDE; i += FWD_THREADS) {
+      const int c = i / K::PSTRIDE, j = i % K::PSTRIDE;
+      s_P[i] = j < 3 * UP ? p.P[c * 3 * UP + j] : 0.f;
+    }
+    for (int i = tid; i < 3 * UP; i += FWD_THREADS) s_b1[i] = p.b1[i];
+    stage_attention_table<UP>(p, s_att, tid);
+    // A pieces start as zeros (h_0 = 0; padded K columns stay zero forever)
+    uint4 *a4 = reinterpret_cast<uint4 *>(s_A);
+    for (int i = tid; i < 6 * K::A_BYTES / 16; i += FWD_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&s_tmem)),
+                 "r"(2 * K::TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+
+  float *scratch0 = p.scratch + (size_t)blockIdx.x * 2 * K::WT * T * UP;
+  float *ff2_0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 5;
+  const int64_t n_windows = p.w_end - p.w_begin;
+  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  uint32_t phase[2] = {0u, 0u};   // mbarrier parity to wait for next, per tile slot
+
+  for (int64_t pair = blockIdx.x; pair * 2 < n_tiles; pair += gridDim.x) {
+    bool live[2];
+    int64_t wpos[2];      // position of this thread's window start in the codes array
+    bool wvalid[2];
+    float hprev[2][K::UPT];
+    int code_next[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int64_t tile = pair * 2 + s;
+      live[s] = tile < n_tiles;
+      const int64_t w = p.w_begin + tile * K::WT + wl;
+      wvalid[s] = live[s] && w < p.w_end;
+      wpos[s] = w * (int64_t)p.step - p.codes_base;
+#pragma unroll
+      for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
+      code_next[s] = 4;
+      if (wvalid[s]) {
+        int c = p.codes[wpos[s] + (dir ? (T - 1) : 0)];
+        code_next[s] = (dir && c < 4) ? 3 - c : c;
+      }
+    }
+
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (!live[s]) continue;   // uniform over the CTA
+        const int code = code_next[s];
+        if (t + 1 < T && wvalid[s]) {   // prefetch next step's base
+          int c = p.codes[wpos[s] + (dir ? (T - 2 - t) : (t + 1))];
+          code_next[s] = (dir && c < 4) ? 3 - c : c;
+        }
+        if (t > 0) {
+          mbar_wait(smem_u32(&s_bar[s]), phase[s]);
+          phase[s] ^= 1u;
+          tc_fence_after();
+        }
+        unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES;
+        float *avg_out = scratch0 + ((size_t)(s * K::WT + wl) * T + t) * UP;
+        const float *prow = s_P + code * K::PSTRIDE;
+#pragma unroll
+        for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
+          const int u0 = half * K::UPT + c8 * 8;
+          float az[8], ar[8], ah[8];
+          if (t > 0) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + u0);
+            tmem_ld8(taddr, az);
+            tmem_ld8(taddr + UP, ar);
+            tmem_ld8(taddr + 2 * UP, ah);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
+          }
+          float hn[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const float4 xz = *reinterpret_cast<const float4 *>(prow + u0 + 4 * j4);
+            const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + u0 + 4 * j4);
+            const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + u0 + 4 * j4);
+            const float4 bz = *reinterpret_cast<const float4 *>(s_b1 + u0 + 4 * j4);
+            const float4 br = *reinterpret_cast<const float4 *>(s_b1 + UP + u0 + 4 * j4);
+            const float4 bh = *reinterpret_cast<const float4 *>(s_b1 + 2 * UP + u0 + 4 * j4);
+            const float xzv[4] = {xz.x, xz.y, xz.z, xz.w}, xrv[4] = {xr.x, xr.y, xr.z, xr.w};
+            const float xhv[4] = {xh.x, xh.y, xh.z, xh.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+            const float brv[4] = {br.x, br.y, br.z, br.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 4 * j4 + j;
+              float z, r;
+              sigmoid2(xzv[j] + (az[e] + bzv[j]), xrv[j] + (ar[e] + brv[j]), z, r);
+              const float hh = tanh_fast(xhv[j] + r * (ah[e] + bhv[j]));
+              const float hp = hprev[s][c8 * 8 + e];
+              const float h = z * hp + (1.0f - z) * hh;
+              hprev[s][c8 * 8 + e] = h;
+              hn[e] = h;
+            }
+          }
+          // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
+          uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split3(hn[2 * j], hn[2 * j + 1], hi[j], mid[j], lo[j]);
+          const int off = (row >> 3) * K::SBO + (u0 >> 3) * 128 + (row & 7) * 16;
+          *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+          *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          // avg[t] = (fwd[t] + rc[t]) / 2: the partner row is the neighbouring lane
+          float av[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] = 0.5f * (hn[j] + __shfl_xor_sync(0xffffffffu, hn[j], 1));
+          if (dir == 0) *reinterpret_cast<float4 *>(avg_out + u0) = make_float4(av[0], av[1], av[2], av[3]);
+          else *reinterpret_cast<float4 *>(avg_out + u0 + 4) = make_float4(av[4], av[5], av[6], av[7]);
+        }
+        if (t + 1 < T) {
+          // hand the new A operand to the tensor core
+          tc_fence_before();
+          fence_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(s_B);
+            const uint32_t d = tmem_base + (uint32_t)(s * K::TCOLS);
+            // (A piece, B piece) pairs, smallest products first: lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi
+            const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+            uint32_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+#pragma unroll
+              for (int kc = 0; kc < UP / 16; ++kc) {
+                const uint64_t ad = umma_desc(a0 + pa[q] * K::A_BYTES + kc * 256, 128, K::SBO);
+                const uint64_t bd = umma_desc(b0 + pb[q] * K::B_BYTES + kc * 256, 128, K::SBO);
+                umma_bf16(d, ad, bd, idesc, acc);
+                acc = 1;
+              }
+            }
+            umma_commit(smem_u32(&s_bar[s]));
+          }
+        }
+      }
+    }
+    // ---- attention + FF + softmax + vote for both tiles ----------------------------------------
+    __threadfence_block();
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (!live[s]) continue;
+      attention_vote_tile<UP, false, K::WT>(p, scratch0 + (size_t)s * K::WT * T * UP,
+                                            ff2_0 + (size_t)s * K::WT * T * 5,
+                                            p.w_begin + (pair * 2 + s) * K::WT, s_att, s_q, s_score);
+      __syncthreads();
+    }
+    // A operands back to zero for the next pair (h_0 = 0)
+    {
+      uint4 *a4 = reinterpret_cast<uint4 *>(s_A);
+      for (int i = tid; i < 6 * K::A_BYTES / 16; i += FWD_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(2 * K::TCOLS)
+                 : "memory");
+  }
+  (void)U;
+}
+
+template <int UP>
+static size_t tc_smem_bytes(int T) {
+  using K = TCfg<UP>;
+  return (size_t)3 * K::B_BYTES + 6 * K::A_BYTES +
+         sizeof(float) * ((size_t)5 * K::PSTRIDE + 3 * UP + (size_t)UP * 12 + 8 * UP + 8 * (size_t)T) + 128;
+}
+
+template <int UP>
+static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+  using K = TCfg<UP>;
+  const int64_t n_windows = p.w_end - p.w_begin;
+  if (n_windows <= 0) return DGRP_OK;
+  const size_t smem = tc_smem_bytes<UP>(p.T);
+  if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
+  auto kern = gru_tc_attention_vote_kernel<UP>;
+  DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int grid = (int)(n_pairs < c->sm_count ? n_pairs : c->sm_count);
+  DGRP_CHECK(c->avg.reserve((size_t)grid * 2 * K::WT * p.T * UP * sizeof(float)));
+  DGRP_CHECK(c->io_c.reserve((size_t)grid * 2 * K::WT * p.T * 5 * sizeof(float)));
+  p.scratch = c->avg.as<float>();
+  p.ff2 = c->io_c.as<float>();
+  kern<<<grid, FWD_THREADS, smem, c->stream>>>(p);
+  c->launches++;
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
+// Returns DGRP_E_UNSUPPORTED when this model/shape has no tcgen05 form (the caller then uses the
+// fp32 kernel): units > 64, or a window too long for the score buffer in shared memory.
+int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+  if (!m->d_Bsplit) return DGRP_E_UNSUPPORTED;
+  p.Bsplit = m->d_Bsplit;
+  switch (m->UP) {
+    case 16: return launch_tc_t<16>(c, m, p);
+    case 32: return launch_tc_t<32>(c, m, p);
+    case 64: return launch_tc_t<64>(c, m, p);
+    default: return DGRP_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace dgrp

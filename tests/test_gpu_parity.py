@@ -277,7 +277,31 @@ def test_predict_generic_route_equals_fused(dg):
         def predict_on_batch(self, batch):
             return w.predict_on_batch(batch)
     generic = dg.pred.predict(Wrapped(), iter(ds), (fwd.shape[1], 5), 50)
-    assert np.array_equal(fused, generic)
+    # the fused call runs the tcgen05 recurrence, predict_on_batch the fp32 FFMA kernel
+    assert dg.ctx.get_int("forward_used_tc") == 0
+    assert np.abs(fused - generic).max() < 2e-6
+    assert np.array_equal(fused == 0, generic == 0)
+    dg.ctx.set_int("forward_tc", 0)
+    try:
+        fused_fp32 = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    finally:
+        dg.ctx.set_int("forward_tc", 1)
+    assert np.array_equal(fused_fp32, generic)      # same kernel arithmetic: bit-identical
+
+
+@pytest.mark.parametrize("T,U", [(150, 32), (342, 60), (64, 16), (100, 50)])
+def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U):
+    """tcgen05 (bf16 x3 split) and fp32 FFMA forwards against the float64 oracle: both within the
+    float32 oracle's own distance from float64 (a few 1e-7), labels identical."""
+    w = dg.model.random_weights(T, U, attention=True, seed=7).scaled(4.0)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(12_000, T + U))
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    assert dg.ctx.get_int("forward_used_tc") == 1
+    ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
+                           oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
+    assert np.abs(tc - ref64).max() < 5e-6
+    assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
 
 
 # ------------------------------------------------------------------ end to end
