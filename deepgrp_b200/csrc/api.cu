@@ -423,7 +423,7 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
     set_error("units=%d not supported by the CUDA forward (max 128)", units);
     return DGRP_E_UNSUPPORTED;
   }
-  int UP = 16;
+  int UP = 32;
   while (UP < units) UP <<= 1;
   const int U = units, G = 3;
   std::vector<float> P((size_t)5 * G * UP, 0.f), Wk((size_t)5 * G * UP, 0.f), b0((size_t)G * UP, 0.f),

@@ -274,7 +274,6 @@ static int launch_fwd_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
 template <bool DENSE>
 static int launch_fwd(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   switch (m->UP) {
-    case 16: return launch_fwd_t<16, DENSE>(c, m, p);
     case 32: return launch_fwd_t<32, DENSE>(c, m, p);
     case 64: return launch_fwd_t<64, DENSE>(c, m, p);
     case 128: return launch_fwd_t<128, DENSE>(c, m, p);

