@@ -91,6 +91,7 @@ SIGNATURES = {
                                     ctypes.POINTER(_P), _PL, _PL, _PL]),
     "dgrp_fasta_rows": (_I, [_P, _P, _L]),
     "dgrp_fasta_records": (_I, [_P, _P, _P, _P, _P, _L]),
+    "dgrp_fasta_record_tsv": (_I, [_P, _P, _P, _P, _L]),
     "dgrp_predict_codes_dev": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _PL]),
 }
 

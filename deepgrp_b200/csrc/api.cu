@@ -243,6 +243,8 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
+  else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
+  else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
   return DGRP_OK;
 }
@@ -642,6 +644,7 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
   *n_rows = 0; *n_records = 0;
   c->fa_rows.clear(); c->fa_hdr_off.clear(); c->fa_hdr_len.clear();
   c->fa_startpos.clear(); c->fa_length.clear();
+  c->fa_tsv_off.clear(); c->fa_tsv_len.clear(); c->fa_owner.clear();
   DGRP_REQUIRE(nbytes >= 0, "negative length");
   stamp(c, 0);
   DGRP_CHECK(c->raw.reserve((size_t)nbytes + 16));
@@ -655,6 +658,31 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
   }
   hseq[n_hdr] = n_seq;
   auto ws = [](uint8_t b) { return (b >= 9 && b <= 13) || (b >= 28 && b <= 32); };
+  // Contig sharding: every rank decodes the file and derives the same
+  // largest-first assignment of the kept records to ranks; it then processes only its own.
+  std::vector<int64_t> owner_of(n_hdr, -1);
+  {
+    std::vector<int64_t> kept;
+    for (int64_t k = 0; k < n_hdr; ++k) {
+      int64_t b = hpos[k] + 1, e = b;
+      while (e < nbytes && fasta[e] != '\n' && !(fasta[e] == '\r' && !(e + 1 < nbytes && fasta[e + 1] == '\n'))) ++e;
+      while (e > b && ws(fasta[e - 1])) --e;
+      if (e > b) kept.push_back(k);
+    }
+    std::vector<int64_t> order(kept);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b2) {
+      return (hseq[a + 1] - hseq[a]) > (hseq[b2 + 1] - hseq[b2]);
+    });
+    const int world = c->shard_world > 0 ? c->shard_world : 1;
+    std::vector<int64_t> load(world, 0);
+    for (int64_t k : order) {
+      int best = 0;
+      for (int r = 1; r < world; ++r)
+        if (load[r] < load[best]) best = r;
+      owner_of[k] = best;
+      load[best] += hseq[k + 1] - hseq[k];
+    }
+  }
   float enc_ms = 0.f, fwd_ms = 0.f, score_ms = 0.f, mss_ms = 0.f, seg_ms = 0.f;
   int64_t windows = 0, bases = 0;
   cudaEvent_t e_begin = c->ev[6], e_end = c->ev[7];
@@ -667,6 +695,12 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
     while (e > b && ws(fasta[e - 1])) --e;
     if (e == b) continue;                         // empty header: record dropped (__main__.py:36)
     const int32_t rec = (int32_t)c->fa_hdr_off.size();
+    if (owner_of[k] != c->shard_rank) {   // another rank's record: table entry only
+      c->fa_hdr_off.push_back(b); c->fa_hdr_len.push_back(e - b);
+      c->fa_startpos.push_back(-1); c->fa_length.push_back(hseq[k + 1] - hseq[k]);
+      c->fa_tsv_off.push_back(c->tsv_len); c->fa_tsv_len.push_back(0); c->fa_owner.push_back(owner_of[k]);
+      continue;
+    }
     const uint8_t *d_seq = c->io_b.as<uint8_t>() + hseq[k];
     const int64_t n = hseq[k + 1] - hseq[k];
     int64_t startpos = 0, length = 0;
@@ -680,6 +714,7 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
     }
     c->fa_hdr_off.push_back(b); c->fa_hdr_len.push_back(e - b);
     c->fa_startpos.push_back(startpos); c->fa_length.push_back(length);
+    c->fa_tsv_off.push_back(c->tsv_len); c->fa_tsv_len.push_back(0); c->fa_owner.push_back(owner_of[k]);
     stamp(c, 1);
     if ((rc = core_predict(c, m, c->codes.as<uint8_t>(), length, step, batch_size, compat))) break;
     windows += c->timings.windows; bases += length;
@@ -720,6 +755,7 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
           set_error("copying the TSV text failed"); rc = DGRP_E_CUDA; break;
         }
         c->tsv_len += need;
+        c->fa_tsv_len.back() = need;
       } else if (cnt > 0) {
         if ((rc = c->pin_a.reserve((size_t)cnt * 24))) break;
         if (cudaMemcpyAsync(c->pin_a.p, d_tri, (size_t)cnt * 24, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -793,6 +829,16 @@ int dgrp_fasta_records(dgrp_ctx *c, int64_t *hdr_off, int64_t *hdr_len, int64_t 
   if (hdr_len) memcpy(hdr_len, c->fa_hdr_len.data(), n * 8);
   if (startpos) memcpy(startpos, c->fa_startpos.data(), n * 8);
   if (length) memcpy(length, c->fa_length.data(), n * 8);
+  return DGRP_OK;
+}
+
+int dgrp_fasta_record_tsv(dgrp_ctx *c, int64_t *owner, int64_t *tsv_off, int64_t *tsv_len, int64_t cap) {
+  const size_t n = c->fa_owner.size();
+  DGRP_REQUIRE((int64_t)n <= cap, "record buffer too small: %lld needed", (long long)n);
+  if (n == 0) return DGRP_OK;
+  if (owner) memcpy(owner, c->fa_owner.data(), n * 8);
+  if (tsv_off) memcpy(tsv_off, c->fa_tsv_off.data(), n * 8);
+  if (tsv_len) memcpy(tsv_len, c->fa_tsv_len.data(), n * 8);
   return DGRP_OK;
 }
 

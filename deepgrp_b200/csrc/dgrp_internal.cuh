@@ -97,7 +97,8 @@ struct dgrp_ctx {
   int forward_used_tc = 0; // what the last forward launch used
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
-  std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length;
+  std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length, fa_tsv_off, fa_tsv_len, fa_owner;
+  int shard_rank = 0, shard_world = 1;   // contig sharding of dgrp_predict_fasta* (dgrp_ctx_set_int)
   dgrp::PinBuf tsv_host;     // finished TSV text of the last dgrp_predict_fasta_tsv
   int64_t tsv_len = 0;
   dgrp::DevBuf tsv_dev, tsv_prefix;

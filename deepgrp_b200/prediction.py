@@ -234,12 +234,9 @@ def predict_fasta(model: ModelWeights, raw: bytes, step_size: int, batch_size: i
     return rows, records
 
 
-def predict_fasta_tsv_view(model: ModelWeights, raw, filename: str, step_size: int,
-                           batch_size: int, use_mss: bool, min_mss_len: int, xdrop_len: int,
-                           compat: str = "reference") -> memoryview:
-    """The TSV text ``deepgrp predict`` writes for one file (reference ``deepgrp/__main__.py:288-292``),
-    formatted on the GPU.  Returns a read-only view of pinned host memory owned by the context: it is
-    valid until the next prediction call, so write it out (or copy it) first."""
+def _fasta_tsv_call(model: ModelWeights, raw, filename: str, step_size: int, batch_size: int,
+                    use_mss: bool, min_mss_len: int, xdrop_len: int, compat: str):
+    """-> (memoryview of the TSV text, number of rows, number of records)."""
     ctx = _lib.context()
     n = len(raw)
     buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
@@ -256,8 +253,42 @@ def predict_fasta_tsv_view(model: ModelWeights, raw, filename: str, step_size: i
         raise ValueError("negative dimensions are not allowed")
     _lib.check(rc)
     if tsv_len.value == 0:
-        return memoryview(b"")
-    return memoryview((ctypes.c_ubyte * tsv_len.value).from_address(tsv.value)).cast("B").toreadonly()
+        return memoryview(b""), int(n_rows.value), int(n_rec.value)
+    view = memoryview((ctypes.c_ubyte * tsv_len.value).from_address(tsv.value)).cast("B").toreadonly()
+    return view, int(n_rows.value), int(n_rec.value)
+
+
+def predict_fasta_tsv_view(model: ModelWeights, raw, filename: str, step_size: int,
+                           batch_size: int, use_mss: bool, min_mss_len: int, xdrop_len: int,
+                           compat: str = "reference") -> memoryview:
+    """The TSV text ``deepgrp predict`` writes for one file (reference ``deepgrp/__main__.py:288-292``),
+    formatted on the GPU.  Returns a read-only view of pinned host memory owned by the context: it is
+    valid until the next prediction call, so write it out (or copy it) first."""
+    return _fasta_tsv_call(model, raw, filename, step_size, batch_size, use_mss, min_mss_len,
+                           xdrop_len, compat)[0]
+
+
+def predict_fasta_tsv_sharded(model: ModelWeights, raw, filename: str, step_size: int, batch_size: int,
+                              use_mss: bool, min_mss_len: int, xdrop_len: int, rank: int, world: int,
+                              compat: str = "reference"):
+    """Contig-sharded form of :func:`predict_fasta_tsv_view`: this rank computes only the records the
+    largest-first assignment gives it and returns ``[(record index, TSV bytes), ...]`` for them; merge
+    the per-rank lists with :func:`deepgrp_b200.sharding.merge_record_texts`."""
+    ctx = _lib.context()
+    ctx.set_int("shard_rank", rank)
+    ctx.set_int("shard_world", world)
+    try:
+        view, _, n_rec = _fasta_tsv_call(model, raw, filename, step_size, batch_size, use_mss,
+                                         min_mss_len, xdrop_len, compat)
+        owner, off, ln = (np.zeros(max(n_rec, 1), np.int64) for _ in range(3))
+        if n_rec:
+            _lib.check(_lib.lib().dgrp_fasta_record_tsv(ctx.handle, _lib.ptr(owner), _lib.ptr(off),
+                                                        _lib.ptr(ln), n_rec))
+        return [(k, bytes(view[off[k]:off[k] + ln[k]])) for k in range(n_rec)
+                if owner[k] == rank and ln[k] > 0]
+    finally:
+        ctx.set_int("shard_rank", 0)
+        ctx.set_int("shard_world", 1)
 
 
 def predict_fasta_tsv(model: ModelWeights, raw, filename: str, step_size: int, batch_size: int,

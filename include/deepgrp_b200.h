@@ -76,8 +76,11 @@ int dgrp_ctx_timings(dgrp_ctx *ctx, dgrp_timings_t *out);
 /* number of kernels this library has launched on the context since creation */
 int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
 /* tuning knobs and diagnostics: "mss_chunk" (elements per MSS scan chunk, 0 = automatic),
- * "mss_max_rounds" (parallel rounds before the sequential completion), and read-only
- * "mss_rounds" (rounds the last MSS call used; negative = completed sequentially), "sm_count". */
+ * "mss_max_rounds" (parallel rounds before the sequential completion), "forward_tc" (1 = tcgen05
+ * recurrence where available, 0 = fp32 kernel), "shard_rank" / "shard_world" (contig sharding of
+ * dgrp_predict_fasta*: records are assigned largest-first to the least loaded rank; a rank
+ * computes only its own records), and read-only "mss_rounds" (rounds the last MSS call used;
+ * negative = completed sequentially), "forward_used_tc", "sm_count". */
 int dgrp_ctx_set_int(dgrp_ctx *ctx, const char *key, int64_t value);
 int dgrp_ctx_get_int(dgrp_ctx *ctx, const char *key, int64_t *value);
 
@@ -200,6 +203,10 @@ int dgrp_fasta_rows(dgrp_ctx *ctx, dgrp_row_t *rows, int64_t cap);
  * length = trimmed length.  Any of the four arrays may be NULL. */
 int dgrp_fasta_records(dgrp_ctx *ctx, int64_t *hdr_off, int64_t *hdr_len, int64_t *startpos,
                        int64_t *length, int64_t cap);
+/* per record: owning rank, and where its rows are in the TSV text of dgrp_predict_fasta_tsv
+ * (tsv_len 0 for records owned by another rank; their startpos is -1 and length untrimmed). */
+int dgrp_fasta_record_tsv(dgrp_ctx *ctx, int64_t *owner, int64_t *tsv_off, int64_t *tsv_len,
+                          int64_t cap);
 
 /* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),
  * runs forward + vote + score + MSS + segment extraction entirely on the device and leaves the

@@ -407,3 +407,38 @@ def test_predict_range_shards_equal_whole(dg):
     parts = [run(a, b, 0, L) for a, b in zip(cuts[:-1], cuts[1:])]
     assert np.array_equal(np.concatenate([p[0] for p in parts]), whole_l)
     assert np.array_equal(np.concatenate([p[1] for p in parts]).view(np.int32), whole_s.view(np.int32))
+
+
+def test_contig_sharding_equals_single_rank(dg, tmp_path):
+    """Every rank decodes the file and computes only its records; merged texts == single-rank text."""
+    from deepgrp_b200 import sharding
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    recs = [("r%d" % i, random_dna(n, 100 + i, "ACGTN")) for i, n in enumerate([9000, 400, 15000, 7000, 120])]
+    path = tmp_path / "multi.fa"
+    write_fasta(str(path), recs)
+    raw = open(path, "rb").read()
+    whole = dg.pred.predict_fasta_tsv(w, raw, "f.fa", 50, 256, True, 50, 50)
+    for world in (2, 3):
+        pieces = [dg.pred.predict_fasta_tsv_sharded(w, raw, "f.fa", 50, 256, True, 50, 50, r, world)
+                  for r in range(world)]
+        owners = sharding.assign_records([len(s) for _, s in recs], world)
+        for r in range(world):
+            assert {k for k, _ in pieces[r]} <= {i for i, o in enumerate(owners) if o == r}
+        assert sharding.merge_record_texts(pieces).decode() == whole
+
+
+def test_position_sharding_then_finish_equals_whole_record(dg):
+    from deepgrp_b200 import sharding
+    T, U = 150, 32
+    w = dg.model.random_weights(T, U, attention=True, seed=0).scaled(4.0)
+    text = "NN" + random_dna(30_000, 77) + "N"
+    labels, startpos, rows = dg.pred.predict_sequence(w, text.encode(), 50, 256, True, 50, 50)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    codes = fwd.argmax(axis=0).astype(np.uint8)
+    L = codes.size
+    parts = [sharding.predict_range(w, codes, L, a, b, 50, 256) for a, b in sharding.split_positions(L, 3)]
+    lab = np.concatenate([p[0] for p in parts])
+    sc = np.concatenate([p[1] for p in parts])
+    out, rows2 = sharding.finish_record(lab, sc, 5, True, 50, 50, st)
+    assert np.array_equal(out, labels)
+    assert np.array_equal(rows2, rows)

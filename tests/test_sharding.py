@@ -1,0 +1,75 @@
+"""Multi-GPU host logic on the CPU: the contig assignment, the position split, and the gather of
+per-range results with torch.distributed (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from deepgrp_b200 import sharding
+
+
+def test_assign_records_largest_first_balanced():
+    lengths = [248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80,
+               58, 64, 46, 50, 156, 57]          # human chromosomes, Mbp
+    for world in (1, 2, 4, 8):
+        owner = sharding.assign_records(lengths, world)
+        assert len(owner) == len(lengths) and set(owner) <= set(range(world))
+        load = [sum(l for l, o in zip(lengths, owner) if o == r) for r in range(world)]
+        assert max(load) - min(load) <= max(lengths)
+        assert max(load) <= 1.15 * sum(lengths) / world + (0 if world < 8 else 20)
+    assert sharding.assign_records([5, 5, 5], 2) == [0, 1, 0]       # ties: stable order, lowest rank
+    assert sharding.assign_records([], 4) == []
+
+
+def test_split_positions_covers_exactly():
+    for length in (0, 1, 7, 1000, 46_700_000):
+        for parts in (1, 2, 3, 8):
+            r = sharding.split_positions(length, parts)
+            assert r[0][0] == 0 and r[-1][1] == length and len(r) == parts
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+            assert all(a <= b for a, b in r)
+
+
+def test_merge_record_texts_orders_by_record():
+    pieces = [[(2, b"c\n"), (0, b"a\n")], [(1, b"b\n")]]
+    assert sharding.merge_record_texts(pieces) == b"a\nb\nc\n"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, length, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # stand-in for the GPU range computation: a deterministic function of the position
+        def compute_range(p0, p1):
+            pos = np.arange(p0, p1, dtype=np.int64)
+            return (pos % 5).astype(np.uint8), (np.sin(pos * 0.001) * 10).astype(np.float32)
+
+        def finish(labels, scores):
+            np.save(os.path.join(out_dir, "labels.npy"), labels)
+            np.save(os.path.join(out_dir, "scores.npy"), scores)
+            return True
+        res = sharding.predict_record_sharded(compute_range, finish, length, rank, world, owner=0, dist=dist)
+        assert (res is True) == (rank == 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_ranges_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    length, world = 100_003, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, length, str(tmp_path)), nprocs=world, join=True)
+    pos = np.arange(length, dtype=np.int64)
+    assert np.array_equal(np.load(tmp_path / "labels.npy"), (pos % 5).astype(np.uint8))
+    assert np.array_equal(np.load(tmp_path / "scores.npy"), (np.sin(pos * 0.001) * 10).astype(np.float32))
