@@ -276,7 +276,9 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": tsv_len + 64, "tsv_bytes_per_step": tsv_len,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gru_attention_vote_kernel (fp32 FFMA form)",
+        "roofline": {"bound": "tensor",
+                     "kernel": ("gru_tc_attention_vote_kernel (tcgen05, bf16 x3 split)"
+                                if ctx.get_int("forward_used_tc") else "gru_attention_vote_kernel (fp32 FFMA)"),
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
                      "frac": achieved / tflops_peak, "traffic": None, "peak_kind": peak_kind,
                      "kernel_ms": kernel_ms, "share_of_step": kernel_ms / (elapsed_ms / args.steps)},

@@ -449,7 +449,8 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
   // bf16 hi|mid|lo pieces of recurrent^T in the tcgen05 operand layout (forward_tc.cu)
   std::vector<uint16_t> Bs;
   if (UP <= 64) {
-    const int N = 3 * UP, SBO = (UP / 8) * 128;
+    const int N = 3 * UP + 16, SBO = (UP / 8) * 128;   // 16 extra rows: FF kernel halves (forward_tc.cu)
+    const bool att = att_scale != nullptr;
     Bs.assign((size_t)3 * N * UP, 0);
     auto f2bf = [](float f) -> uint16_t {
       uint32_t u;
@@ -466,8 +467,16 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
     };
     for (int n = 0; n < N; ++n)
       for (int k = 0; k < UP; ++k) {
-        const int g = n / UP, u = n % UP;
-        const float x = Rp[((size_t)k * G + g) * UP + u];
+        float x = 0.f;
+        if (n < 3 * UP) {
+          const int g = n / UP, u = n % UP;
+          x = Rp[((size_t)k * G + g) * UP + u];
+        } else if (k < U) {
+          const int j = n - 3 * UP;          // 0..4: ctx half (attention only), 8..12: avg half
+          if (j < 5 && j < n_classes && att) x = ff_kernel[(size_t)k * n_classes + j];
+          else if (j >= 8 && j - 8 < n_classes && j < 13)
+            x = ff_kernel[(size_t)((att ? U : 0) + k) * n_classes + (j - 8)];
+        }
         const uint16_t hi = f2bf(x);
         const float r1 = x - bf2f(hi);
         const uint16_t mid = f2bf(r1);

@@ -18,8 +18,10 @@
 //   warp 16      MMA issuer: waits for "ready", issues the 6 x UP/16 tcgen05.mma of the step and
 //                commits them to the tile's "done" mbarrier, which the gate warps wait on.
 // While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
-//   TMEM   2 x [128 lanes x 3*UP columns] fp32 accumulators (z | r | h gate blocks)
-//   smem   B = R^T pieces, [3][3*UP x UP] bf16, K-major core matrices, resident for the whole kernel
+//   TMEM   2 x [128 lanes x (3*UP + 16) columns] fp32 accumulators: z | r | h gate blocks, then 16
+//          projection columns h.K (the FF layer's two halves), so that the second phase needs no
+//          FFMA over the units: avg[t].K = (h_fwd[t].K + h_rc[t].K)/2 comes out of the same MMA
+//   smem   B = [R | K]^T pieces, [3][(3*UP+16) x UP] bf16, K-major core matrices, resident
 //          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate warps
 //   row r of a tile = window r/2, direction r%2, so avg[t] = (fwd + rc)/2 is one lane shuffle.
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 B each; core matrices
@@ -36,7 +38,8 @@ constexpr int TC_THREADS = (TC_GATE_WARPS + 1) * 32;
 
 template <int UP>
 struct TCfg {
-  static constexpr int N = 3 * UP;             // accumulator columns per tile
+  static constexpr int NG = 3 * UP;            // gate columns (z | r | h)
+  static constexpr int N = 3 * UP + 16;        // + 16 projection columns: h.[FF ctx half(5) pad(3) | FF avg half(5) pad(3)]
   static constexpr int ROWS = 128, WT = 64;
   static constexpr int UPT = UP / 4;           // units per gate thread
   static constexpr int KC = UP / 8;            // core matrices along K
@@ -63,6 +66,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+// the issuer's wait: back off between polls so that the spinning warp does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
@@ -93,6 +110,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -133,6 +159,114 @@ __device__ __forceinline__ void sigmoid2(float xz, float xr, float &z, float &r)
   r = inv * a;
 }
 
+// Second phase when the FF projections avg[t].K already exist (`proj`, [WT][T][16]: ctx half in
+// 0..4, avg half in 8..12): additive attention scores with lanes over the units (coalesced row
+// reads, 16-lane reductions), then softmax over t, logits, class softmax and the max-vote with
+// lanes over t.  One warp per window.
+template <int UP, int WT, int NWARPS>
+__device__ __forceinline__ void attention_vote_proj_tile(const FwdParams &p, const float *scratch,
+                                                         const float *proj, int64_t w_tile0,
+                                                         const float *s_att, float *s_score) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp >= NWARPS) return;
+  const int T = p.T, C = p.C;
+  constexpr int LPR = UP / 4;          // lanes per avg row (4 units each)
+  constexpr int RPW = 32 / LPR;        // rows per warp-wide load
+  const int g = lane % LPR, sub = lane / LPR;
+  float *sc = s_score + (size_t)warp * T;
+  float scale[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) scale[j] = s_att[(4 * g + j) * 12 + 10];
+  for (int wl = warp; wl < WT; wl += NWARPS) {
+    const int64_t w = w_tile0 + wl;
+    if (w >= p.w_end) break;
+    const float *av = scratch + (size_t)wl * T * UP;
+    const float *pr = proj + (size_t)wl * T * 16;
+    float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p.attention) {
+      // query = avg[T-1] (model.py:311); score[t] = sum_u scale[u] * tanh(q[u] + avg[t][u])
+      const float4 q4 = *reinterpret_cast<const float4 *>(av + (size_t)(T - 1) * UP + 4 * g);
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+      constexpr int UNR = 4;
+      for (int t0 = 0; t0 < T; t0 += RPW * UNR) {
+        float4 v[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+          const int t = t0 + k * RPW + sub;
+          v[k] = t < T ? *reinterpret_cast<const float4 *>(av + (size_t)t * UP + 4 * g)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+          const int t = t0 + k * RPW + sub;
+          float s = scale[0] * tanh_fast(q[0] + v[k].x);
+          s = fmaf(scale[1], tanh_fast(q[1] + v[k].y), s);
+          s = fmaf(scale[2], tanh_fast(q[2] + v[k].z), s);
+          s = fmaf(scale[3], tanh_fast(q[3] + v[k].w), s);
+#pragma unroll
+          for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+          if (g == 0 && t < T) sc[t] = s;
+        }
+      }
+      __syncwarp();
+      // softmax over t and ctx.K1 = sum_t a_t (avg[t].K1)
+      float m_run = -INFINITY, l_run = 0.f, cacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int t = lane; t < T; t += 32) {
+        const float s = sc[t];
+        const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16);
+        const float k5 = pr[(size_t)t * 16 + 4];
+        const float k1[5] = {k4.x, k4.y, k4.z, k4.w, k5};
+        const float m_new = fmaxf(m_run, s);
+        const float corr = expf(m_run - m_new);
+        const float e = expf(s - m_new);
+        l_run = l_run * corr + e;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) cacc[c] = cacc[c] * corr + e * k1[c];
+        m_run = m_new;
+      }
+      float m_all = m_run;
+      for (int off = 16; off > 0; off >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, off));
+      const float f = (m_run == -INFINITY) ? 0.f : expf(m_run - m_all);
+      float l = l_run * f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) cacc[c] *= f;
+      for (int off = 16; off > 0; off >>= 1) {
+        l += __shfl_xor_sync(0xffffffffu, l, off);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) cacc[c] += __shfl_xor_sync(0xffffffffu, cacc[c], off);
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) ctxk[c] = cacc[c] / l;
+    }
+    // logits[t] = ctx.K1 + avg[t].K2 + b ; softmax over classes ; vote
+    const int64_t place = (w < p.full_windows ? w * (int64_t)p.step
+                                              : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
+                          p.pred_row0;
+    for (int t = lane; t < T; t += 32) {
+      const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8);
+      const float k5 = pr[(size_t)t * 16 + 12];
+      const float k2[5] = {k4.x, k4.y, k4.z, k4.w, k5};
+      float lg[5], mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        lg[c] = c < C ? (ctxk[c] + k2[c]) + p.ffb[c] : -INFINITY;
+        mx = fmaxf(mx, lg[c]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { lg[c] = c < C ? expf(lg[c] - mx) : 0.f; sum += lg[c]; }
+      const int64_t r = place + t;
+      if (r >= 0 && r < p.pred_rows) {
+        int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+          if (c < C) atomicMax(dst + c, __float_as_int(lg[c] / sum));   // probs > 0
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int UP>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
   using K = TCfg<UP>;
@@ -142,8 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [5][PSTRIDE], z/r rows include b_rec
   float *s_bh = s_P + 5 * K::PSTRIDE;                          // [UP] recurrent bias of the h gate
   float *s_att = s_bh + UP;                                    // [UP][12]
-  float *s_q = s_att + UP * 12;                                // [16][UP]
-  float *s_score = s_q + TC_GATE_WARPS * UP;                   // [16][T]
+  float *s_score = s_att + UP * 12;                            // [16][T]
   __shared__ __align__(8) unsigned long long s_ready[2], s_done[2];
   __shared__ uint32_t s_tmem;
 
@@ -184,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   const uint32_t tmem_base = s_tmem;
 
   float *scratch0 = p.scratch + (size_t)blockIdx.x * 2 * K::WT * T * UP;
-  float *ff2_0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 5;
+  float *proj0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 16;   // [2][WT][T][16] h-projections
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   uint32_t phase[2] = {0u, 0u};   // parity to wait for next ("done" for gate warps, "ready" for the issuer)
@@ -197,11 +330,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
-      for (int t = 0; t + 1 < T; ++t) {
+      for (int t = 0; t < T; ++t) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (!live[s]) continue;
-          mbar_wait(smem_u32(&s_ready[s]), phase[s]);
+          mbar_wait_backoff(smem_u32(&s_ready[s]), phase[s]);
           phase[s] ^= 1u;
           tc_fence_after();
           if (lane == 0) {
@@ -264,6 +397,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
           unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES;
           float *avg_out = scratch0 + ((size_t)(s * K::WT + wl) * T + t) * UP;
           const float *prow = s_P + code * K::PSTRIDE;
+          float pj[4];
+          if (t > 0)   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
+            tmem_ld4(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
 #pragma unroll
           for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
             const int u0 = uq * K::UPT + c8 * 8;
@@ -275,6 +411,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
               tmem_ld8(taddr + UP, ar);
               tmem_ld8(taddr + 2 * UP, ah);
               tmem_ld_wait();
+              if (c8 == 0) {
+                // avg[t-1].K = (h_fwd.K + h_rc.K) / 2, stored by the fwd lane
+                float4 o;
+                o.x = 0.5f * (pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1));
+                o.y = 0.5f * (pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1));
+                o.z = 0.5f * (pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1));
+                o.w = 0.5f * (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1));
+                if (dir == 0)
+                  *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (t - 1)) * 16 + 4 * uq) = o;
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
@@ -319,14 +465,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             }
             *reinterpret_cast<float4 *>(avg_out + u0 + (dir ? 4 : 0)) = make_float4(av[0], av[1], av[2], av[3]);
           }
-          if (t + 1 < T) {
-            // hand the new A operand to the tensor core
-            tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(smem_u32(&s_ready[s]));
-          }
+          // hand the new A operand to the tensor core (the last step's MMA only feeds the projection)
+          tc_fence_before();
+          fence_async_smem();
+          mbar_arrive(smem_u32(&s_ready[s]));
         }
       }
+      // projection of the last state h[T-1]
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (!live[s]) continue;
+        mbar_wait(smem_u32(&s_done[s]), phase[s]);
+        phase[s] ^= 1u;
+        tc_fence_after();
+        float pj[4];
+        tmem_ld4(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
+        tmem_ld_wait();
+        float4 o;
+        o.x = 0.5f * (pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1));
+        o.y = 0.5f * (pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1));
+        o.z = 0.5f * (pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1));
+        o.w = 0.5f * (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1));
+        if (dir == 0)
+          *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (T - 1)) * 16 + 4 * uq) = o;
+      }
+      tc_fence_before();
     }
     // ---- attention + FF + softmax + vote for both tiles (gate warps) -----------------------------
     __threadfence_block();
@@ -334,9 +497,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (!live[s]) continue;
-      attention_vote_tile<UP, false, K::WT, TC_GATE_WARPS, true>(
-          p, scratch0 + (size_t)s * K::WT * T * UP, ff2_0 + (size_t)s * K::WT * T * 5,
-          p.w_begin + (pair * 2 + s) * K::WT, s_att, s_q, s_score);
+      attention_vote_proj_tile<UP, K::WT, TC_GATE_WARPS>(
+          p, scratch0 + (size_t)s * K::WT * T * UP, proj0 + (size_t)s * K::WT * T * 16,
+          p.w_begin + (pair * 2 + s) * K::WT, s_att, s_score);
     }
     __syncthreads();
   }
@@ -355,8 +518,7 @@ template <int UP>
 static size_t tc_smem_bytes(int T) {
   using K = TCfg<UP>;
   return (size_t)3 * K::B_BYTES + 6 * K::A_BYTES +
-         sizeof(float) * ((size_t)5 * K::PSTRIDE + UP + (size_t)UP * 12 + TC_GATE_WARPS * UP +
-                          TC_GATE_WARPS * (size_t)T) + 128;
+         sizeof(float) * ((size_t)5 * K::PSTRIDE + UP + (size_t)UP * 12 + TC_GATE_WARPS * (size_t)T) + 128;
 }
 
 template <int UP>
@@ -372,7 +534,7 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < c->sm_count ? n_pairs : c->sm_count);
   DGRP_CHECK(c->avg.reserve((size_t)grid * 2 * K::WT * p.T * UP * sizeof(float)));
-  DGRP_CHECK(c->io_c.reserve((size_t)grid * 2 * K::WT * p.T * 5 * sizeof(float)));
+  DGRP_CHECK(c->io_c.reserve((size_t)grid * 2 * K::WT * p.T * 16 * sizeof(float)));
   p.scratch = c->avg.as<float>();
   p.ff2 = c->io_c.as<float>();
   kern<<<grid, TC_THREADS, smem, c->stream>>>(p);

@@ -442,3 +442,25 @@ def test_position_sharding_then_finish_equals_whole_record(dg):
     out, rows2 = sharding.finish_record(lab, sc, 5, True, 50, 50, st)
     assert np.array_equal(out, labels)
     assert np.array_equal(rows2, rows)
+
+
+def test_cli_end_to_end_with_hdf5_model(dg, oracle, tmp_path, capsys):
+    """`deepgrp predict model.hdf5 a.fa b.fa --output out.tsv` and the README form without the
+    sub-command; fused route vs the reference's five stepwise calls."""
+    import sys
+    from deepgrp_b200 import hdf5
+    from deepgrp_b200.__main__ import CommandLineParser
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    mpath = str(tmp_path / "model.hdf5")
+    hdf5.save_keras_model(mpath, w)
+    fa1, fa2 = str(tmp_path / "a.fa"), str(tmp_path / "b.fa")
+    write_fasta(fa1, [("one", "NN" + random_dna(8000, 1, "ACGTacgtN")), ("two", random_dna(3000, 2))])
+    write_fasta(fa2, [("three", random_dna(5000, 3))])
+    out1, out2 = str(tmp_path / "o1.tsv"), str(tmp_path / "o2.tsv")
+    CommandLineParser().parse_args(["predict", mpath, fa1, fa2, "--output", out1]).set_logging().run()
+    CommandLineParser().parse_args(["-s", "50", "predict", mpath, fa1, fa2, "--output", out2, "--stepwise"]).run()
+    a, b = open(out1).read(), open(out2).read()
+    assert a == b and a.count("\n") > 10
+    assert a.splitlines()[0].split("\t")[:2] == [fa1, "one"]
+    CommandLineParser().parse_args([mpath, fa2]).run()            # README form, stdout
+    assert capsys.readouterr().out == "".join(l + "\n" for l in a.splitlines() if l.startswith(fa2))
