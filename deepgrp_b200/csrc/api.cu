@@ -469,8 +469,9 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       for (int k = 0; k < UP; ++k) {
         float x = 0.f;
         if (n < 3 * UP) {
+          // gate columns are pre-scaled so that the accumulator feeds ex2 directly (forward_tc.cu)
           const int g = n / UP, u = n % UP;
-          x = Rp[((size_t)k * G + g) * UP + u];
+          x = Rp[((size_t)k * G + g) * UP + u] * (g < 2 ? -1.4426950408889634f : 2.8853900817779268f);
         } else if (k < U) {
           const int j = n - 3 * UP;          // 0..4: ctx half (attention only), 8..12: avg half
           if (j < 5 && j < n_classes && att) x = ff_kernel[(size_t)k * n_classes + j];

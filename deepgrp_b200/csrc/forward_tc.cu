@@ -15,9 +15,13 @@
 //                quarter w / 4; they read the finished accumulator (tcgen05.ld), add the input
 //                projection (a table row: x_t is one-hot), apply the gates in fp32, write the new state
 //                as bf16 pieces into the A operand and arrive on the tile's "ready" mbarrier;
-//   warp 16      MMA issuer: waits for "ready", issues the 6 x UP/16 tcgen05.mma of the step and
-//                commits them to the tile's "done" mbarrier, which the gate warps wait on.
+//   warp 16      MMA issuer: waits for "ready" (with back-off), issues the 6 x UP/16 tcgen05.mma of
+//                the step and commits them to the tile's "done" mbarrier, which the gate warps wait on.
+//                (Letting the last-arriving gate warp issue instead -- 16 warps, 128 registers -- was
+//                measured 14 % slower: the issue lands on the slowest warp's critical path.)
 // While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
+// The z, r (h) columns of R, the input table and the biases are pre-scaled by -log2(e) (2 log2(e)) so
+// that the accumulator feeds ex2 directly.
 //   TMEM   2 x [128 lanes x (3*UP + 16) columns] fp32 accumulators: z | r | h gate blocks, then 16
 //          projection columns h.K (the FF layer's two halves), so that the second phase needs no
 //          FFMA over the units: avg[t].K = (h_fwd[t].K + h_rc[t].K)/2 comes out of the same MMA
@@ -35,6 +39,8 @@ namespace dgrp {
 
 constexpr int TC_GATE_WARPS = 16;
 constexpr int TC_THREADS = (TC_GATE_WARPS + 1) * 32;
+constexpr float kNegLog2e = -1.4426950408889634f;   // z, r columns are pre-scaled: ex2(arg) = e^{-x}
+constexpr float kTwoLog2e = 2.8853900817779268f;    // h columns are pre-scaled:    ex2(arg) = e^{2x}
 
 template <int UP>
 struct TCfg {
@@ -151,12 +157,17 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t 
 
 // z = 1/(1+e^-xz), r = 1/(1+e^-xr) with one reciprocal: z = b/(ab), r = a/(ab).
 // Arguments are clamped at -40 so that a*b stays finite (sigmoid(-40) = 4e-18 either way).
-__device__ __forceinline__ void sigmoid2(float xz, float xr, float &z, float &r) {
-  const float a = 1.0f + ex2_approx(fmaxf(xz, -40.0f) * -1.4426950408889634f);
-  const float b = 1.0f + ex2_approx(fmaxf(xr, -40.0f) * -1.4426950408889634f);
+// (arguments arrive multiplied by -log2(e); the clamp at 57.7 is x >= -40)
+__device__ __forceinline__ void sigmoid2(float sz, float sr, float &z, float &r) {
+  const float a = 1.0f + ex2_approx(fminf(sz, 57.7f));
+  const float b = 1.0f + ex2_approx(fminf(sr, 57.7f));
   const float inv = rcp_approx(a * b);
   z = inv * b;
   r = inv * a;
+}
+// tanh(x) for an argument that arrives multiplied by 2 log2(e): 1 - 2/(2^arg + 1)
+__device__ __forceinline__ float tanh_scaled(float sx) {
+  return fmaf(-2.0f, rcp_approx(ex2_approx(sx) + 1.0f), 1.0f);
 }
 
 // Second phase when the FF projections avg[t].K already exist (`proj`, [WT][T][16]: ctx half in
@@ -187,7 +198,7 @@ __device__ __forceinline__ void attention_vote_proj_tile(const FwdParams &p, con
       // query = avg[T-1] (model.py:311); score[t] = sum_u scale[u] * tanh(q[u] + avg[t][u])
       const float4 q4 = *reinterpret_cast<const float4 *>(av + (size_t)(T - 1) * UP + 4 * g);
       const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-      constexpr int UNR = 4;
+      constexpr int UNR = 8;
       for (int t0 = 0; t0 < T; t0 += RPW * UNR) {
         float4 v[UNR];
 #pragma unroll
@@ -291,9 +302,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     for (int i = tid; i < 5 * K::PSTRIDE; i += TC_THREADS) {
       const int c = i / K::PSTRIDE, j = i % K::PSTRIDE;
       // (x.W + b_in) + b_rec for z and r; the h gate keeps b_rec inside r * (h.R + b_rec)
-      s_P[i] = j < 3 * UP ? p.P[c * 3 * UP + j] + (j < 2 * UP ? p.b1[j] : 0.f) : 0.f;
+      float v = 0.f;
+      if (j < 2 * UP) v = (p.P[c * 3 * UP + j] + p.b1[j]) * kNegLog2e;
+      else if (j < 3 * UP) v = p.P[c * 3 * UP + j] * kTwoLog2e;
+      s_P[i] = v;
     }
-    for (int i = tid; i < UP; i += TC_THREADS) s_bh[i] = p.b1[2 * UP + i];
+    for (int i = tid; i < UP; i += TC_THREADS) s_bh[i] = p.b1[2 * UP + i] * kTwoLog2e;
     stage_attention_table<UP, TC_THREADS>(p, s_att, tid);
   }
   if (warp == 0) {
@@ -321,15 +335,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   uint32_t phase[2] = {0u, 0u};   // parity to wait for next ("done" for gate warps, "ready" for the issuer)
+  // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP + 16, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
 
   for (int64_t pair = blockIdx.x; pair * 2 < n_tiles; pair += gridDim.x) {
     const bool live[2] = {pair * 2 < n_tiles, pair * 2 + 1 < n_tiles};
 
     if (warp == TC_GATE_WARPS) {
       // ===================== MMA issuer =====================
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
       for (int t = 0; t < T; ++t) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
                 const int e = 4 * j4 + j;
                 float z, r;
                 sigmoid2(xzv[j] + az[e], xrv[j] + ar[e], z, r);
-                const float hh = tanh_fast(fmaf(r, ah[e] + bhv[j], xhv[j]));
+                const float hh = tanh_scaled(fmaf(r, ah[e] + bhv[j], xhv[j]));
                 const float hp = hprev[s][c8 * 8 + e];
                 const float h = fmaf(z, hp - hh, hh);      // z*h + (1-z)*hh
                 hprev[s][c8 * 8 + e] = h;

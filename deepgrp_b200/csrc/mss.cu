@@ -214,8 +214,9 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   if (n <= 0) return DGRP_OK;
   int CH = c->mss_chunk;
   if (CH <= 0) {
-    CH = 2048;
-    while (CH > 64 && (int64_t)n / CH < 4096) CH >>= 1;
+    // aim at ~4-8 k chunks: the summary pass is sequential over chunks, the scan parallel over them
+    CH = 64;
+    while (CH < 16384 && (int64_t)n / CH > 8192) CH <<= 1;
   }
   CH = (CH + 31) / 32 * 32;
   const int NC = (n + CH - 1) / CH;
