@@ -20,6 +20,9 @@
 //                (Letting the last-arriving gate warp issue instead -- 16 warps, 128 registers -- was
 //                measured 14 % slower: the issue lands on the slowest warp's critical path.)
 // While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
+// (Also measured and dropped: three extra "attention" warps consuming finished tile pairs from a queue
+// while the gate warps run the next pair -- 128 ms vs 127 ms on config 2: the kernel is bound by issue
+// slots and the MUFU pipe, not by the latency of the second phase, so overlapping it gains nothing.)
 // The z, r (h) columns of R, the input table and the biases are pre-scaled by -log2(e) (2 log2(e)) so
 // that the accumulator feeds ex2 directly.
 //   TMEM   2 x [128 lanes x (3*UP + 16) columns] fp32 accumulators: z | r | h gate blocks, then 16
