@@ -49,6 +49,11 @@
 #else
 #define DGRP_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define DGRP_UNROLL _Pragma("unroll")
+#else
+#define DGRP_UNROLL
+#endif
 
 namespace dgrp {
 namespace mss {
@@ -144,41 +149,59 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
   int next_ord = first_ord;
   sum.carryR = 0.0; sum.minT = 0.0; sum.maxAfter = 0.0; sum.maxIn = 0.0; sum.min_st = -1; sum.flags = 0;
   bool carried = (s.flags & 2) != 0;       // the run in progress came from before the chunk
-  for (int i = b; i < e; ++i) {
-    const double v = (double)S[i];
-    if (v > 0) {
-      if (!(s.flags & 2)) {
-        s.flags |= 2;
-        s.run_st = i; s.run_L0 = s.L;
-        // a "run" that begins at a speculative chunk start in the middle of a true run has no
-        // ordinal; it only shapes the (to be discarded) speculative state
-        const bool true_start = (i == 0) || !((double)S[i - 1] > 0);
-        s.run_ord = true_start ? next_ord++ : -1;
-        carried = !true_start;
-      }
-      s.L += v;                                     // R = L + S[i]; R += S[k]  (mss.c:61-63)
-      if (i + 1 == n || !((double)S[i + 1] > 0)) {
-        const double tL = s.run_L0;
-        const int st = s.run_st;
-        finish_run(s, i + 1, rt);
-        const double R = s.L;
-        if (carried) {
-          sum.flags |= 2; sum.carryR = R;
-        } else {
-          if (!(sum.flags & 4) || !(sum.minT < tL)) { sum.minT = tL; sum.min_st = st; sum.maxAfter = R; }
-          else if (R > sum.maxAfter) sum.maxAfter = R;
-          if (!(sum.flags & 4) || R > sum.maxIn) sum.maxIn = R;
-          sum.flags |= 4;
+  // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
+  // a block are independent of the sequential state machine and overlap each other.
+  constexpr int BL = 8;
+  bool prev_pos = b > 0 && ((double)S[b - 1] > 0);
+  for (int i0 = b; i0 < e; i0 += BL) {
+    const int m = e - i0 < BL ? e - i0 : BL;
+    double blk[BL + 1];
+    DGRP_UNROLL
+    for (int j = 0; j <= BL; ++j) {
+      const int idx = i0 + j;
+      blk[j] = (j <= m && idx < n) ? (double)S[idx] : 0.0;
+    }
+    DGRP_UNROLL
+    for (int j = 0; j < BL; ++j) {
+      if (j >= m) break;
+      const int i = i0 + j;
+      const double v = blk[j];
+      if (v > 0) {
+        if (!(s.flags & 2)) {
+          s.flags |= 2;
+          s.run_st = i; s.run_L0 = s.L;
+          // a "run" that begins at a speculative chunk start in the middle of a true run has no
+          // ordinal; it only shapes the (to be discarded) speculative state
+          const bool true_start = !prev_pos;
+          s.run_ord = true_start ? next_ord++ : -1;
+          carried = !true_start;
         }
-        carried = false;
+        s.L += v;                                   // R = L + S[i]; R += S[k]  (mss.c:61-63)
+        if (i + 1 == n || !(blk[j + 1] > 0)) {
+          const double tL = s.run_L0;
+          const int st = s.run_st;
+          finish_run(s, i + 1, rt);
+          const double R = s.L;
+          if (carried) {
+            sum.flags |= 2; sum.carryR = R;
+          } else {
+            if (!(sum.flags & 4) || !(sum.minT < tL)) { sum.minT = tL; sum.min_st = st; sum.maxAfter = R; }
+            else if (R > sum.maxAfter) sum.maxAfter = R;
+            if (!(sum.flags & 4) || R > sum.maxIn) sum.maxIn = R;
+            sum.flags |= 4;
+          }
+          carried = false;
+        }
+        prev_pos = true;
+      } else {
+        if (xdrop > 0.0 && s.L + v + xdrop < s.maxv) {  // mss.c:89
+          s.L = 0.0; s.maxv = kNegInf;              // mss.c:91 (the flush happens at the next run)
+          s.botL = 0.0; s.bot_st = -1; s.flags |= 1;
+          sum.flags = 1;                            // summary restarts after a reset
+        }
+        s.L += v;                                   // mss.c:93
+        prev_pos = false;
       }
-    } else {
-      if (xdrop > 0.0 && s.L + v + xdrop < s.maxv) {  // mss.c:89
-        s.L = 0.0; s.maxv = kNegInf;                // mss.c:91 (the flush happens at the next run)
-        s.botL = 0.0; s.bot_st = -1; s.flags |= 1;
-        sum.flags = 1;                              // summary restarts after a reset
-      }
-      s.L += v;                                     // mss.c:93
     }
   }
   if ((s.flags & 2) && !carried) sum.flags |= 8;

@@ -77,11 +77,18 @@ __global__ void tsv_scan_kernel(unsigned long long *a, int64_t m, unsigned long 
   if (threadIdx.x == 0) total[0] = s_carry;
 }
 
+// One thread formats one row.  The block's rows are contiguous in the output, so the text is first
+// assembled in shared memory (at the same 16-byte phase as its global destination) and then copied
+// out with aligned 16-byte stores; blocks whose text does not fit the staging buffer write directly.
+constexpr int TSV_STAGE = 40 * 1024;
+
 __global__ void tsv_write_kernel(const int64_t *__restrict__ tri, int64_t n,
                                  const uint8_t *__restrict__ prefix, int prefix_len,
                                  const unsigned long long *__restrict__ tile_off,
+                                 const unsigned long long *__restrict__ total,
                                  uint8_t *__restrict__ out) {
   __shared__ unsigned s_w[TSV_THREADS / 32];
+  __shared__ __align__(16) uint8_t s_text[TSV_STAGE + 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * TSV_THREADS + threadIdx.x;
   const unsigned len = i < n ? row_len(tri, i, prefix_len) : 0;
@@ -94,13 +101,32 @@ __global__ void tsv_write_kernel(const int64_t *__restrict__ tri, int64_t n,
   __syncthreads();
   unsigned before = 0;
   for (int w = 0; w < warp; ++w) before += s_w[w];
-  if (i >= n) return;
-  uint8_t *p = out + tile_off[blockIdx.x] + before + (incl - len);
-  for (int k = 0; k < prefix_len; ++k) p[k] = prefix[k];
-  p += prefix_len;
-  p = fmt_put(p, tri[3 * i]);      *p++ = '\t';
-  p = fmt_put(p, tri[3 * i + 1]);  *p++ = '\t';
-  p = fmt_put(p, tri[3 * i + 2]);  *p++ = '\n';
+  const unsigned long long g0 = tile_off[blockIdx.x];
+  const unsigned long long g1 = (blockIdx.x + 1 < gridDim.x) ? tile_off[blockIdx.x + 1] : total[0];
+  const unsigned block_len = (unsigned)(g1 - g0);
+  const unsigned phase = (unsigned)((reinterpret_cast<uintptr_t>(out) + g0) & 15u);
+  const bool staged = block_len + phase <= TSV_STAGE;
+  if (i < n) {
+    uint8_t *p = staged ? s_text + phase + before + (incl - len) : out + g0 + before + (incl - len);
+    for (int k = 0; k < prefix_len; ++k) p[k] = prefix[k];
+    p += prefix_len;
+    p = fmt_put(p, tri[3 * i]);      *p++ = '\t';
+    p = fmt_put(p, tri[3 * i + 1]);  *p++ = '\t';
+    p = fmt_put(p, tri[3 * i + 2]);  *p++ = '\n';
+  }
+  if (!staged) return;
+  __syncthreads();
+  uint8_t *dst = out + g0 - phase;                  // 16-byte aligned
+  const unsigned end = phase + block_len;
+  // head and tail bytes that do not fill a 16-byte word, then whole words
+  const unsigned first_word = phase ? 16u : 0u, last_word = end & ~15u;
+  for (unsigned k = phase + threadIdx.x; k < (first_word < end ? first_word : end); k += TSV_THREADS) dst[k] = s_text[k];
+  if (last_word >= first_word) {
+    for (unsigned k = first_word / 16 + threadIdx.x; k < last_word / 16; k += TSV_THREADS)
+      reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(s_text)[k];
+    for (unsigned k = (last_word > first_word ? last_word : first_word) + threadIdx.x; k < end; k += TSV_THREADS)
+      dst[k] = s_text[k];
+  }
 }
 
 // Format n triples on the device into d_out (reserved by the caller through *need).  Step 1
@@ -127,8 +153,9 @@ int run_tsv_write(dgrp_ctx *c, const int64_t *d_tri, int64_t n, const uint8_t *d
                   int prefix_len, uint8_t *d_out) {
   if (n <= 0) return DGRP_OK;
   const int64_t ntiles = (n + TSV_THREADS - 1) / TSV_THREADS;
-  tsv_write_kernel<<<(unsigned)ntiles, TSV_THREADS, 0, c->stream>>>(
-      d_tri, n, d_prefix, prefix_len, c->scan.as<unsigned long long>(), d_out);
+  const unsigned long long *tile = c->scan.as<unsigned long long>();
+  tsv_write_kernel<<<(unsigned)ntiles, TSV_THREADS, 0, c->stream>>>(d_tri, n, d_prefix, prefix_len, tile,
+                                                                    tile + ntiles, d_out);
   c->launches++;
   DGRP_CUDA(cudaGetLastError());
   return DGRP_OK;

@@ -13,6 +13,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # the shared library and the checker's natives are build products (git-ignored): build them when
+    # a fresh checkout runs the tests before __graft_entry__.build() has been called
+    lib = os.path.join(ROOT, "deepgrp_b200", "libdeepgrp_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

@@ -74,6 +74,14 @@ static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *
       out[c] = t;
     }
     ++rounds;
+    // parallel verification (emulates mss_verify_kernel)
+    int bad = 0;
+    for (int c = 0; c < NC; ++c) {
+      ScanState expect;
+      if (c == 0) state_canonical(expect); else expect = out[c - 1];
+      if (!state_equal(used[c], expect)) ++bad;
+    }
+    if (!bad) break;
   }
   *rounds_out = rounds;
   // regions
