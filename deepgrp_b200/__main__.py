@@ -42,6 +42,19 @@ def _read_multi_fasta(filestream: TextIO) -> Iterator[Tuple[str, str]]:
         yield header, "".join(sequence)
 
 
+def _read_raw(filename: str) -> bytes:
+    """Raw FASTA bytes of `filename` ("-" = stdin; ``.gz`` files are decompressed on the host, as the
+    reference's preprocessing script does, deepgrp/_scripts/preprocess_sequence.py:19-38)."""
+    if filename == "-":
+        return sys.stdin.buffer.read()
+    if filename.endswith(".gz"):
+        import gzip
+        with gzip.open(filename, "rb") as fh:
+            return fh.read()
+    with open(filename, "rb") as fh:
+        return fh.read()
+
+
 def _predict(dnasequence: str, model: dgmodel.ModelWeights, options: dgmodel.Options,
              step_size: int, use_mss: bool) -> Tuple[np.ndarray, int]:
     """Runs a prediction for one sequence (reference ``deepgrp/__main__.py:46-83``): the same five
@@ -156,9 +169,15 @@ class CommandLineParser:
         use_mss = not args.no_use_mss
         for filename in args.FASTA:
             _LOG.info("Processing %s", filename)
-            try:
-                filestream = sys.stdin if filename == "-" else open(filename, "r")
-                if getattr(args, "stepwise", False):
+            if getattr(args, "stepwise", False):
+                if filename == "-":
+                    filestream = sys.stdin
+                elif filename.endswith(".gz"):
+                    import gzip
+                    filestream = gzip.open(filename, "rt")
+                else:
+                    filestream = open(filename, "r")
+                try:
                     for header, dnasequence in _read_multi_fasta(filestream):
                         predictions, startpos = _predict(dnasequence, model, options,
                                                          args.step_size, use_mss=use_mss)
@@ -166,17 +185,15 @@ class CommandLineParser:
                             if segment[2] > 0:
                                 outstream.write("{}\t{}\t{}\t{}\t{}\n".format(
                                     filename, header, *segment))
-                else:
-                    raw = (sys.stdin.buffer.read() if filename == "-"
-                           else open(filename, "rb").read())
-                    view = dgpred.predict_fasta_tsv_view(
-                        model, raw, filename, args.step_size, options.batch_size, use_mss,
-                        options.min_mss_len, options.xdrop_len)
-                    outstream.flush()
-                    getattr(outstream, "buffer", outstream).write(view)
-            finally:
-                if filename != "-":
-                    filestream.close()
+                finally:
+                    if filename != "-":
+                        filestream.close()
+            else:
+                view = dgpred.predict_fasta_tsv_view(
+                    model, _read_raw(filename), filename, args.step_size, options.batch_size, use_mss,
+                    options.min_mss_len, options.xdrop_len)
+                outstream.flush()
+                getattr(outstream, "buffer", outstream).write(view)
         if args.output != "-":
             outstream.close()
 

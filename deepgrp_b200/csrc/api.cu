@@ -415,10 +415,11 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
                       dgrp_model **out) {
   Use use(c->device);
   *out = nullptr;
-  if (rnn != 0) {
-    set_error("only the GRU variant (reset_after=True) is implemented by the CUDA forward");
+  if (rnn != 0 && rnn != 1) {
+    set_error("rnn must be 0 (GRU, reset_after=True) or 1 (LSTM)");
     return DGRP_E_UNSUPPORTED;
   }
+  if (rnn == 1) att_scale = nullptr;   // attention is ignored for LSTM (deepgrp/model.py:308)
   DGRP_REQUIRE(vecsize > 0 && units > 0, "vecsize and units must be positive");
   DGRP_REQUIRE(n_classes >= 2 && n_classes <= 5, "n_classes must be in [2, 5], got %d", n_classes);
   if (units > 128) {
@@ -427,7 +428,7 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
   }
   int UP = 32;
   while (UP < units) UP <<= 1;
-  const int U = units, G = 3;
+  const int U = units, G = rnn == 1 ? 4 : 3;   // LSTM: gates i, f, c, o and a single bias [4U]
   std::vector<float> P((size_t)5 * G * UP, 0.f), Wk((size_t)5 * G * UP, 0.f), b0((size_t)G * UP, 0.f),
       b1((size_t)G * UP, 0.f), Rp((size_t)UP * G * UP, 0.f);
   for (int cc = 0; cc < 5; ++cc)
@@ -440,7 +441,7 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
   for (int g = 0; g < G; ++g)
     for (int u = 0; u < U; ++u) {
       b0[(size_t)g * UP + u] = bias[g * U + u];
-      b1[(size_t)g * UP + u] = bias[(size_t)G * U + g * U + u];
+      b1[(size_t)g * UP + u] = rnn == 1 ? 0.f : bias[(size_t)G * U + g * U + u];
     }
   for (int k = 0; k < U; ++k)
     for (int g = 0; g < G; ++g)
@@ -448,7 +449,7 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
         Rp[((size_t)k * G + g) * UP + u] = recurrent[(size_t)k * G * U + g * U + u];
   // bf16 hi|mid|lo pieces of recurrent^T in the tcgen05 operand layout (forward_tc.cu)
   std::vector<uint16_t> Bs;
-  if (UP <= 64) {
+  if (UP <= 64 && rnn == 0) {
     const int N = 3 * UP + 16, SBO = (UP / 8) * 128;   // 16 extra rows: FF kernel halves (forward_tc.cu)
     const bool att = att_scale != nullptr;
     Bs.assign((size_t)3 * N * UP, 0);

@@ -39,11 +39,13 @@ Placement make_placement(int64_t length, int T, int step, int batch_size, int co
 
 int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p);   // forward_tc.cu
 
-template <int UP>
+// RNN: 0 = GRU (reset_after, gates z, r, h), 1 = LSTM (gates i, f, c, o; one bias)
+template <int UP, int RNN = 0>
 struct Cfg {
+  static constexpr int G = RNN ? 4 : 3;               // gates
   static constexpr int UG = UP / 4;                   // unit groups (4 units each)
   static constexpr int RG = FWD_THREADS / UG;         // row groups
-  static constexpr int ROWS = (UP >= 128) ? 64 : 128; // rows = windows x 2 directions
+  static constexpr int ROWS = (UP >= 128 || (RNN && UP >= 64)) ? 64 : 128;  // rows = windows x 2 directions
   static constexpr int RPT = ROWS / RG;               // rows per thread
   static constexpr int WPT = RPT / 2;                 // windows per thread
   static constexpr int WT = ROWS / 2;                 // windows per tile
@@ -53,16 +55,17 @@ struct Cfg {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-template <int UP, bool DENSE>
+template <int UP, bool DENSE, int RNN>
 __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(const FwdParams p) {
-  using K = Cfg<UP>;
+  using K = Cfg<UP, RNN>;
+  constexpr int G = K::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_R = reinterpret_cast<float *>(smem_raw);                      // [UP][3][UP] or unused
-  float *s_h = s_R + (K::R_SMEM ? UP * 3 * UP : 0);                      // [2][ROWS][HS]
-  float *s_P = s_h + 2 * K::ROWS * K::HS;                                // [5][3][UP] (P or Wk)
-  float *s_b0 = s_P + 5 * 3 * UP;                                        // [3][UP] (dense mode)
-  float *s_b1 = s_b0 + 3 * UP;                                           // [3][UP]
-  float *s_att = s_b1 + 3 * UP;                                          // [UP][12]: K1[5] K2[5] scale 0
+  float *s_R = reinterpret_cast<float *>(smem_raw);                      // [UP][G][UP] or unused
+  float *s_h = s_R + (K::R_SMEM ? UP * G * UP : 0);                      // [2][ROWS][HS]
+  float *s_P = s_h + 2 * K::ROWS * K::HS;                                // [5][G][UP] (P or Wk)
+  float *s_b0 = s_P + 5 * G * UP;                                        // [G][UP] (dense mode)
+  float *s_b1 = s_b0 + G * UP;                                           // [G][UP]
+  float *s_att = s_b1 + G * UP;                                          // [UP][12]: K1[5] K2[5] scale 0
   float *s_q = s_att + UP * 12;                                          // [8 warps][UP]
   float *s_score = s_q + 8 * UP;                                         // [8 warps][T]
 
@@ -73,9 +76,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
 
   // ---- one-time: stage weights ----
   if (K::R_SMEM)
-    for (int i = tid; i < UP * 3 * UP; i += FWD_THREADS) s_R[i] = p.Rp[i];
-  for (int i = tid; i < 5 * 3 * UP; i += FWD_THREADS) s_P[i] = DENSE ? p.Wk[i] : p.P[i];
-  for (int i = tid; i < 3 * UP; i += FWD_THREADS) { s_b0[i] = p.b0[i]; s_b1[i] = p.b1[i]; }
+    for (int i = tid; i < UP * G * UP; i += FWD_THREADS) s_R[i] = p.Rp[i];
+  for (int i = tid; i < 5 * G * UP; i += FWD_THREADS) s_P[i] = DENSE ? p.Wk[i] : p.P[i];
+  for (int i = tid; i < G * UP; i += FWD_THREADS) { s_b0[i] = p.b0[i]; s_b1[i] = p.b1[i]; }
   stage_attention_table<UP>(p, s_att, tid);
   __syncthreads();
 
@@ -100,11 +103,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
       wvalid[q] = w < p.w_end;
       wpos[q] = DENSE ? w : (w * (int64_t)p.step - p.codes_base);
     }
-    float hprev[K::RPT][4];
+    float hprev[K::RPT][4], cprev[RNN ? K::RPT : 1][4];   // cell state (LSTM only)
 #pragma unroll
     for (int i = 0; i < K::RPT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hprev[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) { hprev[i][j] = 0.f; if (RNN) cprev[RNN ? i : 0][j] = 0.f; }
     __syncthreads();
 
     int cur = 0;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
       float *hn = s_h + (cur ^ 1) * K::ROWS * K::HS;
 
       // input part (x_t . kernel + b_in): a table row for one-hot codes
-      float xz[K::RPT][4], xr[K::RPT][4], xh[K::RPT][4];
+      float xg[G][K::RPT][4];
 #pragma unroll
       for (int i = 0; i < K::RPT; ++i) {
         const int q = i >> 1, dir = i & 1;
@@ -124,12 +127,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
             code = p.codes[pos];
             if (dir && code < 4) code = 3 - code;   // complement A<->T, C<->G (model.py:233-237)
           }
-          const float4 vz = *reinterpret_cast<const float4 *>(s_P + (code * 3 + 0) * UP + 4 * tu);
-          const float4 vr = *reinterpret_cast<const float4 *>(s_P + (code * 3 + 1) * UP + 4 * tu);
-          const float4 vh = *reinterpret_cast<const float4 *>(s_P + (code * 3 + 2) * UP + 4 * tu);
-          xz[i][0] = vz.x; xz[i][1] = vz.y; xz[i][2] = vz.z; xz[i][3] = vz.w;
-          xr[i][0] = vr.x; xr[i][1] = vr.y; xr[i][2] = vr.z; xr[i][3] = vr.w;
-          xh[i][0] = vh.x; xh[i][1] = vh.y; xh[i][2] = vh.z; xh[i][3] = vh.w;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const float4 v = *reinterpret_cast<const float4 *>(s_P + (code * G + g) * UP + 4 * tu);
+            xg[g][i][0] = v.x; xg[g][i][1] = v.y; xg[g][i][2] = v.z; xg[g][i][3] = v.w;
+          }
         } else {
           float xv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
           if (wvalid[q]) {
@@ -142,27 +144,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float az = 0.f, ar = 0.f, ah = 0.f;
+          for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              az = fmaf(xv[c], s_P[(c * 3 + 0) * UP + 4 * tu + j], az);
-              ar = fmaf(xv[c], s_P[(c * 3 + 1) * UP + 4 * tu + j], ar);
-              ah = fmaf(xv[c], s_P[(c * 3 + 2) * UP + 4 * tu + j], ah);
+            for (int j = 0; j < 4; ++j) {
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) acc = fmaf(xv[c], s_P[(c * G + g) * UP + 4 * tu + j], acc);
+              xg[g][i][j] = acc + s_b0[g * UP + 4 * tu + j];
             }
-            xz[i][j] = az + s_b0[0 * UP + 4 * tu + j];
-            xr[i][j] = ar + s_b0[1 * UP + 4 * tu + j];
-            xh[i][j] = ah + s_b0[2 * UP + 4 * tu + j];
-          }
         }
       }
 
       // recurrent part h . R (fp32 FFMA, k ascending)
-      float az[K::RPT][4], ar[K::RPT][4], ah[K::RPT][4];
+      float ag[G][K::RPT][4];
 #pragma unroll
-      for (int i = 0; i < K::RPT; ++i)
+      for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { az[i][j] = 0.f; ar[i][j] = 0.f; ah[i][j] = 0.f; }
+        for (int i = 0; i < K::RPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ag[g][i][j] = 0.f;
       if (t > 0) {
         for (int k = 0; k < KU; k += 4) {
           float hv[K::RPT][4];
@@ -173,45 +173,49 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
           }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            float4 rz, rr, rh;
-            if (K::R_SMEM) {
-              rz = *reinterpret_cast<const float4 *>(s_R + ((k + kk) * 3 + 0) * UP + 4 * tu);
-              rr = *reinterpret_cast<const float4 *>(s_R + ((k + kk) * 3 + 1) * UP + 4 * tu);
-              rh = *reinterpret_cast<const float4 *>(s_R + ((k + kk) * 3 + 2) * UP + 4 * tu);
-            } else {
-              rz = __ldg(reinterpret_cast<const float4 *>(p.Rp + ((size_t)(k + kk) * 3 + 0) * UP + 4 * tu));
-              rr = __ldg(reinterpret_cast<const float4 *>(p.Rp + ((size_t)(k + kk) * 3 + 1) * UP + 4 * tu));
-              rh = __ldg(reinterpret_cast<const float4 *>(p.Rp + ((size_t)(k + kk) * 3 + 2) * UP + 4 * tu));
-            }
 #pragma unroll
-            for (int i = 0; i < K::RPT; ++i) {
-              const float h = hv[i][kk];
-              az[i][0] = fmaf(h, rz.x, az[i][0]); az[i][1] = fmaf(h, rz.y, az[i][1]);
-              az[i][2] = fmaf(h, rz.z, az[i][2]); az[i][3] = fmaf(h, rz.w, az[i][3]);
-              ar[i][0] = fmaf(h, rr.x, ar[i][0]); ar[i][1] = fmaf(h, rr.y, ar[i][1]);
-              ar[i][2] = fmaf(h, rr.z, ar[i][2]); ar[i][3] = fmaf(h, rr.w, ar[i][3]);
-              ah[i][0] = fmaf(h, rh.x, ah[i][0]); ah[i][1] = fmaf(h, rh.y, ah[i][1]);
-              ah[i][2] = fmaf(h, rh.z, ah[i][2]); ah[i][3] = fmaf(h, rh.w, ah[i][3]);
+            for (int g = 0; g < G; ++g) {
+              float4 rw;
+              if (K::R_SMEM) rw = *reinterpret_cast<const float4 *>(s_R + ((k + kk) * G + g) * UP + 4 * tu);
+              else rw = __ldg(reinterpret_cast<const float4 *>(p.Rp + ((size_t)(k + kk) * G + g) * UP + 4 * tu));
+#pragma unroll
+              for (int i = 0; i < K::RPT; ++i) {
+                const float h = hv[i][kk];
+                ag[g][i][0] = fmaf(h, rw.x, ag[g][i][0]); ag[g][i][1] = fmaf(h, rw.y, ag[g][i][1]);
+                ag[g][i][2] = fmaf(h, rw.z, ag[g][i][2]); ag[g][i][3] = fmaf(h, rw.w, ag[g][i][3]);
+              }
             }
           }
         }
       }
 
-      // gates (Keras GRU, reset_after=True; order z, r, h): h' = z*h + (1-z)*tanh(x_h + r*(hR_h+b))
-      const float4 bz = *reinterpret_cast<const float4 *>(s_b1 + 0 * UP + 4 * tu);
-      const float4 br = *reinterpret_cast<const float4 *>(s_b1 + 1 * UP + 4 * tu);
-      const float4 bh = *reinterpret_cast<const float4 *>(s_b1 + 2 * UP + 4 * tu);
-      const float bzv[4] = {bz.x, bz.y, bz.z, bz.w};
-      const float brv[4] = {br.x, br.y, br.z, br.w};
-      const float bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+      float bg[G][4];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(s_b1 + g * UP + 4 * tu);
+        bg[g][0] = b4.x; bg[g][1] = b4.y; bg[g][2] = b4.z; bg[g][3] = b4.w;
+      }
 #pragma unroll
       for (int i = 0; i < K::RPT; ++i) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float z = sigmoid_f(xz[i][j] + (az[i][j] + bzv[j]));
-          const float r = sigmoid_f(xr[i][j] + (ar[i][j] + brv[j]));
-          const float hh = tanhf(xh[i][j] + r * (ah[i][j] + bhv[j]));
-          hprev[i][j] = z * hprev[i][j] + (1.0f - z) * hh;
+          if (RNN == 0) {
+            // Keras GRU, reset_after=True, gate order z, r, h: h' = z*h + (1-z)*tanh(x_h + r*(hR_h + b))
+            const float z = sigmoid_f(xg[0][i][j] + (ag[0][i][j] + bg[0][j]));
+            const float r = sigmoid_f(xg[1][i][j] + (ag[1][i][j] + bg[1][j]));
+            const float hh = tanhf(xg[2][i][j] + r * (ag[2][i][j] + bg[2][j]));
+            hprev[i][j] = z * hprev[i][j] + (1.0f - z) * hh;
+          } else {
+            // Keras LSTM, gate order i, f, c, o (one bias, already in the input part):
+            // c' = sig(f)*c + sig(i)*tanh(c~); h' = sig(o)*tanh(c')
+            const float gi = sigmoid_f(xg[0][i][j] + ag[0][i][j]);
+            const float gf = sigmoid_f(xg[1][i][j] + ag[1][i][j]);
+            const float gc = tanhf(xg[2][i][j] + ag[2][i][j]);
+            const float go = sigmoid_f(xg[G - 1][i][j] + ag[G - 1][i][j]);
+            const float c = gf * cprev[RNN ? i : 0][j] + gi * gc;
+            cprev[RNN ? i : 0][j] = c;
+            hprev[i][j] = go * tanhf(c);
+          }
         }
         *reinterpret_cast<float4 *>(hn + (tr * K::RPT + i) * K::HS + 4 * tu) =
             make_float4(hprev[i][0], hprev[i][1], hprev[i][2], hprev[i][3]);
@@ -239,25 +243,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_attention_vote_kernel(cons
   }
 }
 
-template <int UP>
+template <int UP, int RNN>
 static size_t fwd_smem_bytes(int T) {
-  using K = Cfg<UP>;
-  size_t f = (K::R_SMEM ? (size_t)UP * 3 * UP : 0) + 2 * (size_t)K::ROWS * K::HS + 5 * 3 * UP +
-             3 * UP + 3 * UP + (size_t)UP * 12 + 8 * UP + 8 * (size_t)T;
+  using K = Cfg<UP, RNN>;
+  size_t f = (K::R_SMEM ? (size_t)UP * K::G * UP : 0) + 2 * (size_t)K::ROWS * K::HS + 5 * K::G * UP +
+             K::G * UP + K::G * UP + (size_t)UP * 12 + 8 * UP + 8 * (size_t)T;
   return f * sizeof(float);
 }
 
-template <int UP, bool DENSE>
+template <int UP, bool DENSE, int RNN>
 static int launch_fwd_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
-  using K = Cfg<UP>;
+  using K = Cfg<UP, RNN>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
-  const size_t smem = fwd_smem_bytes<UP>(p.T);
+  const size_t smem = fwd_smem_bytes<UP, RNN>(p.T);
   if (smem > 227 * 1024) {
     set_error("vecsize %d needs %zu bytes of shared memory (limit 232448)", p.T, smem);
     return DGRP_E_UNSUPPORTED;
   }
-  auto kern = gru_attention_vote_kernel<UP, DENSE>;
+  auto kern = gru_attention_vote_kernel<UP, DENSE, RNN>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int grid = (int)(n_tiles < c->sm_count ? n_tiles : c->sm_count);
@@ -273,10 +277,18 @@ static int launch_fwd_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
 
 template <bool DENSE>
 static int launch_fwd(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+  if (m->rnn == 1) {
+    switch (m->UP) {
+      case 32: return launch_fwd_t<32, DENSE, 1>(c, m, p);
+      case 64: return launch_fwd_t<64, DENSE, 1>(c, m, p);
+      case 128: return launch_fwd_t<128, DENSE, 1>(c, m, p);
+      default: break;
+    }
+  }
   switch (m->UP) {
-    case 32: return launch_fwd_t<32, DENSE>(c, m, p);
-    case 64: return launch_fwd_t<64, DENSE>(c, m, p);
-    case 128: return launch_fwd_t<128, DENSE>(c, m, p);
+    case 32: return launch_fwd_t<32, DENSE, 0>(c, m, p);
+    case 64: return launch_fwd_t<64, DENSE, 0>(c, m, p);
+    case 128: return launch_fwd_t<128, DENSE, 0>(c, m, p);
     default:
       set_error("units=%d not supported by the CUDA forward (max 128)", m->U);
       return DGRP_E_UNSUPPORTED;

@@ -170,11 +170,11 @@ class ModelWeights:
         key = ctx.device
         handle = self._device_handles.get(key)
         if handle is None:
-            if self.rnn != "GRU":
-                raise NotImplementedError("only rnn='GRU' is implemented by the CUDA forward")
+            if self.rnn not in ("GRU", "LSTM"):
+                raise NotImplementedError("rnn must be 'GRU' or 'LSTM'")
             handle = ctypes.c_void_p()
             _lib.check(_lib.lib().dgrp_model_create(
-                ctx.handle, 0, self.vecsize, self.units, self.n_classes, _lib.ptr(self.kernel),
+                ctx.handle, 1 if self.rnn == "LSTM" else 0, self.vecsize, self.units, self.n_classes, _lib.ptr(self.kernel),
                 _lib.ptr(self.recurrent_kernel), _lib.ptr(self.bias), _lib.ptr(self.att_scale),
                 _lib.ptr(self.ff_kernel), _lib.ptr(self.ff_bias), ctypes.byref(handle)))
             self._device_handles[key] = handle

@@ -124,8 +124,11 @@ int dgrp_find_mss_labels(dgrp_ctx *ctx, const double *scores, const int64_t *lab
 
 /* ---- model (deepgrp/model.py:293-336; weights as stored by Keras) ---------------------- */
 
-/* rnn: 0 = GRU (reset_after, gate order z,r,h).  kernel[5,3U], recurrent[U,3U], bias[2,3U],
- * att_scale[U] or NULL (no attention), ff_kernel[F,C] (F = 2U with attention else U), ff_bias[C]. */
+/* rnn: 0 = GRU (reset_after, gate order z,r,h): kernel[5,3U], recurrent[U,3U], bias[2,3U];
+ *      1 = LSTM (gate order i,f,c,o): kernel[5,4U], recurrent[U,4U], bias[4U]; att_scale is ignored
+ *          (the reference builds no attention for LSTM, deepgrp/model.py:308) and ff_kernel is [U,C].
+ * att_scale[U] or NULL (no attention), ff_kernel[F,C] (F = 2U with attention else U), ff_bias[C].
+ * The tcgen05 recurrence covers GRU with units <= 64; LSTM and wider GRUs run the fp32 kernel. */
 int dgrp_model_create(dgrp_ctx *ctx, int rnn, int vecsize, int units, int n_classes,
                       const float *kernel, const float *recurrent, const float *bias,
                       const float *att_scale, const float *ff_kernel, const float *ff_bias,

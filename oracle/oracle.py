@@ -234,6 +234,48 @@ def gru_sequence_torch(x: np.ndarray, w: Dict[str, np.ndarray], threads: int = 0
     return seq.numpy(), last[0].numpy()
 
 
+def lstm_sequence(x: np.ndarray, w: Dict[str, np.ndarray], dtype=np.float32):
+    """Keras LSTM (implementation 2, gate order i, f, c, o; one bias) over x[B,T,5] from zero states
+    (deepgrp/model.py:219-223): z = x.W + h.R + b; c' = sig(z_f)*c + sig(z_i)*tanh(z_c);
+    h' = sig(z_o)*tanh(c').  Returns (sequence [B,T,U], last h)."""
+    kern = w["kernel"].astype(dtype)
+    rec = w["recurrent_kernel"].astype(dtype)
+    bias = w["bias"].reshape(-1).astype(dtype)
+    units = rec.shape[0]
+    nb, nt, _ = x.shape
+    h = np.zeros((nb, units), dtype=dtype)
+    c = np.zeros((nb, units), dtype=dtype)
+    seq = np.empty((nb, nt, units), dtype=dtype)
+    xs = x.astype(dtype)
+    for t in range(nt):
+        z = xs[:, t, :] @ kern + h @ rec + bias
+        i = _sigmoid(z[:, :units])
+        f = _sigmoid(z[:, units:2 * units])
+        c = f * c + i * np.tanh(z[:, 2 * units:3 * units])
+        o = _sigmoid(z[:, 3 * units:])
+        h = o * np.tanh(c)
+        seq[:, t, :] = h
+    return seq, h
+
+
+def lstm_sequence_torch(x: np.ndarray, w: Dict[str, np.ndarray]):
+    """Second engine: torch.nn.LSTM on CPU (gate order i, f, g, o = Keras' i, f, c, o)."""
+    import torch
+    units = w["recurrent_kernel"].shape[0]
+    lstm = torch.nn.LSTM(5, units, batch_first=True)
+    with torch.no_grad():
+        lstm.weight_ih_l0.copy_(torch.from_numpy(w["kernel"].T.copy()))
+        lstm.weight_hh_l0.copy_(torch.from_numpy(w["recurrent_kernel"].T.copy()))
+        lstm.bias_ih_l0.copy_(torch.from_numpy(w["bias"].reshape(-1).copy()))
+        lstm.bias_hh_l0.zero_()
+        seq, (last, _) = lstm(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)))
+    return seq.numpy(), last[0].numpy()
+
+
+def is_lstm(w: Dict[str, np.ndarray]) -> bool:
+    return w["kernel"].shape[1] == 4 * w["recurrent_kernel"].shape[0]
+
+
 def model_forward(batch: np.ndarray, w: Dict[str, np.ndarray], dtype=np.float32,
                   engine: str = "numpy") -> np.ndarray:
     """The functional graph of deepgrp/model.py:293-336 on one batch float[B,T,5] -> [B,T,C].
@@ -242,7 +284,12 @@ def model_forward(batch: np.ndarray, w: Dict[str, np.ndarray], dtype=np.float32,
     when the model has attention, att_scale[U] (F = 2U with attention, U without)."""
     x = batch.astype(dtype)
     x_rc = np.ascontiguousarray(reverse_complement(x))
-    if engine == "torch":
+    if is_lstm(w):                                         # rnn="LSTM": attention is ignored (model.py:308)
+        run = lstm_sequence_torch if engine == "torch" else (lambda a, b: lstm_sequence(a, b, dtype))
+        fwd, _ = run(x, w)
+        rev, _ = run(x_rc, w)
+        hf = hr = None
+    elif engine == "torch":
         fwd, hf = gru_sequence_torch(x, w)
         rev, hr = gru_sequence_torch(x_rc, w)
     else:
@@ -250,7 +297,7 @@ def model_forward(batch: np.ndarray, w: Dict[str, np.ndarray], dtype=np.float32,
         rev, hr = gru_sequence(x_rc, w, dtype)
     half = dtype(0.5) if dtype is not np.float64 else 0.5
     avg = (fwd + rev) * half                               # Average (model.py:312), not re-reversed
-    if "att_scale" in w and w["att_scale"] is not None:
+    if not is_lstm(w) and "att_scale" in w and w["att_scale"] is not None:
         hidden = (hf + hr) * half                          # model.py:311
         scale = w["att_scale"].astype(dtype)
         # AdditiveAttention(use_scale=True): reduce_sum(scale * tanh(q + k), -1)

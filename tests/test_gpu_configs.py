@@ -176,3 +176,28 @@ def test_no_attention_model_through_the_fused_path(dg, oracle):
     assert startpos == st_o == 1
     assert (labels == lab_o).mean() >= 0.9999
     check_rows_consistent(rows, labels, startpos)
+
+
+@pytest.mark.parametrize("T,U", [(150, 32), (90, 60), (40, 20)])
+def test_lstm_variant(dg, oracle, tmp_path, T, U):
+    """Options.rnn = "LSTM" (reference deepgrp/model.py:219-223): gates i, f, c, o, no attention."""
+    from deepgrp_b200 import hdf5
+    w = dg.model.random_weights(T, U, attention=True, seed=11, rnn="LSTM").scaled(2.0)
+    assert w.att_scale is None and w.kernel.shape == (5, 4 * U)
+    rng = np.random.default_rng(T)
+    batch = np.eye(5, dtype=np.float32)[rng.integers(0, 5, size=(40, T))]
+    got = w.predict_on_batch(batch)
+    exp = oracle.model_forward(batch, w.as_dict())
+    assert np.abs(got - exp).max() < 2e-5
+    text = "NN" + random_dna(15_000, U) + "N"
+    labels, startpos, rows = dg.pred.predict_sequence(w, text.encode(), 50, 256, True, 50, 50)
+    assert dg.ctx.get_int("forward_used_tc") == 0
+    lab_o, st_o = oracle.predict_record(text, w.as_dict(), T, 256, 50, True, engine="torch")
+    assert startpos == st_o and (labels == lab_o).mean() >= 0.9999
+    check_rows_consistent(rows, labels, startpos)
+    path = str(tmp_path / "lstm.hdf5")
+    hdf5.save_keras_model(path, w)
+    w2 = dg.model.load_model(path)
+    assert w2.rnn == "LSTM" and np.array_equal(w2.recurrent_kernel, w.recurrent_kernel)
+    labels2, _, _ = dg.pred.predict_sequence(w2, text.encode(), 50, 256, True, 50, 50)
+    assert np.array_equal(labels, labels2)

@@ -462,5 +462,11 @@ def test_cli_end_to_end_with_hdf5_model(dg, oracle, tmp_path, capsys):
     a, b = open(out1).read(), open(out2).read()
     assert a == b and a.count("\n") > 10
     assert a.splitlines()[0].split("\t")[:2] == [fa1, "one"]
+    import gzip, shutil
+    with open(fa1, "rb") as fi, gzip.open(fa1 + ".gz", "wb") as fo:   # gz input
+        shutil.copyfileobj(fi, fo)
+    out3 = str(tmp_path / "o3.tsv")
+    CommandLineParser().parse_args(["predict", mpath, fa1 + ".gz", "--output", out3]).run()
+    assert open(out3).read().replace(fa1 + ".gz", fa1) == "".join(l + "\n" for l in a.splitlines() if l.startswith(fa1 + "\t"))
     CommandLineParser().parse_args([mpath, fa2]).run()            # README form, stdout
     assert capsys.readouterr().out == "".join(l + "\n" for l in a.splitlines() if l.startswith(fa2))

@@ -160,3 +160,14 @@ def test_oracle_against_compiled_reference(oracle):
             st, fwd = oracle.one_hot_encode_dna_sequence(text)
             assert st == a[0] and np.array_equal(fwd, a[1])
         assert list(ref_seq.yield_segments(lab, 5)) == list(oracle.yield_segments(lab, 5))
+
+
+def test_oracle_lstm_engines_agree(oracle):
+    from deepgrp_b200.model import random_weights
+    w = random_weights(60, 24, attention=True, seed=1, rnn="LSTM").as_dict()
+    rng = np.random.default_rng(0)
+    batch = np.eye(5, dtype=np.float32)[rng.integers(0, 5, size=(4, 60))]
+    a = oracle.model_forward(batch, w, engine="numpy")
+    b = oracle.model_forward(batch, w, engine="torch")
+    c = oracle.model_forward(batch, w, dtype=np.float64)
+    assert np.abs(a - c).max() < 5e-6 and np.abs(b - c).max() < 5e-6
