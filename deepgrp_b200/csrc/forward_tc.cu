@@ -146,31 +146,40 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// (a, b) = hi + mid + lo in bf16 pieces; each output word packs a's piece (low half) and b's (high half)
-__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+// (a, b) = hi + mid + lo in bf16 pieces; each output word packs a's piece (low half) and b's (high half).
+// The residuals are formed with one packed FFMA2 (x - hi exactly, as the scalar subtraction would).
+__device__ __forceinline__ void split3(float2 ab, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+  const float2 neg1 = make_float2(-1.0f, -1.0f);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(ab.x, ab.y);
   hi = *reinterpret_cast<uint32_t *>(&h2);
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
-  __nv_bfloat162 m2 = __floats2bfloat162_rn(ra, rb);
+  const float2 r = __ffma2_rn(make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), neg1, ab);
+  __nv_bfloat162 m2 = __floats2bfloat162_rn(r.x, r.y);
   mid = *reinterpret_cast<uint32_t *>(&m2);
-  const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xffff0000u);
-  __nv_bfloat162 l2 = __floats2bfloat162_rn(sa, sb);
+  const float2 q = __ffma2_rn(make_float2(__uint_as_float(mid << 16), __uint_as_float(mid & 0xffff0000u)), neg1, r);
+  __nv_bfloat162 l2 = __floats2bfloat162_rn(q.x, q.y);
   lo = *reinterpret_cast<uint32_t *>(&l2);
 }
 
-// z = 1/(1+e^-xz), r = 1/(1+e^-xr) with one reciprocal: z = b/(ab), r = a/(ab).
-// Arguments are clamped at -40 so that a*b stays finite (sigmoid(-40) = 4e-18 either way).
-// (arguments arrive multiplied by -log2(e); the clamp at 57.7 is x >= -40)
-__device__ __forceinline__ void sigmoid2(float sz, float sr, float &z, float &r) {
-  const float a = 1.0f + ex2_approx(fminf(sz, 57.7f));
-  const float b = 1.0f + ex2_approx(fminf(sr, 57.7f));
-  const float inv = rcp_approx(a * b);
-  z = inv * b;
-  r = inv * a;
-}
-// tanh(x) for an argument that arrives multiplied by 2 log2(e): 1 - 2/(2^arg + 1)
-__device__ __forceinline__ float tanh_scaled(float sx) {
-  return fmaf(-2.0f, rcp_approx(ex2_approx(sx) + 1.0f), 1.0f);
+// One GRU cell update for two units at once (packed fp32x2 arithmetic: FADD2 / FMUL2 / FFMA2 issue one
+// instruction per pair, with the same IEEE rounding as the scalar forms).  The accumulator and table
+// values arrive pre-scaled (z, r by -log2 e; h by 2 log2 e):
+//   z = 1/(1+2^sz), r = 1/(1+2^sr) with ONE reciprocal (z = b/(ab), r = a/(ab); the clamp at 57.7 is
+//   x >= -40 and keeps a*b finite), hh = tanh = 1 - 2/(2^arg + 1), h' = hh + z (h - hh).
+__device__ __forceinline__ float2 gru_cell2(float2 xz, float2 xr, float2 xh, float2 bh, float2 az,
+                                            float2 ar, float2 ah, float2 hp) {
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 sz = __fadd2_rn(xz, az), sr = __fadd2_rn(xr, ar);
+  const float2 ez = make_float2(ex2_approx(fminf(sz.x, 57.7f)), ex2_approx(fminf(sz.y, 57.7f)));
+  const float2 er = make_float2(ex2_approx(fminf(sr.x, 57.7f)), ex2_approx(fminf(sr.y, 57.7f)));
+  const float2 a = __fadd2_rn(ez, one), b = __fadd2_rn(er, one);
+  const float2 ab = __fmul2_rn(a, b);
+  const float2 inv = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
+  const float2 z = __fmul2_rn(inv, b), r = __fmul2_rn(inv, a);
+  const float2 targ = __ffma2_rn(r, __fadd2_rn(ah, bh), xh);
+  const float2 den = __fadd2_rn(make_float2(ex2_approx(targ.x), ex2_approx(targ.y)), one);
+  const float2 hh = __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(rcp_approx(den.x), rcp_approx(den.y)), one);
+  const float2 d = __ffma2_rn(hh, make_float2(-1.0f, -1.0f), hp);      // h - hh
+  return __ffma2_rn(z, d, hh);
 }
 
 // Second phase when the FF projections avg[t].K already exist (`proj`, [WT][T][16]: ctx half in
@@ -442,44 +451,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
               for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
             }
-            float hn[8];
+            float2 hn2[4];
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
               const float4 xz = *reinterpret_cast<const float4 *>(prow + u0 + 4 * j4);
               const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + u0 + 4 * j4);
               const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + u0 + 4 * j4);
               const float4 bh = *reinterpret_cast<const float4 *>(s_bh + u0 + 4 * j4);
-              const float xzv[4] = {xz.x, xz.y, xz.z, xz.w}, xrv[4] = {xr.x, xr.y, xr.z, xr.w};
-              const float xhv[4] = {xh.x, xh.y, xh.z, xh.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = 4 * j4 + j;
-                float z, r;
-                sigmoid2(xzv[j] + az[e], xrv[j] + ar[e], z, r);
-                const float hh = tanh_scaled(fmaf(r, ah[e] + bhv[j], xhv[j]));
-                const float hp = hprev[s][c8 * 8 + e];
-                const float h = fmaf(z, hp - hh, hh);      // z*h + (1-z)*hh
-                hprev[s][c8 * 8 + e] = h;
-                hn[e] = h;
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                const int e = 4 * j4 + 2 * hlf;
+                const float2 hp = make_float2(hprev[s][c8 * 8 + e], hprev[s][c8 * 8 + e + 1]);
+                const float2 h = gru_cell2(hlf ? make_float2(xz.z, xz.w) : make_float2(xz.x, xz.y),
+                                           hlf ? make_float2(xr.z, xr.w) : make_float2(xr.x, xr.y),
+                                           hlf ? make_float2(xh.z, xh.w) : make_float2(xh.x, xh.y),
+                                           hlf ? make_float2(bh.z, bh.w) : make_float2(bh.x, bh.y),
+                                           make_float2(az[e], az[e + 1]), make_float2(ar[e], ar[e + 1]),
+                                           make_float2(ah[e], ah[e + 1]), hp);
+                hprev[s][c8 * 8 + e] = h.x;
+                hprev[s][c8 * 8 + e + 1] = h.y;
+                hn2[2 * j4 + hlf] = h;
               }
             }
             // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
             uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split3(hn[2 * j], hn[2 * j + 1], hi[j], mid[j], lo[j]);
+            for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
             const int off = (row >> 3) * K::SBO + (u0 >> 3) * 128 + (row & 7) * 16;
             *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
             *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             // avg[t] = (fwd[t] + rc[t]) / 2: the partner row is the neighbouring lane; the fwd lane
             // stores units u0..u0+3, the rc lane u0+4..u0+7
-            float av[4];
+            float2 av2[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float send = dir ? hn[j] : hn[j + 4];
-              const float mine = dir ? hn[j + 4] : hn[j];
-              av[j] = 0.5f * (mine + __shfl_xor_sync(0xffffffffu, send, 1));
+            for (int j = 0; j < 2; ++j) {
+              const float2 send = dir ? hn2[j] : hn2[j + 2];
+              const float2 mine = dir ? hn2[j + 2] : hn2[j];
+              const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 1),
+                                              __shfl_xor_sync(0xffffffffu, send.y, 1));
+              av2[j] = __fmul2_rn(__fadd2_rn(mine, recv), make_float2(0.5f, 0.5f));
             }
+            const float av[4] = {av2[0].x, av2[0].y, av2[1].x, av2[1].y};
             *reinterpret_cast<float4 *>(avg_out + u0 + (dir ? 4 : 0)) = make_float4(av[0], av[1], av[2], av[3]);
           }
           // hand the new A operand to the tensor core (the last step's MMA only feeds the projection)
