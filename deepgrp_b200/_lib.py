@@ -140,6 +140,10 @@ class Context:
         check(lib().dgrp_ctx_create(device, ctypes.byref(handle)))
         self.handle = handle
         self.device = device
+        # tuning knobs from the environment: DEEPGRP_KNOBS="forward_sum16=1,mss_chunk=4096"
+        for item in filter(None, os.environ.get("DEEPGRP_KNOBS", "").split(",")):
+            key, _, value = item.partition("=")
+            self.set_int(key.strip(), int(value))
 
     def close(self) -> None:
         if self.handle:

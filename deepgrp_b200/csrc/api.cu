@@ -243,6 +243,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
+  else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -253,6 +254,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "mss_max_rounds")) *value = c->mss_max_rounds;
   else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
   else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
+  else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -475,9 +477,10 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
           x = Rp[((size_t)k * G + g) * UP + u] * (g < 2 ? -1.4426950408889634f : 2.8853900817779268f);
         } else if (k < U) {
           const int j = n - 3 * UP;          // 0..4: ctx half (attention only), 8..12: avg half
-          if (j < 5 && j < n_classes && att) x = ff_kernel[(size_t)k * n_classes + j];
+          // halved: the kernel adds the projections of the two directions, avg.K = h_fwd.K/2 + h_rc.K/2
+          if (j < 5 && j < n_classes && att) x = 0.5f * ff_kernel[(size_t)k * n_classes + j];
           else if (j >= 8 && j - 8 < n_classes && j < 13)
-            x = ff_kernel[(size_t)((att ? U : 0) + k) * n_classes + (j - 8)];
+            x = 0.5f * ff_kernel[(size_t)((att ? U : 0) + k) * n_classes + (j - 8)];
         }
         const uint16_t hi = f2bf(x);
         const float r1 = x - bf2f(hi);

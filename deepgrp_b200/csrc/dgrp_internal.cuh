@@ -94,6 +94,7 @@ struct dgrp_ctx {
   int mss_max_rounds = 0;  // Jacobi rounds before the sequential completion (0 = default)
   int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
   int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
+  int forward_sum16 = 1;   // tcgen05 forward: keep h_fwd + h_rc (attention scores only) in half precision
   int forward_used_tc = 0; // what the last forward launch used
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;

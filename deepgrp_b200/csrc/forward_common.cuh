@@ -17,7 +17,7 @@ struct FwdParams {
   int64_t full_windows, tail_base;
   const float *P, *Wk, *b0, *Rp, *b1, *scale, *ffk, *ffb;
   const uint16_t *Bsplit; // tcgen05 form: bf16 hi|mid|lo of the recurrent kernel, UMMA layout
-  float *scratch, *ff2;
+  float *scratch, *ff2, *qbuf;
   float *pred;
   int64_t pred_row0, pred_rows;
 };

@@ -10,7 +10,8 @@
 // each a kind::f16 (bf16 x bf16 -> fp32) tcgen05.mma accumulating into the same TMEM tile, smallest
 // terms first.  The gates, sigmoid/tanh and the state update stay in fp32 registers.
 //
-// One CTA = 17 warps, persistent, two tiles of 64 windows x 2 directions (M = 128 rows) in flight:
+// One CTA = 17 warps, persistent, a unit of work = two tiles of 64 windows x 2 directions (M = 128
+// rows) in flight:
 //   warps 0..15  gate warps: TMEM lane quadrant w % 4 (rows 32*(w%4) ..+31, one row per lane), unit
 //                quarter w / 4; they read the finished accumulator (tcgen05.ld), add the input
 //                projection (a table row: x_t is one-hot), apply the gates in fp32, write the new state
@@ -20,28 +21,41 @@
 //                (Letting the last-arriving gate warp issue instead -- 16 warps, 128 registers -- was
 //                measured 14 % slower: the issue lands on the slowest warp's critical path.)
 // While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
-// (Also measured and dropped: three extra "attention" warps consuming finished tile pairs from a queue
-// while the gate warps run the next pair -- 128 ms vs 127 ms on config 2: the kernel is bound by issue
-// slots and the MUFU pipe, not by the latency of the second phase, so overlapping it gains nothing.)
+// Every step, including the first, reads its pre-activations from TMEM: a unit starts with a priming
+// MMA round on an all-zero A operand (h[-1] = 0), so that the step loop has no special case.
 // The z, r (h) columns of R, the input table and the biases are pre-scaled by -log2(e) (2 log2(e)) so
 // that the accumulator feeds ex2 directly.
 //   TMEM   2 x [128 lanes x (3*UP + 16) columns] fp32 accumulators: z | r | h gate blocks, then 16
-//          projection columns h.K (the FF layer's two halves), so that the second phase needs no
-//          FFMA over the units: avg[t].K = (h_fwd[t].K + h_rc[t].K)/2 comes out of the same MMA
-//   smem   B = [R | K]^T pieces, [3][(3*UP+16) x UP] bf16, K-major core matrices, resident
+//          projection columns h.(K/2) (the FF layer's two halves), so that the second phase needs no
+//          FFMA over the units: avg[t].K = h_fwd[t].K/2 + h_rc[t].K/2 comes out of the same MMA
+//   smem   B = [R | K/2]^T pieces, [3][(3*UP+16) x UP] bf16, K-major core matrices, resident
 //          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate warps
-//   row r of a tile = window r/2, direction r%2, so avg[t] = (fwd + rc)/2 is one lane shuffle.
+//   row r of a tile = window r/2, direction r%2, so h_fwd[t] + h_rc[t] is one lane shuffle.
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 B each; core matrices
 // adjacent along K are 128 B apart (leading byte offset), along M/N they are UP/8 * 128 B apart
 // (stride byte offset); one MMA consumes K = 16 = two core matrices.
+//
+// Scratch in HBM (per CTA, rewritten by every unit; the attention query avg[T-1] is only known after
+// the last step, so the scores need a second pass over all avg[t]):
+//   sum    ST[2][64][T][UP]    h_fwd[t] + h_rc[t] (= 2 avg[t]) -- feeds ONLY the additive-attention
+//                               scores; half precision (11 bits, |sum| < 2) perturbs a probability by
+//                               ~1e-7 (measured, tools/accuracy_study.py)
+//   q      f32[2][64][UP]      avg[T-1] in full precision (the query)
+//   proj   f32[2][64][T][16]   avg[t].K, both FF halves (the logits come from these, full precision)
+// = 192 B per (window, t) written once and read once (was 320 B with an fp32 avg).  All CTAs run the
+// same amount of work, so without care their second phases coincide and saturate HBM while the
+// recurrence phases leave it idle; CTA b therefore starts with (b mod 4) single-tile units, which
+// shifts its phase by about 3/4 of a period each.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "forward_common.cuh"
 
 namespace dgrp {
 
 constexpr int TC_GATE_WARPS = 16;
-constexpr int TC_THREADS = (TC_GATE_WARPS + 1) * 32;
+constexpr int TC_THREADS = (TC_GATE_WARPS + 4) * 32;   // + one warpgroup: the issuer warp and three idle warps
+constexpr int TC_GATE_REGS = 112, TC_AUX_REGS = 24;     // setmaxnreg split: the inc (16 warps x 16) must fit into what the dec releases (4 warps x 72)
 constexpr float kNegLog2e = -1.4426950408889634f;   // z, r columns are pre-scaled: ex2(arg) = e^{-x}
 constexpr float kTwoLog2e = 2.8853900817779268f;    // h columns are pre-scaled:    ex2(arg) = e^{2x}
 
@@ -141,7 +155,10 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-
+// named barrier over the gate warps only (the issuer warp is in its own loop)
+__device__ __forceinline__ void gate_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_GATE_WARPS * 32) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -182,50 +199,79 @@ __device__ __forceinline__ float2 gru_cell2(float2 xz, float2 xr, float2 xh, flo
   return __ffma2_rn(z, d, hh);
 }
 
-// Second phase when the FF projections avg[t].K already exist (`proj`, [WT][T][16]: ctx half in
-// 0..4, avg half in 8..12): additive attention scores with lanes over the units (coalesced row
-// reads, 16-lane reductions), then softmax over t, logits, class softmax and the max-vote with
-// lanes over t.  One warp per window.
-template <int UP, int WT, int NWARPS>
-__device__ __forceinline__ void attention_vote_proj_tile(const FwdParams &p, const float *scratch,
-                                                         const float *proj, int64_t w_tile0,
-                                                         const float *s_att, float *s_score) {
+// Second phase for one tile: additive attention scores with lanes over the units (8 units per lane,
+// 16-byte half-precision loads, UP/8-lane reductions), then softmax over t, logits, class softmax and
+// the max-vote with lanes over t.  One warp per window.
+//   sum16 [WT][T][UP]  h_fwd[t] + h_rc[t] in half precision      q [WT][UP]  avg[T-1]
+//   proj  [WT][T][16]  avg[t].K: ctx half in 0..4, avg half in 8..12
+// score[t] = sum_u scale[u] tanh(q[u] + avg[t][u]) = S - 2 sum_u scale[u] / (e^{2(q+avg)} + 1) with
+// S = sum_u scale[u] the same for every t, so the softmax over t only needs the second term.
+template <int UP, int WT, int NWARPS, typename ST>
+__device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, const ST *sum16,
+                                                        const float *qbuf, const float *proj,
+                                                        int64_t w_tile0, const float *s_scale,
+                                                        float *s_score) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp >= NWARPS) return;
   const int T = p.T, C = p.C;
-  constexpr int LPR = UP / 4;          // lanes per avg row (4 units each)
+  constexpr int LPR = UP / 8;          // lanes per row (8 units each)
   constexpr int RPW = 32 / LPR;        // rows per warp-wide load
   const int g = lane % LPR, sub = lane / LPR;
   float *sc = s_score + (size_t)warp * T;
-  float scale[4];
+  float scale2[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) scale[j] = s_att[(4 * g + j) * 12 + 10];
+  for (int j = 0; j < 8; ++j) scale2[j] = -2.0f * s_scale[8 * g + j];
   for (int wl = warp; wl < WT; wl += NWARPS) {
     const int64_t w = w_tile0 + wl;
     if (w >= p.w_end) break;
-    const float *av = scratch + (size_t)wl * T * UP;
     const float *pr = proj + (size_t)wl * T * 16;
     float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (p.attention) {
-      // query = avg[T-1] (model.py:311); score[t] = sum_u scale[u] * tanh(q[u] + avg[t][u])
-      const float4 q4 = *reinterpret_cast<const float4 *>(av + (size_t)(T - 1) * UP + 4 * g);
-      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-      constexpr int UNR = 8;
+      const ST *av = sum16 + (size_t)wl * T * UP + 8 * g;
+      float q2[8];   // 2 log2(e) q[u]
+      {
+        const float4 qa = *reinterpret_cast<const float4 *>(qbuf + (size_t)wl * UP + 8 * g);
+        const float4 qb = *reinterpret_cast<const float4 *>(qbuf + (size_t)wl * UP + 8 * g + 4);
+        q2[0] = qa.x * kTwoLog2e; q2[1] = qa.y * kTwoLog2e; q2[2] = qa.z * kTwoLog2e; q2[3] = qa.w * kTwoLog2e;
+        q2[4] = qb.x * kTwoLog2e; q2[5] = qb.y * kTwoLog2e; q2[6] = qb.z * kTwoLog2e; q2[7] = qb.w * kTwoLog2e;
+      }
+      constexpr bool H16 = sizeof(ST) == 2;
+      constexpr int UNR = H16 ? 8 : 4;            // rows in flight per lane (16 or 32 bytes each)
+      constexpr int NV = H16 ? 1 : 2;             // 16-byte loads per row and lane
       for (int t0 = 0; t0 < T; t0 += RPW * UNR) {
-        float4 v[UNR];
+        uint4 v[UNR][NV];
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
           const int t = t0 + k * RPW + sub;
-          v[k] = t < T ? *reinterpret_cast<const float4 *>(av + (size_t)t * UP + 4 * g)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            v[k][i] = t < T ? __ldcs(reinterpret_cast<const uint4 *>(av + (size_t)t * UP) + i)
+                            : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
           const int t = t0 + k * RPW + sub;
-          float s = scale[0] * tanh_fast(q[0] + v[k].x);
-          s = fmaf(scale[1], tanh_fast(q[1] + v[k].y), s);
-          s = fmaf(scale[2], tanh_fast(q[2] + v[k].z), s);
-          s = fmaf(scale[3], tanh_fast(q[3] + v[k].w), s);
+          float x[8];   // h_fwd[t] + h_rc[t] of this lane's 8 units
+          if (H16) {
+            const uint32_t wv[4] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
+              x[2 * j] = f.x; x[2 * j + 1] = f.y;
+            }
+          } else {
+            const uint32_t wv[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w,
+                                    v[k][NV - 1].x, v[k][NV - 1].y, v[k][NV - 1].z, v[k][NV - 1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(wv[j]);
+          }
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // e^{2 (q + sum/2)} = 2^{2 log2e q + log2e sum}
+            const float e = ex2_approx(fmaf(x[j], 1.4426950408889634f, q2[j]));
+            s = fmaf(scale2[j], rcp_approx(e + 1.0f), s);
+          }
 #pragma unroll
           for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
           if (g == 0 && t < T) sc[t] = s;
@@ -290,16 +336,17 @@ __device__ __forceinline__ void attention_vote_proj_tile(const FwdParams &p, con
   }
 }
 
-template <int UP>
+template <int UP, typename ST>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
   using K = TCfg<UP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
   unsigned char *s_A = s_B + 3 * K::B_BYTES;                   // [2][3][A_BYTES]
-  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [5][PSTRIDE], z/r rows include b_rec
-  float *s_bh = s_P + 5 * K::PSTRIDE;                          // [UP] recurrent bias of the h gate
-  float *s_att = s_bh + UP;                                    // [UP][12]
-  float *s_score = s_att + UP * 12;                            // [16][T]
+  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [10][PSTRIDE]: rows 0..4 forward codes, 5..9
+                                                               // the complemented codes of the rc pass
+  float *s_bh = s_P + 10 * K::PSTRIDE;                         // [UP] recurrent bias of the h gate
+  float *s_scale = s_bh + UP;                                  // [UP] attention scale
+  float *s_score = s_scale + UP;                               // [16][T]
   __shared__ __align__(8) unsigned long long s_ready[2], s_done[2];
   __shared__ uint32_t s_tmem;
 
@@ -311,16 +358,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     const uint4 *src = reinterpret_cast<const uint4 *>(p.Bsplit);
     uint4 *dst = reinterpret_cast<uint4 *>(s_B);
     for (int i = tid; i < 3 * K::B_BYTES / 16; i += TC_THREADS) dst[i] = src[i];
-    for (int i = tid; i < 5 * K::PSTRIDE; i += TC_THREADS) {
-      const int c = i / K::PSTRIDE, j = i % K::PSTRIDE;
+    for (int i = tid; i < 10 * K::PSTRIDE; i += TC_THREADS) {
+      const int row = i / K::PSTRIDE, j = i % K::PSTRIDE;
+      const int code = row % 5;
+      const int c = (row >= 5 && code < 4) ? 3 - code : code;   // reverse complement: [3,2,1,0,4] (model.py:277)
       // (x.W + b_in) + b_rec for z and r; the h gate keeps b_rec inside r * (h.R + b_rec)
       float v = 0.f;
       if (j < 2 * UP) v = (p.P[c * 3 * UP + j] + p.b1[j]) * kNegLog2e;
       else if (j < 3 * UP) v = p.P[c * 3 * UP + j] * kTwoLog2e;
       s_P[i] = v;
     }
-    for (int i = tid; i < UP; i += TC_THREADS) s_bh[i] = p.b1[2 * UP + i] * kTwoLog2e;
-    stage_attention_table<UP, TC_THREADS>(p, s_att, tid);
+    for (int i = tid; i < UP; i += TC_THREADS) {
+      s_bh[i] = p.b1[2 * UP + i] * kTwoLog2e;
+      s_scale[i] = (p.attention && i < p.U) ? p.scale[i] : 0.f;
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -341,27 +392,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-
-  float *scratch0 = p.scratch + (size_t)blockIdx.x * 2 * K::WT * T * UP;
-  float *proj0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 16;   // [2][WT][T][16] h-projections
+  // 20 warps launch with 96 registers each; the issuer's warpgroup hands most of its share to the gate
+  // warps, whose loop otherwise spills.  ptxas budgets registers per role only when each role's whole
+  // code sits inside the setmaxnreg branch, so the two roles have their own copy of the unit loop and
+  // meet only through the mbarriers; the gate warps synchronise among themselves on named barrier 1.
+  const bool is_gate = warp < TC_GATE_WARPS;
+  const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]);
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
-  uint32_t phase[2] = {0u, 0u};   // parity to wait for next ("done" for gate warps, "ready" for the issuer)
+  // this CTA's contiguous tile range; the first `lead` units are single tiles (phase shift, see top)
+  const int64_t tile_lo = n_tiles * blockIdx.x / gridDim.x, tile_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int lead = (tile_hi - tile_lo >= 8) ? (int)(blockIdx.x & 3) : 0;
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP + 16, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
                          ((uint32_t)(128 >> 4) << 24);
 
-  for (int64_t pair = blockIdx.x; pair * 2 < n_tiles; pair += gridDim.x) {
-    const bool live[2] = {pair * 2 < n_tiles, pair * 2 + 1 < n_tiles};
-
-    if (warp == TC_GATE_WARPS) {
-      // ===================== MMA issuer =====================
-      for (int t = 0; t < T; ++t) {
+  if (!is_gate) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_AUX_REGS));
+    if (warp != TC_GATE_WARPS) return;   // the three idle warps of the issuer's warpgroup
+    uint32_t par[2] = {0u, 0u};   // barrier parity of each tile slot at the start of the unit
+    int unit = 0;
+    for (int64_t tile = tile_lo; tile < tile_hi; ++unit) {
+      const int nt = (unit < lead || tile + 1 >= tile_hi) ? 1 : 2;
+      const bool live1 = nt == 2;
+      // ===================== MMA issuer: T + 1 rounds per tile (round 0 = priming on h = 0) =====
+      for (int k = 0; k <= T; ++k) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          if (!live[s]) continue;
-          mbar_wait_backoff(smem_u32(&s_ready[s]), phase[s]);
-          phase[s] ^= 1u;
+          if (s == 1 && !live1) continue;
+          mbar_wait_backoff(bar_ready + 8 * s, par[s] ^ (k & 1));
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a0 = smem_u32(s_A + (size_t)s * 3 * K::A_BYTES), b0 = smem_u32(s_B);
@@ -379,164 +438,193 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
                 acc = 1;
               }
             }
-            umma_commit(smem_u32(&s_done[s]));
+            umma_commit(bar_done + 8 * s);
           }
           __syncwarp();
         }
       }
-    } else {
-      // ===================== gate warps =====================
-      const int quad = warp & 3, uq = warp >> 2;
-      const int row = quad * 32 + lane;        // row of the tile = TMEM lane
-      const int wl = row >> 1, dir = row & 1;  // window in tile, direction
-      int64_t wpos[2];
-      bool wvalid[2];
-      float hprev[2][K::UPT];
-      int code_next[2];
+      par[0] ^= (uint32_t)((T + 1) & 1);   // each live tile slot saw T + 1 phases of its barriers
+      if (live1) par[1] ^= (uint32_t)((T + 1) & 1);
+      tile += nt;
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_GATE_REGS));
+  ST *sum0 = reinterpret_cast<ST *>(p.scratch) + (size_t)blockIdx.x * 2 * K::WT * T * UP;         // [2][WT][T][UP]
+  float *proj0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 16;                                 // [2][WT][T][16]
+  float *q0 = p.qbuf + (size_t)blockIdx.x * 2 * K::WT * UP;                                       // [2][WT][UP]
+  uint32_t par[2] = {0u, 0u};
+  int unit = 0;
+  for (int64_t tile = tile_lo; tile < tile_hi; ++unit) {
+    const int nt = (unit < lead || tile + 1 >= tile_hi) ? 1 : 2;
+    const bool live1 = nt == 2;
+    {
+    // ===================== gate warps =====================
+    const int quad = warp & 3, uq = warp >> 2;
+    const int row = quad * 32 + lane;        // row of the tile = TMEM lane
+    const int wl = row >> 1, dir = row & 1;  // window in tile, direction
+    const float *tblp = s_P + dir * 5 * K::PSTRIDE + uq * K::UPT;
+    const float *bhp = s_bh + uq * K::UPT;
+    const uint32_t a_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + ((uq * K::UPT) >> 3) * 128);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int cstep = dir ? -1 : 1;
+    const uint8_t *cptr[2];   // the base this row reads next step
+    int code[2];
+    float hprev[2][K::UPT];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      // windows past the end replay the last valid one (their results are never used)
+      int64_t w = p.w_begin + (tile + s) * K::WT + wl;
+      w = w < p.w_end ? w : p.w_end - 1;
+      cptr[s] = p.codes + (w * (int64_t)p.step - p.codes_base) + (dir ? T - 1 : 0);
+      code[s] = 4;
+#pragma unroll
+      for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
+      if (s == 1 && !live1) continue;
+      code[s] = *cptr[s];
+      cptr[s] += cstep;
+      // h[-1] = 0: zero this thread's slots of the A operand and let the issuer prime the accumulator
+      unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES + a_off;
+#pragma unroll
+      for (int c8 = 0; c8 < K::UPT / 8; ++c8)
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc)
+          *reinterpret_cast<uint4 *>(a_tile + pc * K::A_BYTES + c8 * 128) = make_uint4(0u, 0u, 0u, 0u);
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(bar_ready + 8 * s);
+    }
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        const int64_t w = p.w_begin + (pair * 2 + s) * K::WT + wl;
-        wvalid[s] = live[s] && w < p.w_end;
-        wpos[s] = w * (int64_t)p.step - p.codes_base;
-#pragma unroll
-        for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
-        code_next[s] = 4;
-        if (wvalid[s]) {
-          const int c = p.codes[wpos[s] + (dir ? (T - 1) : 0)];
-          code_next[s] = (dir && c < 4) ? 3 - c : c;
+        if (s == 1 && !live1) continue;   // uniform over the CTA
+        const float *prow = tblp + code[s] * K::PSTRIDE;
+        if (t + 1 < T) {   // next step's base, consumed one iteration later
+          code[s] = *cptr[s];
+          cptr[s] += cstep;
         }
-      }
-      for (int t = 0; t < T; ++t) {
+        mbar_wait(bar_done + 8 * s, par[s] ^ (t & 1));
+        tc_fence_after();
+        const uint32_t t_tile = t_lane + (uint32_t)(s * K::TCOLS);
+        unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES + a_off;
+        const size_t rt = (size_t)(s * K::WT + wl) * T + t;   // (window, t) row of the scratch arrays
+        float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
+        tmem_ld4(t_tile + (uint32_t)(K::NG + 4 * uq), pj);
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (!live[s]) continue;   // uniform over the CTA
-          const int code = code_next[s];
-          if (t + 1 < T && wvalid[s]) {   // prefetch next step's base
-            const int c = p.codes[wpos[s] + (dir ? (T - 2 - t) : (t + 1))];
-            code_next[s] = (dir && c < 4) ? 3 - c : c;
+        for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
+          float az[8], ar[8], ah[8];
+          const uint32_t taddr = t_tile + (uint32_t)(uq * K::UPT + c8 * 8);
+          tmem_ld8(taddr, az);
+          tmem_ld8(taddr + UP, ar);
+          tmem_ld8(taddr + 2 * UP, ah);
+          tmem_ld_wait();
+          if (c8 == 0) {
+            // avg[t-1].K = h_fwd.(K/2) + h_rc.(K/2), stored by the fwd lane
+            float4 o;
+            o.x = pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1);
+            o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
+            o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
+            o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
+            if (dir == 0 && t > 0) *reinterpret_cast<float4 *>(proj0 + (rt - 1) * 16 + 4 * uq) = o;
           }
-          if (t > 0) {
-            mbar_wait(smem_u32(&s_done[s]), phase[s]);
-            phase[s] ^= 1u;
-            tc_fence_after();
+          float2 hn2[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const float4 xz = *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
+            const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
+            const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
+            const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int e = 4 * j4 + 2 * hlf;
+              const float2 hp = make_float2(hprev[s][c8 * 8 + e], hprev[s][c8 * 8 + e + 1]);
+              const float2 h = gru_cell2(hlf ? make_float2(xz.z, xz.w) : make_float2(xz.x, xz.y),
+                                         hlf ? make_float2(xr.z, xr.w) : make_float2(xr.x, xr.y),
+                                         hlf ? make_float2(xh.z, xh.w) : make_float2(xh.x, xh.y),
+                                         hlf ? make_float2(bh.z, bh.w) : make_float2(bh.x, bh.y),
+                                         make_float2(az[e], az[e + 1]), make_float2(ar[e], ar[e + 1]),
+                                         make_float2(ah[e], ah[e + 1]), hp);
+              hprev[s][c8 * 8 + e] = h.x;
+              hprev[s][c8 * 8 + e + 1] = h.y;
+              hn2[2 * j4 + hlf] = h;
+            }
           }
-          unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES;
-          float *avg_out = scratch0 + ((size_t)(s * K::WT + wl) * T + t) * UP;
-          const float *prow = s_P + code * K::PSTRIDE;
-          float pj[4];
-          if (t > 0)   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
-            tmem_ld4(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
+          // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
+          uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
-          for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
-            const int u0 = uq * K::UPT + c8 * 8;
-            float az[8], ar[8], ah[8];
-            if (t > 0) {
-              const uint32_t taddr =
-                  tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + u0);
-              tmem_ld8(taddr, az);
-              tmem_ld8(taddr + UP, ar);
-              tmem_ld8(taddr + 2 * UP, ah);
-              tmem_ld_wait();
-              if (c8 == 0) {
-                // avg[t-1].K = (h_fwd.K + h_rc.K) / 2, stored by the fwd lane
-                float4 o;
-                o.x = 0.5f * (pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1));
-                o.y = 0.5f * (pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1));
-                o.z = 0.5f * (pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1));
-                o.w = 0.5f * (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1));
-                if (dir == 0)
-                  *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (t - 1)) * 16 + 4 * uq) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { az[j] = 0.f; ar[j] = 0.f; ah[j] = 0.f; }
-            }
-            float2 hn2[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 2; ++j4) {
-              const float4 xz = *reinterpret_cast<const float4 *>(prow + u0 + 4 * j4);
-              const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + u0 + 4 * j4);
-              const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + u0 + 4 * j4);
-              const float4 bh = *reinterpret_cast<const float4 *>(s_bh + u0 + 4 * j4);
-#pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                const int e = 4 * j4 + 2 * hlf;
-                const float2 hp = make_float2(hprev[s][c8 * 8 + e], hprev[s][c8 * 8 + e + 1]);
-                const float2 h = gru_cell2(hlf ? make_float2(xz.z, xz.w) : make_float2(xz.x, xz.y),
-                                           hlf ? make_float2(xr.z, xr.w) : make_float2(xr.x, xr.y),
-                                           hlf ? make_float2(xh.z, xh.w) : make_float2(xh.x, xh.y),
-                                           hlf ? make_float2(bh.z, bh.w) : make_float2(bh.x, bh.y),
-                                           make_float2(az[e], az[e + 1]), make_float2(ar[e], ar[e + 1]),
-                                           make_float2(ah[e], ah[e + 1]), hp);
-                hprev[s][c8 * 8 + e] = h.x;
-                hprev[s][c8 * 8 + e + 1] = h.y;
-                hn2[2 * j4 + hlf] = h;
-              }
-            }
-            // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
-            uint32_t hi[4], mid[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
-            const int off = (row >> 3) * K::SBO + (u0 >> 3) * 128 + (row & 7) * 16;
-            *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-            *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            // avg[t] = (fwd[t] + rc[t]) / 2: the partner row is the neighbouring lane; the fwd lane
-            // stores units u0..u0+3, the rc lane u0+4..u0+7
-            float2 av2[2];
+          for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
+          *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+          *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (p.attention) {
+            // h_fwd[t] + h_rc[t]: the partner row is the neighbouring lane; the fwd lane stores
+            // units u0..u0+3, the rc lane u0+4..u0+7 (u0 = first unit of this block)
+            float2 sm2[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const float2 send = dir ? hn2[j] : hn2[j + 2];
               const float2 mine = dir ? hn2[j + 2] : hn2[j];
               const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 1),
                                               __shfl_xor_sync(0xffffffffu, send.y, 1));
-              av2[j] = __fmul2_rn(__fadd2_rn(mine, recv), make_float2(0.5f, 0.5f));
+              sm2[j] = __fadd2_rn(mine, recv);
             }
-            const float av[4] = {av2[0].x, av2[0].y, av2[1].x, av2[1].y};
-            *reinterpret_cast<float4 *>(avg_out + u0 + (dir ? 4 : 0)) = make_float4(av[0], av[1], av[2], av[3]);
+            const int u = uq * K::UPT + c8 * 8 + (dir ? 4 : 0);
+            if (sizeof(ST) == 2) {
+              const __half2 h0 = __floats2half2_rn(sm2[0].x, sm2[0].y), h1 = __floats2half2_rn(sm2[1].x, sm2[1].y);
+              *reinterpret_cast<uint2 *>(sum0 + rt * UP + u) =
+                  make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+            } else {
+              *reinterpret_cast<float4 *>(sum0 + rt * UP + u) = make_float4(sm2[0].x, sm2[0].y, sm2[1].x, sm2[1].y);
+            }
+            if (t == T - 1)   // the query avg[T-1] in full precision
+              *reinterpret_cast<float4 *>(q0 + (size_t)(s * K::WT + wl) * UP + u) =
+                  make_float4(0.5f * sm2[0].x, 0.5f * sm2[0].y, 0.5f * sm2[1].x, 0.5f * sm2[1].y);
           }
-          // hand the new A operand to the tensor core (the last step's MMA only feeds the projection)
-          tc_fence_before();
-          fence_async_smem();
-          mbar_arrive(smem_u32(&s_ready[s]));
         }
+        // hand the new A operand to the tensor core (the last step's MMA only feeds the projection)
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(bar_ready + 8 * s);
       }
-      // projection of the last state h[T-1]
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (!live[s]) continue;
-        mbar_wait(smem_u32(&s_done[s]), phase[s]);
-        phase[s] ^= 1u;
-        tc_fence_after();
-        float pj[4];
-        tmem_ld4(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
-        tmem_ld_wait();
-        float4 o;
-        o.x = 0.5f * (pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1));
-        o.y = 0.5f * (pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1));
-        o.z = 0.5f * (pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1));
-        o.w = 0.5f * (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1));
-        if (dir == 0)
-          *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (T - 1)) * 16 + 4 * uq) = o;
-      }
-      tc_fence_before();
     }
-    // ---- attention + FF + softmax + vote for both tiles (gate warps) -----------------------------
-    __threadfence_block();
-    __syncthreads();
+    // projection of the last state h[T-1]
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      if (!live[s]) continue;
-      attention_vote_proj_tile<UP, K::WT, TC_GATE_WARPS>(
-          p, scratch0 + (size_t)s * K::WT * T * UP, proj0 + (size_t)s * K::WT * T * 16,
-          p.w_begin + (pair * 2 + s) * K::WT, s_att, s_score);
+      if (s == 1 && !live1) continue;
+      mbar_wait(bar_done + 8 * s, par[s] ^ (T & 1));
+      tc_fence_after();
+      float pj[4];
+      tmem_ld4(t_lane + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
+      tmem_ld_wait();
+      float4 o;
+      o.x = pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1);
+      o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
+      o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
+      o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
+      if (dir == 0)
+        *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (T - 1)) * 16 + 4 * uq) = o;
     }
-    __syncthreads();
+    tc_fence_before();
+    }
+    par[0] ^= (uint32_t)((T + 1) & 1);
+    if (live1) par[1] ^= (uint32_t)((T + 1) & 1);
+    // ---- attention + FF + softmax + vote for the unit's tiles ------------------------------------
+    __threadfence_block();
+    gate_bar_sync();
+#pragma unroll 1
+    for (int s = 0; s < nt; ++s)
+      attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(
+          p, sum0 + (size_t)s * K::WT * T * UP, q0 + (size_t)s * K::WT * UP,
+          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, s_scale, s_score);
+    gate_bar_sync();
+    tile += nt;
   }
 
-  // ---- teardown ---------------------------------------------------------------------------------
+  // ---- teardown (the last "done" wait of every tile saw its MMAs complete) -----------------------
   tc_fence_before();
-  __syncthreads();
+  gate_bar_sync();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(2 * K::TCOLS)
@@ -548,24 +636,26 @@ template <int UP>
 static size_t tc_smem_bytes(int T) {
   using K = TCfg<UP>;
   return (size_t)3 * K::B_BYTES + 6 * K::A_BYTES +
-         sizeof(float) * ((size_t)5 * K::PSTRIDE + UP + (size_t)UP * 12 + TC_GATE_WARPS * (size_t)T) + 128;
+         sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + TC_GATE_WARPS * (size_t)T) + 128;
 }
 
-template <int UP>
+template <int UP, typename ST>
 static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = TCfg<UP>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
   const size_t smem = tc_smem_bytes<UP>(p.T);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
-  auto kern = gru_tc_attention_vote_kernel<UP>;
+  auto kern = gru_tc_attention_vote_kernel<UP, ST>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < c->sm_count ? n_pairs : c->sm_count);
-  DGRP_CHECK(c->avg.reserve((size_t)grid * 2 * K::WT * p.T * UP * sizeof(float)));
-  DGRP_CHECK(c->io_c.reserve((size_t)grid * 2 * K::WT * p.T * 16 * sizeof(float)));
+  const size_t rows = (size_t)grid * 2 * K::WT;   // window slots in flight
+  DGRP_CHECK(c->avg.reserve(rows * p.T * UP * sizeof(ST) + rows * UP * sizeof(float)));
+  DGRP_CHECK(c->io_c.reserve(rows * p.T * 16 * sizeof(float)));
   p.scratch = c->avg.as<float>();
+  p.qbuf = reinterpret_cast<float *>(c->avg.as<unsigned char>() + rows * p.T * UP * sizeof(ST));
   p.ff2 = c->io_c.as<float>();
   kern<<<grid, TC_THREADS, smem, c->stream>>>(p);
   c->launches++;
@@ -579,8 +669,8 @@ int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   if (!m->d_Bsplit) return DGRP_E_UNSUPPORTED;
   p.Bsplit = m->d_Bsplit;
   switch (m->UP) {
-    case 32: return launch_tc_t<32>(c, m, p);
-    case 64: return launch_tc_t<64>(c, m, p);
+    case 32: return c->forward_sum16 ? launch_tc_t<32, __half>(c, m, p) : launch_tc_t<32, float>(c, m, p);
+    case 64: return c->forward_sum16 ? launch_tc_t<64, __half>(c, m, p) : launch_tc_t<64, float>(c, m, p);
     default: return DGRP_E_UNSUPPORTED;
   }
 }

@@ -77,7 +77,10 @@ int dgrp_ctx_timings(dgrp_ctx *ctx, dgrp_timings_t *out);
 int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
 /* tuning knobs and diagnostics: "mss_chunk" (elements per MSS scan chunk, 0 = automatic),
  * "mss_max_rounds" (parallel rounds before the sequential completion), "forward_tc" (1 = tcgen05
- * recurrence where available, 0 = fp32 kernel), "shard_rank" / "shard_world" (contig sharding of
+ * recurrence where available, 0 = fp32 kernel), "forward_sum16" (tcgen05 forward: 1 = the
+ * h_fwd + h_rc scratch that feeds the attention scores is kept in half precision [default; a
+ * probability moves by <= 3e-5 on sharp-attention weights and ~1e-7 on random-init ones], 0 = in
+ * float32 [+8 % forward time]), "shard_rank" / "shard_world" (contig sharding of
  * dgrp_predict_fasta*: records are assigned largest-first to the least loaded rank; a rank
  * computes only its own records), and read-only "mss_rounds" (rounds the last MSS call used;
  * negative = completed sequentially), "forward_used_tc", "sm_count". */

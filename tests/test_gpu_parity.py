@@ -278,7 +278,7 @@ def test_predict_generic_route_equals_fused(dg):
             return w.predict_on_batch(batch)
     generic = dg.pred.predict(Wrapped(), iter(ds), (fwd.shape[1], 5), 50)
     # the fused call runs the tcgen05 recurrence, predict_on_batch the fp32 FFMA kernel
-    assert np.abs(fused - generic).max() < 2e-6
+    assert np.abs(fused - generic).max() < 2e-5   # random-init weights; half-precision score scratch
     assert np.array_equal(fused == 0, generic == 0)
     dg.ctx.set_int("forward_tc", 0)
     try:
@@ -288,18 +288,41 @@ def test_predict_generic_route_equals_fused(dg):
     assert np.array_equal(fused_fp32, generic)      # same kernel arithmetic: bit-identical
 
 
+@pytest.mark.parametrize("sum16", [0, 1])
 @pytest.mark.parametrize("T,U", [(150, 32), (342, 60), (64, 16), (100, 50)])
-def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U):
-    """tcgen05 (bf16 x3 split) and fp32 FFMA forwards against the float64 oracle: both within the
-    float32 oracle's own distance from float64 (a few 1e-7), labels identical."""
+def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U, sum16):
+    """tcgen05 forward (bf16 x3 split) against the float64 oracle on x4-scaled weights (sharp
+    attention, all classes present).  With the h_fwd + h_rc scratch in float32 (`forward_sum16=0`) it
+    stays within the float32 oracle's own distance from float64 (a few 1e-6 here); the default half
+    precision scratch only perturbs the attention scores: <= 1e-4 on a probability (north_star's bar
+    is 1e-3), labels identical to 1e-4."""
     w = dg.model.random_weights(T, U, attention=True, seed=7).scaled(4.0)
     st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(12_000, T + U))
     ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
-    tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    dg.ctx.set_int("forward_sum16", sum16)
+    try:
+        tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    finally:
+        dg.ctx.set_int("forward_sum16", 1)
     assert dg.ctx.get_int("forward_used_tc") == 1
     ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
                            oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
-    assert np.abs(tc - ref64).max() < 5e-6
+    assert np.abs(tc - ref64).max() < (1e-4 if sum16 else 5e-6)
+    assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
+
+
+def test_tensor_core_forward_random_init_regime(dg, oracle):
+    """The benchmark's regime (random-init weights, near-uniform outputs, class margins ~1e-4): the
+    default forward must be float32-faithful there, or labels flip."""
+    T, U = 342, 60
+    w = dg.model.random_weights(T, U, attention=True, seed=0)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(20_000, 77))
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    assert dg.ctx.get_int("forward_used_tc") == 1 and dg.ctx.get_int("forward_sum16") == 1
+    ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
+                           oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
+    assert np.abs(tc - ref64).max() < 1e-6
     assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
 
 
