@@ -177,26 +177,48 @@ __device__ __forceinline__ void split3(float2 ab, uint32_t &hi, uint32_t &mid, u
   lo = *reinterpret_cast<uint32_t *>(&l2);
 }
 
-// One GRU cell update for two units at once (packed fp32x2 arithmetic: FADD2 / FMUL2 / FFMA2 issue one
-// instruction per pair, with the same IEEE rounding as the scalar forms).  The accumulator and table
+// GRU cell update for four units at once.  Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 issue one
+// instruction per pair, with the same IEEE rounding as the scalar forms); the accumulator and table
 // values arrive pre-scaled (z, r by -log2 e; h by 2 log2 e):
-//   z = 1/(1+2^sz), r = 1/(1+2^sr) with ONE reciprocal (z = b/(ab), r = a/(ab); the clamp at 57.7 is
-//   x >= -40 and keeps a*b finite), hh = tanh = 1 - 2/(2^arg + 1), h' = hh + z (h - hh).
-__device__ __forceinline__ float2 gru_cell2(float2 xz, float2 xr, float2 xh, float2 bh, float2 az,
-                                            float2 ar, float2 ah, float2 hp) {
+//   z = 1/(1+2^sz) = 1/A, r = 1/(1+2^sr) = 1/B, hh = tanh = 1 - 2/D with D = 2^arg + 1, h' = hh + z (h - hh).
+// The MUFU pipe (16 lanes/clk/SM) is what bounds this kernel, so reciprocals are shared: the four
+// sigmoid denominators of two units cost ONE rcp (1/(A0 B0 A1 B1), then multiplied back), and so
+// do the four tanh denominators of the quad: 3 ex2 + 0.75 rcp per unit instead of 3 + 2.  The clamps
+// keep the products finite: sz, sr <= 28.85 is x >= -20 (sigmoid error < 2.1e-9), arg <= 30 is
+// tanh = 1 - 2/(2^30 + 1), which rounds to 1.
+__device__ __forceinline__ void sigmoid_pair(float2 sz, float2 sr, float2 &z, float2 &r) {
   const float2 one = make_float2(1.0f, 1.0f);
-  float2 sz = __fadd2_rn(xz, az), sr = __fadd2_rn(xr, ar);
-  const float2 ez = make_float2(ex2_approx(fminf(sz.x, 57.7f)), ex2_approx(fminf(sz.y, 57.7f)));
-  const float2 er = make_float2(ex2_approx(fminf(sr.x, 57.7f)), ex2_approx(fminf(sr.y, 57.7f)));
+  const float2 ez = make_float2(ex2_approx(fminf(sz.x, 28.85f)), ex2_approx(fminf(sz.y, 28.85f)));
+  const float2 er = make_float2(ex2_approx(fminf(sr.x, 28.85f)), ex2_approx(fminf(sr.y, 28.85f)));
   const float2 a = __fadd2_rn(ez, one), b = __fadd2_rn(er, one);
   const float2 ab = __fmul2_rn(a, b);
-  const float2 inv = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
-  const float2 z = __fmul2_rn(inv, b), r = __fmul2_rn(inv, a);
-  const float2 targ = __ffma2_rn(r, __fadd2_rn(ah, bh), xh);
-  const float2 den = __fadd2_rn(make_float2(ex2_approx(targ.x), ex2_approx(targ.y)), one);
-  const float2 hh = __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(rcp_approx(den.x), rcp_approx(den.y)), one);
-  const float2 d = __ffma2_rn(hh, make_float2(-1.0f, -1.0f), hp);      // h - hh
-  return __ffma2_rn(z, d, hh);
+  const float inv = rcp_approx(ab.x * ab.y);
+  const float2 iab = make_float2(inv * ab.y, inv * ab.x);   // 1/(a.x b.x), 1/(a.y b.y)
+  z = __fmul2_rn(iab, b);
+  r = __fmul2_rn(iab, a);
+}
+__device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, const float4 xh, const float4 bh,
+                                          const float *az, const float *ar, const float *ah, float *hp,
+                                          float2 &h01, float2 &h23) {
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 z0, r0, z1, r1;
+  sigmoid_pair(__fadd2_rn(make_float2(xz.x, xz.y), make_float2(az[0], az[1])),
+               __fadd2_rn(make_float2(xr.x, xr.y), make_float2(ar[0], ar[1])), z0, r0);
+  sigmoid_pair(__fadd2_rn(make_float2(xz.z, xz.w), make_float2(az[2], az[3])),
+               __fadd2_rn(make_float2(xr.z, xr.w), make_float2(ar[2], ar[3])), z1, r1);
+  const float2 t0 = __ffma2_rn(r0, __fadd2_rn(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y)), make_float2(xh.x, xh.y));
+  const float2 t1 = __ffma2_rn(r1, __fadd2_rn(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w)), make_float2(xh.z, xh.w));
+  const float2 d0 = __fadd2_rn(make_float2(ex2_approx(fminf(t0.x, 30.0f)), ex2_approx(fminf(t0.y, 30.0f))), one);
+  const float2 d1 = __fadd2_rn(make_float2(ex2_approx(fminf(t1.x, 30.0f)), ex2_approx(fminf(t1.y, 30.0f))), one);
+  const float2 m = __fmul2_rn(d0, d1);              // {d0.x d1.x, d0.y d1.y}
+  const float inv = rcp_approx(m.x * m.y);
+  const float2 j = make_float2(inv * m.y, inv * m.x);
+  const float2 i0 = __fmul2_rn(j, d1), i1 = __fmul2_rn(j, d0);   // 1/d0, 1/d1
+  const float2 m2 = make_float2(-2.0f, -2.0f), neg1 = make_float2(-1.0f, -1.0f);
+  const float2 hh0 = __ffma2_rn(m2, i0, one), hh1 = __ffma2_rn(m2, i1, one);
+  h01 = __ffma2_rn(z0, __ffma2_rn(hh0, neg1, make_float2(hp[0], hp[1])), hh0);   // hh + z (h - hh)
+  h23 = __ffma2_rn(z1, __ffma2_rn(hh1, neg1, make_float2(hp[2], hp[3])), hh1);
+  hp[0] = h01.x; hp[1] = h01.y; hp[2] = h23.x; hp[3] = h23.y;
 }
 
 // Second phase for one tile: additive attention scores with lanes over the units (8 units per lane,
@@ -402,7 +424,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   // this CTA's contiguous tile range; the first `lead` units are single tiles (phase shift, see top)
   const int64_t tile_lo = n_tiles * blockIdx.x / gridDim.x, tile_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
-  const int lead = (tile_hi - tile_lo >= 8) ? (int)(blockIdx.x & 3) : 0;
+  const int64_t my_tiles = tile_hi - tile_lo;   // a single-tile unit costs ~3/4 of a period for half the work
+  const int lead = my_tiles >= 32 ? (int)(blockIdx.x & 3) : (my_tiles >= 16 ? (int)(blockIdx.x & 1) : 0);
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP + 16, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
                          ((uint32_t)(128 >> 4) << 24);
@@ -536,20 +559,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
             const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
             const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-              const int e = 4 * j4 + 2 * hlf;
-              const float2 hp = make_float2(hprev[s][c8 * 8 + e], hprev[s][c8 * 8 + e + 1]);
-              const float2 h = gru_cell2(hlf ? make_float2(xz.z, xz.w) : make_float2(xz.x, xz.y),
-                                         hlf ? make_float2(xr.z, xr.w) : make_float2(xr.x, xr.y),
-                                         hlf ? make_float2(xh.z, xh.w) : make_float2(xh.x, xh.y),
-                                         hlf ? make_float2(bh.z, bh.w) : make_float2(bh.x, bh.y),
-                                         make_float2(az[e], az[e + 1]), make_float2(ar[e], ar[e + 1]),
-                                         make_float2(ah[e], ah[e + 1]), hp);
-              hprev[s][c8 * 8 + e] = h.x;
-              hprev[s][c8 * 8 + e + 1] = h.y;
-              hn2[2 * j4 + hlf] = h;
-            }
+            gru_cell4(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4, &hprev[s][c8 * 8 + 4 * j4],
+                      hn2[2 * j4], hn2[2 * j4 + 1]);
           }
           // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
           uint32_t hi[4], mid[4], lo[4];
