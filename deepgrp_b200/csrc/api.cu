@@ -7,6 +7,9 @@
 
 #include <algorithm>
 
+#include <cuda_fp16.h>
+#include <cmath>
+
 #include "dgrp_internal.cuh"
 
 namespace dgrp {
@@ -244,6 +247,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
+  else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -255,6 +259,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
   else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
+  else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -450,7 +455,8 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       for (int u = 0; u < U; ++u)
         Rp[((size_t)k * G + g) * UP + u] = recurrent[(size_t)k * G * U + g * U + u];
   // bf16 hi|mid|lo pieces of recurrent^T in the tcgen05 operand layout (forward_tc.cu)
-  std::vector<uint16_t> Bs;
+  std::vector<uint16_t> Bs, Bh;
+  int b16_shift = 0;
   if (UP <= 64 && rnn == 0) {
     const int N = 3 * UP + 16, SBO = (UP / 8) * 128;   // 16 extra rows: FF kernel halves (forward_tc.cu)
     const bool att = att_scale != nullptr;
@@ -468,20 +474,26 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       memcpy(&f, &u, 4);
       return f;
     };
+    // x(n, k): column n of [R | K/2] (pre-scaled gate columns, halved projection columns), row k
+    auto entry = [&](int n, int k) -> float {
+      if (n < 3 * UP) {
+        // gate columns are pre-scaled so that the accumulator feeds ex2 directly (forward_tc.cu)
+        const int g = n / UP, u = n % UP;
+        return Rp[((size_t)k * G + g) * UP + u] * (g < 2 ? -1.4426950408889634f : 2.8853900817779268f);
+      }
+      if (k >= U) return 0.f;
+      const int j = n - 3 * UP;          // 0..4: ctx half (attention only), 8..12: avg half
+      // halved: the kernel adds the projections of the two directions, avg.K = h_fwd.K/2 + h_rc.K/2
+      if (j < 5 && j < n_classes && att) return 0.5f * ff_kernel[(size_t)k * n_classes + j];
+      if (j >= 8 && j - 8 < n_classes && j < 13)
+        return 0.5f * ff_kernel[(size_t)((att ? U : 0) + k) * n_classes + (j - 8)];
+      return 0.f;
+    };
+    float bmax = 0.f;
     for (int n = 0; n < N; ++n)
       for (int k = 0; k < UP; ++k) {
-        float x = 0.f;
-        if (n < 3 * UP) {
-          // gate columns are pre-scaled so that the accumulator feeds ex2 directly (forward_tc.cu)
-          const int g = n / UP, u = n % UP;
-          x = Rp[((size_t)k * G + g) * UP + u] * (g < 2 ? -1.4426950408889634f : 2.8853900817779268f);
-        } else if (k < U) {
-          const int j = n - 3 * UP;          // 0..4: ctx half (attention only), 8..12: avg half
-          // halved: the kernel adds the projections of the two directions, avg.K = h_fwd.K/2 + h_rc.K/2
-          if (j < 5 && j < n_classes && att) x = 0.5f * ff_kernel[(size_t)k * n_classes + j];
-          else if (j >= 8 && j - 8 < n_classes && j < 13)
-            x = 0.5f * ff_kernel[(size_t)((att ? U : 0) + k) * n_classes + (j - 8)];
-        }
+        const float x = entry(n, k);
+        bmax = std::fmax(bmax, std::fabs(x));
         const uint16_t hi = f2bf(x);
         const float r1 = x - bf2f(hi);
         const uint16_t mid = f2bf(r1);
@@ -492,10 +504,30 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
         Bs[(size_t)N * UP + off] = mid;
         Bs[(size_t)2 * N * UP + off] = lo;
       }
+    // fp16 hi|lo of the same matrix times 2^shift (largest entry just below 2^14, so that the low
+    // pieces of all but negligible entries are normal half-precision numbers)
+    if (bmax > 0.f && std::isfinite(bmax)) {
+      int e = 0;
+      std::frexp(bmax, &e);             // bmax = f * 2^e, f in [0.5, 1)
+      b16_shift = 14 - e;
+      if (b16_shift > 24) b16_shift = 24;
+      if (b16_shift < -24) b16_shift = -24;
+    }
+    Bh.assign((size_t)2 * N * UP, 0);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < UP; ++k) {
+        const float x = std::ldexp(entry(n, k), b16_shift);
+        const __half hi = __float2half_rn(x);
+        const __half lo = __float2half_rn(x - __half2float(hi));
+        const size_t off = ((size_t)(n / 8) * SBO + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2;
+        memcpy(&Bh[off], &hi, 2);
+        memcpy(&Bh[(size_t)N * UP + off], &lo, 2);
+      }
   }
   dgrp_model *m = new dgrp_model();
   m->device = c->device; m->rnn = rnn; m->T = vecsize; m->U = U; m->C = n_classes; m->UP = UP;
   m->attention = att_scale != nullptr;
+  m->b16_shift = b16_shift;
   const int F = m->attention ? 2 * U : U;
   auto up = [&](float **dst, const float *src, size_t count) -> int {
     DGRP_CUDA(cudaMalloc((void **)dst, count * sizeof(float)));
@@ -510,7 +542,9 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       (rc = up(&m->d_ffb, ff_bias, (size_t)n_classes)) ||
       (m->attention && (rc = up(&m->d_scale, att_scale, (size_t)U))) ||
       (!Bs.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit),
-                               reinterpret_cast<const float *>(Bs.data()), Bs.size() / 2)))) {
+                               reinterpret_cast<const float *>(Bs.data()), Bs.size() / 2))) ||
+      (!Bh.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit16),
+                               reinterpret_cast<const float *>(Bh.data()), Bh.size() / 2)))) {
     cudaStreamSynchronize(c->stream);
     dgrp_model_destroy(m);
     return rc;
@@ -528,6 +562,7 @@ int dgrp_model_destroy(dgrp_model *m) {
   for (float *p : ptrs)
     if (p) cudaFree(p);
   if (m->d_Bsplit) cudaFree(m->d_Bsplit);
+  if (m->d_Bsplit16) cudaFree(m->d_Bsplit16);
   delete m;
   return DGRP_OK;
 }

@@ -73,6 +73,8 @@ struct dgrp_model {
   float *d_Rp = nullptr;         // [UP, 3, UP] recurrent[k, g*U+u], zero padded
   float *d_b1 = nullptr;         // [3, UP]     bias[1, g*U+u], zero padded
   uint16_t *d_Bsplit = nullptr;  // [3][3UP x UP] bf16 hi|mid|lo of recurrent^T, UMMA K-major core matrices
+  uint16_t *d_Bsplit16 = nullptr;  // [2][..] fp16 hi|lo of (recurrent^T * 2^b16_shift), same layout
+  int b16_shift = 0;
   float *d_scale = nullptr;      // [U] or null
   float *d_ffk = nullptr;        // [F, C]
   float *d_ffb = nullptr;        // [C]
@@ -95,6 +97,7 @@ struct dgrp_ctx {
   int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
   int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
   int forward_sum16 = 1;   // tcgen05 forward: keep h_fwd + h_rc (attention scores only) in half precision
+  int forward_fp16x2 = 1;  // tcgen05 forward: operands as 2 fp16 pieces / 3 products instead of 3 bf16 pieces / 6 products
   int forward_used_tc = 0; // what the last forward launch used
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;

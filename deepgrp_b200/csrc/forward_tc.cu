@@ -177,6 +177,19 @@ __device__ __forceinline__ void split3(float2 ab, uint32_t &hi, uint32_t &mid, u
   lo = *reinterpret_cast<uint32_t *>(&l2);
 }
 
+// fp16 x2 form: (a, b) * 2^8 = hi + lo in half-precision pieces (11 + 11 significant bits; the scale keeps
+// the low piece a normal number for every |h| > 5e-4 and exact-to-2^-33 below)
+constexpr float kStateScale = 256.0f;
+__device__ __forceinline__ void split2h(float2 ab, uint32_t &hi, uint32_t &lo) {
+  const float2 x = __fmul2_rn(ab, make_float2(kStateScale, kStateScale));
+  const __half2 h2 = __floats2half2_rn(x.x, x.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h2);
+  const float2 hf = __half22float2(h2);
+  const float2 r = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), x);
+  const __half2 l2 = __floats2half2_rn(r.x, r.y);
+  lo = *reinterpret_cast<const uint32_t *>(&l2);
+}
+
 // GRU cell update for four units at once.  Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 issue one
 // instruction per pair, with the same IEEE rounding as the scalar forms); the accumulator and table
 // values arrive pre-scaled (z, r by -log2 e; h by 2 log2 e):
@@ -197,17 +210,24 @@ __device__ __forceinline__ void sigmoid_pair(float2 sz, float2 sr, float2 &z, fl
   z = __fmul2_rn(iab, b);
   r = __fmul2_rn(iab, a);
 }
+// SCALED: the accumulator holds (state scale * weight scale) h.R and is multiplied by `us` on the way in
+// (an FFMA2 in place of the FADD2, so the scaling is free).
+template <bool SCALED>
+__device__ __forceinline__ float2 acc_add(float2 acc, float2 x, float2 us) {
+  return SCALED ? __ffma2_rn(acc, us, x) : __fadd2_rn(x, acc);
+}
+template <bool SCALED>
 __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, const float4 xh, const float4 bh,
                                           const float *az, const float *ar, const float *ah, float *hp,
-                                          float2 &h01, float2 &h23) {
+                                          float2 us, float2 &h01, float2 &h23) {
   const float2 one = make_float2(1.0f, 1.0f);
   float2 z0, r0, z1, r1;
-  sigmoid_pair(__fadd2_rn(make_float2(xz.x, xz.y), make_float2(az[0], az[1])),
-               __fadd2_rn(make_float2(xr.x, xr.y), make_float2(ar[0], ar[1])), z0, r0);
-  sigmoid_pair(__fadd2_rn(make_float2(xz.z, xz.w), make_float2(az[2], az[3])),
-               __fadd2_rn(make_float2(xr.z, xr.w), make_float2(ar[2], ar[3])), z1, r1);
-  const float2 t0 = __ffma2_rn(r0, __fadd2_rn(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y)), make_float2(xh.x, xh.y));
-  const float2 t1 = __ffma2_rn(r1, __fadd2_rn(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w)), make_float2(xh.z, xh.w));
+  sigmoid_pair(acc_add<SCALED>(make_float2(az[0], az[1]), make_float2(xz.x, xz.y), us),
+               acc_add<SCALED>(make_float2(ar[0], ar[1]), make_float2(xr.x, xr.y), us), z0, r0);
+  sigmoid_pair(acc_add<SCALED>(make_float2(az[2], az[3]), make_float2(xz.z, xz.w), us),
+               acc_add<SCALED>(make_float2(ar[2], ar[3]), make_float2(xr.z, xr.w), us), z1, r1);
+  const float2 t0 = __ffma2_rn(r0, acc_add<SCALED>(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y), us), make_float2(xh.x, xh.y));
+  const float2 t1 = __ffma2_rn(r1, acc_add<SCALED>(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w), us), make_float2(xh.z, xh.w));
   const float2 d0 = __fadd2_rn(make_float2(ex2_approx(fminf(t0.x, 30.0f)), ex2_approx(fminf(t0.y, 30.0f))), one);
   const float2 d1 = __fadd2_rn(make_float2(ex2_approx(fminf(t1.x, 30.0f)), ex2_approx(fminf(t1.y, 30.0f))), one);
   const float2 m = __fmul2_rn(d0, d1);              // {d0.x d1.x, d0.y d1.y}
@@ -358,13 +378,16 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
   }
 }
 
-template <int UP, typename ST>
+// NP = 3: bf16 hi|mid|lo pieces, 6 products (fp32-faithful).  NP = 2: fp16 hi|lo pieces of the scaled
+// operands, 3 products (hi.hi + hi.lo + lo.hi, relative error ~2^-21 per product): half the tensor
+// work, half the operand traffic out of shared memory.
+template <int UP, typename ST, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
   using K = TCfg<UP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
-  unsigned char *s_A = s_B + 3 * K::B_BYTES;                   // [2][3][A_BYTES]
-  float *s_P = reinterpret_cast<float *>(s_A + 6 * K::A_BYTES);  // [10][PSTRIDE]: rows 0..4 forward codes, 5..9
+  unsigned char *s_A = s_B + NP * K::B_BYTES;                  // [2][NP][A_BYTES]
+  float *s_P = reinterpret_cast<float *>(s_A + 2 * NP * K::A_BYTES);  // [10][PSTRIDE]: rows 0..4 forward codes, 5..9
                                                                // the complemented codes of the rc pass
   float *s_bh = s_P + 10 * K::PSTRIDE;                         // [UP] recurrent bias of the h gate
   float *s_scale = s_bh + UP;                                  // [UP] attention scale
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.Bsplit);
     uint4 *dst = reinterpret_cast<uint4 *>(s_B);
-    for (int i = tid; i < 3 * K::B_BYTES / 16; i += TC_THREADS) dst[i] = src[i];
+    for (int i = tid; i < NP * K::B_BYTES / 16; i += TC_THREADS) dst[i] = src[i];
     for (int i = tid; i < 10 * K::PSTRIDE; i += TC_THREADS) {
       const int row = i / K::PSTRIDE, j = i % K::PSTRIDE;
       const int code = row % 5;
@@ -427,7 +450,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   const int64_t my_tiles = tile_hi - tile_lo;   // a single-tile unit costs ~3/4 of a period for half the work
   const int lead = my_tiles >= 32 ? (int)(blockIdx.x & 3) : (my_tiles >= 16 ? (int)(blockIdx.x & 1) : 0);
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = 3*UP + 16, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K::N >> 3) << 17) |
+  const uint32_t ab_fmt = NP == 3 ? 1u : 0u;   // operand format: 1 = bf16, 0 = fp16
+  const uint32_t idesc = (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(K::N >> 3) << 17) |
                          ((uint32_t)(128 >> 4) << 24);
 
   if (!is_gate) {
@@ -446,13 +470,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
           mbar_wait_backoff(bar_ready + 8 * s, par[s] ^ (k & 1));
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a0 = smem_u32(s_A + (size_t)s * 3 * K::A_BYTES), b0 = smem_u32(s_B);
+            const uint32_t a0 = smem_u32(s_A + (size_t)s * NP * K::A_BYTES), b0 = smem_u32(s_B);
             const uint32_t d = tmem_base + (uint32_t)(s * K::TCOLS);
             // (A piece, B piece), smallest products first: lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi
-            const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+            // (fp16 x2: lo.hi, hi.lo, hi.hi)
+            const int pa[6] = {NP == 3 ? 2 : 1, 0, NP == 3 ? 1 : 0, 1, 0, 0};
+            const int pb[6] = {0, NP == 3 ? 2 : 1, NP == 3 ? 1 : 0, 0, 1, 0};
             uint32_t acc = 0;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
+            for (int q = 0; q < (NP == 3 ? 6 : 3); ++q) {
 #pragma unroll
               for (int kc = 0; kc < UP / 16; ++kc) {
                 const uint64_t ad = umma_desc(a0 + pa[q] * K::A_BYTES + kc * 256, 128, K::SBO);
@@ -477,6 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   ST *sum0 = reinterpret_cast<ST *>(p.scratch) + (size_t)blockIdx.x * 2 * K::WT * T * UP;         // [2][WT][T][UP]
   float *proj0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 16;                                 // [2][WT][T][16]
   float *q0 = p.qbuf + (size_t)blockIdx.x * 2 * K::WT * UP;                                       // [2][WT][UP]
+  const float2 us = make_float2(p.b_unscale, p.b_unscale);
   uint32_t par[2] = {0u, 0u};
   int unit = 0;
   for (int64_t tile = tile_lo; tile < tile_hi; ++unit) {
@@ -508,11 +535,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       code[s] = *cptr[s];
       cptr[s] += cstep;
       // h[-1] = 0: zero this thread's slots of the A operand and let the issuer prime the accumulator
-      unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES + a_off;
+      unsigned char *a_tile = s_A + (size_t)s * NP * K::A_BYTES + a_off;
 #pragma unroll
       for (int c8 = 0; c8 < K::UPT / 8; ++c8)
 #pragma unroll
-        for (int pc = 0; pc < 3; ++pc)
+        for (int pc = 0; pc < NP; ++pc)
           *reinterpret_cast<uint4 *>(a_tile + pc * K::A_BYTES + c8 * 128) = make_uint4(0u, 0u, 0u, 0u);
       tc_fence_before();
       fence_async_smem();
@@ -531,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
         mbar_wait(bar_done + 8 * s, par[s] ^ (t & 1));
         tc_fence_after();
         const uint32_t t_tile = t_lane + (uint32_t)(s * K::TCOLS);
-        unsigned char *a_tile = s_A + (size_t)s * 3 * K::A_BYTES + a_off;
+        unsigned char *a_tile = s_A + (size_t)s * NP * K::A_BYTES + a_off;
         const size_t rt = (size_t)(s * K::WT + wl) * T + t;   // (window, t) row of the scratch arrays
         float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
         tmem_ld4(t_tile + (uint32_t)(K::NG + 4 * uq), pj);
@@ -550,6 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
             o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
             o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
+            if (NP == 2) { o.x *= us.x; o.y *= us.x; o.z *= us.x; o.w *= us.x; }
             if (dir == 0 && t > 0) *reinterpret_cast<float4 *>(proj0 + (rt - 1) * 16 + 4 * uq) = o;
           }
           float2 hn2[4];
@@ -559,16 +587,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
             const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
             const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
-            gru_cell4(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4, &hprev[s][c8 * 8 + 4 * j4],
-                      hn2[2 * j4], hn2[2 * j4 + 1]);
+            gru_cell4<NP == 2>(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4,
+                               &hprev[s][c8 * 8 + 4 * j4], us, hn2[2 * j4], hn2[2 * j4 + 1]);
           }
           // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
           uint32_t hi[4], mid[4], lo[4];
+          if (NP == 3) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
-          *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-          *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
+            *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split2h(hn2[j], hi[j], lo[j]);
+            *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
           if (p.attention) {
             // h_fwd[t] + h_rc[t]: the partner row is the neighbouring lane; the fwd lane stores
             // units u0..u0+3, the rc lane u0+4..u0+7 (u0 = first unit of this block)
@@ -614,6 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
       o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
       o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
+      if (NP == 2) { o.x *= us.x; o.y *= us.x; o.z *= us.x; o.w *= us.x; }
       if (dir == 0)
         *reinterpret_cast<float4 *>(proj0 + ((size_t)(s * K::WT + wl) * T + (T - 1)) * 16 + 4 * uq) = o;
     }
@@ -643,21 +679,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   }
 }
 
-template <int UP>
+template <int UP, int NP>
 static size_t tc_smem_bytes(int T) {
   using K = TCfg<UP>;
-  return (size_t)3 * K::B_BYTES + 6 * K::A_BYTES +
+  return (size_t)NP * K::B_BYTES + 2 * NP * K::A_BYTES +
          sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + TC_GATE_WARPS * (size_t)T) + 128;
 }
 
-template <int UP, typename ST>
+template <int UP, typename ST, int NP>
 static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = TCfg<UP>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
-  const size_t smem = tc_smem_bytes<UP>(p.T);
+  const size_t smem = tc_smem_bytes<UP, NP>(p.T);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
-  auto kern = gru_tc_attention_vote_kernel<UP, ST>;
+  auto kern = gru_tc_attention_vote_kernel<UP, ST, NP>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_pairs = (n_tiles + 1) / 2;
@@ -676,12 +712,20 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
 
 // Returns DGRP_E_UNSUPPORTED when this model/shape has no tcgen05 form (the caller then uses the
 // fp32 kernel): units > 64, or a window too long for the score buffer in shared memory.
+template <int UP>
+static int launch_tc_up(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+  if (c->forward_fp16x2)
+    return c->forward_sum16 ? launch_tc_t<UP, __half, 2>(c, m, p) : launch_tc_t<UP, float, 2>(c, m, p);
+  return c->forward_sum16 ? launch_tc_t<UP, __half, 3>(c, m, p) : launch_tc_t<UP, float, 3>(c, m, p);
+}
+
 int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
-  if (!m->d_Bsplit) return DGRP_E_UNSUPPORTED;
-  p.Bsplit = m->d_Bsplit;
+  if (!m->d_Bsplit || !m->d_Bsplit16) return DGRP_E_UNSUPPORTED;
+  p.Bsplit = c->forward_fp16x2 ? m->d_Bsplit16 : m->d_Bsplit;
+  p.b_unscale = c->forward_fp16x2 ? ldexpf(1.0f, -(8 + m->b16_shift)) : 1.0f;
   switch (m->UP) {
-    case 32: return c->forward_sum16 ? launch_tc_t<32, __half>(c, m, p) : launch_tc_t<32, float>(c, m, p);
-    case 64: return c->forward_sum16 ? launch_tc_t<64, __half>(c, m, p) : launch_tc_t<64, float>(c, m, p);
+    case 32: return launch_tc_up<32>(c, m, p);
+    case 64: return launch_tc_up<64>(c, m, p);
     default: return DGRP_E_UNSUPPORTED;
   }
 }

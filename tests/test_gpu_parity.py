@@ -288,22 +288,26 @@ def test_predict_generic_route_equals_fused(dg):
     assert np.array_equal(fused_fp32, generic)      # same kernel arithmetic: bit-identical
 
 
+@pytest.mark.parametrize("fp16x2", [0, 1])
 @pytest.mark.parametrize("sum16", [0, 1])
 @pytest.mark.parametrize("T,U", [(150, 32), (342, 60), (64, 16), (100, 50)])
-def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U, sum16):
+def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U, sum16, fp16x2):
     """tcgen05 forward (bf16 x3 split) against the float64 oracle on x4-scaled weights (sharp
     attention, all classes present).  With the h_fwd + h_rc scratch in float32 (`forward_sum16=0`) it
     stays within the float32 oracle's own distance from float64 (a few 1e-6 here); the default half
     precision scratch only perturbs the attention scores: <= 1e-4 on a probability (north_star's bar
-    is 1e-3), labels identical to 1e-4."""
+    is 1e-3), labels identical to 1e-4.  Both operand formats of the recurrent product (three bf16
+    pieces / six products, and the default two scaled fp16 pieces / three products) must pass."""
     w = dg.model.random_weights(T, U, attention=True, seed=7).scaled(4.0)
     st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(12_000, T + U))
     ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
     dg.ctx.set_int("forward_sum16", sum16)
+    dg.ctx.set_int("forward_fp16x2", fp16x2)
     try:
         tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
     finally:
         dg.ctx.set_int("forward_sum16", 1)
+        dg.ctx.set_int("forward_fp16x2", 1)
     assert dg.ctx.get_int("forward_used_tc") == 1
     ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
                            oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
@@ -320,6 +324,7 @@ def test_tensor_core_forward_random_init_regime(dg, oracle):
     ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
     tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
     assert dg.ctx.get_int("forward_used_tc") == 1 and dg.ctx.get_int("forward_sum16") == 1
+    assert dg.ctx.get_int("forward_fp16x2") == 1
     ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
                            oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
     assert np.abs(tc - ref64).max() < 1e-6
