@@ -14,7 +14,8 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeepgrp_b200.so")
+# DEEPGRP_B200_LIB: an alternative build of the same library (developer builds, e.g. tools/tc_trace.py)
+LIB_PATH = os.environ.get("DEEPGRP_B200_LIB") or os.path.join(_HERE, "libdeepgrp_b200.so")
 
 OK, E_CUDA, E_ARG, E_NOGPU, E_ALLN, E_CAPACITY, E_UNSUPPORTED, E_FASTA = 0, -1, -2, -3, -4, -5, -6, -7
 COMPAT_REFERENCE, COMPAT_FIXED = 0, 1

@@ -59,6 +59,23 @@ constexpr int TC_GATE_REGS = 112, TC_AUX_REGS = 24;     // setmaxnreg split: the
 constexpr float kNegLog2e = -1.4426950408889634f;   // z, r columns are pre-scaled: ex2(arg) = e^{-x}
 constexpr float kTwoLog2e = 2.8853900817779268f;    // h columns are pre-scaled:    ex2(arg) = e^{2x}
 
+#ifdef DGRP_TC_TRACE
+// Developer instrumentation (not compiled into the product): cycles of CTA 0's gate warps per segment
+// of the step loop, [warp][tile slot][segment]: 0 wait for "done", 1 TMEM loads, 2 gates + A operand
+// stores, 3 fences + arrive, 4 scratch stores + loop; [16][.][5..6] the issuer's wait / issue.
+__device__ unsigned long long g_tc_trace[17][2][8];
+#define TC_TRACE_DECL long long tr_t = clock64()
+#define TC_TRACE(seg)                                                         \
+  do {                                                                        \
+    const long long now__ = clock64();                                        \
+    if (blockIdx.x == 0 && lane == 0) g_tc_trace[warp][s][seg] += (unsigned long long)(now__ - tr_t); \
+    tr_t = now__;                                                             \
+  } while (0)
+#else
+#define TC_TRACE_DECL
+#define TC_TRACE(seg)
+#endif
+
 template <int UP>
 struct TCfg {
   static constexpr int NG = 3 * UP;            // gate columns (z | r | h)
@@ -387,8 +404,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
   unsigned char *s_A = s_B + NP * K::B_BYTES;                  // [2][NP][A_BYTES]
-  float *s_P = reinterpret_cast<float *>(s_A + 2 * NP * K::A_BYTES);  // [10][PSTRIDE]: rows 0..4 forward codes, 5..9
-                                                               // the complemented codes of the rc pass
+  float *s_P = reinterpret_cast<float *>(s_A + 2 * NP * K::A_BYTES);  // [10][PSTRIDE]: rows 0..3 A,C,G,T of the forward
+                                                               // pass, 4..7 of the rc pass (complemented), 8, 9
+                                                               // 'N' of either: the eight common rows start 4
+                                                               // banks apart, so a warp's mixed reads do not conflict
   float *s_bh = s_P + 10 * K::PSTRIDE;                         // [UP] recurrent bias of the h gate
   float *s_scale = s_bh + UP;                                  // [UP] attention scale
   float *s_score = s_scale + UP;                               // [16][T]
@@ -405,8 +424,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     for (int i = tid; i < NP * K::B_BYTES / 16; i += TC_THREADS) dst[i] = src[i];
     for (int i = tid; i < 10 * K::PSTRIDE; i += TC_THREADS) {
       const int row = i / K::PSTRIDE, j = i % K::PSTRIDE;
-      const int code = row % 5;
-      const int c = (row >= 5 && code < 4) ? 3 - code : code;   // reverse complement: [3,2,1,0,4] (model.py:277)
+      // reverse complement: [3,2,1,0,4] (model.py:277)
+      const int c = row >= 8 ? 4 : (row >= 4 ? 7 - row : row);
       // (x.W + b_in) + b_rec for z and r; the h gate keeps b_rec inside r * (h.R + b_rec)
       float v = 0.f;
       if (j < 2 * UP) v = (p.P[c * 3 * UP + j] + p.b1[j]) * kNegLog2e;
@@ -463,12 +482,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       const int nt = (unit < lead || tile + 1 >= tile_hi) ? 1 : 2;
       const bool live1 = nt == 2;
       // ===================== MMA issuer: T + 1 rounds per tile (round 0 = priming on h = 0) =====
+      TC_TRACE_DECL;
       for (int k = 0; k <= T; ++k) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (s == 1 && !live1) continue;
+          TC_TRACE(6);
           mbar_wait_backoff(bar_ready + 8 * s, par[s] ^ (k & 1));
           tc_fence_after();
+          TC_TRACE(5);
           if (lane == 0) {
             const uint32_t a0 = smem_u32(s_A + (size_t)s * NP * K::A_BYTES), b0 = smem_u32(s_B);
             const uint32_t d = tmem_base + (uint32_t)(s * K::TCOLS);
@@ -514,7 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     const int quad = warp & 3, uq = warp >> 2;
     const int row = quad * 32 + lane;        // row of the tile = TMEM lane
     const int wl = row >> 1, dir = row & 1;  // window in tile, direction
-    const float *tblp = s_P + dir * 5 * K::PSTRIDE + uq * K::UPT;
+    const float *tblp = s_P + uq * K::UPT;
     const float *bhp = s_bh + uq * K::UPT;
     const uint32_t a_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + ((uq * K::UPT) >> 3) * 128);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -545,42 +567,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       fence_async_smem();
       mbar_arrive(bar_ready + 8 * s);
     }
+    TC_TRACE_DECL;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (s == 1 && !live1) continue;   // uniform over the CTA
-        const float *prow = tblp + code[s] * K::PSTRIDE;
+        const float *prow = tblp + (code[s] < 4 ? code[s] + 4 * dir : 8 + dir) * K::PSTRIDE;
         if (t + 1 < T) {   // next step's base, consumed one iteration later
           code[s] = *cptr[s];
           cptr[s] += cstep;
         }
+        TC_TRACE(4);
         mbar_wait(bar_done + 8 * s, par[s] ^ (t & 1));
         tc_fence_after();
+        TC_TRACE(0);
         const uint32_t t_tile = t_lane + (uint32_t)(s * K::TCOLS);
         unsigned char *a_tile = s_A + (size_t)s * NP * K::A_BYTES + a_off;
         const size_t rt = (size_t)(s * K::WT + wl) * T + t;   // (window, t) row of the scratch arrays
         float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
         tmem_ld4(t_tile + (uint32_t)(K::NG + 4 * uq), pj);
+        float azf[K::UPT / 8][8], arf[K::UPT / 8][8], ahf[K::UPT / 8][8];
 #pragma unroll
         for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
-          float az[8], ar[8], ah[8];
           const uint32_t taddr = t_tile + (uint32_t)(uq * K::UPT + c8 * 8);
-          tmem_ld8(taddr, az);
-          tmem_ld8(taddr + UP, ar);
-          tmem_ld8(taddr + 2 * UP, ah);
-          tmem_ld_wait();
-          if (c8 == 0) {
-            // avg[t-1].K = h_fwd.(K/2) + h_rc.(K/2), stored by the fwd lane
-            float4 o;
-            o.x = pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1);
-            o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
-            o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
-            o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
-            if (NP == 2) { o.x *= us.x; o.y *= us.x; o.z *= us.x; o.w *= us.x; }
-            if (dir == 0 && t > 0) *reinterpret_cast<float4 *>(proj0 + (rt - 1) * 16 + 4 * uq) = o;
-          }
-          float2 hn2[4];
+          tmem_ld8(taddr, azf[c8]);
+          tmem_ld8(taddr + UP, arf[c8]);
+          tmem_ld8(taddr + 2 * UP, ahf[c8]);
+        }
+        tmem_ld_wait();
+        TC_TRACE(1);
+        float2 hn2[K::UPT / 8][4];   // the new state of this thread's units
+#pragma unroll
+        for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
+          const float *az = azf[c8], *ar = arf[c8], *ah = ahf[c8];
 #pragma unroll
           for (int j4 = 0; j4 < 2; ++j4) {
             const float4 xz = *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
@@ -588,30 +608,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
             const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
             gru_cell4<NP == 2>(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4,
-                               &hprev[s][c8 * 8 + 4 * j4], us, hn2[2 * j4], hn2[2 * j4 + 1]);
+                               &hprev[s][c8 * 8 + 4 * j4], us, hn2[c8][2 * j4], hn2[c8][2 * j4 + 1]);
           }
-          // new state -> bf16 pieces in the A operand (one 16-byte core-matrix row per piece)
+          // new state -> operand pieces in A (one 16-byte core-matrix row per piece)
           uint32_t hi[4], mid[4], lo[4];
           if (NP == 3) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split3(hn2[j], hi[j], mid[j], lo[j]);
+            for (int j = 0; j < 4; ++j) split3(hn2[c8][j], hi[j], mid[j], lo[j]);
             *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
             *reinterpret_cast<uint4 *>(a_tile + 2 * K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split2h(hn2[j], hi[j], lo[j]);
+            for (int j = 0; j < 4; ++j) split2h(hn2[c8][j], hi[j], lo[j]);
             *reinterpret_cast<uint4 *>(a_tile + c8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          if (p.attention) {
+        }
+        TC_TRACE(2);
+        // Hand the new A operand to the tensor core (the last step's MMA only feeds the projection).
+        // The release fence waits for this thread's outstanding stores, so it comes BEFORE the scratch
+        // stores of this step: only the A operand writes are in flight here.
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(bar_ready + 8 * s);
+        TC_TRACE(3);
+        {
+          // avg[t-1].K = h_fwd.(K/2) + h_rc.(K/2), stored by the fwd lane
+          float4 o;
+          o.x = pj[0] + __shfl_xor_sync(0xffffffffu, pj[0], 1);
+          o.y = pj[1] + __shfl_xor_sync(0xffffffffu, pj[1], 1);
+          o.z = pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1);
+          o.w = pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1);
+          if (NP == 2) { o.x *= us.x; o.y *= us.x; o.z *= us.x; o.w *= us.x; }
+          if (dir == 0 && t > 0) *reinterpret_cast<float4 *>(proj0 + (rt - 1) * 16 + 4 * uq) = o;
+        }
+        if (p.attention) {
+#pragma unroll
+          for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
             // h_fwd[t] + h_rc[t]: the partner row is the neighbouring lane; the fwd lane stores
             // units u0..u0+3, the rc lane u0+4..u0+7 (u0 = first unit of this block)
             float2 sm2[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const float2 send = dir ? hn2[j] : hn2[j + 2];
-              const float2 mine = dir ? hn2[j + 2] : hn2[j];
+              const float2 send = dir ? hn2[c8][j] : hn2[c8][j + 2];
+              const float2 mine = dir ? hn2[c8][j + 2] : hn2[c8][j];
               const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 1),
                                               __shfl_xor_sync(0xffffffffu, send.y, 1));
               sm2[j] = __fadd2_rn(mine, recv);
@@ -629,10 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
                   make_float4(0.5f * sm2[0].x, 0.5f * sm2[0].y, 0.5f * sm2[1].x, 0.5f * sm2[1].y);
           }
         }
-        // hand the new A operand to the tensor core (the last step's MMA only feeds the projection)
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(bar_ready + 8 * s);
+        TC_TRACE(4);
       }
     }
     // projection of the last state h[T-1]
@@ -712,6 +750,16 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
 
 // Returns DGRP_E_UNSUPPORTED when this model/shape has no tcgen05 form (the caller then uses the
 // fp32 kernel): units > 64, or a window too long for the score buffer in shared memory.
+#ifdef DGRP_TC_TRACE
+extern "C" int dgrp_debug_tc_trace(unsigned long long *out, int reset) {
+  if (reset) {
+    static unsigned long long zero[17][2][8];
+    return (int)cudaMemcpyToSymbol(g_tc_trace, zero, sizeof(zero));
+  }
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 17 * 2 * 8);
+}
+#endif
+
 template <int UP>
 static int launch_tc_up(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   if (c->forward_fp16x2)
