@@ -17,6 +17,7 @@ struct FwdParams {
   int64_t full_windows, tail_base;
   const float *P, *Wk, *b0, *Rp, *b1, *scale, *ffk, *ffb;
   const uint16_t *Bsplit; // tcgen05 form: operand pieces of [R | K/2]^T, UMMA layout (bf16 x3 or fp16 x2)
+  int wpp;                // tcgen05 form: windows per pass of the second phase (8..64)
   float b_unscale;        // fp16 x2 form: 1 / (state scale * weight scale), applied to the accumulator
   float *scratch, *ff2, *qbuf;
   float *pred;

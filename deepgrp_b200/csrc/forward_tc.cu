@@ -64,11 +64,12 @@ constexpr float kTwoLog2e = 2.8853900817779268f;    // h columns are pre-scaled:
 // of the step loop, [warp][tile slot][segment]: 0 wait for "done", 1 TMEM loads, 2 gates + A operand
 // stores, 3 fences + arrive, 4 scratch stores + loop; [16][.][5..6] the issuer's wait / issue.
 __device__ unsigned long long g_tc_trace[17][2][8];
-#define TC_TRACE_DECL long long tr_t = clock64()
+__shared__ unsigned int s_tc_trace[17][2][8];   // accumulated with fire-and-forget shared atomics
+#define TC_TRACE_DECL unsigned int tr_t = (unsigned int)clock64()
 #define TC_TRACE(seg)                                                         \
   do {                                                                        \
-    const long long now__ = clock64();                                        \
-    if (blockIdx.x == 0 && lane == 0) g_tc_trace[warp][s][seg] += (unsigned long long)(now__ - tr_t); \
+    const unsigned int now__ = (unsigned int)clock64();                       \
+    if (lane == 0) atomicAdd(&s_tc_trace[warp][s][seg], now__ - tr_t);        \
     tr_t = now__;                                                             \
   } while (0)
 #else
@@ -258,140 +259,162 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
   hp[0] = h01.x; hp[1] = h01.y; hp[2] = h23.x; hp[3] = h23.y;
 }
 
-// Second phase for one tile: additive attention scores with lanes over the units (8 units per lane,
-// 16-byte half-precision loads, UP/8-lane reductions), then softmax over t, logits, class softmax and
-// the max-vote with lanes over t.  One warp per window.
-//   sum16 [WT][T][UP]  h_fwd[t] + h_rc[t] in half precision      q [WT][UP]  avg[T-1]
-//   proj  [WT][T][16]  avg[t].K: ctx half in 0..4, avg half in 8..12
-// score[t] = sum_u scale[u] tanh(q[u] + avg[t][u]) = S - 2 sum_u scale[u] / (e^{2(q+avg)} + 1) with
-// S = sum_u scale[u] the same for every t, so the softmax over t only needs the second term.
+// Second phase for one tile, in passes of WPP windows (WPP * T floats of scores fit in shared memory).
+//   sum   [T][UP/8 chunks][64 windows][8 units]  h_fwd[t] + h_rc[t]; the layout the gate warps can
+//         write with full 128-byte lines (a warp's 32 rows are 16 windows x 2 directions x 4 units)
+//   q     [64][UP]       avg[T-1]
+//   proj  [64][T][16]    avg[t].K: ctx half in 0..4, avg half in 8..12
+// (a) scores: score[t] = sum_u scale[u] tanh(q[u] + avg[t][u]) = S - 2 sum_u scale[u] / D[t][u] with
+//     D = e^{2(q+avg)} + 1 and S = sum_u scale[u] the same for every t, so the softmax over t only needs
+//     the second term.  A warp takes 8 adjacent windows x a slice of t; a lane takes one window and every
+//     fourth chunk, so each load instruction reads whole 128-byte lines; four denominators share one rcp.
+// (b) one warp per window, lanes over t: softmax over t, logits, class softmax and the max-vote.
+__device__ __forceinline__ float inv4_dot(const float *d, const float *sc) {
+  // sum_k sc[k] / d[k], k < 4, with one reciprocal (d[k] <= 2^30 + 1, so the product is finite)
+  const float2 d01 = make_float2(d[0], d[1]), d23 = make_float2(d[2], d[3]);
+  const float2 m = __fmul2_rn(d01, d23);
+  const float inv = rcp_approx(m.x * m.y);
+  const float2 j = make_float2(inv * m.y, inv * m.x);
+  const float2 i01 = __fmul2_rn(j, d23), i23 = __fmul2_rn(j, d01);
+  return fmaf(sc[0], i01.x, fmaf(sc[1], i01.y, fmaf(sc[2], i23.x, sc[3] * i23.y)));
+}
+
 template <int UP, int WT, int NWARPS, typename ST>
-__device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, const ST *sum16,
-                                                        const float *qbuf, const float *proj,
-                                                        int64_t w_tile0, const float *s_scale,
-                                                        float *s_score) {
+__device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, const ST *sum, const float *qbuf,
+                                                        const float *proj, int64_t w_tile0, int wpp,
+                                                        const float *s_scale, float *s_score) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp >= NWARPS) return;
   const int T = p.T, C = p.C;
-  constexpr int LPR = UP / 8;          // lanes per row (8 units each)
-  constexpr int RPW = 32 / LPR;        // rows per warp-wide load
-  const int g = lane % LPR, sub = lane / LPR;
-  float *sc = s_score + (size_t)warp * T;
-  float scale2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) scale2[j] = -2.0f * s_scale[8 * g + j];
-  for (int wl = warp; wl < WT; wl += NWARPS) {
-    const int64_t w = w_tile0 + wl;
-    if (w >= p.w_end) break;
-    const float *pr = proj + (size_t)wl * T * 16;
-    float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr int NCH = UP / 8;          // 8-unit chunks per avg row
+  constexpr int CPL = NCH / 4;         // chunks per lane: cj, cj + 4, ...
+  constexpr bool H16 = sizeof(ST) == 2;
+  constexpr int NV = H16 ? 1 : 2;      // 16-byte loads per chunk
+  constexpr int UNR = H16 ? 4 : 2;     // t's in flight per lane
+  for (int w0 = 0; w0 < WT; w0 += wpp) {
+    if (w_tile0 + w0 >= p.w_end) break;
     if (p.attention) {
-      const ST *av = sum16 + (size_t)wl * T * UP + 8 * g;
-      float q2[8];   // 2 log2(e) q[u]
-      {
-        const float4 qa = *reinterpret_cast<const float4 *>(qbuf + (size_t)wl * UP + 8 * g);
-        const float4 qb = *reinterpret_cast<const float4 *>(qbuf + (size_t)wl * UP + 8 * g + 4);
-        q2[0] = qa.x * kTwoLog2e; q2[1] = qa.y * kTwoLog2e; q2[2] = qa.z * kTwoLog2e; q2[3] = qa.w * kTwoLog2e;
-        q2[4] = qb.x * kTwoLog2e; q2[5] = qb.y * kTwoLog2e; q2[6] = qb.z * kTwoLog2e; q2[7] = qb.w * kTwoLog2e;
+      const int ngrp = wpp >> 3, grp = warp % ngrp, sl = warp / ngrp, nsl = NWARPS / ngrp;
+      const int wi = lane & 7, cj = lane >> 3;
+      const int wl = w0 + grp * 8 + wi;
+      const int t_begin = (int)((int64_t)T * sl / nsl), t_end = (int)((int64_t)T * (sl + 1) / nsl);
+      float q2[CPL][8], sc2[CPL][8];   // 2 log2(e) q[u], -2 scale[u]
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int u0 = (cj + 4 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          q2[i][j] = qbuf[(size_t)wl * UP + u0 + j] * kTwoLog2e;
+          sc2[i][j] = -2.0f * s_scale[u0 + j];
+        }
       }
-      constexpr bool H16 = sizeof(ST) == 2;
-      constexpr int UNR = H16 ? 8 : 4;            // rows in flight per lane (16 or 32 bytes each)
-      constexpr int NV = H16 ? 1 : 2;             // 16-byte loads per row and lane
-      for (int t0 = 0; t0 < T; t0 += RPW * UNR) {
-        uint4 v[UNR][NV];
+      const ST *base = sum + ((size_t)cj * WT + wl) * 8;
+      for (int t0 = t_begin; t0 < t_end; t0 += UNR) {
+        uint4 v[UNR][CPL][NV];
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
-          const int t = t0 + k * RPW + sub;
+          const int t = min(t0 + k, t_end - 1);
 #pragma unroll
-          for (int i = 0; i < NV; ++i)
-            v[k][i] = t < T ? __ldcs(reinterpret_cast<const uint4 *>(av + (size_t)t * UP) + i)
-                            : make_uint4(0u, 0u, 0u, 0u);
+          for (int i = 0; i < CPL; ++i)
+#pragma unroll
+            for (int n = 0; n < NV; ++n)
+              v[k][i][n] = __ldcs(reinterpret_cast<const uint4 *>(base + ((size_t)t * NCH + 4 * i) * WT * 8) + n);
         }
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
-          const int t = t0 + k * RPW + sub;
-          float x[8];   // h_fwd[t] + h_rc[t] of this lane's 8 units
-          if (H16) {
-            const uint32_t wv[4] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w};
+          float sacc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
-              x[2 * j] = f.x; x[2 * j + 1] = f.y;
+          for (int i = 0; i < CPL; ++i) {
+            float x[8];   // h_fwd[t] + h_rc[t] of 8 units
+            if (H16) {
+              const uint32_t wv[4] = {v[k][i][0].x, v[k][i][0].y, v[k][i][0].z, v[k][i][0].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
+                x[2 * j] = f.x; x[2 * j + 1] = f.y;
+              }
+            } else {
+              const uint32_t wv[8] = {v[k][i][0].x, v[k][i][0].y, v[k][i][0].z, v[k][i][0].w,
+                                      v[k][i][NV - 1].x, v[k][i][NV - 1].y, v[k][i][NV - 1].z, v[k][i][NV - 1].w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(wv[j]);
             }
-          } else {
-            const uint32_t wv[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w,
-                                    v[k][NV - 1].x, v[k][NV - 1].y, v[k][NV - 1].z, v[k][NV - 1].w};
+            float d[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(wv[j]);
+            for (int j = 0; j < 8; ++j)   // e^{2 (q + sum/2)} + 1 = 2^{2 log2e q + log2e sum} + 1
+              d[j] = ex2_approx(fminf(fmaf(x[j], 1.4426950408889634f, q2[i][j]), 30.0f)) + 1.0f;
+            sacc += inv4_dot(d, sc2[i]) + inv4_dot(d + 4, sc2[i] + 4);
           }
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // e^{2 (q + sum/2)} = 2^{2 log2e q + log2e sum}
-            const float e = ex2_approx(fmaf(x[j], 1.4426950408889634f, q2[j]));
-            s = fmaf(scale2[j], rcp_approx(e + 1.0f), s);
-          }
-#pragma unroll
-          for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-          if (g == 0 && t < T) sc[t] = s;
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+          if (cj == 0 && t0 + k < t_end) s_score[(size_t)(grp * 8 + wi) * T + t0 + k] = sacc;
         }
       }
-      __syncwarp();
-      // softmax over t and ctx.K1 = sum_t a_t (avg[t].K1)
-      float m_run = -INFINITY, l_run = 0.f, cacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");
+    for (int wq = warp; wq < wpp; wq += NWARPS) {
+      const int wl = w0 + wq;
+      const int64_t w = w_tile0 + wl;
+      if (w >= p.w_end) break;
+      const float *pr = proj + (size_t)wl * T * 16;
+      const float *sc = s_score + (size_t)wq * T;
+      float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.attention) {
+        // softmax over t and ctx.K1 = sum_t a_t (avg[t].K1)
+        float m_run = -INFINITY, l_run = 0.f, cacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = lane; t < T; t += 32) {
+          const float s = sc[t];
+          const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16);
+          const float k5 = pr[(size_t)t * 16 + 4];
+          const float k1[5] = {k4.x, k4.y, k4.z, k4.w, k5};
+          const float m_new = fmaxf(m_run, s);
+          const float corr = expf(m_run - m_new);
+          const float e = expf(s - m_new);
+          l_run = l_run * corr + e;
+#pragma unroll
+          for (int c = 0; c < 5; ++c) cacc[c] = cacc[c] * corr + e * k1[c];
+          m_run = m_new;
+        }
+        float m_all = m_run;
+        for (int off = 16; off > 0; off >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, off));
+        const float f = (m_run == -INFINITY) ? 0.f : expf(m_run - m_all);
+        float l = l_run * f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) cacc[c] *= f;
+        for (int off = 16; off > 0; off >>= 1) {
+          l += __shfl_xor_sync(0xffffffffu, l, off);
+#pragma unroll
+          for (int c = 0; c < 5; ++c) cacc[c] += __shfl_xor_sync(0xffffffffu, cacc[c], off);
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ctxk[c] = cacc[c] / l;
+      }
+      // logits[t] = ctx.K1 + avg[t].K2 + b ; softmax over classes ; vote
+      const int64_t place = (w < p.full_windows ? w * (int64_t)p.step
+                                                : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
+                            p.pred_row0;
       for (int t = lane; t < T; t += 32) {
-        const float s = sc[t];
-        const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16);
-        const float k5 = pr[(size_t)t * 16 + 4];
-        const float k1[5] = {k4.x, k4.y, k4.z, k4.w, k5};
-        const float m_new = fmaxf(m_run, s);
-        const float corr = expf(m_run - m_new);
-        const float e = expf(s - m_new);
-        l_run = l_run * corr + e;
+        const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8);
+        const float k5 = pr[(size_t)t * 16 + 12];
+        const float k2[5] = {k4.x, k4.y, k4.z, k4.w, k5};
+        float lg[5], mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) cacc[c] = cacc[c] * corr + e * k1[c];
-        m_run = m_new;
-      }
-      float m_all = m_run;
-      for (int off = 16; off > 0; off >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, off));
-      const float f = (m_run == -INFINITY) ? 0.f : expf(m_run - m_all);
-      float l = l_run * f;
+        for (int c = 0; c < 5; ++c) {
+          lg[c] = c < C ? (ctxk[c] + k2[c]) + p.ffb[c] : -INFINITY;
+          mx = fmaxf(mx, lg[c]);
+        }
+        float sum_e = 0.f;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) cacc[c] *= f;
-      for (int off = 16; off > 0; off >>= 1) {
-        l += __shfl_xor_sync(0xffffffffu, l, off);
+        for (int c = 0; c < 5; ++c) { lg[c] = c < C ? expf(lg[c] - mx) : 0.f; sum_e += lg[c]; }
+        const int64_t r = place + t;
+        if (r >= 0 && r < p.pred_rows) {
+          int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) cacc[c] += __shfl_xor_sync(0xffffffffu, cacc[c], off);
-      }
-#pragma unroll
-      for (int c = 0; c < 5; ++c) ctxk[c] = cacc[c] / l;
-    }
-    // logits[t] = ctx.K1 + avg[t].K2 + b ; softmax over classes ; vote
-    const int64_t place = (w < p.full_windows ? w * (int64_t)p.step
-                                              : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
-                          p.pred_row0;
-    for (int t = lane; t < T; t += 32) {
-      const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8);
-      const float k5 = pr[(size_t)t * 16 + 12];
-      const float k2[5] = {k4.x, k4.y, k4.z, k4.w, k5};
-      float lg[5], mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        lg[c] = c < C ? (ctxk[c] + k2[c]) + p.ffb[c] : -INFINITY;
-        mx = fmaxf(mx, lg[c]);
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) { lg[c] = c < C ? expf(lg[c] - mx) : 0.f; sum += lg[c]; }
-      const int64_t r = place + t;
-      if (r >= 0 && r < p.pred_rows) {
-        int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
-#pragma unroll
-        for (int c = 0; c < 5; ++c)
-          if (c < C) atomicMax(dst + c, __float_as_int(lg[c] / sum));   // probs > 0
+          for (int c = 0; c < 5; ++c)
+            if (c < C) atomicMax(dst + c, __float_as_int(lg[c] / sum_e));   // probs > 0
+        }
       }
     }
-    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");   // s_score is rewritten by the next pass
   }
 }
 
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
                                                                // banks apart, so a warp's mixed reads do not conflict
   float *s_bh = s_P + 10 * K::PSTRIDE;                         // [UP] recurrent bias of the h gate
   float *s_scale = s_bh + UP;                                  // [UP] attention scale
-  float *s_score = s_scale + UP;                               // [16][T]
+  float *s_score = s_scale + UP;                               // [wpp][T]
   __shared__ __align__(8) unsigned long long s_ready[2], s_done[2];
   __shared__ uint32_t s_tmem;
 
@@ -444,6 +467,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+#ifdef DGRP_TC_TRACE
+  for (int i = tid; i < 17 * 2 * 8; i += TC_THREADS) (&s_tc_trace[0][0][0])[i] = 0u;
+#endif
   if (tid == 0) {
     mbar_init(smem_u32(&s_ready[0]), TC_GATE_WARPS * 32);
     mbar_init(smem_u32(&s_ready[1]), TC_GATE_WARPS * 32);
@@ -518,6 +544,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       if (live1) par[1] ^= (uint32_t)((T + 1) & 1);
       tile += nt;
     }
+#ifdef DGRP_TC_TRACE
+    __syncwarp();
+    if (blockIdx.x == 0 && lane < 16) g_tc_trace[16][lane >> 3][lane & 7] += s_tc_trace[16][lane >> 3][lane & 7];
+#endif
     return;
   }
 
@@ -643,6 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
           if (NP == 2) { o.x *= us.x; o.y *= us.x; o.z *= us.x; o.w *= us.x; }
           if (dir == 0 && t > 0) *reinterpret_cast<float4 *>(proj0 + (rt - 1) * 16 + 4 * uq) = o;
         }
+        TC_TRACE(5);
         if (p.attention) {
 #pragma unroll
           for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
@@ -658,19 +689,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
               sm2[j] = __fadd2_rn(mine, recv);
             }
             const int u = uq * K::UPT + c8 * 8 + (dir ? 4 : 0);
+            // [slot][t][chunk][window][8 units]: the warp's 32 rows write 32 consecutive 4-unit groups
+            ST *dst = sum0 + ((((size_t)s * T + t) * (UP / 8) + (uq * (K::UPT / 8) + c8)) * K::WT + wl) * 8 + (dir ? 4 : 0);
             if (sizeof(ST) == 2) {
               const __half2 h0 = __floats2half2_rn(sm2[0].x, sm2[0].y), h1 = __floats2half2_rn(sm2[1].x, sm2[1].y);
-              *reinterpret_cast<uint2 *>(sum0 + rt * UP + u) =
+              *reinterpret_cast<uint2 *>(dst) =
                   make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
             } else {
-              *reinterpret_cast<float4 *>(sum0 + rt * UP + u) = make_float4(sm2[0].x, sm2[0].y, sm2[1].x, sm2[1].y);
+              *reinterpret_cast<float4 *>(dst) = make_float4(sm2[0].x, sm2[0].y, sm2[1].x, sm2[1].y);
             }
             if (t == T - 1)   // the query avg[T-1] in full precision
               *reinterpret_cast<float4 *>(q0 + (size_t)(s * K::WT + wl) * UP + u) =
                   make_float4(0.5f * sm2[0].x, 0.5f * sm2[0].y, 0.5f * sm2[1].x, 0.5f * sm2[1].y);
           }
         }
-        TC_TRACE(4);
+        TC_TRACE(6);
       }
     }
     // projection of the last state h[T-1]
@@ -702,14 +735,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     for (int s = 0; s < nt; ++s)
       attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(
           p, sum0 + (size_t)s * K::WT * T * UP, q0 + (size_t)s * K::WT * UP,
-          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, s_scale, s_score);
-    gate_bar_sync();
+          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, p.wpp, s_scale, s_score);
     tile += nt;
   }
 
   // ---- teardown (the last "done" wait of every tile saw its MMAs complete) -----------------------
   tc_fence_before();
   gate_bar_sync();
+#ifdef DGRP_TC_TRACE
+  if (blockIdx.x == 0 && tid < 16 * 16) g_tc_trace[tid >> 4][(tid >> 3) & 1][tid & 7] += s_tc_trace[tid >> 4][(tid >> 3) & 1][tid & 7];
+#endif
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(2 * K::TCOLS)
@@ -718,10 +753,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 }
 
 template <int UP, int NP>
-static size_t tc_smem_bytes(int T) {
+static size_t tc_smem_bytes(int T, int wpp) {
   using K = TCfg<UP>;
   return (size_t)NP * K::B_BYTES + 2 * NP * K::A_BYTES +
-         sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + TC_GATE_WARPS * (size_t)T) + 128;
+         sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + (size_t)wpp * T) + 128;
 }
 
 template <int UP, typename ST, int NP>
@@ -729,8 +764,12 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = TCfg<UP>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
-  const size_t smem = tc_smem_bytes<UP, NP>(p.T);
+  // windows per pass of the second phase: as many score rows as shared memory holds
+  int wpp = K::WT;
+  while (wpp > 8 && tc_smem_bytes<UP, NP>(p.T, wpp) > 227 * 1024) wpp >>= 1;
+  const size_t smem = tc_smem_bytes<UP, NP>(p.T, wpp);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
+  p.wpp = wpp;
   auto kern = gru_tc_attention_vote_kernel<UP, ST, NP>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;

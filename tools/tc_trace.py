@@ -52,9 +52,9 @@ def run(bases):
     tiles0 = n_tiles * 1 // 148 - 0            # CTA 0's tile range is [0, n_tiles/148)
     steps = tiles0 * T / 1.0                   # tile-steps of CTA 0 (each slot does about half)
     print("windows %d, tiles of CTA 0: %d, forward %.2f ms" % (n_windows, tiles0, ctx.timings()["forward_ms"]))
-    names = ["wait done", "tmem loads", "gates+A stores", "fence+arrive", "scratch stores+loop"]
+    names = ["wait done", "tmem loads", "gates+A stores", "fence+arrive", "loop top (prefetch)", "proj shfl+store", "sum shfl+store"]
     g = tr[:16]
-    per = g[:, :, :5].sum(axis=1) / steps      # cycles per tile-step, per warp
+    per = g[:, :, :7].sum(axis=1) / steps      # cycles per tile-step, per warp
     print("cycles per tile-step (mean over the 16 gate warps; min..max):")
     for k, name in enumerate(names):
         print("  %-18s %7.0f   (%5.0f .. %5.0f)" % (name, per[:, k].mean(), per[:, k].min(), per[:, k].max()))
