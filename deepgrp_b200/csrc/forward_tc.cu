@@ -269,6 +269,9 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
 //     the second term.  A warp takes 8 adjacent windows x a slice of t; a lane takes one window and every
 //     fourth chunk, so each load instruction reads whole 128-byte lines; four denominators share one rcp.
 // (b) one warp per window, lanes over t: softmax over t, logits, class softmax and the max-vote.
+__device__ __forceinline__ float exp_fast(float x) {   // e^x through ex2.approx (2 ulp), e^{-inf} = 0
+  return ex2_approx(x * 1.4426950408889634f);
+}
 __device__ __forceinline__ float inv4_dot(const float *d, const float *sc) {
   // sum_k sc[k] / d[k], k < 4, with one reciprocal (d[k] <= 2^30 + 1, so the product is finite)
   const float2 d01 = make_float2(d[0], d[1]), d23 = make_float2(d[2], d[3]);
@@ -289,7 +292,8 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
   constexpr int CPL = NCH / 4;         // chunks per lane: cj, cj + 4, ...
   constexpr bool H16 = sizeof(ST) == 2;
   constexpr int NV = H16 ? 1 : 2;      // 16-byte loads per chunk
-  constexpr int UNR = H16 ? 4 : 2;     // t's in flight per lane
+  constexpr int UNR = H16 ? 4 : 2;     // t's in flight per lane (scores)
+  constexpr int PU = 4;                // rows in flight per lane (softmax / vote passes)
   for (int w0 = 0; w0 < WT; w0 += wpp) {
     if (w_tile0 + w0 >= p.w_end) break;
     if (p.attention) {
@@ -359,24 +363,40 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
       const float *sc = s_score + (size_t)wq * T;
       float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       if (p.attention) {
-        // softmax over t and ctx.K1 = sum_t a_t (avg[t].K1)
+        // softmax over t and ctx.K1 = sum_t a_t (avg[t].K1); four rows per lane in flight
         float m_run = -INFINITY, l_run = 0.f, cacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t = lane; t < T; t += 32) {
-          const float s = sc[t];
-          const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16);
-          const float k5 = pr[(size_t)t * 16 + 4];
-          const float k1[5] = {k4.x, k4.y, k4.z, k4.w, k5};
-          const float m_new = fmaxf(m_run, s);
-          const float corr = expf(m_run - m_new);
-          const float e = expf(s - m_new);
-          l_run = l_run * corr + e;
+        for (int t0 = lane; t0 < T; t0 += 32 * PU) {
+          float sv[PU], k1[PU][5];
 #pragma unroll
-          for (int c = 0; c < 5; ++c) cacc[c] = cacc[c] * corr + e * k1[c];
-          m_run = m_new;
+          for (int k = 0; k < PU; ++k) {
+            const int t = t0 + 32 * k;
+            const bool ok = t < T;
+            const float4 k4 = ok ? *reinterpret_cast<const float4 *>(pr + (size_t)t * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            k1[k][0] = k4.x; k1[k][1] = k4.y; k1[k][2] = k4.z; k1[k][3] = k4.w;
+            k1[k][4] = ok ? pr[(size_t)t * 16 + 4] : 0.f;
+            sv[k] = ok ? sc[t] : -INFINITY;
+          }
+          float m_new = m_run;
+#pragma unroll
+          for (int k = 0; k < PU; ++k) m_new = fmaxf(m_new, sv[k]);
+          if (m_new > -INFINITY) {
+            const float corr = exp_fast(m_run - m_new);   // exp(-inf) = 0 on the first rows
+            l_run *= corr;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) cacc[c] *= corr;
+#pragma unroll
+            for (int k = 0; k < PU; ++k) {
+              const float e = exp_fast(sv[k] - m_new);
+              l_run += e;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) cacc[c] = fmaf(e, k1[k][c], cacc[c]);
+            }
+            m_run = m_new;
+          }
         }
         float m_all = m_run;
         for (int off = 16; off > 0; off >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, off));
-        const float f = (m_run == -INFINITY) ? 0.f : expf(m_run - m_all);
+        const float f = (m_run == -INFINITY) ? 0.f : exp_fast(m_run - m_all);
         float l = l_run * f;
 #pragma unroll
         for (int c = 0; c < 5; ++c) cacc[c] *= f;
@@ -392,25 +412,39 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
       const int64_t place = (w < p.full_windows ? w * (int64_t)p.step
                                                 : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
                             p.pred_row0;
-      for (int t = lane; t < T; t += 32) {
-        const float4 k4 = *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8);
-        const float k5 = pr[(size_t)t * 16 + 12];
-        const float k2[5] = {k4.x, k4.y, k4.z, k4.w, k5};
-        float lg[5], mx = -INFINITY;
+      float cb[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          lg[c] = c < C ? (ctxk[c] + k2[c]) + p.ffb[c] : -INFINITY;
-          mx = fmaxf(mx, lg[c]);
+      for (int c = 0; c < 5; ++c) cb[c] = c < C ? ctxk[c] + p.ffb[c] : 0.f;
+      for (int t0 = lane; t0 < T; t0 += 32 * PU) {
+        float k2[PU][5];
+#pragma unroll
+        for (int k = 0; k < PU; ++k) {
+          const int t = t0 + 32 * k;
+          const bool ok = t < T;
+          const float4 k4 = ok ? *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+          k2[k][0] = k4.x; k2[k][1] = k4.y; k2[k][2] = k4.z; k2[k][3] = k4.w;
+          k2[k][4] = ok ? pr[(size_t)t * 16 + 12] : 0.f;
         }
-        float sum_e = 0.f;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) { lg[c] = c < C ? expf(lg[c] - mx) : 0.f; sum_e += lg[c]; }
-        const int64_t r = place + t;
-        if (r >= 0 && r < p.pred_rows) {
-          int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
+        for (int k = 0; k < PU; ++k) {
+          const int t = t0 + 32 * k;
+          float lg[5], mx = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 5; ++c)
-            if (c < C) atomicMax(dst + c, __float_as_int(lg[c] / sum_e));   // probs > 0
+          for (int c = 0; c < 5; ++c) {
+            lg[c] = c < C ? k2[k][c] + cb[c] : -INFINITY;
+            mx = fmaxf(mx, lg[c]);
+          }
+          float sum_e = 0.f;
+#pragma unroll
+          for (int c = 0; c < 5; ++c) { lg[c] = c < C ? exp_fast(lg[c] - mx) : 0.f; sum_e += lg[c]; }
+          const float inv = 1.0f / sum_e;
+          const int64_t r = place + t;
+          if (t < T && r >= 0 && r < p.pred_rows) {
+            int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+              if (c < C) atomicMax(dst + c, __float_as_int(lg[c] * inv));   // probs > 0
+          }
         }
       }
     }
