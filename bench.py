@@ -116,6 +116,25 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01d_*); None for any other workload."""
+    if (args.bases, args.vecsize, args.units) != (CONFIG2_BASES, T_DEFAULT, U_DEFAULT):
+        return None
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01d_fwd_tc_ncu_raw.csv"))))
+        col = {name: (unit, val) for name, unit, val in zip(rows[0], rows[1], rows[2])}
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            unit, val = col[key]
+            total += float(val) * scale[unit]
+        return total
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+
+
 def cpu_reference_step(codes_prefix, weights, T, threads):
     """The reference path restated on CPU (oracle port; TF absent): encode, windows, forward
     (torch.nn.GRU engine), max-vote incl. the partial-batch placement, MSS, segments, TSV."""
@@ -277,10 +296,13 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
-                     "kernel": ("gru_tc_attention_vote_kernel (tcgen05, bf16 x3 split)"
+                     "kernel": (("gru_tc_attention_vote_kernel (tcgen05, %s operand pieces)"
+                                 % ("fp16 x2" if ctx.get_int("forward_fp16x2") else "bf16 x3"))
                                 if ctx.get_int("forward_used_tc") else "gru_attention_vote_kernel (fp32 FFMA)"),
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
-                     "frac": achieved / tflops_peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / tflops_peak, "traffic": ncu_traffic(args),
+                     "traffic_unit": "bytes of DRAM read + written per launch (ncu, profiles/r01d_fwd_tc_ncu_raw.csv)",
+                     "peak_kind": peak_kind,
                      "kernel_ms": kernel_ms, "share_of_step": kernel_ms / (elapsed_ms / args.steps)},
         "stages_ms": mean_stage, "rows_per_step": rows_per_step,
         "mss_rounds": ctx.get_int("mss_rounds"),

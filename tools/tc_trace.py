@@ -51,7 +51,7 @@ def run(bases):
     n_tiles = (n_windows + 63) // 64
     tiles0 = n_tiles * 1 // 148 - 0            # CTA 0's tile range is [0, n_tiles/148)
     steps = tiles0 * T / 1.0                   # tile-steps of CTA 0 (each slot does about half)
-    print("windows %d, tiles of CTA 0: %d, forward %.2f ms" % (n_windows, tiles0, ctx.timings()["forward_ms"]))
+    print("windows %d, tiles of CTA 0: %d" % (n_windows, tiles0))
     names = ["wait done", "tmem loads", "gates+A stores", "fence+arrive", "loop top (prefetch)", "proj shfl+store", "sum shfl+store"]
     g = tr[:16]
     per = g[:, :, :7].sum(axis=1) / steps      # cycles per tile-step, per warp
