@@ -414,6 +414,41 @@ int dgrp_find_mss_labels(dgrp_ctx *c, const double *scores, const int64_t *label
   return DGRP_OK;
 }
 
+int dgrp_filter_segments(dgrp_ctx *c, uint8_t *labels, int64_t n, int64_t min_len) {
+  Use use(c->device);
+  if (n <= 0) return DGRP_OK;
+  DGRP_CHECK(c->labels.reserve((size_t)n));
+  DGRP_CHECK(c->labels2.reserve((size_t)n));
+  DGRP_CUDA(cudaMemcpyAsync(c->labels.p, labels, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  DGRP_CHECK(launch_filter_segments(c, c->labels.as<uint8_t>(), c->labels2.as<uint8_t>(), n, min_len));
+  DGRP_CUDA(cudaMemcpyAsync(labels, c->labels2.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return DGRP_OK;
+}
+
+int dgrp_confusion_matrix(dgrp_ctx *c, const uint8_t *truelbl, const uint8_t *predictedlbl, int64_t n,
+                          int64_t *cnf) {
+  Use use(c->device);
+  DGRP_REQUIRE(n >= 0, "n must be non-negative");
+  DGRP_CHECK(c->labels.reserve((size_t)(n > 0 ? n : 1)));
+  DGRP_CHECK(c->labels2.reserve((size_t)(n > 0 ? n : 1)));
+  DGRP_CHECK(c->small.reserve(4096));
+  DGRP_CHECK(c->pin_small.reserve(4096));
+  if (n > 0) {
+    DGRP_CUDA(cudaMemcpyAsync(c->labels.p, truelbl, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    DGRP_CUDA(cudaMemcpyAsync(c->labels2.p, predictedlbl, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  unsigned long long *d_cnf = c->small.as<unsigned long long>() + 64;
+  int *d_bad = reinterpret_cast<int *>(d_cnf + 256);
+  DGRP_CHECK(launch_confusion(c, c->labels.as<uint8_t>(), c->labels2.as<uint8_t>(), n, d_cnf, d_bad));
+  unsigned long long *h = c->pin_small.as<unsigned long long>() + 64;
+  DGRP_CUDA(cudaMemcpyAsync(h, d_cnf, 257 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  DGRP_REQUIRE(*reinterpret_cast<int *>(h + 256) == 0, "confusion_matrix: labels must be < 16");
+  for (int i = 0; i < 256; ++i) cnf[i] = (int64_t)h[i];
+  return DGRP_OK;
+}
+
 /* ---------------------------------------- model ---------------------------------------- */
 
 int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classes,

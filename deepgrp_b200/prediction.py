@@ -297,3 +297,89 @@ def predict_fasta_tsv(model: ModelWeights, raw, filename: str, step_size: int, b
     """``predict_fasta_tsv_view`` copied into a ``str``."""
     return bytes(predict_fasta_tsv_view(model, raw, filename, step_size, batch_size, use_mss,
                                         min_mss_len, xdrop_len, compat)).decode("utf-8", "replace")
+
+
+# ---- evaluation helpers (deepgrp/prediction.py:144-260; used by deepgrp/optimization.py:58-69) -------
+
+def calculate_multiclass_matthews_cc(cnf_matrix: np.ndarray) -> float:
+    """R_K / multi-class Matthews correlation coefficient of a confusion matrix
+    (deepgrp/prediction.py:144-164; O(C^2) host arithmetic on the GPU-built matrix)."""
+    t_sum = cnf_matrix.sum(axis=1, dtype=float)
+    p_sum = cnf_matrix.sum(axis=0, dtype=float)
+    n_correct = np.trace(cnf_matrix, dtype=float)
+    n_samples = p_sum.sum()
+    cov_ytyp = n_correct * n_samples - np.dot(t_sum, p_sum)
+    cov_ypyp = n_samples**2 - np.dot(p_sum, p_sum)
+    cov_ytyt = n_samples**2 - np.dot(t_sum, t_sum)
+    return cov_ytyp / np.sqrt(cov_ytyt * cov_ypyp)
+
+
+def _calculate_metrics(cnf_matrix: np.ndarray) -> dict:
+    """Per-class rates from a confusion matrix (deepgrp/prediction.py:167-197)."""
+    true_positive = np.diag(cnf_matrix).astype(float)
+    false_positive = (cnf_matrix.sum(axis=0) - true_positive).astype(float)
+    false_negative = (cnf_matrix.sum(axis=1) - true_positive).astype(float)
+    true_negative = (cnf_matrix.sum() - (false_positive + false_negative + true_positive)).astype(float)
+    metrics = {}
+    metrics["TPR"] = true_positive / (true_positive + false_negative)
+    metrics["TNR"] = true_negative / (true_negative + false_positive)
+    metrics["PPV"] = true_positive / (true_positive + false_positive)
+    metrics["NPV"] = true_negative / (true_negative + false_negative)
+    metrics["FPR"] = false_positive / (false_positive + true_negative)
+    metrics["FNR"] = false_negative / (true_positive + false_negative)
+    metrics["FDR"] = false_positive / (true_positive + false_positive)
+    metrics["ACC"] = (true_positive + true_negative) / \
+        (true_positive + false_positive + false_negative + true_negative)
+    metrics["F1"] = 2 * metrics["TPR"] * metrics["PPV"] / (metrics["TPR"] + metrics["PPV"])
+    metrics["MCC"] = calculate_multiclass_matthews_cc(cnf_matrix)
+    return metrics
+
+
+def _labels_u8(name: str, a) -> np.ndarray:
+    arr = np.asarray(a)
+    if arr.size and (arr.min() < 0 or arr.max() >= 16):
+        raise IndexError("%s: labels must be in [0, 16) for the GPU confusion matrix" % name)
+    return np.ascontiguousarray(arr.reshape(-1), dtype=np.uint8)
+
+
+def confusion_matrix(truelbl: np.ndarray, predictedlbl: np.ndarray) -> np.ndarray:
+    """Confusion matrix of two integer label arrays (deepgrp/prediction.py:200-218): one GPU pass
+    (shared-memory counters per block).  As in the reference the matrix has
+    ``max(labels) - min(labels) + 1`` rows and a label beyond that raises IndexError."""
+    truelbl, predictedlbl = np.asarray(truelbl), np.asarray(predictedlbl)
+    assert truelbl.size == predictedlbl.size
+    n_classes = int(max(truelbl.max(), predictedlbl.max()) - min(truelbl.min(), predictedlbl.min()) + 1)
+    t8, p8 = _labels_u8("truelbl", truelbl), _labels_u8("predictedlbl", predictedlbl)
+    full = np.zeros(256, dtype=np.int64)
+    ctx = _lib.context()
+    _lib.check(_lib.lib().dgrp_confusion_matrix(ctx.handle, _lib.ptr(t8), _lib.ptr(p8), t8.size, _lib.ptr(full)))
+    full = full.reshape(16, 16)
+    if full[n_classes:, :].any() or full[:, n_classes:].any():
+        raise IndexError("index %d is out of bounds for axis 0 with size %d"
+                         % (int(max(truelbl.max(), predictedlbl.max())), n_classes))
+    return full[:n_classes, :n_classes].astype(int)
+
+
+def calculate_metrics(predictions_class: np.ndarray, true_class: np.ndarray):
+    """(confusion matrix, metrics dict incl. TotalACC) -- deepgrp/prediction.py:221-239."""
+    predictions_class, true_class = np.asarray(predictions_class), np.asarray(true_class)
+    cnf_matrix = confusion_matrix(true_class, predictions_class)
+    metrics = _calculate_metrics(cnf_matrix)
+    metrics["TotalACC"] = np.trace(cnf_matrix) / true_class.shape[0]
+    return cnf_matrix, metrics
+
+
+def filter_segments(array: np.ndarray, min_len: int = 50) -> None:
+    """Zero every run of one identical positive label that is shorter than `min_len`, in place
+    (deepgrp/prediction.py:242-260).  Runs are found and cleared on the GPU."""
+    if array.size == 0:
+        return
+    flat = array.reshape(-1)
+    lab = _labels_u8("array", np.where(flat > 0, flat, 0))
+    if not np.array_equal(lab, np.where(flat > 0, flat, 0)):
+        raise ValueError("filter_segments: labels must be integers in [0, 16)")
+    keep = lab.copy()
+    ctx = _lib.context()
+    _lib.check(_lib.lib().dgrp_filter_segments(ctx.handle, _lib.ptr(keep), keep.size, int(min_len)))
+    flat[(lab > 0) & (keep == 0)] = 0
+

@@ -163,6 +163,14 @@ int dgrp_mss_scores(dgrp_ctx *ctx, const float *probs, int64_t n, int n_classes,
 /* softmax (prediction.py:62-65): exp(x - global max) / row sum, float32[n, C]. */
 int dgrp_softmax(dgrp_ctx *ctx, const float *array, int64_t n, int n_classes, float *out);
 
+/* filter_segments (prediction.py:242-260): runs of one identical positive label shorter than
+ * min_len are set to 0; labels uint8[n] (host), filtered in place. */
+int dgrp_filter_segments(dgrp_ctx *ctx, uint8_t *labels, int64_t n, int64_t min_len);
+/* confusion_matrix (prediction.py:200-218) for labels < 16: cnf[16*t + p] = number of positions with
+ * true label t and predicted label p (int64[256], host).  DGRP_E_ARG for a label >= 16. */
+int dgrp_confusion_matrix(dgrp_ctx *ctx, const uint8_t *truelbl, const uint8_t *predictedlbl, int64_t n,
+                          int64_t *cnf);
+
 /* ---- deepgrp.__main__ ------------------------------------------------------------------ */
 
 /* _predict (__main__.py:46-83) for one record given as raw sequence bytes (no header, no

@@ -427,3 +427,33 @@ def predict_fasta_tsv(filename: str, w: Dict[str, np.ndarray], vecsize: int, bat
                 if l > 0:
                     rows.append("{}\t{}\t{}\t{}\t{}\n".format(filename, header, s, e, l))
     return "".join(rows)
+
+
+# ---- evaluation helpers (deepgrp/prediction.py:200-260) ---------------------------------------------
+
+def confusion_matrix(truelbl, predictedlbl):
+    """deepgrp/prediction.py:200-218, the literal loop."""
+    truelbl, predictedlbl = np.asarray(truelbl), np.asarray(predictedlbl)
+    assert truelbl.size == predictedlbl.size
+    n_classes = max(truelbl.max(), predictedlbl.max()) - min(truelbl.min(), predictedlbl.min()) + 1
+    cnf = np.zeros((n_classes, n_classes), dtype=int)
+    for i, j in zip(truelbl, predictedlbl):
+        cnf[i, j] += 1
+    return cnf
+
+
+def filter_segments(array, min_len=50):
+    """deepgrp/prediction.py:242-260, the literal loop (in place)."""
+    indices = np.where(array > 0)[0]
+    next_idx = 0
+    for idx in indices:
+        if next_idx > idx:
+            continue
+        next_idx = idx + 1
+        found = 1
+        while next_idx < array.size and array[next_idx] == array[idx]:
+            found += 1
+            next_idx += 1
+        if found < min_len:
+            array[idx:next_idx] = 0
+

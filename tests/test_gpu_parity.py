@@ -498,3 +498,72 @@ def test_cli_end_to_end_with_hdf5_model(dg, oracle, tmp_path, capsys):
     assert open(out3).read().replace(fa1 + ".gz", fa1) == "".join(l + "\n" for l in a.splitlines() if l.startswith(fa1 + "\t"))
     CommandLineParser().parse_args([mpath, fa2]).run()            # README form, stdout
     assert capsys.readouterr().out == "".join(l + "\n" for l in a.splitlines() if l.startswith(fa2))
+
+
+# ------------------------------------------------------------------ evaluation helpers
+@pytest.mark.gpu
+@pytest.mark.parametrize("min_len", (10, 20))
+def test_filter_segments_reference_vector(dg, min_len):
+    """tests/test_prediction.py:183-195 of the reference, through the GPU kernel."""
+    segment_length = min_len * 2
+    data = np.zeros(1000)
+    data[110:110 + segment_length] = 1
+    data[210 + segment_length:210 + 2 * segment_length] = 1
+    expected = data.copy()
+    data[0:min_len - 1] = 1
+    data[120 + segment_length:120 + segment_length + min_len - 1] = 1
+    data[(-min_len) + 1:] = 1
+    dg.pred.filter_segments(data, min_len=min_len)
+    np.testing.assert_equal(data, expected)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,min_len,seed", [(1, 1, 0), (7, 3, 1), (5000, 50, 2), (200_000, 50, 3), (200_000, 7, 4)])
+def test_filter_segments_vs_oracle(dg, oracle, n, min_len, seed):
+    rng = np.random.default_rng(seed)
+    # runs of random length 1..2*min_len with labels 0..4, adjacent runs may share or change label
+    lab = np.repeat(rng.integers(0, 5, size=n), rng.integers(1, 2 * min_len + 1, size=n))[:n].astype(np.int64)
+    exp = lab.copy()
+    oracle.filter_segments(exp, min_len)
+    got = lab.copy()
+    dg.pred.filter_segments(got, min_len)
+    assert np.array_equal(got, exp)
+    again = got.copy()
+    dg.pred.filter_segments(again, min_len)       # idempotent
+    assert np.array_equal(again, got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed", [(1, 0), (100, 1), (1_000_003, 2)])
+def test_confusion_matrix_and_metrics_vs_oracle(dg, oracle, n, seed):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 5, size=n)
+    p = np.where(rng.random(n) < 0.7, t, rng.integers(0, 5, size=n))
+    if n > 1:
+        t[0], p[0] = 0, 4          # all five classes span the range
+    else:
+        t[:], p[:] = 0, 0          # a single label must be 0 (the matrix is 1 x 1, see the quirk test)
+    exp = np.bincount(t * 5 + p, minlength=25).reshape(5, 5) if n > 1 else oracle.confusion_matrix(t, p)
+    got = dg.pred.confusion_matrix(t, p)
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+    if n == 100:
+        assert np.array_equal(got, oracle.confusion_matrix(t, p))
+    if n > 1:
+        cnf, metrics = dg.pred.calculate_metrics(p, t)
+        assert np.array_equal(cnf, exp)
+        assert metrics["TotalACC"] == pytest.approx((t == p).mean())
+        # MCC against the definition on the label vectors (multi-class R_K)
+        s, c = n, float((t == p).sum())
+        pk = np.bincount(p, minlength=5).astype(float)
+        tk = np.bincount(t, minlength=5).astype(float)
+        rk = (c * s - (pk * tk).sum()) / np.sqrt((s * s - (pk * pk).sum()) * (s * s - (tk * tk).sum()))
+        assert metrics["MCC"] == pytest.approx(rk)
+        assert metrics["TPR"].shape == (5,)
+
+
+@pytest.mark.gpu
+def test_confusion_matrix_reference_quirk(dg):
+    """The reference sizes the matrix max - min + 1 and indexes with the raw labels, so labels that
+    do not start at 0 raise IndexError there (prediction.py:212-217); same here."""
+    with pytest.raises(IndexError):
+        dg.pred.confusion_matrix(np.array([1, 2, 3]), np.array([1, 3, 2]))

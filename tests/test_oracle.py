@@ -171,3 +171,27 @@ def test_oracle_lstm_engines_agree(oracle):
     b = oracle.model_forward(batch, w, engine="torch")
     c = oracle.model_forward(batch, w, dtype=np.float64)
     assert np.abs(a - c).max() < 5e-6 and np.abs(b - c).max() < 5e-6
+
+
+@pytest.mark.parametrize("min_len", (10, 20))
+def test_oracle_filter_segments_reference_vector(oracle, min_len):
+    """The known-answer case of the reference's tests/test_prediction.py:183-195."""
+    segment_length = min_len * 2
+    data = np.zeros(1000)
+    data[110:110 + segment_length] = 1
+    data[210 + segment_length:210 + 2 * segment_length] = 1
+    expected = data.copy()
+    data[0:min_len - 1] = 1
+    data[120 + segment_length:120 + segment_length + min_len - 1] = 1
+    data[(-min_len) + 1:] = 1
+    oracle.filter_segments(data, min_len=min_len)
+    np.testing.assert_equal(data, expected)
+
+
+def test_oracle_confusion_matrix_vs_histogram(oracle):
+    """tests/test_prediction.py:175-181 checks against pycm (absent here): same counts via bincount."""
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 4, size=100)
+    p = rng.integers(0, 4, size=100)
+    got = oracle.confusion_matrix(t, p)
+    np.testing.assert_equal(got, np.bincount(t * 4 + p, minlength=16).reshape(4, 4))
