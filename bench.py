@@ -320,6 +320,110 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_chunk(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: ONE record split by position ranges over the ranks (halo recompute, no
+    max-merge exchange); label (1 B) + score (4 B) per base are gathered to rank 0 over NCCL, which runs
+    MSS, gap fill and segment extraction for the whole record.  Strong scaling: `value` = record bases /
+    max-over-ranks time of the whole step."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from deepgrp_b200 import _lib, model, sharding
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.context(local_rank)
+    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    handle = weights.device_handle(ctx)
+    L = args.bases
+    d_codes = torch.from_numpy(synth_codes(L, [1, 0])).cuda()       # the same record on every rank
+    ranges = sharding.split_positions(L, world)
+    p0, p1 = ranges[rank]
+    pad = max(b - a for a, b in ranges)
+    d_lab = torch.zeros(pad, dtype=torch.uint8, device="cuda")
+    d_sc = torch.zeros(pad, dtype=torch.float32, device="cuda")
+    labs = [torch.empty(pad, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+    scs = [torch.empty(pad, dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
+    full_lab = torch.empty(L, dtype=torch.uint8, device="cuda") if rank == 0 else None
+    full_sc = torch.empty(L, dtype=torch.float32, device="cuda") if rank == 0 else None
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    n_rows = ctypes.c_int64(0)
+    lib = _lib.lib()
+    stage = {"range_ms": [], "finish_ms": []}
+
+    def step():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        _lib.check(lib.dgrp_predict_range_dev(
+            ctx.handle, handle, ctypes.c_void_p(d_codes.data_ptr()), 0, L, L, p0, p1, STEP, BATCH,
+            _lib.COMPAT_REFERENCE, ctypes.c_void_p(d_lab.data_ptr()), ctypes.c_void_p(d_sc.data_ptr())))
+        stage["range_ms"].append(ctx.timings()["total_ms"])
+        with torch.cuda.stream(stream):
+            if world > 1:
+                dist.gather(d_lab, labs, dst=0)
+                dist.gather(d_sc, scs, dst=0)
+            if rank == 0:
+                for r, (a, b) in enumerate(ranges):
+                    full_lab[a:b] = (labs[r] if world > 1 else d_lab)[:b - a]
+                    full_sc[a:b] = (scs[r] if world > 1 else d_sc)[:b - a]
+        if rank == 0:
+            _lib.check(lib.dgrp_finish_record_dev(
+                ctx.handle, ctypes.c_void_p(full_lab.data_ptr()), ctypes.c_void_p(full_sc.data_ptr()), L,
+                5, 1, MIN_MSS, XDROP, ctypes.byref(n_rows)))
+            stage["finish_ms"].append(ctx.timings()["total_ms"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    stage = {"range_ms": [], "finish_ms": []}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([elapsed_ms, float(np.mean(stage["range_ms"]))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, range_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        cfg = workload_config(args, L)
+        cfg["workload"] = ("BASELINE.json configs[2]: defaults.toml architecture (vecsize %d, units %d, attention), "
+                           "random-init weights seed 0, ONE synthetic iid-ACGT record split by position ranges "
+                           "over the ranks" % (args.vecsize, args.units))
+        cfg["sharding"] = ("position ranges with halo recompute; NCCL gather of label (u8) + score (f32) to rank 0, "
+                           "which runs MSS + segments for the whole record")
+        line = {
+            "metric": "bases classified/sec end-to-end", "value": L * args.steps / (elapsed_ms / 1e3) / 1e6,
+            "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "gpu_launches": int(launches),
+            "stages_ms": {"range_forward_score_max_over_ranks": range_ms,
+                          "finish_mss_segments_rank0": float(np.mean(stage["finish_ms"])),
+                          "gather_and_rest": elapsed_ms / args.steps - range_ms - float(np.mean(stage["finish_ms"]))},
+            "gather_bytes_per_step": 5 * (L - (ranges[0][1] - ranges[0][0])) if world > 1 else 0,
+            "rows_per_step": int(n_rows.value), "mss_rounds": ctx.get_int("mss_rounds"),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,12 +436,17 @@ def main():
     ap.add_argument("--ref-bases", type=int, default=100_000,
                     help="bases per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="contig", choices=["contig", "chunk"],
+                    help="contig (default): one record per rank, weak scaling; chunk: ONE record split by "
+                         "position ranges over the ranks (BASELINE.json configs[2], strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.shard == "chunk":
+        run_chunk(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -94,6 +94,8 @@ SIGNATURES = {
     "dgrp_fasta_records": (_I, [_P, _P, _P, _P, _P, _L]),
     "dgrp_fasta_record_tsv": (_I, [_P, _P, _P, _P, _L]),
     "dgrp_predict_codes_dev": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _PL]),
+    "dgrp_predict_range_dev": (_I, [_P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
+    "dgrp_finish_record_dev": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _PL]),
     "dgrp_filter_segments": (_I, [_P, _P, _L, _L]),
     "dgrp_confusion_matrix": (_I, [_P, _P, _P, _L, _P]),
 }

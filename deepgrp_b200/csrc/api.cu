@@ -945,12 +945,15 @@ int dgrp_predict_codes_dev(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, i
   return rc;
 }
 
-int dgrp_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *codes, int64_t codes_base,
-                       int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
-                       int batch_size, int compat, uint8_t *labels, float *scores) {
-  Use use(c->device);
+}  // extern "C"
+
+// positions [pos0, pos1) of a record from device codes: label + score into device buffers
+static int core_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
+                              int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                              int batch_size, int compat, uint8_t *d_labels, float *d_scores) {
   DGRP_REQUIRE(0 <= pos0 && pos0 <= pos1 && pos1 <= length, "bad range [%lld, %lld) of %lld",
                (long long)pos0, (long long)pos1, (long long)length);
+  DGRP_REQUIRE(step > 0, "step_size must be positive");
   const int64_t rows = pos1 - pos0;
   if (rows == 0) return DGRP_OK;
   const Placement pl = make_placement(length, m->T, step, batch_size, compat);
@@ -976,20 +979,49 @@ int dgrp_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *codes, int64_t
     DGRP_REQUIRE(codes_base <= need_lo && need_hi <= codes_base + codes_len,
                  "codes [%lld, %lld) do not cover the needed bases [%lld, %lld)", (long long)codes_base,
                  (long long)(codes_base + codes_len), (long long)need_lo, (long long)need_hi);
-  DGRP_CHECK(c->codes.reserve((size_t)codes_len + 16));
-  DGRP_CUDA(cudaMemcpyAsync(c->codes.p, codes, (size_t)codes_len, cudaMemcpyHostToDevice, c->stream));
+  c->timings.windows = (a1 - a0) + (t1 - t0);
+  c->timings.bases = rows;
   DGRP_CHECK(c->pred.reserve((size_t)rows * m->C * 4));
   DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)rows * m->C * 4, c->stream));
-  DGRP_CHECK(run_forward_vote(c, m, c->codes.as<uint8_t>(), codes_base, a0, a1, pl, c->pred.as<float>(), pos0, rows));
-  DGRP_CHECK(run_forward_vote(c, m, c->codes.as<uint8_t>(), codes_base, t0, t1, pl, c->pred.as<float>(), pos0, rows));
+  DGRP_CHECK(run_forward_vote(c, m, d_codes, codes_base, a0, a1, pl, c->pred.as<float>(), pos0, rows));
+  DGRP_CHECK(run_forward_vote(c, m, d_codes, codes_base, t0, t1, pl, c->pred.as<float>(), pos0, rows));
+  return launch_score(c, c->pred.as<float>(), rows, m->C, d_labels, d_scores, nullptr, nullptr);
+}
+
+extern "C" {
+
+int dgrp_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *codes, int64_t codes_base,
+                       int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                       int batch_size, int compat, uint8_t *labels, float *scores) {
+  Use use(c->device);
+  DGRP_REQUIRE(0 <= pos0 && pos0 <= pos1 && pos1 <= length, "bad range [%lld, %lld) of %lld",
+               (long long)pos0, (long long)pos1, (long long)length);
+  const int64_t rows = pos1 - pos0;
+  if (rows == 0) return DGRP_OK;
+  DGRP_CHECK(c->codes.reserve((size_t)codes_len + 16));
+  DGRP_CUDA(cudaMemcpyAsync(c->codes.p, codes, (size_t)codes_len, cudaMemcpyHostToDevice, c->stream));
   DGRP_CHECK(c->labels.reserve((size_t)rows));
   DGRP_CHECK(c->scores32.reserve((size_t)rows * 4));
-  DGRP_CHECK(launch_score(c, c->pred.as<float>(), rows, m->C, c->labels.as<uint8_t>(),
-                          c->scores32.as<float>(), nullptr, nullptr));
+  DGRP_CHECK(core_predict_range(c, m, c->codes.as<uint8_t>(), codes_base, codes_len, length, pos0, pos1, step,
+                                batch_size, compat, c->labels.as<uint8_t>(), c->scores32.as<float>()));
   if (labels) DGRP_CUDA(cudaMemcpyAsync(labels, c->labels.p, (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
   if (scores) DGRP_CUDA(cudaMemcpyAsync(scores, c->scores32.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->stream));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   return DGRP_OK;
+}
+
+int dgrp_predict_range_dev(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
+                           int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                           int batch_size, int compat, uint8_t *d_labels, float *d_scores) {
+  Use use(c->device);
+  const int64_t launches0 = c->launches;
+  stamp(c, 0);
+  stamp(c, 1);
+  const int rc = core_predict_range(c, m, d_codes, codes_base, codes_len, length, pos0, pos1, step, batch_size,
+                                    compat, d_labels, d_scores);
+  stamp(c, 2); stamp(c, 3); stamp(c, 4); stamp(c, 5);
+  finish_timings(c, launches0);
+  return rc;
 }
 
 int dgrp_finish_record(dgrp_ctx *c, const uint8_t *labels, const float *scores, int64_t length,
@@ -1009,6 +1041,21 @@ int dgrp_finish_record(dgrp_ctx *c, const uint8_t *labels, const float *scores, 
     DGRP_CUDA(cudaMemcpyAsync(labels_out, c->labels2.p, (size_t)length, cudaMemcpyDeviceToHost, c->stream));
   const int rc = core_rows(c, length, startpos, 0, true, rows, cap, n_rows);
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+int dgrp_finish_record_dev(dgrp_ctx *c, const uint8_t *d_labels, const float *d_scores, int64_t length,
+                           int n_classes, int use_mss, int min_mss_len, int xdrop_len, int64_t *n_rows) {
+  Use use(c->device);
+  const int64_t launches0 = c->launches;
+  *n_rows = 0;
+  stamp(c, 0); stamp(c, 1); stamp(c, 2);
+  DGRP_CHECK(core_labels(c, nullptr, d_labels, d_scores, length, n_classes, use_mss, min_mss_len, xdrop_len));
+  stamp(c, 4);
+  int rc = DGRP_OK;
+  if (length > 0) rc = core_rows(c, length, 0, 0, false, nullptr, 0, n_rows);
+  stamp(c, 5);
+  finish_timings(c, launches0);
   return rc;
 }
 

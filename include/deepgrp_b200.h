@@ -195,6 +195,15 @@ int dgrp_finish_record(dgrp_ctx *ctx, const uint8_t *labels, const float *scores
                        int n_classes, int use_mss, int min_mss_len, int xdrop_len,
                        int64_t startpos, uint8_t *labels_out, dgrp_row_t *rows, int64_t cap,
                        int64_t *n_rows);
+/* Device-pointer forms of the two calls above, for chunk sharding inside one box: the codes, the
+ * per-range (label, score) outputs and the gathered inputs of the owner stay in HBM and travel
+ * between GPUs with one NCCL gather (bench.py --shard chunk).  _finish_record_dev leaves labels and
+ * segment triples on the device and returns the row count (like dgrp_predict_codes_dev). */
+int dgrp_predict_range_dev(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *d_codes, int64_t codes_base,
+                           int64_t codes_len, int64_t length, int64_t pos0, int64_t pos1, int step,
+                           int batch_size, int compat, uint8_t *d_labels, float *d_scores);
+int dgrp_finish_record_dev(dgrp_ctx *ctx, const uint8_t *d_labels, const float *d_scores, int64_t length,
+                           int n_classes, int use_mss, int min_mss_len, int xdrop_len, int64_t *n_rows);
 
 /* Whole-file driver (__main__.py:275-292 for one FASTA): raw FASTA text in, rows out.  The text is
  * decoded on the GPU (_read_multi_fasta, __main__.py:20-43: line stripping, '>' records, records

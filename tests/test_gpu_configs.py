@@ -201,3 +201,44 @@ def test_lstm_variant(dg, oracle, tmp_path, T, U):
     assert w2.rnn == "LSTM" and np.array_equal(w2.recurrent_kernel, w.recurrent_kernel)
     labels2, _, _ = dg.pred.predict_sequence(w2, text.encode(), 50, 256, True, 50, 50)
     assert np.array_equal(labels, labels2)
+
+
+@pytest.mark.gpu
+def test_chunk_sharding_device_entry_points(dg):
+    """bench.py --shard chunk on one GPU: three position ranges through dgrp_predict_range_dev, concatenated
+    on the device and finished with dgrp_finish_record_dev, give the row count of the whole-record call
+    (and the same labels/scores as the host-pointer dgrp_predict_range)."""
+    import ctypes
+    import torch
+    from deepgrp_b200 import _lib, sharding
+    ctx = dg.ctx
+    T, U, L = 150, 32, 61_234
+    w = dg.model.random_weights(T, U, attention=True, seed=3).scaled(4.0)
+    h = w.device_handle(ctx)
+    codes = np.random.default_rng(5).integers(0, 4, size=L, dtype=np.uint8)
+    d_codes = torch.from_numpy(codes).cuda()
+    lib = _lib.lib()
+    n_whole = ctypes.c_int64(0)
+    _lib.check(lib.dgrp_predict_codes_dev(ctx.handle, h, ctypes.c_void_p(d_codes.data_ptr()), L, 50, 256, 1, 50, 50,
+                                          _lib.COMPAT_REFERENCE, ctypes.byref(n_whole)))
+    full_lab = torch.empty(L, dtype=torch.uint8, device="cuda")
+    full_sc = torch.empty(L, dtype=torch.float32, device="cuda")
+    for (a, b) in sharding.split_positions(L, 3):
+        lab = torch.empty(b - a, dtype=torch.uint8, device="cuda")
+        sc = torch.empty(b - a, dtype=torch.float32, device="cuda")
+        _lib.check(lib.dgrp_predict_range_dev(ctx.handle, h, ctypes.c_void_p(d_codes.data_ptr()), 0, L, L, a, b, 50, 256,
+                                              _lib.COMPAT_REFERENCE, ctypes.c_void_p(lab.data_ptr()),
+                                              ctypes.c_void_p(sc.data_ptr())))
+        ctx.synchronize()
+        host_lab, host_sc = sharding.predict_range(w, codes, L, a, b, 50, 256)
+        assert np.array_equal(lab.cpu().numpy(), host_lab)
+        assert np.array_equal(sc.cpu().numpy(), host_sc)
+        full_lab[a:b] = lab
+        full_sc[a:b] = sc
+    torch.cuda.synchronize()
+    n_rows = ctypes.c_int64(0)
+    _lib.check(lib.dgrp_finish_record_dev(ctx.handle, ctypes.c_void_p(full_lab.data_ptr()),
+                                          ctypes.c_void_p(full_sc.data_ptr()), L, 5, 1, 50, 50, ctypes.byref(n_rows)))
+    assert n_rows.value == n_whole.value and n_rows.value > 0
+    out, rows = sharding.finish_record(full_lab.cpu().numpy(), full_sc.cpu().numpy(), 5, True, 50, 50, 0)
+    assert rows.size == n_rows.value
