@@ -221,7 +221,7 @@ int dgrp_ctx_destroy(dgrp_ctx *c) {
   Use use(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->raw, &c->codes, &c->onehot, &c->avg, &c->pred, &c->labels, &c->labels2,
-                    &c->scores32, &c->scores64, &c->classes64, &c->io_a, &c->io_b, &c->io_c,
+                    &c->scores32, &c->scores64, &c->classes64, &c->io_a, &c->io_b, &c->io_c, &c->winprobs,
                     &c->small, &c->segs, &c->rows, &c->mss_a, &c->mss_b, &c->mss_c, &c->mss_d,
                     &c->mss_e, &c->scan};
   for (auto b : bufs) b->release();
@@ -248,6 +248,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
+  else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -260,6 +261,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
+  else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }

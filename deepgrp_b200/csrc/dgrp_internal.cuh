@@ -89,7 +89,7 @@ struct dgrp_ctx {
   dgrp_timings_t timings = {};
   // workspaces (grow-only)
   dgrp::DevBuf raw, codes, onehot, avg, pred, labels, labels2, scores32, scores64, classes64,
-      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, mss_e, scan;
+      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, mss_e, scan, winprobs;
   dgrp::PinBuf pin_small, pin_a, pin_b;
   // tuning knobs / diagnostics (dgrp_ctx_set_int / dgrp_ctx_get_int)
   int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)
@@ -98,6 +98,8 @@ struct dgrp_ctx {
   int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
   int forward_sum16 = 1;   // tcgen05 forward: keep h_fwd + h_rc (attention scores only) in half precision
   int forward_fp16x2 = 1;  // tcgen05 forward: operands as 2 fp16 pieces / 3 products instead of 3 bf16 pieces / 6 products
+  int forward_gather = 1;  // tcgen05 forward: write window probabilities and max-merge them in a gather pass
+                           // (1) instead of 5 atomicMax per window-step (0); falls back to 0 above 40 GB
   int forward_used_tc = 0; // what the last forward launch used
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
@@ -131,6 +133,9 @@ int launch_onehot(dgrp_ctx *c, const uint8_t *d_seq, int64_t start, int64_t len,
 int launch_codes(dgrp_ctx *c, const uint8_t *d_seq, int64_t start, int64_t len, uint8_t *d_codes);
 int launch_onehot_to_codes(dgrp_ctx *c, const int8_t *d_fwd, int64_t len, uint8_t *d_codes);
 // vote.cu
+int launch_vote_gather(dgrp_ctx *c, const float *d_win, int64_t w_begin, int64_t w_end, int T, int C,
+                       int64_t full_windows, int64_t tail_base, int step, float *d_pred, int64_t pred_row0,
+                       int64_t pred_rows);
 int launch_get_max(dgrp_ctx *c, float *d_out, const float *d_in, int64_t batch, int64_t dim0,
                    int64_t dim1, int64_t stride);
 int launch_score(dgrp_ctx *c, const float *d_pred, int64_t n, int C, uint8_t *d_label,

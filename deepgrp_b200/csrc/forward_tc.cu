@@ -72,9 +72,18 @@ __shared__ unsigned int s_tc_trace[17][2][8];   // accumulated with fire-and-for
     if (lane == 0) atomicAdd(&s_tc_trace[warp][s][seg], now__ - tr_t);        \
     tr_t = now__;                                                             \
   } while (0)
+#define TC_TRACE2(seg)                                                        \
+  do {                                                                        \
+    const unsigned int now__ = (unsigned int)clock64();                       \
+    if (lane == 0) atomicAdd(&s_tc_trace2[warp][seg], now__ - tr_t);          \
+    tr_t = now__;                                                             \
+  } while (0)
+__shared__ unsigned int s_tc_trace2[16][8];   // second phase: 0 scores, 1 barrier, 2 softmax over t, 3 vote, 4 barrier
+__device__ unsigned long long g_tc_trace2[16][8];
 #else
 #define TC_TRACE_DECL
 #define TC_TRACE(seg)
+#define TC_TRACE2(seg)
 #endif
 
 template <int UP>
@@ -269,6 +278,12 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
 //     the second term.  A warp takes 8 adjacent windows x a slice of t; a lane takes one window and every
 //     fourth chunk, so each load instruction reads whole 128-byte lines; four denominators share one rcp.
 // (b) one warp per window, lanes over t: softmax over t, logits, class softmax and the max-vote.
+// Ask the L2 to fetch `bytes` (multiple of 16) from HBM: one instruction, no registers, no L1 miss entries.
+// The second phase reads scratch that left the L2 long ago; a single SM's demand loads sustain only
+// ~17 B/clk against HBM latency, but ~4x that against L2 hits.
+__device__ __forceinline__ void l2_prefetch(const void *ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float exp_fast(float x) {   // e^x through ex2.approx (2 ulp), e^{-inf} = 0
   return ex2_approx(x * 1.4426950408889634f);
 }
@@ -293,7 +308,8 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
   constexpr bool H16 = sizeof(ST) == 2;
   constexpr int NV = H16 ? 1 : 2;      // 16-byte loads per chunk
   constexpr int UNR = H16 ? 4 : 2;     // t's in flight per lane (scores)
-  constexpr int PU = 4;                // rows in flight per lane (softmax / vote passes)
+  constexpr int PU = 11;               // rows in flight per lane (softmax / vote passes): all of T <= 352 at once
+  TC_TRACE_DECL;
   for (int w0 = 0; w0 < WT; w0 += wpp) {
     if (w_tile0 + w0 >= p.w_end) break;
     if (p.attention) {
@@ -312,7 +328,19 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
         }
       }
       const ST *base = sum + ((size_t)cj * WT + wl) * 8;
+      // one warp per t-slice keeps the L2 PF_AHEAD rows ahead of the demand loads, PF_BLOCK rows at a time
+      // (a t-row of the tile is NCH * WT * 8 contiguous elements)
+      constexpr int PF_BLOCK = 4, PF_AHEAD = 12;
+      constexpr uint32_t ROW_BYTES = NCH * WT * 8 * sizeof(ST);
+      if (grp == 0 && lane == 0) {
+        const int n0 = min(PF_AHEAD, t_end - t_begin);
+        l2_prefetch(sum + (size_t)t_begin * NCH * WT * 8, (uint32_t)n0 * ROW_BYTES);
+      }
       for (int t0 = t_begin; t0 < t_end; t0 += UNR) {
+        if (grp == 0 && lane == 0 && (t0 - t_begin) % PF_BLOCK == 0) {
+          const int ta = t0 + PF_AHEAD;
+          if (ta < t_end) l2_prefetch(sum + (size_t)ta * NCH * WT * 8, (uint32_t)min(PF_BLOCK, t_end - ta) * ROW_BYTES);
+        }
         uint4 v[UNR][CPL][NV];
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
@@ -354,9 +382,14 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
         }
       }
     }
+    if (lane == 0 && warp < wpp) l2_prefetch(proj + (size_t)(w0 + warp) * T * 16, (uint32_t)T * 64u);
+    TC_TRACE2(0);
     asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");
+    TC_TRACE2(1);
     for (int wq = warp; wq < wpp; wq += NWARPS) {
       const int wl = w0 + wq;
+      if (lane == 0 && wq + NWARPS < wpp)   // the next window of this warp
+        l2_prefetch(proj + (size_t)(wl + NWARPS) * T * 16, (uint32_t)T * 64u);
       const int64_t w = w_tile0 + wl;
       if (w >= p.w_end) break;
       const float *pr = proj + (size_t)wl * T * 16;
@@ -408,6 +441,7 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
 #pragma unroll
         for (int c = 0; c < 5; ++c) ctxk[c] = cacc[c] / l;
       }
+      TC_TRACE2(2);
       // logits[t] = ctx.K1 + avg[t].K2 + b ; softmax over classes ; vote
       const int64_t place = (w < p.full_windows ? w * (int64_t)p.step
                                                 : p.tail_base + (w - p.full_windows) * (int64_t)p.step) -
@@ -438,17 +472,29 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
 #pragma unroll
           for (int c = 0; c < 5; ++c) { lg[c] = c < C ? exp_fast(lg[c] - mx) : 0.f; sum_e += lg[c]; }
           const float inv = 1.0f / sum_e;
-          const int64_t r = place + t;
-          if (t < T && r >= 0 && r < p.pred_rows) {
-            int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
+          if (p.win_probs) {
+            // plain stores of the window's probabilities; vote_gather_kernel max-merges them
+            if (t < T) {
+              float *dst = p.win_probs + ((size_t)(w - p.w_begin) * T + t) * C;
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-              if (c < C) atomicMax(dst + c, __float_as_int(lg[c] * inv));   // probs > 0
+              for (int c = 0; c < 5; ++c)
+                if (c < C) dst[c] = lg[c] * inv;
+            }
+          } else {
+            const int64_t r = place + t;
+            if (t < T && r >= 0 && r < p.pred_rows) {
+              int *dst = reinterpret_cast<int *>(p.pred + (size_t)r * C);
+#pragma unroll
+              for (int c = 0; c < 5; ++c)
+                if (c < C) atomicMax(dst + c, __float_as_int(lg[c] * inv));   // probs > 0
+            }
           }
         }
       }
     }
+    TC_TRACE2(3);
     asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");   // s_score is rewritten by the next pass
+    TC_TRACE2(4);
   }
 }
 
@@ -468,6 +514,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   float *s_bh = s_P + 10 * K::PSTRIDE;                         // [UP] recurrent bias of the h gate
   float *s_scale = s_bh + UP;                                  // [UP] attention scale
   float *s_score = s_scale + UP;                               // [wpp][T]
+  uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_score + (size_t)p.wpp * p.T);   // [2 tiles][fwd | rc][code_span] staged bases
   __shared__ __align__(8) unsigned long long s_ready[2], s_done[2];
   __shared__ uint32_t s_tmem;
 
@@ -503,6 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   }
 #ifdef DGRP_TC_TRACE
   for (int i = tid; i < 17 * 2 * 8; i += TC_THREADS) (&s_tc_trace[0][0][0])[i] = 0u;
+  for (int i = tid; i < 16 * 8; i += TC_THREADS) (&s_tc_trace2[0][0])[i] = 0u;
 #endif
   if (tid == 0) {
     mbar_init(smem_u32(&s_ready[0]), TC_GATE_WARPS * 32);
@@ -521,6 +569,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   // code sits inside the setmaxnreg branch, so the two roles have their own copy of the unit loop and
   // meet only through the mbarriers; the gate warps synchronise among themselves on named barrier 1.
   const bool is_gate = warp < TC_GATE_WARPS;
+  // Rounds per unit and tile slot: 1 priming round (2 when T is even) + T steps = an EVEN number, so that
+  // every unit starts with both mbarriers of a slot at phase parity 0 and the parity of a wait is a
+  // function of the step alone (a per-slot parity register was spilled and reloaded inside the step loop).
+  const int extra = (T & 1) ? 0 : 1;
   const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]);
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
@@ -536,19 +588,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   if (!is_gate) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_AUX_REGS));
     if (warp != TC_GATE_WARPS) return;   // the three idle warps of the issuer's warpgroup
-    uint32_t par[2] = {0u, 0u};   // barrier parity of each tile slot at the start of the unit
     int unit = 0;
     for (int64_t tile = tile_lo; tile < tile_hi; ++unit) {
       const int nt = (unit < lead || tile + 1 >= tile_hi) ? 1 : 2;
       const bool live1 = nt == 2;
       // ===================== MMA issuer: T + 1 rounds per tile (round 0 = priming on h = 0) =====
       TC_TRACE_DECL;
-      for (int k = 0; k <= T; ++k) {
+      for (int k = 0; k <= T + extra; ++k) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (s == 1 && !live1) continue;
           TC_TRACE(6);
-          mbar_wait_backoff(bar_ready + 8 * s, par[s] ^ (k & 1));
+          mbar_wait_backoff(bar_ready + 8 * s, (uint32_t)(k & 1));
           tc_fence_after();
           TC_TRACE(5);
           if (lane == 0) {
@@ -574,8 +625,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
           __syncwarp();
         }
       }
-      par[0] ^= (uint32_t)((T + 1) & 1);   // each live tile slot saw T + 1 phases of its barriers
-      if (live1) par[1] ^= (uint32_t)((T + 1) & 1);
       tile += nt;
     }
 #ifdef DGRP_TC_TRACE
@@ -590,7 +639,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   float *proj0 = p.ff2 + (size_t)blockIdx.x * 2 * K::WT * T * 16;                                 // [2][WT][T][16]
   float *q0 = p.qbuf + (size_t)blockIdx.x * 2 * K::WT * UP;                                       // [2][WT][UP]
   const float2 us = make_float2(p.b_unscale, p.b_unscale);
-  uint32_t par[2] = {0u, 0u};
   int unit = 0;
   for (int64_t tile = tile_lo; tile < tile_hi; ++unit) {
     const int nt = (unit < lead || tile + 1 >= tile_hi) ? 1 : 2;
@@ -604,22 +652,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     const float *bhp = s_bh + uq * K::UPT;
     const uint32_t a_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + ((uq * K::UPT) >> 3) * 128);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int cstep = dir ? -1 : 1;
-    const uint8_t *cptr[2];   // the base this row reads next step
-    int code[2];
+    // The bases of a tile are one contiguous span of 63 * step + T codes: staged in shared memory once
+    // per unit, so that the step loop has no global load (an L2 miss there stalls the whole tile).  Two
+    // copies, already translated to input-table rows: forward (rows 0..3, 8 for 'N') and reversed +
+    // complemented for the rc pass (rows 4..7, 9), so that both directions read position base + t.
+    int cbase[2];   // offset of this row's first base in its copy of the tile's span
+    {
+      const int nthr = TC_GATE_WARPS * 32;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        cbase[s] = 0;
+        if (s == 1 && !live1) continue;
+        const int64_t w_first = p.w_begin + (tile + s) * K::WT;
+        int64_t w_last = w_first + K::WT - 1;
+        w_last = w_last < p.w_end ? w_last : p.w_end - 1;
+        const int span = (int)((w_last - w_first) * p.step) + T;
+        const uint8_t *src = p.codes + (w_first * (int64_t)p.step - p.codes_base);
+        uint8_t *fwd_copy = s_codes + (size_t)(2 * s) * p.code_span, *rc_copy = fwd_copy + p.code_span;
+        for (int i = tid; i < span; i += nthr) {
+          const int c = src[i];
+          fwd_copy[i] = (uint8_t)(c < 4 ? c : 8);
+          rc_copy[span - 1 - i] = (uint8_t)(c < 4 ? c + 4 : 9);
+        }
+        // windows past the end replay the last valid one (their results are never used)
+        int64_t w = w_first + wl;
+        w = w < p.w_end ? w : p.w_end - 1;
+        const int off = (int)((w - w_first) * p.step);
+        cbase[s] = (2 * s + dir) * p.code_span + (dir ? span - off - T : off);
+      }
+      gate_bar_sync();
+    }
     float hprev[2][K::UPT];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      // windows past the end replay the last valid one (their results are never used)
-      int64_t w = p.w_begin + (tile + s) * K::WT + wl;
-      w = w < p.w_end ? w : p.w_end - 1;
-      cptr[s] = p.codes + (w * (int64_t)p.step - p.codes_base) + (dir ? T - 1 : 0);
-      code[s] = 4;
 #pragma unroll
       for (int j = 0; j < K::UPT; ++j) hprev[s][j] = 0.f;
       if (s == 1 && !live1) continue;
-      code[s] = *cptr[s];
-      cptr[s] += cstep;
       // h[-1] = 0: zero this thread's slots of the A operand and let the issuer prime the accumulator
       unsigned char *a_tile = s_A + (size_t)s * NP * K::A_BYTES + a_off;
 #pragma unroll
@@ -630,6 +698,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_ready + 8 * s);
+      if (extra) {   // second priming round on the same all-zero operand
+        mbar_wait(bar_done + 8 * s, 0u);
+        mbar_arrive(bar_ready + 8 * s);
+      }
     }
     TC_TRACE_DECL;
 #pragma unroll 1
@@ -637,15 +709,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (s == 1 && !live1) continue;   // uniform over the CTA
-        const float *prow = tblp + (code[s] < 4 ? code[s] + 4 * dir : 8 + dir) * K::PSTRIDE;
-        if (t + 1 < T) {   // next step's base, consumed one iteration later
-          code[s] = *cptr[s];
-          cptr[s] += cstep;
-        }
+        const int trow = s_codes[cbase[s] + t];   // input-table row of this step's base
         TC_TRACE(4);
-        mbar_wait(bar_done + 8 * s, par[s] ^ (t & 1));
+        mbar_wait(bar_done + 8 * s, (uint32_t)((t + extra) & 1));
         tc_fence_after();
         TC_TRACE(0);
+        const float *prow = tblp + trow * K::PSTRIDE;
         const uint32_t t_tile = t_lane + (uint32_t)(s * K::TCOLS);
         unsigned char *a_tile = s_A + (size_t)s * NP * K::A_BYTES + a_off;
         const size_t rt = (size_t)(s * K::WT + wl) * T + t;   // (window, t) row of the scratch arrays
@@ -744,7 +813,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (s == 1 && !live1) continue;
-      mbar_wait(bar_done + 8 * s, par[s] ^ (T & 1));
+      mbar_wait(bar_done + 8 * s, (uint32_t)((T + extra) & 1));
       tc_fence_after();
       float pj[4];
       tmem_ld4(t_lane + (uint32_t)(s * K::TCOLS + K::NG + 4 * uq), pj);
@@ -760,8 +829,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     }
     tc_fence_before();
     }
-    par[0] ^= (uint32_t)((T + 1) & 1);
-    if (live1) par[1] ^= (uint32_t)((T + 1) & 1);
     // ---- attention + FF + softmax + vote for the unit's tiles ------------------------------------
     __threadfence_block();
     gate_bar_sync();
@@ -778,6 +845,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   gate_bar_sync();
 #ifdef DGRP_TC_TRACE
   if (blockIdx.x == 0 && tid < 16 * 16) g_tc_trace[tid >> 4][(tid >> 3) & 1][tid & 7] += s_tc_trace[tid >> 4][(tid >> 3) & 1][tid & 7];
+  if (blockIdx.x == 0 && tid < 16 * 8) g_tc_trace2[tid >> 3][tid & 7] += s_tc_trace2[tid >> 3][tid & 7];
 #endif
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -787,10 +855,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 }
 
 template <int UP, int NP>
-static size_t tc_smem_bytes(int T, int wpp) {
+static size_t tc_smem_bytes(int T, int wpp, int code_span) {
   using K = TCfg<UP>;
   return (size_t)NP * K::B_BYTES + 2 * NP * K::A_BYTES +
-         sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + (size_t)wpp * T) + 128;
+         sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + (size_t)wpp * T) + 4 * (size_t)code_span + 128;
 }
 
 template <int UP, typename ST, int NP>
@@ -799,9 +867,13 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
   // windows per pass of the second phase: as many score rows as shared memory holds
+  // staged base codes of a tile: 63 * step + T bytes; very large steps have no tcgen05 form
+  const int64_t span = (int64_t)(K::WT - 1) * p.step + p.T;
+  if (span > 16384) return DGRP_E_UNSUPPORTED;
+  p.code_span = (int)((span + 15) & ~(int64_t)15);
   int wpp = K::WT;
-  while (wpp > 8 && tc_smem_bytes<UP, NP>(p.T, wpp) > 227 * 1024) wpp >>= 1;
-  const size_t smem = tc_smem_bytes<UP, NP>(p.T, wpp);
+  while (wpp > 8 && tc_smem_bytes<UP, NP>(p.T, wpp, p.code_span) > 227 * 1024) wpp >>= 1;
+  const size_t smem = tc_smem_bytes<UP, NP>(p.T, wpp, p.code_span);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
   p.wpp = wpp;
   auto kern = gru_tc_attention_vote_kernel<UP, ST, NP>;
@@ -815,9 +887,20 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   p.scratch = c->avg.as<float>();
   p.qbuf = reinterpret_cast<float *>(c->avg.as<unsigned char>() + rows * p.T * UP * sizeof(ST));
   p.ff2 = c->io_c.as<float>();
+  // the vote: window probabilities + gather pass (5 plain stores per window-step instead of 5 atomics,
+  // whose issue rate bounded the second phase), when the [windows][T][C] buffer is affordable
+  p.win_probs = nullptr;
+  const size_t win_bytes = (size_t)n_windows * p.T * p.C * sizeof(float);
+  if (c->forward_gather && win_bytes <= ((size_t)40 << 30)) {
+    if (c->winprobs.reserve(win_bytes) == DGRP_OK) p.win_probs = c->winprobs.as<float>();
+    else cudaGetLastError();   // out of memory: keep the atomic vote
+  }
   kern<<<grid, TC_THREADS, smem, c->stream>>>(p);
   c->launches++;
   DGRP_CUDA(cudaGetLastError());
+  if (p.win_probs)
+    DGRP_CHECK(launch_vote_gather(c, p.win_probs, p.w_begin, p.w_end, p.T, p.C, p.full_windows, p.tail_base,
+                                  p.step, p.pred, p.pred_row0, p.pred_rows));
   return DGRP_OK;
 }
 
@@ -830,6 +913,13 @@ extern "C" int dgrp_debug_tc_trace(unsigned long long *out, int reset) {
     return (int)cudaMemcpyToSymbol(g_tc_trace, zero, sizeof(zero));
   }
   return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 17 * 2 * 8);
+}
+extern "C" int dgrp_debug_tc_trace2(unsigned long long *out, int reset) {
+  if (reset) {
+    static unsigned long long zero[16][8];
+    return (int)cudaMemcpyToSymbol(g_tc_trace2, zero, sizeof(zero));
+  }
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace2, sizeof(unsigned long long) * 16 * 8);
 }
 #endif
 

@@ -46,6 +46,65 @@ int launch_get_max(dgrp_ctx *c, float *d_out, const float *d_in, int64_t batch, 
   return DGRP_OK;
 }
 
+// Max-merge of window probabilities into the prediction rows (the vote of prediction.py:103-111 /
+// maxcalc.c:10-24 in gather form): row r takes the maximum over the windows of [w_begin, w_end) whose
+// PLACED rows cover it -- windows of complete batches sit at w * step, those of the short last batch
+// at tail_base + (w - full_windows) * step (prediction.py:105).  `win` is [w - w_begin][T][C].  One
+// thread per row; consecutive rows read consecutive 4C-byte records of the same window.  The row's
+// current value takes part in the maximum (zero-initialised, or the other window family's result).
+__global__ void vote_gather_kernel(const float *__restrict__ win, int64_t w_begin, int64_t w_end, int T, int C,
+                                   int64_t full_windows, int64_t tail_base, int step,
+                                   float *__restrict__ pred, int64_t pred_row0, int64_t pred_rows) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < pred_rows; r += gs) {
+    const int64_t g = r + pred_row0;   // record position
+    float acc[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] = k < C ? pred[r * C + k] : 0.f;
+    bool any = false;
+#pragma unroll
+    for (int fam = 0; fam < 2; ++fam) {
+      // family 0: windows [w_begin, min(w_end, full)) placed at w * step
+      // family 1: windows [max(w_begin, full), w_end) placed at tail_base + (w - full) * step
+      const int64_t w_lo = fam == 0 ? w_begin : (w_begin > full_windows ? w_begin : full_windows);
+      const int64_t w_hi = fam == 0 ? (w_end < full_windows ? w_end : full_windows) : w_end;
+      if (w_lo >= w_hi) continue;
+      const int64_t origin = fam == 0 ? 0 : tail_base - full_windows * (int64_t)step;   // place(w) = origin + w*step
+      const int64_t x = g - origin;                                                      // w*step <= x < w*step + T
+      if (x < 0) continue;
+      int64_t a = x >= T ? (x - T) / step + 1 : 0, b = x / step;
+      if (a < w_lo) a = w_lo;
+      if (b > w_hi - 1) b = w_hi - 1;
+      for (int64_t w = a; w <= b; ++w) {
+        const float *src = win + ((size_t)(w - w_begin) * T + (size_t)(x - w * step)) * C;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (k < C) acc[k] = fmaxf(acc[k], src[k]);
+        any = true;
+      }
+    }
+    if (any) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < C) pred[r * C + k] = acc[k];
+    }
+  }
+}
+
+int launch_vote_gather(dgrp_ctx *c, const float *d_win, int64_t w_begin, int64_t w_end, int T, int C,
+                       int64_t full_windows, int64_t tail_base, int step, float *d_pred, int64_t pred_row0,
+                       int64_t pred_rows) {
+  if (pred_rows <= 0 || w_end <= w_begin) return DGRP_OK;
+  const int threads = 256;
+  const int64_t want = (pred_rows + threads - 1) / threads;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  vote_gather_kernel<<<(unsigned)(want < cap ? want : cap), threads, 0, c->stream>>>(
+      d_win, w_begin, w_end, T, C, full_windows, tail_base, step, d_pred, pred_row0, pred_rows);
+  c->launches++;
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
 // prediction.py:51-57 (float32 arithmetic, then widened):
 //   cls = argmax(p) (first maximum); m = max(p) + 1e-6f; m > 0.99f -> 0.99f;
 //   t = logf(m / (1 - m)); score = cls > 0 ? t : -10 * t.

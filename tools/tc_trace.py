@@ -43,6 +43,7 @@ def run(bases):
     lib = _lib.lib()
     prediction.predict(w, ds, (bases, 5), 50)          # warm-up
     lib.dgrp_debug_tc_trace(None, 1)
+    lib.dgrp_debug_tc_trace2(None, 1)
     prediction.predict(w, ds, (bases, 5), 50)
     buf = (ctypes.c_ulonglong * (17 * 2 * 8))()
     lib.dgrp_debug_tc_trace(buf, 0)
@@ -59,6 +60,12 @@ def run(bases):
     for k, name in enumerate(names):
         print("  %-18s %7.0f   (%5.0f .. %5.0f)" % (name, per[:, k].mean(), per[:, k].min(), per[:, k].max()))
     print("  %-18s %7.0f" % ("sum", per.sum(axis=1).mean()))
+    buf2 = (ctypes.c_ulonglong * (16 * 8))()
+    lib.dgrp_debug_tc_trace2(buf2, 0)
+    tr2 = np.array(buf2[:], dtype=np.float64).reshape(16, 8) / tiles0
+    print("second phase, cycles per tile (mean over the 16 warps; the recurrence of a tile is %d x the tile-step):" % T)
+    for k, name in enumerate(["scores", "barrier", "softmax over t", "logits + vote", "barrier"]):
+        print("  %-18s %8.0f   (%6.0f .. %6.0f)" % (name, tr2[:, k].mean(), tr2[:, k].min(), tr2[:, k].max()))
     iss = tr[16, :, 5:7].sum(axis=0) / steps
     print("issuer per tile-step: waiting for ready %.0f, issuing %.0f" % (iss[0], iss[1]))
 
