@@ -315,6 +315,26 @@ def test_tensor_core_forward_is_fp32_faithful(dg, oracle, T, U, sum16, fp16x2):
     assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
 
 
+@pytest.mark.parametrize("T,U,step,L", [(512, 40, 50, 9_000),     # scores of 64 windows do not fit: passes of 32
+                                        (151, 32, 50, 6_000),     # odd window: one priming round
+                                        (342, 60, 7, 3_000),      # small step: dense overlap in the gather
+                                        (150, 32, 200, 30_000),   # step > T: uncovered gaps between windows
+                                        (33, 20, 50, 4_000),      # window barely longer than a warp
+                                        (342, 60, 250, 40_000)])  # largest staged span per tile
+def test_tensor_core_forward_shapes(dg, oracle, T, U, step, L):
+    """Shapes that exercise the kernel's less travelled paths, against the float64 oracle."""
+    w = dg.model.random_weights(T, U, attention=True, seed=11).scaled(2.0)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(random_dna(L, T + step))
+    ds = dg.pred.fetch_validation_batch(fwd, step, 16, T)
+    tc = dg.pred.predict(w, ds, (fwd.shape[1], 5), step)
+    assert dg.ctx.get_int("forward_used_tc") == 1
+    ref64 = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict(), dtype=np.float64).astype(np.float32),
+                           oracle.fetch_validation_batch(fwd, step, 16, T), (fwd.shape[1], 5), step)
+    assert np.array_equal(tc == 0, ref64 == 0)          # the same rows are covered
+    assert np.abs(tc - ref64).max() < 2e-5
+    assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
+
+
 def test_tensor_core_forward_random_init_regime(dg, oracle):
     """The benchmark's regime (random-init weights, near-uniform outputs, class margins ~1e-4): the
     default forward must be float32-faithful there, or labels flip."""
