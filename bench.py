@@ -63,12 +63,18 @@ def flops_per_window(T, U):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  Started before
+    the warm-up (nvidia-smi needs ~0.2 s to come up); only the samples that arrive between mark_begin()
+    and stop() count."""
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t_begin = None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -77,23 +83,27 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "40"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.perf_counter() + 0.05   # the row in flight when the region ended
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        for ts, r in self.rows:
+            if ts < t0 or ts > t_end:
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -237,15 +247,16 @@ def run_ours(args, rank, world, local_rank):
         devnull.write(view)
         return len(view)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fwd_ms, stage_ms = [], []
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     for _ in range(args.steps):
         t = device_step()
@@ -379,15 +390,16 @@ def run_chunk(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     stage = {"range_ms": [], "finish_ms": []}
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     for _ in range(args.steps):
         step()

@@ -656,29 +656,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     // per unit, so that the step loop has no global load (an L2 miss there stalls the whole tile).  Two
     // copies, already translated to input-table rows: forward (rows 0..3, 8 for 'N') and reversed +
     // complemented for the rc pass (rows 4..7, 9), so that both directions read position base + t.
-    int cbase[2];   // offset of this row's first base in its copy of the tile's span
+    // Offset of this row's first base in its copy of tile slot 0's span; slot 1 is 2 * code_span further.
+    // The reversed copy is laid out against the FULL span (63 * step + T) so that the offset does not
+    // depend on the slot; what a short last tile does not cover is filled with 'N' rows (the windows
+    // past the end compute on them; their results are never used).
+    const int full_span = (K::WT - 1) * p.step + T;
+    const int cbase = dir * p.code_span + (dir ? full_span - wl * p.step - T : wl * p.step);
     {
       const int nthr = TC_GATE_WARPS * 32;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        cbase[s] = 0;
-        if (s == 1 && !live1) continue;
+      for (int s = 0; s < nt; ++s) {
         const int64_t w_first = p.w_begin + (tile + s) * K::WT;
         int64_t w_last = w_first + K::WT - 1;
         w_last = w_last < p.w_end ? w_last : p.w_end - 1;
         const int span = (int)((w_last - w_first) * p.step) + T;
         const uint8_t *src = p.codes + (w_first * (int64_t)p.step - p.codes_base);
         uint8_t *fwd_copy = s_codes + (size_t)(2 * s) * p.code_span, *rc_copy = fwd_copy + p.code_span;
-        for (int i = tid; i < span; i += nthr) {
-          const int c = src[i];
+        for (int i = tid; i < full_span; i += nthr) {
+          const int c = i < span ? src[i] : 4;
           fwd_copy[i] = (uint8_t)(c < 4 ? c : 8);
-          rc_copy[span - 1 - i] = (uint8_t)(c < 4 ? c + 4 : 9);
+          rc_copy[full_span - 1 - i] = (uint8_t)(c < 4 ? c + 4 : 9);
         }
-        // windows past the end replay the last valid one (their results are never used)
-        int64_t w = w_first + wl;
-        w = w < p.w_end ? w : p.w_end - 1;
-        const int off = (int)((w - w_first) * p.step);
-        cbase[s] = (2 * s + dir) * p.code_span + (dir ? span - off - T : off);
       }
       gate_bar_sync();
     }
@@ -709,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (s == 1 && !live1) continue;   // uniform over the CTA
-        const int trow = s_codes[cbase[s] + t];   // input-table row of this step's base
+        const int trow = s_codes[cbase + s * 2 * p.code_span + t];   // input-table row of this step's base
         TC_TRACE(4);
         mbar_wait(bar_done + 8 * s, (uint32_t)((t + extra) & 1));
         tc_fence_after();
@@ -720,20 +717,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
         const size_t rt = (size_t)(s * K::WT + wl) * T + t;   // (window, t) row of the scratch arrays
         float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
         tmem_ld4(t_tile + (uint32_t)(K::NG + 4 * uq), pj);
-        float azf[K::UPT / 8][8], arf[K::UPT / 8][8], ahf[K::UPT / 8][8];
-#pragma unroll
-        for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
-          const uint32_t taddr = t_tile + (uint32_t)(uq * K::UPT + c8 * 8);
-          tmem_ld8(taddr, azf[c8]);
-          tmem_ld8(taddr + UP, arf[c8]);
-          tmem_ld8(taddr + 2 * UP, ahf[c8]);
-        }
-        tmem_ld_wait();
-        TC_TRACE(1);
         float2 hn2[K::UPT / 8][4];   // the new state of this thread's units
 #pragma unroll
         for (int c8 = 0; c8 < K::UPT / 8; ++c8) {
-          const float *az = azf[c8], *ar = arf[c8], *ah = ahf[c8];
+          float az[8], ar[8], ah[8];
+          {
+            const uint32_t taddr = t_tile + (uint32_t)(uq * K::UPT + c8 * 8);
+            tmem_ld8(taddr, az);
+            tmem_ld8(taddr + UP, ar);
+            tmem_ld8(taddr + 2 * UP, ah);
+            tmem_ld_wait();
+            if (c8 == 0) TC_TRACE(1);
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 2; ++j4) {
             const float4 xz = *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
