@@ -148,6 +148,56 @@ __global__ void mss_chain_kernel(int NC, ScanBufs b) {
   if (lane == 0) *b.n_dirty = n_dirty;
 }
 
+// The same chain in three parallel-friendly steps (used for float32 scores, whose sums are exact so that
+// composed predictions equal the sequential ones): (1) one thread per group of MSS_GROUP chunks
+// composes the group's chunk effects (mss::compose), (2) one thread walks the group composites -- NC / 32
+// steps instead of NC -- and leaves every group's start state, (3) one thread per group walks its own
+// chunks from that state, predicting their start states and marking the stale ones.
+constexpr int MSS_GROUP = 32;
+
+__global__ void mss_group_compose_kernel(int NC, ScanBufs b, mss::Composite *comp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = g * MSS_GROUP;
+  if (c0 >= NC) return;
+  const int c1 = c0 + MSS_GROUP < NC ? c0 + MSS_GROUP : NC;
+  mss::Composite acc;
+  acc.sum = b.sum[c0]; acc.x_in = b.used[c0]; acc.x_out = b.out[c0];
+  for (int c = c0 + 1; c < c1; ++c) {
+    mss::Composite nx;
+    nx.sum = b.sum[c]; nx.x_in = b.used[c]; nx.x_out = b.out[c];
+    acc = mss::compose(acc, nx);
+  }
+  comp[g] = acc;
+}
+
+__global__ void mss_group_chain_kernel(int NG, const mss::Composite *comp, ScanState *gstart, int *n_dirty) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ScanState s;
+  mss::state_canonical(s);
+  for (int g = 0; g < NG; ++g) {
+    gstart[g] = s;
+    const mss::Composite k = comp[g];
+    s = mss::state_equal(k.x_in, s) ? k.x_out : mss::apply_summary(k.sum, k.x_in, k.x_out, s);
+  }
+  *n_dirty = 0;
+}
+
+__global__ void mss_group_fill_kernel(int NC, ScanBufs b, const ScanState *gstart) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = g * MSS_GROUP;
+  if (c0 >= NC) return;
+  const int c1 = c0 + MSS_GROUP < NC ? c0 + MSS_GROUP : NC;
+  ScanState s = gstart[g];
+  int n_dirty = 0;
+  for (int c = c0; c < c1; ++c) {
+    b.pred[c] = s;
+    const ScanState used = b.used[c], out = b.out[c];
+    if (mss::state_equal(used, s)) { b.dirty[c] = 0; s = out; }
+    else { b.dirty[c] = 1; ++n_dirty; s = mss::apply_summary(b.sum[c], used, out, s); }
+  }
+  if (n_dirty) atomicAdd(b.n_dirty, n_dirty);
+}
+
 // Parallel verification of the fixed point: every chunk must have started from exactly the state its
 // predecessor ended in (chunk 0 from the canonical state).  Counts the chunks for which that fails.
 __global__ void mss_verify_kernel(int NC, ScanBufs b) {
@@ -306,9 +356,24 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 8;
   bool converged = NC == 1;
   while (!converged) {
-    // predict all start states from the chunk summaries (sequential over chunks, O(1) each) ...
-    mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);
-    c->launches++;
+    // predict all start states from the chunk summaries ...
+    if (sizeof(T) == 4 && NC > 4 * MSS_GROUP) {
+      // ... float32 scores: composed per group in parallel, a sequential pass over the groups only
+      const int NG = (NC + MSS_GROUP - 1) / MSS_GROUP;
+      DGRP_CHECK(c->mss_d.reserve((size_t)NG * (sizeof(mss::Composite) + sizeof(ScanState)) + 512));
+      mss::Composite *comp = c->mss_d.as<mss::Composite>();
+      ScanState *gstart = reinterpret_cast<ScanState *>(c->mss_d.as<unsigned char>() +
+                                                        align256((size_t)NG * sizeof(mss::Composite)));
+      const int gb = (NG + 63) / 64;
+      mss_group_compose_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, comp);
+      mss_group_chain_kernel<<<1, 32, 0, c->stream>>>(NG, comp, gstart, sb.n_dirty);
+      mss_group_fill_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, gstart);
+      c->launches += 3;
+    } else {
+      // ... sequential over chunks, O(1) each (float64 scores: sums round, composed shifts would miss)
+      mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);
+      c->launches++;
+    }
     DGRP_CUDA(cudaMemcpyAsync(h_dirty, sb.n_dirty, 4, cudaMemcpyDeviceToHost, c->stream));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
     if (*h_dirty == 0) { converged = true; break; }

@@ -243,6 +243,59 @@ DGRP_HD ScanState apply_summary(const ChunkSummary &sum, const ScanState &x_in,
   return o;
 }
 
+// ---- composition of chunk effects (parallel summary chain) -------------------------------------
+// A chunk's recorded execution x_in -> x_out plus its summary predicts its end state for any start
+// state (apply_summary).  Two consecutive chunks compose into one object of the same kind: the runs
+// that started and ended inside either chunk, plus the run that crosses the boundary, fold into one
+// (latest minimum t.L, maximum R from there on, maximum R overall) triple -- the fold the state machine
+// itself applies run by run (finish_run: a run whose t.L is not above the bottom replaces the bottom).
+// Like apply_summary this is exact in exact arithmetic and only a prediction otherwise; every
+// predicted start state is verified bitwise by the caller.
+struct Composite {
+  ChunkSummary sum;
+  ScanState x_in, x_out;
+};
+
+// append the summary (minT, min_st, maxAfter, maxIn) of a later run list to p's
+DGRP_HD void fold_runs(ChunkSummary &p, double minT, int min_st, double maxAfter, double maxIn) {
+  if (!(p.flags & 4) || !(p.minT < minT)) { p.minT = minT; p.min_st = min_st; p.maxAfter = maxAfter; }
+  else if (maxIn > p.maxAfter) p.maxAfter = maxIn;
+  if (!(p.flags & 4) || maxIn > p.maxIn) p.maxIn = maxIn;
+  p.flags |= 4;
+}
+
+DGRP_HD Composite compose(const Composite &A, const Composite &B) {
+  Composite C;
+  C.x_in = A.x_in;
+  C.x_out = apply_summary(B.sum, B.x_in, B.x_out, A.x_out);
+  ChunkSummary c;
+  c.carryR = 0.0; c.minT = 0.0; c.maxAfter = 0.0; c.maxIn = 0.0; c.min_st = -1; c.flags = 0;
+  if ((A.sum.flags & 1) || (B.sum.flags & 1)) {   // a reset inside: the end state is absolute
+    c.flags = 1;
+    C.sum = c;
+    return C;
+  }
+  const double dB = A.x_out.L - B.x_in.L;         // B's recorded frame -> the frame of A's execution
+  c = A.sum;
+  c.flags = A.sum.flags & (2 | 4);
+  const bool a_in_run = (A.x_out.flags & 2) != 0, a_run_inside = (A.sum.flags & 8) != 0;
+  bool open_inside = false;                       // run in progress at the end started inside A+B
+  if (a_in_run) {
+    if (B.sum.flags & 2) {                        // the run crossing the boundary ends in B
+      const double R = B.sum.carryR + dB;
+      if (a_run_inside) fold_runs(c, A.x_out.run_L0, A.x_out.run_st, R, R);
+      else { c.flags |= 2; c.carryR = R; }        // it was carried into A as well
+    } else if (a_run_inside) {
+      open_inside = true;                         // still running at the end of B
+    }
+  }
+  if (B.sum.flags & 4) fold_runs(c, B.sum.minT + dB, B.sum.min_st, B.sum.maxAfter + dB, B.sum.maxIn + dB);
+  if (B.sum.flags & 8) open_inside = true;
+  if (open_inside) c.flags |= 8;
+  C.sum = c;
+  return C;
+}
+
 // Stack evolution of one region: runs [k0, k1) where k0 is a FLUSH/ABSORB run (its record is the
 // single candidate on the stack) and no other event lies inside.  The push/merge loop of
 // mss.c:65-86, with the stack stored in place at slots k0.. .  Returns the final depth.

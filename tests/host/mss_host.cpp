@@ -11,9 +11,42 @@ using namespace dgrp::mss;
 
 struct Seg { int st, en; double sc; };
 
+// Hierarchical summary chain (emulates mss_group_kernel / mss_group_chain_kernel / mss_group_fill_kernel):
+// groups of G chunks are composed in parallel, one sequential pass over the group composites gives the
+// group start states, every group then walks its own chunks.  Returns the number of stale chunks.
+static int chain_grouped(int NC, int G, const std::vector<ScanState> &used, const std::vector<ScanState> &out,
+                         const std::vector<ChunkSummary> &sum, std::vector<ScanState> &pred,
+                         std::vector<uint8_t> &dirty) {
+  const int NG = (NC + G - 1) / G;
+  std::vector<Composite> comp(NG);
+  for (int g = 0; g < NG; ++g) {
+    const int c0 = g * G, c1 = c0 + G < NC ? c0 + G : NC;
+    Composite acc{sum[c0], used[c0], out[c0]};
+    for (int c = c0 + 1; c < c1; ++c) acc = compose(acc, Composite{sum[c], used[c], out[c]});
+    comp[g] = acc;
+  }
+  std::vector<ScanState> gstart(NG);
+  ScanState s; state_canonical(s);
+  for (int g = 0; g < NG; ++g) {
+    gstart[g] = s;
+    s = state_equal(comp[g].x_in, s) ? comp[g].x_out : apply_summary(comp[g].sum, comp[g].x_in, comp[g].x_out, s);
+  }
+  int n_dirty = 0;
+  for (int g = 0; g < NG; ++g) {
+    const int c0 = g * G, c1 = c0 + G < NC ? c0 + G : NC;
+    ScanState t = gstart[g];
+    for (int c = c0; c < c1; ++c) {
+      pred[c] = t;
+      if (state_equal(used[c], t)) { dirty[c] = 0; t = out[c]; }
+      else { dirty[c] = 1; ++n_dirty; t = apply_summary(sum[c], used[c], out[c], t); }
+    }
+  }
+  return n_dirty;
+}
+
 template <typename T>
 static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *segs_out, int cap,
-                   int *rounds_out, int max_rounds) {
+                   int *rounds_out, int max_rounds, int group = 0, int *chain_mismatch = nullptr) {
   if (n <= 0) { *rounds_out = 0; return 0; }
   const int min_sc_int = (int)min_sc;
   const int NC = (n + CH - 1) / CH;
@@ -49,6 +82,17 @@ static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *
       pred[c] = s;
       if (state_equal(used[c], s)) { dirty[c] = 0; s = out[c]; }
       else { dirty[c] = 1; ++n_dirty; s = apply_summary(sum[c], used[c], out[c], s); }
+    }
+    if (group > 0) {
+      // the grouped chain must predict what the sequential chain predicts (counted for the tests;
+      // its predictions are then the ones used, as on the GPU)
+      std::vector<ScanState> pred2(NC);
+      std::vector<uint8_t> dirty2(NC, 0);
+      const int nd2 = chain_grouped(NC, group, used, out, sum, pred2, dirty2);
+      if (chain_mismatch)
+        for (int c = 0; c < NC; ++c)
+          if (!state_equal(pred2[c], pred[c])) ++*chain_mismatch;
+      pred = pred2; dirty = dirty2; n_dirty = nd2;
     }
     if (!n_dirty) break;
     if (max_rounds > 0 && rounds >= max_rounds) {
@@ -101,6 +145,16 @@ static int run_all(int n, const T *S, double min_sc, double xdrop, int CH, Seg *
   return m;
 }
 
+extern "C" int host_mss_grouped_f64(int n, const double *S, double min_sc, double xdrop, int CH, int group, Seg *out,
+                                    int cap, int *rounds, int max_rounds, int *chain_mismatch) {
+  *chain_mismatch = 0;
+  return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds, max_rounds, group, chain_mismatch);
+}
+extern "C" int host_mss_grouped_f32(int n, const float *S, double min_sc, double xdrop, int CH, int group, Seg *out,
+                                    int cap, int *rounds, int max_rounds, int *chain_mismatch) {
+  *chain_mismatch = 0;
+  return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds, max_rounds, group, chain_mismatch);
+}
 extern "C" int host_mss_f64(int n, const double *S, double min_sc, double xdrop, int CH, Seg *out,
                             int cap, int *rounds, int max_rounds) { return run_all(n, S, min_sc, xdrop, CH, out, cap, rounds, max_rounds); }
 extern "C" int host_mss_f32(int n, const float *S, double min_sc, double xdrop, int CH, Seg *out,

@@ -71,6 +71,18 @@ def host_mss():
         m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
                CH, out, cap, ctypes.byref(rounds), max_rounds)
         return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value
+
+    def run_grouped(S, min_sc, xdrop, CH, group, max_rounds=0):
+        S = np.ascontiguousarray(S)
+        cap = S.size // 2 + 2
+        out = (_Seg * cap)()
+        rounds, mism = ctypes.c_int(0), ctypes.c_int(0)
+        fn = lib.host_mss_grouped_f64 if S.dtype == np.float64 else lib.host_mss_grouped_f32
+        fn.restype = ctypes.c_int
+        m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
+               CH, group, out, cap, ctypes.byref(rounds), max_rounds, ctypes.byref(mism))
+        return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value, mism.value
+    run.grouped = run_grouped
     return run
 
 
@@ -103,6 +115,40 @@ def test_chunked_mss_logic_bit_exact(host_mss, oracle):
                         assert got == ref, (trial, xdrop, min_sc, CH, max_rounds)
 
 
+def test_grouped_summary_chain(host_mss, oracle):
+    """The parallel (grouped) summary chain: composing chunk effects (mss_core.cuh compose) must predict
+    exactly the start states the sequential chain predicts whenever the additions are exact (integer
+    and few-bit scores), and the final segments are the oracle's for ANY input (a wrong prediction is
+    caught by the bitwise verification and only costs another round)."""
+    rng = np.random.default_rng(11)
+    for trial in range(160):
+        n = int(rng.integers(1, 600))
+        kind = trial % 5
+        if kind == 0:
+            S = rng.integers(-3, 4, size=n).astype(float)                 # exact arithmetic, many ties
+        elif kind == 1:
+            S = rng.choice([-4.5, 4.5, -45.5, 0.0, 0.25, -0.25], size=n)  # exact, reset regimes
+        elif kind == 2:
+            S = np.where(rng.random(n) < 0.3, 13.25, -1.25)               # exact, positive drift, no reset
+        elif kind == 3:
+            S = rng.normal(size=n)                                        # inexact: predictions may miss
+        else:
+            S = np.where(rng.random(n) < 0.05, 13.2, -1.32) * (1 + 1e-3 * rng.normal(size=n))
+        if trial % 2:
+            S = S.astype(np.float32)
+        exact = kind <= 2
+        for xdrop in (-1.0, 3.0, 40.0):
+            for min_sc in (0.0, 2.7):
+                ref = [(int(a), int(b), float(c)) for a, b, c in
+                       oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+                for CH in (1, 2, 5, 16, 64):
+                    for group in (1, 2, 3, 8, 32):
+                        got, rounds, mism = host_mss.grouped(S, min_sc, xdrop, CH, group, 12)
+                        assert got == ref, (trial, xdrop, min_sc, CH, group)
+                        if exact:
+                            assert mism == 0, (trial, xdrop, min_sc, CH, group, mism)
+
+
 def test_chunked_mss_converges_in_few_rounds(host_mss, oracle):
     """float32-valued scores (what the fused path produces) add exactly in double, so the predicted
     chunk start states are right and the scan needs O(1) parallel rounds in every drift regime --
@@ -121,6 +167,9 @@ def test_chunked_mss_converges_in_few_rounds(host_mss, oracle):
         ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
         assert got == ref, name
         assert 0 < rounds <= 4, (name, rounds)
+        # the grouped (parallel) chain predicts the same start states on float32-valued scores
+        got_g, rounds_g, mism = host_mss.grouped(S, min_sc, xdrop, 1024, 32, 12)
+        assert got_g == ref and rounds_g == rounds and mism == 0, (name, rounds_g, mism)
 
 
 # ---- Options / weights / CLI ---------------------------------------------------------------------
