@@ -275,10 +275,12 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   if (n <= 0) return DGRP_OK;
   int CH = c->mss_chunk;
   if (CH <= 0) {
-    // the summary pass is sequential over chunks (~0.25 us each), the scan sequential inside a chunk
-    // (~0.25 us per score, twice): chunk ~ sqrt(n) / 2 balances the two (measured optimum 4096 at 46.7 M)
+    // The scan is sequential inside a chunk (~0.25 us per score, twice); the summary pass is sequential
+    // over chunks (~0.25 us each, float64 scores) or over groups of 32 chunks (float32 scores): chunk ~
+    // sqrt(n) / 2 resp. sqrt(n / 64) balances the two (measured optima: 1024 at 46.7 M, 2048 at 248 M).
+    const int64_t per = sizeof(T) == 4 ? 2 * MSS_GROUP : 4;
     CH = 64;
-    while (CH < 16384 && (int64_t)CH * CH * 4 < (int64_t)n) CH <<= 1;
+    while (CH < 16384 && (int64_t)CH * CH * per < (int64_t)n) CH <<= 1;
   }
   CH = (CH + 31) / 32 * 32;
   const int NC = (n + CH - 1) / CH;
