@@ -80,9 +80,9 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
  * recurrence where available, 0 = fp32 kernel), "forward_sum16" (tcgen05 forward: 1 = the
  * h_fwd + h_rc scratch that feeds the attention scores is kept in half precision [default; a
  * probability moves by <= 3e-5 on sharp-attention weights and ~1e-7 on random-init ones], 0 = in
- * float32 [+8 % forward time]), "forward_fp16x2" (tcgen05 forward: operands of the recurrent
+ * float32 [+5 % forward time]), "forward_fp16x2" (tcgen05 forward: operands of the recurrent
  * product as 1 = two scaled fp16 pieces, three products [default], 0 = three bf16 pieces, six
- * products [+12 % forward time, same measured accuracy]), "shard_rank" / "shard_world" (contig sharding of
+ * products [+15 % forward time, same measured accuracy]), "shard_rank" / "shard_world" (contig sharding of
  * dgrp_predict_fasta*: records are assigned largest-first to the least loaded rank; a rank
  * computes only its own records), and read-only "mss_rounds" (rounds the last MSS call used;
  * negative = completed sequentially), "forward_used_tc", "sm_count". */
