@@ -1,51 +1,62 @@
 // K2-K6, tcgen05 form: the recurrent product h.R of both GRU passes on the 5th-generation tensor
-// cores, everything else as in forward.cu.
+// cores, attention + FF + softmax in a second phase of the same persistent kernel, the max-vote as
+// plain stores + a gather pass (vote.cu).  forward.cu holds the fp32 FFMA form of the same math.
 //
-// Why not plain bf16: the parity bar (>= 99.99 % identical labels against a float32 CPU run, on
-// random-init weights whose class margins are ~1e-4) needs fp32-faithful pre-activations through
-// a 150..512 step recurrence.  Both operands are therefore split into three bf16
-// pieces, x = hi + mid + lo (8+8+8 mantissa bits = the full fp32 significand), and the product is
-// formed from the six piece products whose weight is >= 2^-16:
-//     h.R ~= hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi      (dropped terms <= 2^-24 |h||R|)
-// each a kind::f16 (bf16 x bf16 -> fp32) tcgen05.mma accumulating into the same TMEM tile, smallest
-// terms first.  The gates, sigmoid/tanh and the state update stay in fp32 registers.
+// Precision.  The parity bar (>= 99.99 % identical labels against a float32 CPU run, on random-init
+// weights whose class margins are ~1e-4) needs fp32-faithful pre-activations through a 150..512 step
+// recurrence; plain bf16 misses it by orders of magnitude.  Both operands are
+// therefore split into pieces and the product is formed from the piece products that matter, each a
+// kind::f16 tcgen05.mma accumulating in fp32 into the same TMEM tile, smallest terms first:
+//   NP = 2 (default)  two fp16 pieces of the scaled value (state x 2^8, weights x 2^shift so that the
+//                     low pieces stay normal): hi.hi + hi.lo + lo.hi, relative error ~2^-21 per product;
+//   NP = 3            three bf16 pieces (8+8+8 bits = the fp32 significand), the six products of weight
+//                     >= 2^-16: hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi.
+// Both measure the same distance from the float64 oracle as the fp32 kernel (tools/accuracy_study.py).
+// The gates, sigmoid/tanh and the state update stay in fp32 registers.
 //
-// One CTA = 17 warps, persistent, a unit of work = two tiles of 64 windows x 2 directions (M = 128
-// rows) in flight:
+// One CTA = 20 warps, persistent, one per SM; a unit of work = two tiles of 64 windows x 2 directions
+// (M = 128 rows; row r = window r/2, direction r%2) in flight:
 //   warps 0..15  gate warps: TMEM lane quadrant w % 4 (rows 32*(w%4) ..+31, one row per lane), unit
-//                quarter w / 4; they read the finished accumulator (tcgen05.ld), add the input
-//                projection (a table row: x_t is one-hot), apply the gates in fp32, write the new state
-//                as bf16 pieces into the A operand and arrive on the tile's "ready" mbarrier;
-//   warp 16      MMA issuer: waits for "ready" (with back-off), issues the 6 x UP/16 tcgen05.mma of
-//                the step and commits them to the tile's "done" mbarrier, which the gate warps wait on.
-//                (Letting the last-arriving gate warp issue instead -- 16 warps, 128 registers -- was
-//                measured 14 % slower: the issue lands on the slowest warp's critical path.)
-// While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.
-// Every step, including the first, reads its pre-activations from TMEM: a unit starts with a priming
-// MMA round on an all-zero A operand (h[-1] = 0), so that the step loop has no special case.
-// The z, r (h) columns of R, the input table and the biases are pre-scaled by -log2(e) (2 log2(e)) so
-// that the accumulator feeds ex2 directly.
+//                quarter w / 4; they wait for the tile's "done" mbarrier, read the accumulator
+//                (tcgen05.ld), add the input projection (a table row: x_t is one-hot), apply the gates,
+//                write the new state as operand pieces into A (shared memory), fence, arrive on the
+//                tile's "ready" mbarrier, and only then store the step's scratch;
+//   warp 16      MMA issuer: waits for "ready" (with back-off), issues the step's NP(NP+1)/2 x UP/16
+//                tcgen05.mma (M128, N = 3*UP + 16, K16) and commits them to "done".
+//                (Letting the last-arriving gate warp issue instead was measured 14 % slower.)
+//   warps 17..19 exit after setmaxnreg: the CTA launches with 96 registers per thread, the issuer's
+//                warpgroup drops to 24 and the gate warps rise to 112 (their loop spills at 96).
+// While the tensor core multiplies tile X's new state by R, the gate warps work on tile Y.  A unit starts
+// with a priming MMA round on an all-zero A operand (h[-1] = 0; two rounds when T is even), so the step
+// loop has no special case and every unit runs an even number of rounds (barrier parities are a
+// function of the step).  The z, r (h) columns of R, the input table and the biases are pre-scaled by
+// -log2(e) (2 log2(e)) so that the accumulator feeds ex2 directly; reciprocals are shared four ways.
 //   TMEM   2 x [128 lanes x (3*UP + 16) columns] fp32 accumulators: z | r | h gate blocks, then 16
-//          projection columns h.(K/2) (the FF layer's two halves), so that the second phase needs no
-//          FFMA over the units: avg[t].K = h_fwd[t].K/2 + h_rc[t].K/2 comes out of the same MMA
-//   smem   B = [R | K/2]^T pieces, [3][(3*UP+16) x UP] bf16, K-major core matrices, resident
-//          A = state pieces, [2 tiles][3][128 x UP] bf16, rewritten every step by the gate warps
-//   row r of a tile = window r/2, direction r%2, so h_fwd[t] + h_rc[t] is one lane shuffle.
+//          projection columns h.(K/2) (the FF layer's two halves): avg[t].K = h_fwd[t].K/2 + h_rc[t].K/2
+//          comes out of the same MMA and the second phase needs no FFMA over the units
+//   smem   B = [R | K/2]^T pieces, [NP][(3*UP+16) x UP], K-major core matrices, resident
+//          A = state pieces, [2 tiles][NP][128 x UP], rewritten every step by the gate warps
+//          input table [10 rows][3*UP + 4] (A,C,G,T of either direction 4 banks apart, then 'N')
+//          staged bases of the unit's tiles as table rows, [2 tiles][forward | reversed+complemented]
+//          scores of one pass of the second phase, [wpp windows][T]
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 B each; core matrices
 // adjacent along K are 128 B apart (leading byte offset), along M/N they are UP/8 * 128 B apart
 // (stride byte offset); one MMA consumes K = 16 = two core matrices.
 //
 // Scratch in HBM (per CTA, rewritten by every unit; the attention query avg[T-1] is only known after
 // the last step, so the scores need a second pass over all avg[t]):
-//   sum    ST[2][64][T][UP]    h_fwd[t] + h_rc[t] (= 2 avg[t]) -- feeds ONLY the additive-attention
-//                               scores; half precision (11 bits, |sum| < 2) perturbs a probability by
-//                               ~1e-7 (measured, tools/accuracy_study.py)
-//   q      f32[2][64][UP]      avg[T-1] in full precision (the query)
-//   proj   f32[2][64][T][16]   avg[t].K, both FF halves (the logits come from these, full precision)
-// = 192 B per (window, t) written once and read once (was 320 B with an fp32 avg).  All CTAs run the
-// same amount of work, so without care their second phases coincide and saturate HBM while the
-// recurrence phases leave it idle; CTA b therefore starts with (b mod 4) single-tile units, which
-// shifts its phase by about 3/4 of a period each.
+//   sum    ST[2][T][UP/8][64][8]  h_fwd[t] + h_rc[t] (= 2 avg[t], one lane shuffle) -- feeds ONLY the
+//                                 additive-attention scores; ST = half by default (|sum| < 2; a
+//                                 probability moves by ~1e-7 on random-init weights, <= 3e-5 on sharp
+//                                 ones), float with forward_sum16 = 0
+//   q      f32[2][64][UP]         avg[T-1] in full precision (the query)
+//   proj   f32[2][64][T][16]      avg[t].K, both FF halves (the logits come from these, full precision)
+// = 192 B per (window, t), written once and read once.  All CTAs run the same amount of work, so without
+// care their second phases coincide and saturate HBM while the recurrence phases leave it idle: CTA b
+// starts with (b mod 4) single-tile units, which shifts its phase by ~3/4 of a period each.  By the time
+// the scratch is read back it has left the L2, and one SM's demand loads sustain only ~17 B/clk against
+// HBM latency, so the second phase asks the L2 for it a few rows ahead (cp.async.bulk.prefetch.L2).
+// The window probabilities go to [window][T][C] with plain stores; vote_gather_kernel max-merges them.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
