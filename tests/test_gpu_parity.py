@@ -335,6 +335,30 @@ def test_tensor_core_forward_shapes(dg, oracle, T, U, step, L):
     assert (tc.argmax(axis=1) != ref64.argmax(axis=1)).mean() <= 1e-4
 
 
+@pytest.mark.parametrize("compat", ["reference", "fixed"])
+def test_vote_gather_equals_atomic_vote(dg, compat):
+    """The two forms of the max-vote (window probabilities + gather pass, and atomicMax from inside the
+    forward kernel) are the same exact maximum: bit-identical predictions, including the displaced
+    last batch of the reference placement and a range call that does not start at row 0."""
+    from deepgrp_b200 import sharding
+    T, U, L = 150, 32, 23_457
+    w = dg.model.random_weights(T, U, attention=True, seed=21).scaled(3.0)
+    codes = np.random.default_rng(8).integers(0, 4, size=L, dtype=np.uint8)
+    out = {}
+    for g in (1, 0):
+        dg.ctx.set_int("forward_gather", g)
+        try:
+            whole = sharding.predict_range(w, codes, L, 0, L, 50, 48, compat={"reference": 0, "fixed": 1}[compat])
+            part = sharding.predict_range(w, codes, L, 7_001, 19_990, 50, 48, compat={"reference": 0, "fixed": 1}[compat])
+        finally:
+            dg.ctx.set_int("forward_gather", 1)
+        out[g] = (whole, part)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(out[1][0][0][7_001:19_990], out[1][1][0])
+    assert np.array_equal(out[1][0][1][7_001:19_990], out[1][1][1])
+
+
 def test_tensor_core_forward_random_init_regime(dg, oracle):
     """The benchmark's regime (random-init weights, near-uniform outputs, class margins ~1e-4): the
     default forward must be float32-faithful there, or labels flip."""
