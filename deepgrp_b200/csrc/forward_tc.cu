@@ -295,6 +295,14 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
 __device__ __forceinline__ void l2_prefetch(const void *ptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
+// One 32-byte sector in one request (LDG.256): the softmax / vote passes read one sector of a `proj` row
+// per lane, every lane a different line, and the LSU resolves one line per cycle -- the request count,
+// not the bytes, bounds those passes.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ float exp_fast(float x) {   // e^x through ex2.approx (2 ulp), e^{-inf} = 0
   return ex2_approx(x * 1.4426950408889634f);
 }
@@ -415,9 +423,10 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
           for (int k = 0; k < PU; ++k) {
             const int t = t0 + 32 * k;
             const bool ok = t < T;
-            const float4 k4 = ok ? *reinterpret_cast<const float4 *>(pr + (size_t)t * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-            k1[k][0] = k4.x; k1[k][1] = k4.y; k1[k][2] = k4.z; k1[k][3] = k4.w;
-            k1[k][4] = ok ? pr[(size_t)t * 16 + 4] : 0.f;
+            float row[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (ok) ldg256(pr + (size_t)t * 16, row);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) k1[k][c] = row[c];
             sv[k] = ok ? sc[t] : -INFINITY;
           }
           float m_new = m_run;
@@ -466,9 +475,10 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
         for (int k = 0; k < PU; ++k) {
           const int t = t0 + 32 * k;
           const bool ok = t < T;
-          const float4 k4 = ok ? *reinterpret_cast<const float4 *>(pr + (size_t)t * 16 + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-          k2[k][0] = k4.x; k2[k][1] = k4.y; k2[k][2] = k4.z; k2[k][3] = k4.w;
-          k2[k][4] = ok ? pr[(size_t)t * 16 + 12] : 0.f;
+          float row[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (ok) ldg256(pr + (size_t)t * 16 + 8, row);
+#pragma unroll
+          for (int c = 0; c < 5; ++c) k2[k][c] = row[c];
         }
 #pragma unroll
         for (int k = 0; k < PU; ++k) {
