@@ -182,6 +182,31 @@ __global__ void mss_group_chain_kernel(int NG, const mss::Composite *comp, ScanS
   *n_dirty = 0;
 }
 
+// second level: composites of MSS_GROUP group composites, and the walk back down to the group starts
+__global__ void mss_super_compose_kernel(int NG, const mss::Composite *comp, mss::Composite *super) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g0 = q * MSS_GROUP;
+  if (g0 >= NG) return;
+  const int g1 = g0 + MSS_GROUP < NG ? g0 + MSS_GROUP : NG;
+  mss::Composite acc = comp[g0];
+  for (int g = g0 + 1; g < g1; ++g) acc = mss::compose(acc, comp[g]);
+  super[q] = acc;
+}
+
+__global__ void mss_super_fill_kernel(int NG, const mss::Composite *comp, const ScanState *sstart,
+                                      ScanState *gstart) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g0 = q * MSS_GROUP;
+  if (g0 >= NG) return;
+  const int g1 = g0 + MSS_GROUP < NG ? g0 + MSS_GROUP : NG;
+  ScanState s = sstart[q];
+  for (int g = g0; g < g1; ++g) {
+    gstart[g] = s;
+    const mss::Composite k = comp[g];
+    s = mss::state_equal(k.x_in, s) ? k.x_out : mss::apply_summary(k.sum, k.x_in, k.x_out, s);
+  }
+}
+
 __global__ void mss_group_fill_kernel(int NC, ScanBufs b, const ScanState *gstart) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = g * MSS_GROUP;
@@ -361,16 +386,25 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
     // predict all start states from the chunk summaries ...
     if (sizeof(T) == 4 && NC > 4 * MSS_GROUP) {
       // ... float32 scores: composed per group in parallel, a sequential pass over the groups only
-      const int NG = (NC + MSS_GROUP - 1) / MSS_GROUP;
-      DGRP_CHECK(c->mss_d.reserve((size_t)NG * (sizeof(mss::Composite) + sizeof(ScanState)) + 512));
-      mss::Composite *comp = c->mss_d.as<mss::Composite>();
-      ScanState *gstart = reinterpret_cast<ScanState *>(c->mss_d.as<unsigned char>() +
-                                                        align256((size_t)NG * sizeof(mss::Composite)));
-      const int gb = (NG + 63) / 64;
+      // (two levels: groups of 32 chunks, super-groups of 32 groups; only the super-groups are walked
+      // by a single thread -- NC / 1024 steps)
+      const int NG = (NC + MSS_GROUP - 1) / MSS_GROUP, NS = (NG + MSS_GROUP - 1) / MSS_GROUP;
+      const size_t o_g = align256((size_t)NG * sizeof(mss::Composite));
+      const size_t o_s = o_g + align256((size_t)NG * sizeof(ScanState));
+      const size_t o_ss = o_s + align256((size_t)NS * sizeof(mss::Composite));
+      DGRP_CHECK(c->mss_d.reserve(o_ss + (size_t)NS * sizeof(ScanState) + 512));
+      unsigned char *pd = c->mss_d.as<unsigned char>();
+      mss::Composite *comp = reinterpret_cast<mss::Composite *>(pd);
+      ScanState *gstart = reinterpret_cast<ScanState *>(pd + o_g);
+      mss::Composite *super = reinterpret_cast<mss::Composite *>(pd + o_s);
+      ScanState *sstart = reinterpret_cast<ScanState *>(pd + o_ss);
+      const int gb = (NG + 63) / 64, sbk = (NS + 63) / 64;
       mss_group_compose_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, comp);
-      mss_group_chain_kernel<<<1, 32, 0, c->stream>>>(NG, comp, gstart, sb.n_dirty);
+      mss_super_compose_kernel<<<sbk, 64, 0, c->stream>>>(NG, comp, super);
+      mss_group_chain_kernel<<<1, 32, 0, c->stream>>>(NS, super, sstart, sb.n_dirty);
+      mss_super_fill_kernel<<<sbk, 64, 0, c->stream>>>(NG, comp, sstart, gstart);
       mss_group_fill_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, gstart);
-      c->launches += 3;
+      c->launches += 5;
     } else {
       // ... sequential over chunks, O(1) each (float64 scores: sums round, composed shifts would miss)
       mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);

@@ -9,7 +9,7 @@ w = model.random_weights(342, 60, attention=True, seed=0)
 h = w.device_handle(ctx)
 codes = torch.from_numpy(np.random.default_rng([1, 0]).integers(0, 4, size=L, dtype=np.uint8)).cuda()
 n_rows = ctypes.c_int64(0)
-for ch in (0, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+for ch in (0, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
     ctx.set_int("mss_chunk", ch)
     for rep in range(2):
         _lib.check(_lib.lib().dgrp_predict_codes_dev(ctx.handle, h, ctypes.c_void_p(codes.data_ptr()), L, 50, 256, 1,
