@@ -542,7 +542,20 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
         Bs[(size_t)2 * N * UP + off] = lo;
       }
     // fp16 hi|lo of the same matrix times 2^shift (largest entry just below 2^14, so that the low
-    // pieces of all but negligible entries are normal half-precision numbers)
+    // pieces of all but negligible entries are normal half-precision numbers), with 16 more K rows:
+    // rows UP + c (c = 0..4) hold the z / r entries of the input table for base c -- the kernel puts
+    // one_hot(x_t) * 2^8 into the matching K columns of A, so the MMA adds the input projection of the
+    // z and r gates (the h gate's stays outside r * (.), reset_after=True).
+    const int KP = UP + 16, SBO16 = (KP / 8) * 128;
+    auto entry16 = [&](int n, int k) -> float {
+      if (k < UP) return entry(n, k);
+      const int cc = k - UP;
+      if (cc >= 5 || n >= 2 * UP) return 0.f;
+      return (P[(size_t)cc * G * UP + n] + b1[n]) * -1.4426950408889634f;   // n = g * UP + u, g < 2
+    };
+    bmax = 0.f;
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < KP; ++k) bmax = std::fmax(bmax, std::fabs(entry16(n, k)));
     if (bmax > 0.f && std::isfinite(bmax)) {
       int e = 0;
       std::frexp(bmax, &e);             // bmax = f * 2^e, f in [0.5, 1)
@@ -550,15 +563,15 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       if (b16_shift > 24) b16_shift = 24;
       if (b16_shift < -24) b16_shift = -24;
     }
-    Bh.assign((size_t)2 * N * UP, 0);
+    Bh.assign((size_t)2 * N * KP, 0);
     for (int n = 0; n < N; ++n)
-      for (int k = 0; k < UP; ++k) {
-        const float x = std::ldexp(entry(n, k), b16_shift);
+      for (int k = 0; k < KP; ++k) {
+        const float x = std::ldexp(entry16(n, k), b16_shift);
         const __half hi = __float2half_rn(x);
         const __half lo = __float2half_rn(x - __half2float(hi));
-        const size_t off = ((size_t)(n / 8) * SBO + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2;
+        const size_t off = ((size_t)(n / 8) * SBO16 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2;
         memcpy(&Bh[off], &hi, 2);
-        memcpy(&Bh[(size_t)N * UP + off], &lo, 2);
+        memcpy(&Bh[(size_t)N * KP + off], &lo, 2);
       }
   }
   dgrp_model *m = new dgrp_model();

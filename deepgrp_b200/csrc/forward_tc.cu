@@ -97,16 +97,21 @@ __device__ unsigned long long g_tc_trace2[16][8];
 #define TC_TRACE2(seg)
 #endif
 
-template <int UP>
+template <int UP, int NP>
 struct TCfg {
   static constexpr int NG = 3 * UP;            // gate columns (z | r | h)
   static constexpr int N = 3 * UP + 16;        // + 16 projection columns: h.[FF ctx half(5) pad(3) | FF avg half(5) pad(3)]
   static constexpr int ROWS = 128, WT = 64;
   static constexpr int UPT = UP / 4;           // units per gate thread
-  static constexpr int KC = UP / 8;            // core matrices along K
+  // NP = 2 folds the z / r input projection into the MMA: 16 more K columns hold one_hot(x_t) * 2^8 in A
+  // (5 used) and the z / r rows of the input table in B, so the gate warps read only the h-gate row of
+  // the table (the z / r table rows were half of their shared-memory loads: -12 % forward time).
+  static constexpr bool FOLD = NP == 2;
+  static constexpr int KP = UP + (FOLD ? 16 : 0);   // K of the operands
+  static constexpr int KC = KP / 8;            // core matrices along K
   static constexpr int SBO = KC * 128;         // bytes between 8-row groups
-  static constexpr int A_BYTES = ROWS * UP * 2;  // one piece of one tile
-  static constexpr int B_BYTES = N * UP * 2;     // one piece
+  static constexpr int A_BYTES = ROWS * KP * 2;  // one piece of one tile
+  static constexpr int B_BYTES = N * KP * 2;     // one piece
   static constexpr int PSTRIDE = 3 * UP + 4;     // floats per code row of the input table
   static constexpr int TCOLS = N <= 64 ? 64 : (N <= 128 ? 128 : 256);  // TMEM columns per tile
 };
@@ -228,6 +233,16 @@ __device__ __forceinline__ void split2h(float2 ab, uint32_t &hi, uint32_t &lo) {
   lo = *reinterpret_cast<const uint32_t *>(&l2);
 }
 
+// FOLD: the 16-byte core-matrix row that holds one_hot(x) * 2^8 (half precision, 0x5C00 = 256) for the
+// input-table row `trow` (0..3 forward A,C,G,T; 4..7 the rc pass, already complemented; 8, 9 'N'):
+// K position p = the base the table row stands for.
+__device__ __forceinline__ uint4 onehot_row(int trow) {
+  const int p = trow < 4 ? trow : (trow < 8 ? 7 - trow : 4);
+  const uint32_t v = 0x5C00u << ((p & 1) * 16);
+  const int j = p >> 1;
+  return make_uint4(j == 0 ? v : 0u, j == 1 ? v : 0u, j == 2 ? v : 0u, 0u);
+}
+
 // GRU cell update for four units at once.  Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 issue one
 // instruction per pair, with the same IEEE rounding as the scalar forms); the accumulator and table
 // values arrive pre-scaled (z, r by -log2 e; h by 2 log2 e):
@@ -254,16 +269,22 @@ template <bool SCALED>
 __device__ __forceinline__ float2 acc_add(float2 acc, float2 x, float2 us) {
   return SCALED ? __ffma2_rn(acc, us, x) : __fadd2_rn(x, acc);
 }
-template <bool SCALED>
+// FOLD: the z / r pre-activations already contain the input projection (one-hot K columns of the MMA).
+template <bool SCALED, bool FOLD>
 __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, const float4 xh, const float4 bh,
                                           const float *az, const float *ar, const float *ah, float *hp,
                                           float2 us, float2 &h01, float2 &h23) {
   const float2 one = make_float2(1.0f, 1.0f);
   float2 z0, r0, z1, r1;
-  sigmoid_pair(acc_add<SCALED>(make_float2(az[0], az[1]), make_float2(xz.x, xz.y), us),
-               acc_add<SCALED>(make_float2(ar[0], ar[1]), make_float2(xr.x, xr.y), us), z0, r0);
-  sigmoid_pair(acc_add<SCALED>(make_float2(az[2], az[3]), make_float2(xz.z, xz.w), us),
-               acc_add<SCALED>(make_float2(ar[2], ar[3]), make_float2(xr.z, xr.w), us), z1, r1);
+  if (FOLD) {
+    sigmoid_pair(__fmul2_rn(make_float2(az[0], az[1]), us), __fmul2_rn(make_float2(ar[0], ar[1]), us), z0, r0);
+    sigmoid_pair(__fmul2_rn(make_float2(az[2], az[3]), us), __fmul2_rn(make_float2(ar[2], ar[3]), us), z1, r1);
+  } else {
+    sigmoid_pair(acc_add<SCALED>(make_float2(az[0], az[1]), make_float2(xz.x, xz.y), us),
+                 acc_add<SCALED>(make_float2(ar[0], ar[1]), make_float2(xr.x, xr.y), us), z0, r0);
+    sigmoid_pair(acc_add<SCALED>(make_float2(az[2], az[3]), make_float2(xz.z, xz.w), us),
+                 acc_add<SCALED>(make_float2(ar[2], ar[3]), make_float2(xr.z, xr.w), us), z1, r1);
+  }
   const float2 t0 = __ffma2_rn(r0, acc_add<SCALED>(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y), us), make_float2(xh.x, xh.y));
   const float2 t1 = __ffma2_rn(r1, acc_add<SCALED>(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w), us), make_float2(xh.z, xh.w));
   const float2 d0 = __fadd2_rn(make_float2(ex2_approx(fminf(t0.x, 30.0f)), ex2_approx(fminf(t0.y, 30.0f))), one);
@@ -524,7 +545,7 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
 // work, half the operand traffic out of shared memory.
 template <int UP, typename ST, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(const FwdParams p) {
-  using K = TCfg<UP>;
+  using K = TCfg<UP, NP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                               // [3][B_BYTES]
   unsigned char *s_A = s_B + NP * K::B_BYTES;                  // [2][NP][A_BYTES]
@@ -634,7 +655,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
             for (int q = 0; q < (NP == 3 ? 6 : 3); ++q) {
 #pragma unroll
-              for (int kc = 0; kc < UP / 16; ++kc) {
+              // the one-hot K chunk only exists in the hi piece of A (its lo piece is zero)
+              const int nkc = UP / 16 + ((K::FOLD && pa[q] == 0) ? 1 : 0);
+#pragma unroll
+              for (int kc = 0; kc < UP / 16 + 1; ++kc) {
+                if (kc >= nkc) break;
                 const uint64_t ad = umma_desc(a0 + pa[q] * K::A_BYTES + kc * 256, 128, K::SBO);
                 const uint64_t bd = umma_desc(b0 + pb[q] * K::B_BYTES + kc * 256, 128, K::SBO);
                 umma_bf16(d, ad, bd, idesc, acc);
@@ -672,6 +697,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     const float *tblp = s_P + uq * K::UPT;
     const float *bhp = s_bh + uq * K::UPT;
     const uint32_t a_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + ((uq * K::UPT) >> 3) * 128);
+    const uint32_t oh_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + (UP / 8) * 128);   // FOLD: one-hot K chunk
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     // The bases of a tile are one contiguous span of 63 * step + T codes: staged in shared memory once
     // per unit, so that the step loop has no global load (an L2 miss there stalls the whole tile).  Two
@@ -713,6 +739,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 #pragma unroll
         for (int pc = 0; pc < NP; ++pc)
           *reinterpret_cast<uint4 *>(a_tile + pc * K::A_BYTES + c8 * 128) = make_uint4(0u, 0u, 0u, 0u);
+      if (K::FOLD && uq == 0) {   // one_hot(x_0) in the hi piece's extra K chunk (its second half stays zero)
+        unsigned char *oh = s_A + (size_t)s * NP * K::A_BYTES + oh_off;
+        *reinterpret_cast<uint4 *>(oh) = onehot_row(s_codes[cbase + s * 2 * p.code_span]);
+        *reinterpret_cast<uint4 *>(oh + 128) = make_uint4(0u, 0u, 0u, 0u);
+      }
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_ready + 8 * s);
@@ -752,11 +783,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
           }
 #pragma unroll
           for (int j4 = 0; j4 < 2; ++j4) {
-            const float4 xz = *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
-            const float4 xr = *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 xz = K::FOLD ? zero4 : *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
+            const float4 xr = K::FOLD ? zero4 : *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
             const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
             const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
-            gru_cell4<NP == 2>(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4,
+            gru_cell4<NP == 2, K::FOLD>(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4,
                                &hprev[s][c8 * 8 + 4 * j4], us, hn2[c8][2 * j4], hn2[c8][2 * j4 + 1]);
           }
           // new state -> operand pieces in A (one 16-byte core-matrix row per piece)
@@ -774,6 +806,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             *reinterpret_cast<uint4 *>(a_tile + K::A_BYTES + c8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
+        if (K::FOLD && uq == 0 && t + 1 < T)   // the next step's base for the MMA's one-hot K columns
+          *reinterpret_cast<uint4 *>(s_A + (size_t)s * NP * K::A_BYTES + oh_off) =
+              onehot_row(s_codes[cbase + s * 2 * p.code_span + t + 1]);
         TC_TRACE(2);
         // Hand the new A operand to the tensor core (the last step's MMA only feeds the projection).
         // The release fence waits for this thread's outstanding stores, so it comes BEFORE the scratch
@@ -872,14 +907,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
 
 template <int UP, int NP>
 static size_t tc_smem_bytes(int T, int wpp, int code_span) {
-  using K = TCfg<UP>;
+  using K = TCfg<UP, NP>;
   return (size_t)NP * K::B_BYTES + 2 * NP * K::A_BYTES +
          sizeof(float) * ((size_t)10 * K::PSTRIDE + 2 * UP + (size_t)wpp * T) + 4 * (size_t)code_span + 128;
 }
 
 template <int UP, typename ST, int NP>
 static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
-  using K = TCfg<UP>;
+  using K = TCfg<UP, NP>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
   // windows per pass of the second phase: as many score rows as shared memory holds
