@@ -545,12 +545,13 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
     // pieces of all but negligible entries are normal half-precision numbers), with 16 more K rows:
     // rows UP + c (c = 0..4) hold the z / r entries of the input table for base c -- the kernel puts
     // one_hot(x_t) * 2^8 into the matching K columns of A, so the MMA adds the input projection of the
-    // z and r gates (the h gate's stays outside r * (.), reset_after=True).
+    // z and r gates (the h gate's stays outside r * (.), reset_after=True) and the h gate's recurrent bias.
     const int KP = UP + 16, SBO16 = (KP / 8) * 128;
     auto entry16 = [&](int n, int k) -> float {
       if (k < UP) return entry(n, k);
       const int cc = k - UP;
-      if (cc >= 5 || n >= 2 * UP) return 0.f;
+      if (cc >= 5 || n >= 3 * UP) return 0.f;
+      if (n >= 2 * UP) return b1[n] * 2.8853900817779268f;   // h gate: its recurrent bias (inside r * (.))
       return (P[(size_t)cc * G * UP + n] + b1[n]) * -1.4426950408889634f;   // n = g * UP + u, g < 2
     };
     bmax = 0.f;

@@ -104,8 +104,8 @@ struct TCfg {
   static constexpr int ROWS = 128, WT = 64;
   static constexpr int UPT = UP / 4;           // units per gate thread
   // NP = 2 folds the z / r input projection into the MMA: 16 more K columns hold one_hot(x_t) * 2^8 in A
-  // (5 used) and the z / r rows of the input table in B, so the gate warps read only the h-gate row of
-  // the table (the z / r table rows were half of their shared-memory loads: -12 % forward time).
+  // (5 used) and, in B, the z / r rows of the input table plus the h gate's recurrent bias, so the gate
+  // warps read only the h-gate row of the table (a quarter of their former shared-memory loads).
   static constexpr bool FOLD = NP == 2;
   static constexpr int KP = UP + (FOLD ? 16 : 0);   // K of the operands
   static constexpr int KC = KP / 8;            // core matrices along K
@@ -285,8 +285,13 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
     sigmoid_pair(acc_add<SCALED>(make_float2(az[2], az[3]), make_float2(xz.z, xz.w), us),
                  acc_add<SCALED>(make_float2(ar[2], ar[3]), make_float2(xr.z, xr.w), us), z1, r1);
   }
-  const float2 t0 = __ffma2_rn(r0, acc_add<SCALED>(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y), us), make_float2(xh.x, xh.y));
-  const float2 t1 = __ffma2_rn(r1, acc_add<SCALED>(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w), us), make_float2(xh.z, xh.w));
+  // FOLD: the h-gate accumulator already contains its recurrent bias (the one-hot K rows of B)
+  const float2 g0 = FOLD ? __fmul2_rn(make_float2(ah[0], ah[1]), us)
+                         : acc_add<SCALED>(make_float2(ah[0], ah[1]), make_float2(bh.x, bh.y), us);
+  const float2 g1 = FOLD ? __fmul2_rn(make_float2(ah[2], ah[3]), us)
+                         : acc_add<SCALED>(make_float2(ah[2], ah[3]), make_float2(bh.z, bh.w), us);
+  const float2 t0 = __ffma2_rn(r0, g0, make_float2(xh.x, xh.y));
+  const float2 t1 = __ffma2_rn(r1, g1, make_float2(xh.z, xh.w));
   const float2 d0 = __fadd2_rn(make_float2(ex2_approx(fminf(t0.x, 30.0f)), ex2_approx(fminf(t0.y, 30.0f))), one);
   const float2 d1 = __fadd2_rn(make_float2(ex2_approx(fminf(t1.x, 30.0f)), ex2_approx(fminf(t1.y, 30.0f))), one);
   const float2 m = __fmul2_rn(d0, d1);              // {d0.x d1.x, d0.y d1.y}
@@ -654,7 +659,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             uint32_t acc = 0;
 #pragma unroll
             for (int q = 0; q < (NP == 3 ? 6 : 3); ++q) {
-#pragma unroll
               // the one-hot K chunk only exists in the hi piece of A (its lo piece is zero)
               const int nkc = UP / 16 + ((K::FOLD && pa[q] == 0) ? 1 : 0);
 #pragma unroll
@@ -787,7 +791,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
             const float4 xz = K::FOLD ? zero4 : *reinterpret_cast<const float4 *>(prow + c8 * 8 + 4 * j4);
             const float4 xr = K::FOLD ? zero4 : *reinterpret_cast<const float4 *>(prow + UP + c8 * 8 + 4 * j4);
             const float4 xh = *reinterpret_cast<const float4 *>(prow + 2 * UP + c8 * 8 + 4 * j4);
-            const float4 bh = *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
+            const float4 bh = K::FOLD ? zero4 : *reinterpret_cast<const float4 *>(bhp + c8 * 8 + 4 * j4);
             gru_cell4<NP == 2, K::FOLD>(xz, xr, xh, bh, az + 4 * j4, ar + 4 * j4, ah + 4 * j4,
                                &hprev[s][c8 * 8 + 4 * j4], us, hn2[c8][2 * j4], hn2[c8][2 * j4 + 1]);
           }
