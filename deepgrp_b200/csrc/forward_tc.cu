@@ -45,7 +45,7 @@
 //
 // Scratch in HBM (per CTA, rewritten by every unit; the attention query avg[T-1] is only known after
 // the last step, so the scores need a second pass over all avg[t]):
-//   sum    ST[2][T][UP/8][64][8]  h_fwd[t] + h_rc[t] (= 2 avg[t], one lane shuffle) -- feeds ONLY the
+//   sum    ST[2][64/wpp][T][UP/8][wpp][8]  h_fwd[t] + h_rc[t] (= 2 avg[t], one lane shuffle) -- feeds ONLY the
 //                                 additive-attention scores; ST = half by default (|sum| < 2; a
 //                                 probability moves by ~1e-7 on random-init weights, <= 3e-5 on sharp
 //                                 ones), float with forward_sum16 = 0
@@ -372,19 +372,21 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
           sc2[i][j] = -2.0f * s_scale[u0 + j];
         }
       }
-      const ST *base = sum + ((size_t)cj * WT + wl) * 8;
+      // the pass's windows are contiguous per (t, chunk): [pass][t][chunk][wpp windows][8 units]
+      const ST *sum_pass = sum + (size_t)(w0 / wpp) * T * NCH * wpp * 8;
+      const ST *base = sum_pass + ((size_t)cj * wpp + (grp * 8 + wi)) * 8;
       // one warp per t-slice keeps the L2 PF_AHEAD rows ahead of the demand loads, PF_BLOCK rows at a time
       // (a t-row of the tile is NCH * WT * 8 contiguous elements)
       constexpr int PF_BLOCK = 4, PF_AHEAD = 12;
-      constexpr uint32_t ROW_BYTES = NCH * WT * 8 * sizeof(ST);
+      const uint32_t ROW_BYTES = (uint32_t)(NCH * wpp * 8 * sizeof(ST));
       if (grp == 0 && lane == 0) {
         const int n0 = min(PF_AHEAD, t_end - t_begin);
-        l2_prefetch(sum + (size_t)t_begin * NCH * WT * 8, (uint32_t)n0 * ROW_BYTES);
+        l2_prefetch(sum_pass + (size_t)t_begin * NCH * wpp * 8, (uint32_t)n0 * ROW_BYTES);
       }
       for (int t0 = t_begin; t0 < t_end; t0 += UNR) {
         if (grp == 0 && lane == 0 && (t0 - t_begin) % PF_BLOCK == 0) {
           const int ta = t0 + PF_AHEAD;
-          if (ta < t_end) l2_prefetch(sum + (size_t)ta * NCH * WT * 8, (uint32_t)min(PF_BLOCK, t_end - ta) * ROW_BYTES);
+          if (ta < t_end) l2_prefetch(sum_pass + (size_t)ta * NCH * wpp * 8, (uint32_t)min(PF_BLOCK, t_end - ta) * ROW_BYTES);
         }
         uint4 v[UNR][CPL][NV];
 #pragma unroll
@@ -394,7 +396,7 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
           for (int i = 0; i < CPL; ++i)
 #pragma unroll
             for (int n = 0; n < NV; ++n)
-              v[k][i][n] = __ldcs(reinterpret_cast<const uint4 *>(base + ((size_t)t * NCH + 4 * i) * WT * 8) + n);
+              v[k][i][n] = __ldcs(reinterpret_cast<const uint4 *>(base + ((size_t)t * NCH + 4 * i) * wpp * 8) + n);
         }
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
@@ -701,6 +703,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     const float *tblp = s_P + uq * K::UPT;
     const float *bhp = s_bh + uq * K::UPT;
     const uint32_t a_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + ((uq * K::UPT) >> 3) * 128);
+    // this thread's constant part of the `sum` index: pass of its window, window within the pass, half
+    const size_t sum_thr = ((size_t)(wl / p.wpp) * T * (UP / 8) * p.wpp + (size_t)(wl % p.wpp)) * 8 + (dir ? 4 : 0);
     const uint32_t oh_off = (uint32_t)((row >> 3) * K::SBO + (row & 7) * 16 + (UP / 8) * 128);   // FOLD: one-hot K chunk
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     // The bases of a tile are one contiguous span of 63 * step + T codes: staged in shared memory once
@@ -847,8 +851,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
               sm2[j] = __fadd2_rn(mine, recv);
             }
             const int u = uq * K::UPT + c8 * 8 + (dir ? 4 : 0);
-            // [slot][t][chunk][window][8 units]: the warp's 32 rows write 32 consecutive 4-unit groups
-            ST *dst = sum0 + ((((size_t)s * T + t) * (UP / 8) + (uq * (K::UPT / 8) + c8)) * K::WT + wl) * 8 + (dir ? 4 : 0);
+            // [slot][pass][t][chunk][wpp windows][8 units]: the warp's 32 rows write 32 consecutive 4-unit groups
+            ST *dst = sum0 + (size_t)s * K::WT * T * UP + sum_thr + ((size_t)t * (UP / 8) + (uq * (K::UPT / 8) + c8)) * p.wpp * 8;
             if (sizeof(ST) == 2) {
               const __half2 h0 = __floats2half2_rn(sm2[0].x, sm2[0].y), h1 = __floats2half2_rn(sm2[1].x, sm2[1].y);
               *reinterpret_cast<uint2 *>(dst) =
