@@ -128,12 +128,12 @@ def peaks():
 
 def ncu_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the forward kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01i_*); None for any other workload."""
+    `ncu --set full` capture of this same workload (profiles/r01j_*); None for any other workload."""
     if (args.bases, args.vecsize, args.units) != (CONFIG2_BASES, T_DEFAULT, U_DEFAULT):
         return None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01i_fwd_tc_ncu_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01j_fwd_tc_ncu_raw.csv"))))
         col = {name: (unit, val) for name, unit, val in zip(rows[0], rows[1], rows[2])}
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         total = 0.0
@@ -312,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
                                 if ctx.get_int("forward_used_tc") else "gru_attention_vote_kernel (fp32 FFMA)"),
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
                      "frac": achieved / tflops_peak, "traffic": ncu_traffic(args),
-                     "traffic_unit": "bytes of DRAM read + written per launch (ncu, profiles/r01i_fwd_tc_ncu_raw.csv)",
+                     "traffic_unit": "bytes of DRAM read + written per launch (ncu, profiles/r01j_fwd_tc_ncu_raw.csv)",
                      "peak_kind": peak_kind,
                      "kernel_ms": kernel_ms, "share_of_step": kernel_ms / (elapsed_ms / args.steps)},
         "stages_ms": mean_stage, "rows_per_step": rows_per_step,
