@@ -11,9 +11,10 @@ using namespace dgrp::mss;
 
 struct Seg { int st, en; double sc; };
 
-// Hierarchical summary chain (emulates mss_group_kernel / mss_group_chain_kernel / mss_group_fill_kernel):
-// groups of G chunks are composed in parallel, one sequential pass over the group composites gives the
-// group start states, every group then walks its own chunks.  Returns the number of stale chunks.
+// Hierarchical summary chain (emulates mss_group_compose / mss_super_compose / mss_group_chain /
+// mss_super_fill / mss_group_fill of mss.cu): groups of G chunks and super-groups of G groups are composed
+// in parallel, one sequential pass walks the super-groups, the start states are filled in level by
+// level.  Returns the number of stale chunks.
 static int chain_grouped(int NC, int G, const std::vector<ScanState> &used, const std::vector<ScanState> &out,
                          const std::vector<ChunkSummary> &sum, std::vector<ScanState> &pred,
                          std::vector<uint8_t> &dirty) {
@@ -25,11 +26,29 @@ static int chain_grouped(int NC, int G, const std::vector<ScanState> &used, cons
     for (int c = c0 + 1; c < c1; ++c) acc = compose(acc, Composite{sum[c], used[c], out[c]});
     comp[g] = acc;
   }
-  std::vector<ScanState> gstart(NG);
+  // second level, as on the GPU: super-groups of G groups are composed, one sequential pass over the
+  // super-groups, then every super-group fills in its groups' start states
+  const int NS = (NG + G - 1) / G;
+  std::vector<Composite> super(NS);
+  for (int q = 0; q < NS; ++q) {
+    const int g0 = q * G, g1 = g0 + G < NG ? g0 + G : NG;
+    Composite acc = comp[g0];
+    for (int g = g0 + 1; g < g1; ++g) acc = compose(acc, comp[g]);
+    super[q] = acc;
+  }
+  std::vector<ScanState> sstart(NS), gstart(NG);
   ScanState s; state_canonical(s);
-  for (int g = 0; g < NG; ++g) {
-    gstart[g] = s;
-    s = state_equal(comp[g].x_in, s) ? comp[g].x_out : apply_summary(comp[g].sum, comp[g].x_in, comp[g].x_out, s);
+  for (int q = 0; q < NS; ++q) {
+    sstart[q] = s;
+    s = state_equal(super[q].x_in, s) ? super[q].x_out : apply_summary(super[q].sum, super[q].x_in, super[q].x_out, s);
+  }
+  for (int q = 0; q < NS; ++q) {
+    const int g0 = q * G, g1 = g0 + G < NG ? g0 + G : NG;
+    ScanState t = sstart[q];
+    for (int g = g0; g < g1; ++g) {
+      gstart[g] = t;
+      t = state_equal(comp[g].x_in, t) ? comp[g].x_out : apply_summary(comp[g].sum, comp[g].x_in, comp[g].x_out, t);
+    }
   }
   int n_dirty = 0;
   for (int g = 0; g < NG; ++g) {
