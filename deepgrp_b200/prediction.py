@@ -117,15 +117,24 @@ def softmax(array: np.ndarray) -> np.ndarray:
 
 
 def setup_prediction_from_options_checkpoint(options: Options, logdir) -> ModelWeights:
-    """Reference ``deepgrp/prediction.py:68-86``.  ``logdir`` is a weights file (Keras ``.hdf5`` /
-    ``.h5`` or ``.npz``) or a directory holding one; the newest file wins, as the latest checkpoint
-    does in the reference.  (TensorFlow's checkpoint format itself is not read.)"""
+    """Reference ``deepgrp/prediction.py:68-86``: the model of ``options`` with the weights of the latest
+    checkpoint in ``logdir``.  ``logdir`` may hold TensorFlow-format checkpoints as the reference's
+    training writes them (``ModelCheckpoint(save_weights_only=True)``, ``deepgrp/training.py:53-59``; read
+    by :mod:`deepgrp_b200.tfckpt` without TensorFlow), or a Keras ``.hdf5`` / ``.h5`` / ``.npz`` weights file
+    (the newest wins); it may also be such a file itself."""
     path = os.fspath(logdir)
     if os.path.isdir(path):
+        from . import tfckpt
+        prefix = tfckpt.latest_checkpoint(path)
+        if prefix is not None:
+            w = tfckpt.deepgrp_weights(tfckpt.read_bundle(prefix))
+            return ModelWeights(int(options.vecsize), int(w["recurrent_kernel"].shape[0]), w["kernel"],
+                                w["recurrent_kernel"], w["bias"], w["ff_kernel"], w["ff_bias"],
+                                w.get("att_scale"), w["rnn"])
         cands = [os.path.join(path, f) for f in os.listdir(path)
                  if f.endswith((".hdf5", ".h5", ".npz"))]
         if not cands:
-            raise FileNotFoundError("no .hdf5/.h5/.npz weights in %s" % path)
+            raise FileNotFoundError("no TensorFlow checkpoint and no .hdf5/.h5/.npz weights in %s" % path)
         path = max(cands, key=os.path.getmtime)
     model = load_model(path)
     if model.vecsize != options.vecsize:
