@@ -12,7 +12,9 @@ the raw little-endian tensor bytes.  The directory's ``checkpoint`` text file na
 PARITY UNPINNED: neither TensorFlow nor a checkpoint written by it is available in this environment
 (the reference ships none); the format is restated from the TensorFlow / LevelDB sources
 (tensorflow/core/util/tensor_bundle, tensorflow/core/lib/io/table, tensor_bundle.proto) and is
-exercised only against bundles produced by :func:`write_bundle` below and hand-made Snappy streams.
+exercised only against bundles produced by :func:`write_bundle` below and hand-made Snappy streams;
+what IS pinned by published values: CRC-32C (RFC 3720 check vectors), its LevelDB mask, the table magic.
+Block trailers and per-tensor checksums are verified on read, so a misparsed offset fails loudly.
 No GPU work happens here: this is host-side file parsing, like ``hdf5.py``.
 """
 from __future__ import annotations
@@ -115,6 +117,35 @@ def _parse_entry(buf: bytes) -> dict:
     return e
 
 
+# ---- crc32c ---------------------------------------------------------------------------------------
+def _crc32c_table():
+    tbl = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tbl.append(c)
+    return tbl
+
+
+_CRC_TABLE = _crc32c_table()
+
+
+def crc32c(data: bytes) -> int:
+    """CRC-32C (Castagnoli, reflected polynomial 0x82F63B78); crc32c(b"123456789") == 0xE3069283."""
+    c = 0xFFFFFFFF
+    for b in data:
+        c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def _masked_crc(data: bytes) -> int:
+    """The masked form both LevelDB block trailers and BundleEntryProto.crc32c store:
+    rotate right by 15, add 0xa282ead8."""
+    c = crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
 # ---- Snappy (raw format) -------------------------------------------------------------------------
 def snappy_decompress(buf: bytes) -> bytes:
     """Raw Snappy block: varint uncompressed length, then literal (tag & 3 == 0) and copy elements."""
@@ -159,6 +190,9 @@ def snappy_decompress(buf: bytes) -> bytes:
 def _read_block(data: bytes, offset: int, size: int) -> bytes:
     block = data[offset:offset + size]
     ctype = data[offset + size]                          # 1-byte type, then a 4-byte masked crc32c
+    stored = struct.unpack("<I", data[offset + size + 1:offset + size + 5])[0]
+    if stored != _masked_crc(data[offset:offset + size + 1]):
+        raise ValueError("table block at %d: checksum mismatch" % offset)
     if ctype == 0:
         return block
     if ctype == 1:
@@ -200,8 +234,10 @@ def read_table(path: str) -> Dict[bytes, bytes]:
 
 
 # ---- bundle --------------------------------------------------------------------------------------
-def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
-    """name -> array for every numeric, unsliced tensor of the bundle ``prefix``(.index / .data-*)."""
+def read_bundle(prefix: str, verify: bool = True, select=None) -> Dict[str, np.ndarray]:
+    """name -> array for every numeric, unsliced tensor of the bundle ``prefix``(.index / .data-*).
+    ``verify`` checks each tensor's stored crc32c (as TensorFlow's BundleReader does); ``select`` is an
+    optional predicate on the key (str) to skip tensors, e.g. optimizer slots."""
     table = read_table(prefix + ".index")
     num_shards = 1
     if b"" in table:
@@ -215,6 +251,8 @@ def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
     for key, val in table.items():
         if key == b"":
             continue
+        if select is not None and not select(key.decode("utf-8", "replace")):
+            continue
         e = _parse_entry(val)
         if e["sliced"] or e["dtype"] not in _DTYPES:
             continue                                     # strings (object graph), partitioned variables
@@ -226,6 +264,8 @@ def read_bundle(prefix: str) -> Dict[str, np.ndarray]:
         raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
         if len(raw) != count * dt.itemsize:
             raise ValueError("tensor %r: %d bytes for shape %s" % (key, len(raw), e["shape"]))
+        if verify and e["crc32c"] is not None and e["crc32c"] != _masked_crc(raw):
+            raise ValueError("tensor %r: checksum mismatch" % key)
         out[key.decode("utf-8", "replace")] = np.frombuffer(raw, dtype=dt).reshape(e["shape"]).copy()
     return out
 
@@ -277,31 +317,6 @@ def deepgrp_weights(tensors: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
 
 
 # ---- writer (tests only: produces what read_bundle expects) ---------------------------------------
-def _crc32c_table():
-    tbl = []
-    for i in range(256):
-        c = i
-        for _ in range(8):
-            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
-        tbl.append(c)
-    return tbl
-
-
-_CRC_TABLE = _crc32c_table()
-
-
-def crc32c(data: bytes) -> int:
-    c = 0xFFFFFFFF
-    for b in data:
-        c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
-
-
-def _masked_crc(data: bytes) -> int:
-    c = crc32c(data)
-    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
-
-
 def _build_block(items, restart_interval: int = 16) -> bytes:
     out, restarts, last = bytearray(), [], b""
     for i, (k, v) in enumerate(items):

@@ -74,22 +74,19 @@ def test_compressed_block_is_read(tmp_path):
     else:
         comp = tfckpt._put_varint(bsz) + bytes([61 << 2]) + struct.pack("<H", bsz - 1) + block
     # rebuild the file: compressed data block, then a fresh meta block, index block and footer
-    out = bytearray(comp + b"\x01" + b"\0\0\0\0")
+    crc = lambda b: struct.pack("<I", tfckpt._masked_crc(b))
+    out = bytearray(comp + b"\x01" + crc(comp + b"\x01"))
     meta = tfckpt._build_block([])
     mh = tfckpt._put_varint(len(out)) + tfckpt._put_varint(len(meta))
-    out += meta + b"\x00" + b"\0\0\0\0"
+    out += meta + b"\x00" + crc(meta + b"\x00")
     ib = tfckpt._build_block([(b"w", tfckpt._put_varint(0) + tfckpt._put_varint(len(comp)))], restart_interval=1)
     ih = tfckpt._put_varint(len(out)) + tfckpt._put_varint(len(ib))
-    out += ib + b"\x00" + b"\0\0\0\0"
+    out += ib + b"\x00" + crc(ib + b"\x00")
     f = mh + ih
     out += f + b"\x00" * (40 - len(f)) + struct.pack("<Q", tfckpt.TABLE_MAGIC)
     open(prefix + ".index", "wb").write(bytes(out))
     got = tfckpt.read_bundle(prefix)
     assert np.array_equal(got["w"], np.arange(6, dtype=np.float32).reshape(2, 3))
-
-
-def test_crc32c_known_answer():
-    assert tfckpt.crc32c(b"123456789") == 0xE3069283
 
 
 @pytest.mark.parametrize("rnn,attention", [("GRU", True), ("GRU", False), ("LSTM", False)])
@@ -123,3 +120,33 @@ def test_directory_without_checkpoint_falls_back_to_weight_files(tmp_path):
     assert got.vecsize == 200 and np.array_equal(got.kernel, ref.kernel)
     with pytest.raises(FileNotFoundError):
         prediction.setup_prediction_from_options_checkpoint(opts, tmp_path / "nothing" if (tmp_path / "nothing").mkdir() is None else tmp_path)
+
+
+def test_crc32c_known_answers():
+    """Standard CRC-32C check values (RFC 3720 B.4; the same vectors LevelDB's crc32c_test.cc uses)."""
+    assert tfckpt.crc32c(b"123456789") == 0xE3069283
+    assert tfckpt.crc32c(bytes(32)) == 0x8A9136AA
+    assert tfckpt.crc32c(b"\xff" * 32) == 0x62A8AB43
+    assert tfckpt.crc32c(bytes(range(32))) == 0x46DD794E
+    assert tfckpt.crc32c(bytes(range(31, -1, -1))) == 0x113FDB5C
+    c = tfckpt.crc32c(b"foo")
+    m = tfckpt._masked_crc(b"foo")
+    assert m != c
+    u = (m - 0xA282EAD8) & 0xFFFFFFFF                      # LevelDB's Unmask
+    assert ((u >> 17) | (u << 15)) & 0xFFFFFFFF == c
+
+
+def test_corrupt_bundle_is_rejected(tmp_path):
+    prefix = str(tmp_path / "01")
+    tfckpt.write_bundle(prefix, {"a": np.arange(6, dtype=np.float32).reshape(2, 3)})
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[5] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(ValueError, match="checksum"):
+        tfckpt.read_bundle(prefix)
+    assert tfckpt.read_bundle(prefix, verify=False)["a"].shape == (2, 3)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[3] ^= 0x01
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(ValueError, match="checksum"):
+        tfckpt.read_bundle(prefix, verify=False)
