@@ -223,7 +223,7 @@ int dgrp_ctx_destroy(dgrp_ctx *c) {
   DevBuf *bufs[] = {&c->raw, &c->codes, &c->onehot, &c->avg, &c->pred, &c->labels, &c->labels2,
                     &c->scores32, &c->scores64, &c->classes64, &c->io_a, &c->io_b, &c->io_c, &c->winprobs,
                     &c->small, &c->segs, &c->rows, &c->mss_a, &c->mss_b, &c->mss_c, &c->mss_d,
-                    &c->mss_e, &c->scan};
+                    &c->mss_e, &c->scan, &c->gapfill};
   for (auto b : bufs) b->release();
   c->pin_small.release(); c->pin_a.release(); c->pin_b.release(); c->tsv_host.release();
   c->tsv_dev.release(); c->tsv_prefix.release();

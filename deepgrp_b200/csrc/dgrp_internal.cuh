@@ -89,7 +89,7 @@ struct dgrp_ctx {
   dgrp_timings_t timings = {};
   // workspaces (grow-only)
   dgrp::DevBuf raw, codes, onehot, avg, pred, labels, labels2, scores32, scores64, classes64,
-      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, mss_e, scan, winprobs;
+      io_a, io_b, io_c, small, segs, rows, mss_a, mss_b, mss_c, mss_d, mss_e, scan, winprobs, gapfill;
   dgrp::PinBuf pin_small, pin_a, pin_b;
   // tuning knobs / diagnostics (dgrp_ctx_set_int / dgrp_ctx_get_int)
   int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)

@@ -25,7 +25,33 @@ __global__ void trim_kernel(const uint8_t *__restrict__ seq, int64_t n, int fold
                             unsigned long long *first_last) {
   int64_t lo = n, hi = -1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 16 bytes per load over the 16-byte aligned body; the unaligned head and the tail go byte by byte
+  int64_t head = (int64_t)((16 - (reinterpret_cast<uintptr_t>(seq) & 15)) & 15);
+  head = head < n ? head : n;
+  const int64_t nvec = (n - head) / 16;
+  const uint4 *body = reinterpret_cast<const uint4 *>(seq + head);
+  const unsigned int fold = fold_case ? 0xDFDFDFDFu : 0xFFFFFFFFu;   // 'n' ^ 'N' == 0x20
+  for (int64_t v = tid; v < nvec; v += stride) {
+    const uint4 q = __ldg(body + v);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+    unsigned int m = 0;                                              // bit j: byte j is not an edge-N candidate
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned int x = (w[k] ^ 0x4E4E4E4Eu) & fold;             // zero byte <=> 'N' (or 'n')
+#pragma unroll
+      for (int b = 0; b < 4; ++b) m |= (((x >> (8 * b)) & 0xffu) != 0u ? 1u : 0u) << (4 * k + b);
+    }
+    if (m) {
+      const int64_t at = head + v * 16;
+      const int64_t f = at + (__ffs(m) - 1), l = at + (31 - __clz(m));
+      lo = lo < f ? lo : f;
+      hi = hi > l ? hi : l;
+    }
+  }
+  const int64_t tail0 = head + nvec * 16;
+  for (int64_t j = tid; j < head + (n - tail0); j += stride) {
+    const int64_t i = j < head ? j : tail0 + (j - head);
     unsigned int b = seq[i];
     bool is_n = (b == 'N') || (fold_case && b == 'n');
     if (!is_n) {
@@ -55,7 +81,7 @@ int launch_trim(dgrp_ctx *c, const uint8_t *d_seq, int64_t n, int fold_case, int
   c->launches++;
   if (n > 0) {
     int threads = 256;
-    int64_t want = (n + threads - 1) / threads;
+    int64_t want = (n / 16 + threads) / threads;
     int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
     trim_kernel<<<blocks, threads, 0, c->stream>>>(d_seq, n, fold_case,
                                                    (unsigned long long *)d_first_last);

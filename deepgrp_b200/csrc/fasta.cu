@@ -71,16 +71,60 @@ __device__ unsigned block_scan_fn(unsigned f, unsigned *total) {
   return compose(before, excl);
 }
 
+// f followed by one byte: a terminator sends every start state to ST_START, whitespace changes nothing,
+// any other byte moves the fields that are ST_START (== 0) to ST_HDR ('>') or ST_SEQ.  Equal to
+// compose(f, byte_fn(b, term)) for every f and byte, without the three table look-ups.
+__device__ __forceinline__ unsigned push_byte(unsigned f, unsigned b, bool term) {
+  const unsigned z = ~(f | (f >> 1)) & 0x15u;        // low bit of every field that holds ST_START
+  unsigned g = f | (b == '>' ? (z << 1) : z);
+  g = is_ws(b) ? f : g;
+  return term ? 0u : g;
+}
+
+// The FA_ITEMS bytes of one thread plus one look-ahead byte, in registers: one 16-byte load per thread
+// (byte loads for the last, partial vector of the buffer or an unaligned source).  Bytes past the end
+// read as 0, which is neither '\n' nor whitespace.  Every thread of the block must call load_items.
+struct Items {
+  unsigned b[FA_ITEMS + 1];
+  int cnt;                                           // bytes of this thread that are inside the buffer
+  // terminator: '\n', or '\r' not followed by '\n' (is_term on the registers)
+  __device__ __forceinline__ bool term(int k) const {
+    return b[k] == '\n' || (b[k] == '\r' && b[k + 1] != '\n');
+  }
+};
+__device__ __forceinline__ void load_items(const uint8_t *__restrict__ raw, int64_t n, int64_t base, Items &it) {
+  static_assert(FA_ITEMS == 16, "one uint4 per thread");
+  const int64_t left = n - base;
+  it.cnt = left <= 0 ? 0 : (left < FA_ITEMS ? (int)left : FA_ITEMS);
+  if (it.cnt == FA_ITEMS && (reinterpret_cast<uintptr_t>(raw + base) & 15) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + base));
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < FA_ITEMS; ++k) it.b[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+  } else {
+#pragma unroll
+    for (int k = 0; k < FA_ITEMS; ++k) it.b[k] = k < it.cnt ? (unsigned)raw[base + k] : 0u;
+  }
+  // look-ahead byte = first byte of the next thread; the last lane of a warp reads it from memory
+  unsigned next = __shfl_down_sync(0xffffffffu, it.b[0], 1);
+  if ((threadIdx.x & 31) == 31) next = left > FA_ITEMS ? (unsigned)raw[base + FA_ITEMS] : 0u;
+  it.b[FA_ITEMS] = next;
+}
+// state function of the thread's bytes
+__device__ __forceinline__ unsigned items_fn(const Items &it) {
+  unsigned f = FN_IDENT;
+#pragma unroll
+  for (int k = 0; k < FA_ITEMS; ++k)
+    if (k < it.cnt) f = push_byte(f, it.b[k], it.term(k));
+  return f;
+}
+
 __global__ void fa_tile_fn_kernel(const uint8_t *__restrict__ raw, int64_t n, unsigned *tile_fn) {
   const int64_t base = (int64_t)blockIdx.x * FA_TILE + (int64_t)threadIdx.x * FA_ITEMS;
-  unsigned f = FN_IDENT;
-#pragma unroll 4
-  for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i < n) f = compose(f, byte_fn(raw[i], is_term(raw, n, i)));
-  }
+  Items it;
+  load_items(raw, n, base, it);
   unsigned tot;
-  block_scan_fn(f, &tot);
+  block_scan_fn(items_fn(it), &tot);
   if (threadIdx.x == 0) tile_fn[blockIdx.x] = tot;
 }
 
@@ -110,10 +154,9 @@ struct ByteClass {
   bool hdr;      // the '>' that starts a record
   bool blank;    // terminator of a line that is empty after strip()
 };
-__device__ __forceinline__ ByteClass classify(const uint8_t *raw, int64_t n, int64_t i, unsigned s) {
+__device__ __forceinline__ ByteClass classify(const uint8_t *raw, int64_t n, int64_t i, unsigned b, bool term,
+                                              unsigned s) {
   ByteClass c = {false, false, false};
-  const unsigned b = raw[i];
-  const bool term = is_term(raw, n, i);
   if (term) { c.blank = (s == ST_START); return c; }
   if (s == ST_START) {
     if (is_ws(b)) return c;
@@ -123,6 +166,7 @@ __device__ __forceinline__ ByteClass classify(const uint8_t *raw, int64_t n, int
   if (s == ST_SEQ) {
     if (!is_ws(b)) { c.seq = true; return c; }
     // whitespace inside a sequence line is kept unless only whitespace follows up to the line end
+    // (rare: walks the text in global memory)
     int64_t j = i + 1;
     while (j < n && !is_term(raw, n, j) && is_ws(raw[j])) ++j;
     c.seq = !(j >= n || is_term(raw, n, j));
@@ -137,22 +181,21 @@ __global__ void fa_count_kernel(const uint8_t *__restrict__ raw, int64_t n,
   __shared__ unsigned s_c[2];
   if (threadIdx.x == 0) { s_c[0] = 0; s_c[1] = 0; }
   const int64_t base = (int64_t)blockIdx.x * FA_TILE + (int64_t)threadIdx.x * FA_ITEMS;
-  unsigned f = FN_IDENT;
-  for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i < n) f = compose(f, byte_fn(raw[i], is_term(raw, n, i)));
-  }
+  Items it;
+  load_items(raw, n, base, it);
   unsigned tot;
-  const unsigned excl = block_scan_fn(f, &tot);
+  const unsigned excl = block_scan_fn(items_fn(it), &tot);
   unsigned s = apply_fn(excl, tile_state[blockIdx.x]);
   unsigned cs = 0, ch = 0;
   bool blank = false;
+#pragma unroll
   for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i >= n) break;
-    const ByteClass c = classify(raw, n, i, s);
-    cs += c.seq; ch += c.hdr; blank |= c.blank;
-    s = step_state(s, raw[i], is_term(raw, n, i));
+    if (k < it.cnt) {
+      const bool term = it.term(k);
+      const ByteClass c = classify(raw, n, base + k, it.b[k], term, s);
+      cs += c.seq; ch += c.hdr; blank |= c.blank;
+      s = step_state(s, it.b[k], term);
+    }
   }
   for (int off = 16; off > 0; off >>= 1) {
     cs += __shfl_xor_sync(0xffffffffu, cs, off);
@@ -165,7 +208,9 @@ __global__ void fa_count_kernel(const uint8_t *__restrict__ raw, int64_t n,
 }
 
 // pass 3: ordered scatter.  seq_out[rank] = byte; hdr_pos[k] = offset of the k-th '>' in raw,
-// hdr_seq[k] = number of sequence bytes in front of it.
+// hdr_seq[k] = number of sequence bytes in front of it.  The tile's sequence bytes are contiguous in
+// seq_out: they are compacted in shared memory (shifted by the destination's offset inside its 16-byte
+// vector) and leave as aligned 16-byte stores.
 __global__ void fa_scatter_kernel(const uint8_t *__restrict__ raw, int64_t n,
                                   const uint8_t *__restrict__ tile_state,
                                   const unsigned *__restrict__ seq_off,
@@ -173,25 +218,26 @@ __global__ void fa_scatter_kernel(const uint8_t *__restrict__ raw, int64_t n,
                                   uint8_t *__restrict__ seq_out, int64_t *__restrict__ hdr_pos,
                                   int64_t *__restrict__ hdr_seq) {
   __shared__ unsigned s_ws[FA_THREADS / 32], s_wh[FA_THREADS / 32];
+  __shared__ __align__(16) uint8_t s_buf[FA_TILE + 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = (int64_t)blockIdx.x * FA_TILE + (int64_t)threadIdx.x * FA_ITEMS;
-  unsigned f = FN_IDENT;
-  for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i < n) f = compose(f, byte_fn(raw[i], is_term(raw, n, i)));
-  }
+  Items it;
+  load_items(raw, n, base, it);
   unsigned tot;
-  const unsigned excl = block_scan_fn(f, &tot);
+  const unsigned excl = block_scan_fn(items_fn(it), &tot);
   const unsigned s0 = apply_fn(excl, tile_state[blockIdx.x]);
-  // thread-local counts, then exclusive offsets across the block
-  unsigned s = s0, cs = 0, ch = 0;
+  // thread-local classes (bit k of ms / mh: byte k is a sequence byte / a record's '>') and counts
+  unsigned s = s0, ms = 0, mh = 0;
+#pragma unroll
   for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i >= n) break;
-    const ByteClass c = classify(raw, n, i, s);
-    cs += c.seq; ch += c.hdr;
-    s = step_state(s, raw[i], is_term(raw, n, i));
+    if (k < it.cnt) {
+      const bool term = it.term(k);
+      const ByteClass c = classify(raw, n, base + k, it.b[k], term, s);
+      ms |= (unsigned)c.seq << k; mh |= (unsigned)c.hdr << k;
+      s = step_state(s, it.b[k], term);
+    }
   }
+  const unsigned cs = __popc(ms), ch = __popc(mh);
   unsigned is_ = cs, ih = ch;
   for (int off = 1; off < 32; off <<= 1) {
     const unsigned a = __shfl_up_sync(0xffffffffu, is_, off), b = __shfl_up_sync(0xffffffffu, ih, off);
@@ -199,17 +245,28 @@ __global__ void fa_scatter_kernel(const uint8_t *__restrict__ raw, int64_t n,
   }
   if (lane == 31) { s_ws[warp] = is_; s_wh[warp] = ih; }
   __syncthreads();
-  unsigned ps = seq_off[blockIdx.x], ph = hdr_off[blockIdx.x];
-  for (int w = 0; w < warp; ++w) { ps += s_ws[w]; ph += s_wh[w]; }
-  ps += is_ - cs; ph += ih - ch;
-  s = s0;
+  unsigned ls = is_ - cs, ph = hdr_off[blockIdx.x] + ih - ch, tile_total = 0;
+  for (int w = 0; w < FA_THREADS / 32; ++w) {
+    if (w < warp) { ls += s_ws[w]; ph += s_wh[w]; }
+    tile_total += s_ws[w];
+  }
+  const int64_t tile_seq0 = seq_base + seq_off[blockIdx.x];          // rank of the tile's first sequence byte
+  const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(seq_out + tile_seq0) & 15);
+#pragma unroll
   for (int k = 0; k < FA_ITEMS; ++k) {
-    const int64_t i = base + k;
-    if (i >= n) break;
-    const ByteClass c = classify(raw, n, i, s);
-    if (c.seq) seq_out[seq_base + ps++] = raw[i];
-    if (c.hdr) { hdr_pos[ph] = i; hdr_seq[ph] = seq_base + ps; ++ph; }
-    s = step_state(s, raw[i], is_term(raw, n, i));
+    if ((ms >> k) & 1u) s_buf[shift + ls++] = (uint8_t)it.b[k];
+    if ((mh >> k) & 1u) { hdr_pos[ph] = base + k; hdr_seq[ph] = tile_seq0 + ls; ++ph; }
+  }
+  __syncthreads();
+  uint8_t *gbase = seq_out + tile_seq0 - shift;                      // 16-byte aligned
+  const unsigned end = shift + tile_total;
+  for (unsigned lo = threadIdx.x * 16; lo < end; lo += FA_THREADS * 16) {
+    const unsigned hi = lo + 16;
+    if (lo >= shift && hi <= end) {
+      *reinterpret_cast<uint4 *>(gbase + lo) = *reinterpret_cast<const uint4 *>(s_buf + lo);
+    } else {
+      for (unsigned j = lo < shift ? shift : lo; j < (hi < end ? hi : end); ++j) gbase[j] = s_buf[j];
+    }
   }
 }
 

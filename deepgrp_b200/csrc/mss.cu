@@ -465,15 +465,27 @@ int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n
 // One warp per segment: count labels 1..nof-1, majority (ties -> lowest, default 1), rewrite zeros.
 constexpr int GF_MAXC = 16;
 
+// Segments longer than GF_LONG positions leave the warp-per-segment kernel (one warp walking a segment
+// of millions of positions is the whole step: 385 ms for one 24.8 Mbp segment) and are processed
+// position-parallel by gap_long_kernel, GF_PIECE positions per block.  Disjoint segments longer than
+// GF_LONG cannot start inside the same aligned window of GF_LONG positions, so st / GF_LONG is a
+// collision-free key for their label counts.
+constexpr int GF_LONG = 8192;
+constexpr int GF_PIECE = 8192;
+
 template <typename LabT>
 __global__ void gap_fill_kernel(const dgrp_seg_t *__restrict__ segs, int n_seg,
                                 const LabT *__restrict__ lab_in, int nof,
-                                uint8_t *__restrict__ lab_out) {
+                                uint8_t *__restrict__ lab_out, int *__restrict__ any_long) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int g = blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < n_seg;
        g += gridDim.x * warps_per_block) {
     const int st = segs[g].st, en = segs[g].en;
+    if (en - st > GF_LONG) {
+      if (lane == 0) *any_long = 1;
+      continue;
+    }
     unsigned int cnt[GF_MAXC];
 #pragma unroll
     for (int k = 0; k < GF_MAXC; ++k) cnt[k] = 0;
@@ -492,6 +504,64 @@ __global__ void gap_fill_kernel(const dgrp_seg_t *__restrict__ segs, int n_seg,
       if (k < nof && bestv < cnt[k]) { best = k; bestv = cnt[k]; }
     for (int i = st + lane; i < en; i += 32)
       if (lab_in[i] == 0) lab_out[i] = (uint8_t)best;
+  }
+}
+
+// Long segments, position-parallel: block b owns positions [b * GF_PIECE, (b + 1) * GF_PIECE) and visits the
+// long segments that intersect them (found by bisection; segments are sorted and disjoint).  FILL = false
+// adds the label counts of the intersection to the segment's table entry, FILL = true (a second launch)
+// takes the majority over classes 1..nof-1 (ties -> lowest, default 1, pymss.pyx:62-67) and rewrites
+// the zeros.  Every condition on the way is block-uniform.
+template <typename LabT, bool FILL>
+__global__ void gap_long_kernel(const dgrp_seg_t *__restrict__ segs, int n_seg,
+                                const LabT *__restrict__ lab_in, int n, int nof,
+                                const int *__restrict__ any_long, unsigned int *__restrict__ table,
+                                uint8_t *__restrict__ lab_out) {
+  if (*any_long == 0) return;
+  __shared__ unsigned int s_cnt[GF_MAXC];
+  const int64_t r0 = (int64_t)blockIdx.x * GF_PIECE;
+  const int64_t r1 = r0 + GF_PIECE < (int64_t)n ? r0 + GF_PIECE : (int64_t)n;
+  int lo = 0, hi = n_seg;                      // first segment with en > r0
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)segs[mid].en > r0) hi = mid; else lo = mid + 1;
+  }
+  for (int g = lo; g < n_seg; ++g) {
+    const int st = segs[g].st, en = segs[g].en;
+    if ((int64_t)st >= r1) break;
+    if (en - st <= GF_LONG) continue;
+    const int a = (int64_t)st > r0 ? st : (int)r0, b = (int64_t)en < r1 ? en : (int)r1;
+    unsigned int *entry = table + (size_t)(st / GF_LONG) * GF_MAXC;
+    if (!FILL) {
+      if (threadIdx.x < GF_MAXC) s_cnt[threadIdx.x] = 0;
+      __syncthreads();
+      unsigned int cnt[GF_MAXC];
+#pragma unroll
+      for (int k = 0; k < GF_MAXC; ++k) cnt[k] = 0;
+      for (int i = a + (int)threadIdx.x; i < b; i += (int)blockDim.x) {
+        const int l = (int)lab_in[i];
+#pragma unroll
+        for (int k = 1; k < GF_MAXC; ++k) cnt[k] += (l == k);
+      }
+#pragma unroll
+      for (int k = 1; k < GF_MAXC; ++k) {
+        for (int off = 16; off > 0; off >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], off);
+        if ((threadIdx.x & 31) == 0 && cnt[k]) atomicAdd(&s_cnt[k], cnt[k]);
+      }
+      __syncthreads();
+      if (threadIdx.x >= 1 && threadIdx.x < GF_MAXC && s_cnt[threadIdx.x])
+        atomicAdd(&entry[threadIdx.x], s_cnt[threadIdx.x]);
+      __syncthreads();
+    } else {
+      int best = 1;
+      unsigned int bestv = entry[1];
+      for (int k = 2; k < GF_MAXC; ++k) {
+        const unsigned int v = entry[k];
+        if (k < nof && bestv < v) { best = k; bestv = v; }
+      }
+      for (int i = a + (int)threadIdx.x; i < b; i += (int)blockDim.x)
+        if (lab_in[i] == 0) lab_out[i] = (uint8_t)best;
+    }
   }
 }
 
@@ -517,13 +587,26 @@ int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t
   }
   c->launches++;
   if (n_seg > 0) {
+    // [0] "a long segment exists" flag, [64..] label counts of the long segments keyed by st / GF_LONG
+    const size_t entries = (size_t)n / GF_LONG + 1;
+    const size_t table_bytes = 256 + entries * GF_MAXC * sizeof(unsigned int);
+    DGRP_CHECK(c->gapfill.reserve(table_bytes));
+    DGRP_CUDA(cudaMemsetAsync(c->gapfill.p, 0, table_bytes, c->stream));
+    int *any_long = c->gapfill.as<int>();
+    unsigned int *table = c->gapfill.as<unsigned int>() + 64;
     want = ((int64_t)n_seg + 7) / 8;
     blocks = (int)(want < (int64_t)c->sm_count * 8 ? want : (int64_t)c->sm_count * 8);
-    if (d_label_in)
-      gap_fill_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label_in, nof_labels, d_label_out);
-    else
-      gap_fill_kernel<int64_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label64_in, nof_labels, d_label_out);
-    c->launches++;
+    const int pieces = (int)(((int64_t)n + GF_PIECE - 1) / GF_PIECE);
+    if (d_label_in) {
+      gap_fill_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label_in, nof_labels, d_label_out, any_long);
+      gap_long_kernel<uint8_t, false><<<pieces, threads, 0, c->stream>>>(d_segs, n_seg, d_label_in, n, nof_labels, any_long, table, d_label_out);
+      gap_long_kernel<uint8_t, true><<<pieces, threads, 0, c->stream>>>(d_segs, n_seg, d_label_in, n, nof_labels, any_long, table, d_label_out);
+    } else {
+      gap_fill_kernel<int64_t><<<blocks, threads, 0, c->stream>>>(d_segs, n_seg, d_label64_in, nof_labels, d_label_out, any_long);
+      gap_long_kernel<int64_t, false><<<pieces, threads, 0, c->stream>>>(d_segs, n_seg, d_label64_in, n, nof_labels, any_long, table, d_label_out);
+      gap_long_kernel<int64_t, true><<<pieces, threads, 0, c->stream>>>(d_segs, n_seg, d_label64_in, n, nof_labels, any_long, table, d_label_out);
+    }
+    c->launches += 3;
   }
   DGRP_CUDA(cudaGetLastError());
   return DGRP_OK;

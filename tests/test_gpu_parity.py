@@ -180,6 +180,46 @@ def test_find_mss_labels_matches_oracle_large(dg, oracle):
         assert np.array_equal(got, exp)
 
 
+def _long_segment_case(rng, lengths, gap=3):
+    """Scores whose maximal segments are exactly the given positive runs (float32-valued; runs separated by `gap`
+    positions negative enough that no two runs merge), labels with zeros to fill in every run."""
+    t = float(np.float32(np.log(0.99 / 0.01)))
+    scores, labels = [], []
+    for k, ln in enumerate(lengths):
+        scores.append(np.full(ln, t)); scores.append(np.full(gap, -float(2 ** 24)))
+        lab = rng.integers(0, 5, size=ln)
+        lab[rng.random(ln) < 0.5] = 0
+        if k % 3 == 1:
+            lab[lab == 1] = 0                   # the majority is not class 1
+        if k % 5 == 4:
+            lab[:] = 0                          # no positive label at all: default class 1
+        labels.append(lab); labels.append(np.zeros(gap, dtype=lab.dtype))
+    return np.concatenate(scores), np.concatenate(labels).astype(np.int64)
+
+
+@pytest.mark.parametrize("lengths", [
+    [200_000],                                   # one segment spanning many blocks
+    [8192, 8193, 8191, 50, 16_384, 16_385, 3, 70_000, 8193],   # both sides of the long-segment threshold
+    [100, 30_000, 60, 60, 60, 9000, 9000, 20, 123_457, 51],
+])
+def test_gap_fill_long_segments(dg, oracle, lengths):
+    """Segments longer than a warp should walk alone (mss.cu: gap_long_kernel): label counts and the fill of
+    segments that span many blocks, start and end anywhere, next to short ones -- int64 labels through
+    find_mss_labels, uint8 labels + float32 scores through dgrp_finish_record."""
+    from deepgrp_b200 import sharding
+    rng = np.random.default_rng(len(lengths))
+    scores, labels = _long_segment_case(rng, lengths)
+    for min_len, xdrop in ((50, 50), (1, -1)):
+        exp = oracle.find_mss_labels(scores, labels, 5, min_len, xdrop)
+        got = dg.mss.find_mss_labels(scores, labels, 5, min_len, xdrop)
+        assert np.array_equal(got, exp)
+        out, rows = sharding.finish_record(labels.astype(np.uint8), scores.astype(np.float32), 5, True, min_len,
+                                           xdrop, 7)
+        assert np.array_equal(out, exp.argmax(axis=1).astype(np.uint8))
+        exp_rows = [(a, b, l) for a, b, l in oracle.yield_segments(exp.argmax(axis=1).astype(np.int64), 7) if l > 0]
+        assert list(zip(rows["start"].tolist(), rows["end"].tolist(), rows["label"].tolist())) == exp_rows
+
+
 # ------------------------------------------------------------------ score transform / softmax
 def test_mss_scores_and_softmax(dg, oracle):
     rng = np.random.default_rng(5)
@@ -453,6 +493,80 @@ def test_predict_fasta_tsv_vs_oracle(dg, oracle, tmp_path):
         dg.pred.predict_fasta_tsv(w, b">x\nACGT\n\nACGT\n", "f", 50, 256, True, 50, 50)
     with pytest.raises(ValueError):
         dg.pred.predict_fasta_tsv(w, b">x\nNNNN\n", "f", 50, 256, True, 50, 50)
+
+
+def _messy_fasta(seed):
+    """FASTA text with mixed line ends (LF, CRLF, lone CR), whitespace around and inside lines, headers with
+    blanks, ragged line widths, text before the first '>', an empty-header record, an optional missing final
+    line end and (sometimes) a blank line."""
+    import random
+    r = random.Random(seed)
+    parts = []
+    if r.random() < 0.3:
+        parts.append("ACGT" * r.randint(1, 50) + r.choice(["\n", "\r\n"]))
+    for i in range(r.randint(1, 4)):
+        nl = r.choice(["\n", "\r\n", "\r", "\n"])
+        hdr = r.choice(["chr%d desc" % i, "x", "", " spaced\t", "h>h"])
+        parts.append(r.choice(["", " ", "\t"]) + ">" + hdr + r.choice(["", " ", "\t "]) + nl)
+        for _ in range(r.randint(20, 400)):
+            w = r.choice([60, 60, 60, 1, 7, 80, 16, 15, 17])
+            line = "".join(r.choice("ACGTacgtNn") for _ in range(w))
+            if r.random() < 0.05:
+                line = line[:w // 2] + r.choice([" ", "\t", "  "]) + line[w // 2:]
+            if r.random() < 0.05:
+                line = r.choice([" ", "\t"]) + line
+            if r.random() < 0.05:
+                line = line + r.choice([" ", "\t", " \t "])
+            parts.append(line + nl)
+    text = "".join(parts)
+    if r.random() < 0.3:
+        text = text.rstrip("\r\n")
+    if r.random() < 0.1:
+        text += r.choice(["\n\n", "\n \n", " ", "\n\t"])
+    return text
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fasta_decode_messy_text_equals_python_reader(dg, seed):
+    """The GPU FASTA decode against `_read_multi_fasta` (reference deepgrp/__main__.py:20-43) on hostile text:
+    same records (header, trimmed length, startpos), and the rows of the messy file equal those of the same
+    records written canonically -- identical decoded bytes give bit-identical rows."""
+    from deepgrp_b200.__main__ import _read_multi_fasta
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    text = _messy_fasta(seed)
+    try:
+        exp = list(_read_multi_fasta(io.StringIO(text, newline=None)))
+    except IndexError:
+        with pytest.raises(IndexError):
+            dg.pred.predict_fasta(w, text.encode(), 50, 256, True, 50, 50)
+        return
+    rows, records = dg.pred.predict_fasta(w, text.encode(), 50, 256, True, 50, 50)
+    assert [r[0] for r in records] == [h for h, _ in exp]
+    for (_, startpos, length), (_, seq) in zip(records, exp):
+        assert startpos == len(seq) - len(seq.lstrip("N"))
+        assert length == len(seq.strip("N"))
+    # whitespace kept inside a line encodes like any non-ACGT byte (channel 4): 'X' stands in for it so that
+    # the canonical line breaks cannot strip it
+    canon = "".join(">%s\n%s\n" % (h, "\n".join(q[i:i + 60] for i in range(0, len(q), 60)))
+                    for h, q in ((h, "".join("X" if c.isspace() else c for c in q)) for h, q in exp))
+    rows_c, records_c = dg.pred.predict_fasta(w, canon.encode(), 50, 256, True, 50, 50)
+    assert [r[1:] for r in records_c] == [r[1:] for r in records]
+    assert np.array_equal(rows, rows_c)
+
+
+@pytest.mark.parametrize("lead,trail,offset", [(0, 0, 0), (3, 5, 1), (17, 33, 7), (4096, 1, 15), (100_003, 70_001, 3)])
+def test_one_hot_trim_unaligned_and_long_n_runs(dg, lead, trail, offset):
+    """Edge-N trim with 16-byte loads: N runs longer than a vector / a block, records that start at an odd
+    address inside a multi-FASTA buffer (`offset` bases of a first record in front)."""
+    body = random_dna(5000, lead + trail, "ACGTN")
+    body = "A" + body + "C"
+    seq = "N" * lead + body + "N" * trail
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(seq)
+    assert st == lead and fwd.shape == (5, len(body))
+    w = dg.model.random_weights(150, 32, attention=True, seed=0)
+    text = ">a\n" + "ACGTACGTACGTACGTA"[:offset + 1] + "\n>b\n" + seq + "\n"
+    _, records = dg.pred.predict_fasta(w, text.encode(), 50, 256, False, 50, 50)
+    assert records[1] == ("b", lead, len(body))
 
 
 def test_predict_range_shards_equal_whole(dg):
