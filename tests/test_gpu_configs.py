@@ -242,3 +242,51 @@ def test_chunk_sharding_device_entry_points(dg):
     assert n_rows.value == n_whole.value and n_rows.value > 0
     out, rows = sharding.finish_record(full_lab.cpu().numpy(), full_sc.cpu().numpy(), 5, True, 50, 50, 0)
     assert rows.size == n_rows.value
+
+
+def test_predict_complete_from_files_on_disk(dg, oracle, tmp_path):
+    """The evaluation route of the reference (deepgrp/optimization.py:58-69 around prediction.py:114-141) fed
+    from the formats on disk: a gzip FASTA turned into the .npz one-hot file (preprocess_sequence), a
+    training log directory holding TensorFlow checkpoints (training.py:53-59), the edge-N cut, predict_complete
+    with and without MSS, then confusion matrix and metrics -- against the oracle on the same arrays."""
+    import gzip
+    from deepgrp_b200 import preprocessing, tfckpt
+    T, U, step = 150, 32, 50
+    w = dg.model.random_weights(T, U, attention=True, seed=3).scaled(4.0)
+    wd = w.as_dict()
+    logdir = tmp_path / "log"
+    logdir.mkdir()
+    names = {"layer_with_weights-0/cell/kernel": "kernel", "layer_with_weights-0/cell/recurrent_kernel": "recurrent_kernel",
+             "layer_with_weights-0/cell/bias": "bias", "layer_with_weights-1/scale": "att_scale",
+             "layer_with_weights-2/kernel": "ff_kernel", "layer_with_weights-2/bias": "ff_bias"}
+    for epoch, factor in (("01", 0.5), ("02", 1.0)):            # the latest checkpoint holds the weights
+        tfckpt.write_bundle(str(logdir / epoch), {k + "/.ATTRIBUTES/VARIABLE_VALUE": wd[v] * np.float32(factor)
+                                                  for k, v in names.items()})
+    fasta = tmp_path / "chrT.fa.gz"
+    seq = "N" * 40 + random_dna(14_000, 21, "ACGTN") + "N" * 25
+    with gzip.open(fasta, "wb") as fh:
+        fh.write((">chrT\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode())
+    assert preprocessing.preprocess_sequence(str(fasta)) is True
+    fwd, _ = preprocessing.load_onehot_npz(str(fasta) + ".npz")
+    assert fwd.shape == (5, len(seq)) and fwd[4, :40].all() and fwd[4, -25:].all()
+    rng = np.random.default_rng(4)
+    truth = np.repeat(rng.integers(0, 5, size=400), rng.integers(20, 90, size=400))[:len(seq)]
+    y = np.zeros((5, len(seq)), dtype=np.int8)
+    y[truth, np.arange(len(seq))] = 1
+    fwd_cut, y_cut = preprocessing.drop_start_end_n(fwd, y)
+    data = preprocessing.Data(fwd_cut, y_cut)
+    opts = dg.model.Options(vecsize=T, batch_size=256, min_mss_len=50, xdrop_len=50)
+    probs_o = oracle.predict(lambda b: oracle.model_forward(b, wd), oracle.fetch_validation_batch(fwd_cut, step, 256, T),
+                             y_cut.shape[::-1], step)
+    got_sm = dg.pred.predict_complete(step, opts, logdir, data, use_mss=False)
+    assert got_sm.shape == y_cut.shape[::-1]
+    assert np.abs(got_sm - oracle.softmax(probs_o)).max() < 1e-3
+    got = dg.pred.predict_complete(step, opts, logdir, data, use_mss=True)
+    exp = oracle.apply_mss(probs_o, 50, 50)
+    assert got.shape == exp.shape and (got.sum(axis=1) == 1).all()
+    agree = float((got.argmax(axis=1) == exp.argmax(axis=1)).mean())
+    assert agree >= 0.9999, agree
+    true_cls = y_cut.argmax(axis=0)
+    cnf = dg.pred.confusion_matrix(true_cls, got.argmax(axis=1))
+    assert np.array_equal(cnf, oracle.confusion_matrix(true_cls, got.argmax(axis=1)))
+    assert int(np.asarray(cnf).sum()) == true_cls.size
