@@ -13,40 +13,14 @@
 // the state in front of every tile.  Sequence bytes are then compacted in order, and the number
 // of sequence bytes in front of every header gives the record boundaries.
 #include "dgrp_internal.cuh"
+#include "fasta_core.cuh"
 
 namespace dgrp {
 
+using namespace fa;
+
 constexpr int FA_THREADS = 256;
-constexpr int FA_ITEMS = 16;
 constexpr int FA_TILE = FA_THREADS * FA_ITEMS;
-
-enum : unsigned { ST_START = 0, ST_SEQ = 1, ST_HDR = 2 };
-constexpr unsigned FN_IDENT = (0u) | (1u << 2) | (2u << 4);
-
-__device__ __forceinline__ bool is_ws(unsigned b) { return (b >= 9 && b <= 13) || (b >= 28 && b <= 32); }
-
-// terminator: '\n', or '\r' not followed by '\n' (the '\r' of "\r\n" is plain whitespace)
-__device__ __forceinline__ bool is_term(const uint8_t *raw, int64_t n, int64_t i) {
-  const unsigned b = raw[i];
-  if (b == '\n') return true;
-  if (b == '\r') return !(i + 1 < n && raw[i + 1] == '\n');
-  return false;
-}
-
-__device__ __forceinline__ unsigned step_state(unsigned s, unsigned b, bool term) {
-  if (term) return ST_START;
-  if (s == ST_START) return is_ws(b) ? ST_START : (b == '>' ? ST_HDR : ST_SEQ);
-  return s;
-}
-__device__ __forceinline__ unsigned byte_fn(unsigned b, bool term) {
-  return step_state(0, b, term) | (step_state(1, b, term) << 2) | (step_state(2, b, term) << 4);
-}
-// (f then g)
-__device__ __forceinline__ unsigned compose(unsigned f, unsigned g) {
-  return ((g >> (2 * (f & 3))) & 3) | (((g >> (2 * ((f >> 2) & 3))) & 3) << 2) |
-         (((g >> (2 * ((f >> 4) & 3))) & 3) << 4);
-}
-__device__ __forceinline__ unsigned apply_fn(unsigned f, unsigned s) { return (f >> (2 * s)) & 3; }
 
 // Exclusive block scan of per-thread functions; returns the function of everything before this
 // thread in the tile, *total receives the whole tile's function.
@@ -71,27 +45,9 @@ __device__ unsigned block_scan_fn(unsigned f, unsigned *total) {
   return compose(before, excl);
 }
 
-// f followed by one byte: a terminator sends every start state to ST_START, whitespace changes nothing,
-// any other byte moves the fields that are ST_START (== 0) to ST_HDR ('>') or ST_SEQ.  Equal to
-// compose(f, byte_fn(b, term)) for every f and byte, without the three table look-ups.
-__device__ __forceinline__ unsigned push_byte(unsigned f, unsigned b, bool term) {
-  const unsigned z = ~(f | (f >> 1)) & 0x15u;        // low bit of every field that holds ST_START
-  unsigned g = f | (b == '>' ? (z << 1) : z);
-  g = is_ws(b) ? f : g;
-  return term ? 0u : g;
-}
-
 // The FA_ITEMS bytes of one thread plus one look-ahead byte, in registers: one 16-byte load per thread
 // (byte loads for the last, partial vector of the buffer or an unaligned source).  Bytes past the end
 // read as 0, which is neither '\n' nor whitespace.  Every thread of the block must call load_items.
-struct Items {
-  unsigned b[FA_ITEMS + 1];
-  int cnt;                                           // bytes of this thread that are inside the buffer
-  // terminator: '\n', or '\r' not followed by '\n' (is_term on the registers)
-  __device__ __forceinline__ bool term(int k) const {
-    return b[k] == '\n' || (b[k] == '\r' && b[k + 1] != '\n');
-  }
-};
 __device__ __forceinline__ void load_items(const uint8_t *__restrict__ raw, int64_t n, int64_t base, Items &it) {
   static_assert(FA_ITEMS == 16, "one uint4 per thread");
   const int64_t left = n - base;
@@ -110,15 +66,6 @@ __device__ __forceinline__ void load_items(const uint8_t *__restrict__ raw, int6
   if ((threadIdx.x & 31) == 31) next = left > FA_ITEMS ? (unsigned)raw[base + FA_ITEMS] : 0u;
   it.b[FA_ITEMS] = next;
 }
-// state function of the thread's bytes
-__device__ __forceinline__ unsigned items_fn(const Items &it) {
-  unsigned f = FN_IDENT;
-#pragma unroll
-  for (int k = 0; k < FA_ITEMS; ++k)
-    if (k < it.cnt) f = push_byte(f, it.b[k], it.term(k));
-  return f;
-}
-
 __global__ void fa_tile_fn_kernel(const uint8_t *__restrict__ raw, int64_t n, unsigned *tile_fn) {
   const int64_t base = (int64_t)blockIdx.x * FA_TILE + (int64_t)threadIdx.x * FA_ITEMS;
   Items it;
@@ -146,32 +93,6 @@ __global__ void fa_tile_state_kernel(const unsigned *__restrict__ tile_fn, int64
     __syncthreads();
   }
   if (threadIdx.x == 0) *final_state = s_carry;
-}
-
-// classification of byte i given the state in front of it
-struct ByteClass {
-  bool seq;      // sequence byte that survives strip()
-  bool hdr;      // the '>' that starts a record
-  bool blank;    // terminator of a line that is empty after strip()
-};
-__device__ __forceinline__ ByteClass classify(const uint8_t *raw, int64_t n, int64_t i, unsigned b, bool term,
-                                              unsigned s) {
-  ByteClass c = {false, false, false};
-  if (term) { c.blank = (s == ST_START); return c; }
-  if (s == ST_START) {
-    if (is_ws(b)) return c;
-    if (b == '>') c.hdr = true; else c.seq = true;
-    return c;
-  }
-  if (s == ST_SEQ) {
-    if (!is_ws(b)) { c.seq = true; return c; }
-    // whitespace inside a sequence line is kept unless only whitespace follows up to the line end
-    // (rare: walks the text in global memory)
-    int64_t j = i + 1;
-    while (j < n && !is_term(raw, n, j) && is_ws(raw[j])) ++j;
-    c.seq = !(j >= n || is_term(raw, n, j));
-  }
-  return c;
 }
 
 // pass 2: per tile counts of sequence bytes and headers, and the blank-line flag

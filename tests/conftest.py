@@ -47,3 +47,34 @@ def write_fasta(path, records, width=60):
             fh.write(">" + header + "\n")
             for i in range(0, len(seq), width):
                 fh.write(seq[i:i + width] + "\n")
+
+
+def messy_fasta(seed):
+    """FASTA text with mixed line ends (LF, CRLF, lone CR), whitespace around and inside lines, headers with
+    blanks, ragged line widths, text before the first '>', an empty-header record, an optional missing final
+    line end and (sometimes) a blank line."""
+    import random
+    r = random.Random(seed)
+    parts = []
+    if r.random() < 0.3:
+        parts.append("ACGT" * r.randint(1, 50) + r.choice(["\n", "\r\n"]))
+    for i in range(r.randint(1, 4)):
+        nl = r.choice(["\n", "\r\n", "\r", "\n"])
+        hdr = r.choice(["chr%d desc" % i, "x", "", " spaced\t", "h>h"])
+        parts.append(r.choice(["", " ", "\t"]) + ">" + hdr + r.choice(["", " ", "\t "]) + nl)
+        for _ in range(r.randint(20, 400)):
+            w = r.choice([60, 60, 60, 1, 7, 80, 16, 15, 17])
+            line = "".join(r.choice("ACGTacgtNn") for _ in range(w))
+            if r.random() < 0.05:
+                line = line[:w // 2] + r.choice([" ", "\t", "  "]) + line[w // 2:]
+            if r.random() < 0.05:
+                line = r.choice([" ", "\t"]) + line
+            if r.random() < 0.05:
+                line = line + r.choice([" ", "\t", " \t "])
+            parts.append(line + nl)
+    text = "".join(parts)
+    if r.random() < 0.3:
+        text = text.rstrip("\r\n")
+    if r.random() < 0.1:
+        text += r.choice(["\n\n", "\n \n", " ", "\n\t"])
+    return text

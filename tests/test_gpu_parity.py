@@ -8,7 +8,7 @@ import io
 import numpy as np
 import pytest
 
-from conftest import random_dna, write_fasta
+from conftest import messy_fasta, random_dna, write_fasta
 
 pytestmark = pytest.mark.gpu
 
@@ -495,37 +495,6 @@ def test_predict_fasta_tsv_vs_oracle(dg, oracle, tmp_path):
         dg.pred.predict_fasta_tsv(w, b">x\nNNNN\n", "f", 50, 256, True, 50, 50)
 
 
-def _messy_fasta(seed):
-    """FASTA text with mixed line ends (LF, CRLF, lone CR), whitespace around and inside lines, headers with
-    blanks, ragged line widths, text before the first '>', an empty-header record, an optional missing final
-    line end and (sometimes) a blank line."""
-    import random
-    r = random.Random(seed)
-    parts = []
-    if r.random() < 0.3:
-        parts.append("ACGT" * r.randint(1, 50) + r.choice(["\n", "\r\n"]))
-    for i in range(r.randint(1, 4)):
-        nl = r.choice(["\n", "\r\n", "\r", "\n"])
-        hdr = r.choice(["chr%d desc" % i, "x", "", " spaced\t", "h>h"])
-        parts.append(r.choice(["", " ", "\t"]) + ">" + hdr + r.choice(["", " ", "\t "]) + nl)
-        for _ in range(r.randint(20, 400)):
-            w = r.choice([60, 60, 60, 1, 7, 80, 16, 15, 17])
-            line = "".join(r.choice("ACGTacgtNn") for _ in range(w))
-            if r.random() < 0.05:
-                line = line[:w // 2] + r.choice([" ", "\t", "  "]) + line[w // 2:]
-            if r.random() < 0.05:
-                line = r.choice([" ", "\t"]) + line
-            if r.random() < 0.05:
-                line = line + r.choice([" ", "\t", " \t "])
-            parts.append(line + nl)
-    text = "".join(parts)
-    if r.random() < 0.3:
-        text = text.rstrip("\r\n")
-    if r.random() < 0.1:
-        text += r.choice(["\n\n", "\n \n", " ", "\n\t"])
-    return text
-
-
 @pytest.mark.parametrize("seed", range(24))
 def test_fasta_decode_messy_text_equals_python_reader(dg, seed):
     """The GPU FASTA decode against `_read_multi_fasta` (reference deepgrp/__main__.py:20-43) on hostile text:
@@ -533,7 +502,7 @@ def test_fasta_decode_messy_text_equals_python_reader(dg, seed):
     records written canonically -- identical decoded bytes give bit-identical rows."""
     from deepgrp_b200.__main__ import _read_multi_fasta
     w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
-    text = _messy_fasta(seed)
+    text = messy_fasta(seed)
     try:
         exp = list(_read_multi_fasta(io.StringIO(text, newline=None)))
     except IndexError:

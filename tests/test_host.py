@@ -248,3 +248,83 @@ def test_cli_fasta_reader_matches_oracle(oracle):
     assert list(_read_multi_fasta(io.StringIO(text))) == list(oracle.read_multi_fasta(io.StringIO(text)))
     with pytest.raises(IndexError):
         list(_read_multi_fasta(io.StringIO(">a\nAC\n\nGT\n")))
+
+
+# ---- GPU FASTA decode logic on the host ---------------------------------------------------------------
+@pytest.fixture(scope="module")
+def host_fasta():
+    so = os.path.join(HERE, "host", "libfasta_host.so")
+    src = os.path.join(HERE, "host", "fasta_host.cpp")
+    core = os.path.join(ROOT, "deepgrp_b200", "csrc", "fasta_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    lib = ctypes.CDLL(so)
+    lib.fasta_host_decode.restype = ctypes.c_int
+
+    def decode(raw: bytes):
+        """-> list of (header, sequence) as api.cu assembles them from the decode's tables, or IndexError."""
+        n = len(raw)
+        buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        seq = np.zeros(max(n, 1), np.uint8)
+        hpos, hseq = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.int64)
+        n_seq, n_hdr = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = lib.fasta_host_decode(ctypes.c_void_p(buf.ctypes.data), ctypes.c_int64(n), ctypes.c_void_p(seq.ctypes.data),
+                                   ctypes.byref(n_seq), ctypes.c_void_p(hpos.ctypes.data),
+                                   ctypes.c_void_p(hseq.ctypes.data), ctypes.byref(n_hdr))
+        if rc:
+            raise IndexError("string index out of range")
+        bounds = hseq[:n_hdr.value].tolist() + [n_seq.value]
+        records = []
+        for k in range(n_hdr.value):
+            e = b = int(hpos[k]) + 1                        # header = rest of the line, right-stripped (api.cu)
+            while e < n and raw[e] != 10 and not (raw[e] == 13 and not (e + 1 < n and raw[e + 1] == 10)):
+                e += 1
+            header = raw[b:e].decode("latin-1").rstrip("\t\n\x0b\x0c\r\x1c\x1d\x1e\x1f ")
+            if header:
+                records.append((header, seq[bounds[k]:bounds[k + 1]].tobytes().decode("latin-1").upper()))
+        return records
+
+    decode.lib = lib
+    return decode
+
+
+def _python_reader(text):
+    import io
+    from deepgrp_b200.__main__ import _read_multi_fasta
+    return list(_read_multi_fasta(io.StringIO(text, newline=None)))
+
+
+def test_fasta_push_byte_equals_table_form(host_fasta):
+    assert host_fasta.lib.fasta_host_push_byte_mismatches() == 0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fasta_kernel_logic_on_hostile_text(host_fasta, seed):
+    """The kernel logic of csrc/fasta.cu (compiled for the host) against `_read_multi_fasta` (reference
+    deepgrp/__main__.py:20-43): mixed line ends, whitespace around and inside lines, ragged widths, dropped
+    records, blank lines."""
+    from conftest import messy_fasta
+    text = messy_fasta(seed)
+    try:
+        exp = _python_reader(text)
+    except IndexError:
+        with pytest.raises(IndexError):
+            host_fasta(text.encode("latin-1"))
+        return
+    assert host_fasta(text.encode("latin-1")) == exp
+
+
+@pytest.mark.parametrize("text", [
+    "", ">a\nACGT\n", ">a\nACGT", ">a\r\nAC\r\nGT\r\n", ">a\rAC\rGT\r", "ACGT\n>a\nAC\n", ">\nACGT\n>b\nGG\n",
+    ">a\n\nAC\n", ">a\nAC\n\n", ">a\nAC\n \n", ">a\nAC\n ", ">a\n A C \n", " \t>a b \t\nAC\n", ">a\nAC\r", "\n", " ",
+    ">a\n" + "ACGT" * 5000 + "\n>b\n" + "N" * 4095 + "\n" + "T" * 4097 + "\n",     # lines across tile borders
+    ">a\n" + ("ACGTACGTACGTACG\r\n" * 600),                                          # CR LF split between threads
+])
+def test_fasta_kernel_logic_edge_cases(host_fasta, text):
+    try:
+        exp = _python_reader(text)
+    except IndexError:
+        with pytest.raises(IndexError):
+            host_fasta(text.encode("latin-1"))
+        return
+    assert host_fasta(text.encode("latin-1")) == exp
