@@ -440,32 +440,117 @@ class H5Builder:
 # =================================================================================================
 # Keras model files
 # =================================================================================================
+def _node(*inbound):
+    """One Keras ``inbound_nodes`` entry: [[layer, node_index, tensor_index, {}], ...]."""
+    return [[name, node, tensor, {}] for name, node, tensor in inbound]
+
+
 def keras_model_config(vecsize: int, units: int, attention: bool, n_classes: int, rnn: str = "GRU") -> dict:
-    """A ``model.get_config()``-shaped description of ``create_model`` (reference ``deepgrp/model.py:293-336``;
-    field names as in the reference's ``tests/test_model.json``)."""
+    """The ``model.get_config()`` of ``create_model`` (reference ``deepgrp/model.py:293-336``): the layer graph
+    the reference's ``tests/test_model.json`` pins (class names, layer names, inbound nodes, the fields that
+    decide the arithmetic), for the GRU with attention, the GRU without and the LSTM."""
+    rname = "BGRU" if rnn == "GRU" else "BLSTM"
+    rcfg = {"name": rname, "trainable": True, "dtype": "float32", "return_sequences": True,
+            "return_state": bool(attention), "go_backwards": False, "stateful": False, "unroll": False,
+            "time_major": False, "units": units, "activation": "tanh", "recurrent_activation": "sigmoid",
+            "use_bias": True, "dropout": 0.25, "recurrent_dropout": 0.0, "implementation": 2}
+    if rnn == "GRU":
+        rcfg["reset_after"] = True
+    else:
+        rcfg["unit_forget_bias"] = True
+
+    def layer(cls, name, inbound, **cfg):
+        return {"class_name": cls, "name": name, "inbound_nodes": inbound,
+                "config": dict({"name": name, "trainable": True, "dtype": "float32"}, **cfg)}
     layers = [
-        {"class_name": "InputLayer", "name": "input_1",
-         "config": {"batch_input_shape": [None, vecsize, 5], "dtype": "float32", "name": "input_1"}},
-        {"class_name": "ReverseComplement", "name": "reverse_complement",
-         "config": {"name": "reverse_complement", "complement_indices": [3, 2, 1, 0, 4]}},
-        {"class_name": rnn, "name": "BGRU" if rnn == "GRU" else "BLSTM",
-         "config": {"name": "BGRU" if rnn == "GRU" else "BLSTM", "units": units, "return_sequences": True,
-                    "return_state": bool(attention), "activation": "tanh",
-                    "recurrent_activation": "sigmoid", "use_bias": True, "reset_after": True,
-                    "implementation": 2}},
-        {"class_name": "Average", "name": "average_1", "config": {"name": "average_1"}},
+        {"class_name": "InputLayer", "name": "input_1", "inbound_nodes": [],
+         "config": {"batch_input_shape": [None, vecsize, 5], "dtype": "float32", "sparse": False,
+                    "ragged": False, "name": "input_1"}},
+        layer("Custom>ReverseComplement", "reverse_complement", [_node(("input_1", 0, 0))],
+              complements=[3, 2, 1, 0, 4]),
+        {"class_name": rnn, "name": rname, "config": rcfg,
+         "inbound_nodes": [_node(("input_1", 0, 0)), _node(("reverse_complement", 0, 0))]},
     ]
     if attention:
-        layers.append({"class_name": "AdditiveAttention", "name": "additive_attention",
-                       "config": {"name": "additive_attention", "use_scale": True, "causal": False}})
-    layers.append({"class_name": "Dense", "name": "FF",
-                   "config": {"name": "FF", "units": n_classes, "activation": "linear", "use_bias": True}})
-    layers.append({"class_name": "Softmax", "name": "softmax", "config": {"name": "softmax", "axis": 2}})
-    return {"class_name": "Functional", "config": {"name": "model", "layers": layers}}
+        layers += [
+            layer("Average", "average", [_node((rname, 0, 1), (rname, 1, 1))]),                 # the two last states
+            layer("Reshape", "reshape", [_node(("average", 0, 0))], batch_input_shape=[None, units],
+                  target_shape=[1, units]),
+            layer("Average", "average_1", [_node((rname, 0, 0), (rname, 1, 0))]),               # the two sequences
+            layer("AdditiveAttention", "additive_attention", [_node(("reshape", 0, 0), ("average_1", 0, 0))],
+                  causal=False, dropout=0.0, use_scale=True),
+            layer("Flatten", "flatten", [_node(("additive_attention", 0, 0))], data_format="channels_last"),
+            layer("RepeatVector", "repeat_vector", [_node(("flatten", 0, 0))], n=vecsize),
+            layer("Concatenate", "concatenate", [_node(("repeat_vector", 0, 0), ("average_1", 0, 0))], axis=-1),
+        ]
+        last = "concatenate"
+    else:
+        layers.append(layer("Average", "average", [_node((rname, 0, 0), (rname, 1, 0))]))
+        last = "average"
+    layers.append(layer("Dense", "FF", [_node((last, 0, 0))], units=n_classes, activation="linear", use_bias=True))
+    layers.append(layer("Softmax", "softmax", [_node(("FF", 0, 0))], axis=2))
+    return {"class_name": "Functional",
+            "config": {"name": "model", "layers": layers, "input_layers": [["input_1", 0, 0]],
+                       "output_layers": [["softmax", 0, 0]]}}
 
 
-def save_keras_model(path: str, weights) -> None:
-    """Write ``weights`` (a :class:`deepgrp_b200.model.ModelWeights`) as a Keras-layout HDF5 file."""
+def check_keras_topology(config: dict) -> Tuple[str, int, int, bool]:
+    """Refuse a ``model_config`` whose arithmetic the CUDA path does not implement, instead of computing
+    something else silently: -> (rnn, vecsize, units, attention) of a DeepGRP graph (reference
+    ``deepgrp/model.py:293-336`` / ``tests/test_model.json``), :class:`HDF5Error` otherwise."""
+    layers = config["config"]["layers"] if "config" in config and "layers" in config["config"] else config["layers"]
+    by_class: Dict[str, list] = {}
+    for entry in layers:
+        by_class.setdefault(entry["class_name"].split(">")[-1], []).append(entry)
+
+    def need(cond, what):
+        if not cond:
+            raise HDF5Error("unsupported model: " + what)
+    need("InputLayer" in by_class, "no InputLayer")
+    shape = by_class["InputLayer"][0]["config"]["batch_input_shape"]
+    need(len(shape) == 3 and shape[2] == 5, "input shape %s is not [None, vecsize, 5]" % (shape,))
+    rnns = [k for k in ("GRU", "LSTM") if k in by_class]
+    need(len(rnns) == 1 and len(by_class[rnns[0]]) == 1, "expected exactly one shared GRU or LSTM layer")
+    rnn = rnns[0]
+    entry = by_class[rnn][0]
+    cfg = entry["config"]
+    need(cfg.get("activation", "tanh") == "tanh" and cfg.get("recurrent_activation", "sigmoid") == "sigmoid",
+         "%s activations %r / %r (tanh / sigmoid are implemented)" % (rnn, cfg.get("activation"), cfg.get("recurrent_activation")))
+    need(cfg.get("use_bias", True) and cfg.get("return_sequences", True) and not cfg.get("go_backwards", False)
+         and not cfg.get("stateful", False) and not cfg.get("time_major", False),
+         "%s must use a bias, return sequences and run forward, stateless, batch-major" % rnn)
+    if rnn == "GRU":
+        need(cfg.get("reset_after", True), "GRU with reset_after=False (the reference builds reset_after=True)")
+    need(len(entry.get("inbound_nodes", [[], []])) == 2, "the %s layer must be applied twice (input and its reverse complement)" % rnn)
+    for rc in by_class.get("ReverseComplement", []):
+        comp = rc["config"].get("complements", [3, 2, 1, 0, 4])
+        need(list(comp) == [3, 2, 1, 0, 4], "ReverseComplement complements %s" % (comp,))
+    attention = "AdditiveAttention" in by_class
+    if attention:
+        acfg = by_class["AdditiveAttention"][0]["config"]
+        need(rnn == "GRU", "attention on an LSTM (the reference builds it for the GRU only)")
+        need(acfg.get("use_scale", True) and not acfg.get("causal", False),
+             "AdditiveAttention must have use_scale=True and causal=False")
+        need(cfg.get("return_state", True), "attention needs the GRU's last state (return_state=True)")
+        for cat in by_class.get("Concatenate", []):
+            names = [x[0] for x in cat["inbound_nodes"][0]] if cat.get("inbound_nodes") else []
+            need(len(names) != 2 or names[0].startswith("repeat_vector"),
+                 "Concatenate order %s (attention context first, then the averaged sequence)" % (names,))
+    need("Attention" not in by_class, "dot-product Attention layer")
+    need("Dense" in by_class and len(by_class["Dense"]) == 1, "expected one Dense layer")
+    dcfg = by_class["Dense"][0]["config"]
+    need(dcfg.get("activation", "linear") == "linear" and dcfg.get("use_bias", True), "Dense must be linear with a bias")
+    need("Softmax" in by_class and by_class["Softmax"][0]["config"].get("axis", -1) in (2, -1), "Softmax over the class axis")
+    for cls in by_class:
+        need(cls in ("InputLayer", "ReverseComplement", "GRU", "LSTM", "Average", "Reshape", "AdditiveAttention", "Flatten",
+                     "RepeatVector", "Concatenate", "Dense", "Softmax", "Dropout"), "layer class %s" % cls)
+    return rnn, int(shape[1]), int(cfg["units"]), attention
+
+
+def save_keras_model(path: str, weights, config: Optional[dict] = None) -> None:
+    """Write ``weights`` (a :class:`deepgrp_b200.model.ModelWeights`) as a Keras-layout HDF5 file; ``config``
+    replaces the ``model_config`` (a ``get_config()`` dict or a Functional wrapper of one) and its layer names
+    name the weight groups."""
     b = H5Builder()
     rnn_name = "BGRU" if weights.rnn == "GRU" else "BLSTM"
     cell = "gru_cell" if weights.rnn == "GRU" else "lstm_cell"
@@ -475,11 +560,18 @@ def save_keras_model(path: str, weights) -> None:
                    ("%s/%s/bias:0" % (rnn_name, cell), weights.bias)],
         "FF": [("FF/kernel:0", weights.ff_kernel), ("FF/bias:0", weights.ff_bias)],
     }
-    order = ["input_1", "reverse_complement", rnn_name, "average_1"]
+    if config is None:
+        config = keras_model_config(weights.vecsize, weights.units, weights.attention, weights.n_classes,
+                                    weights.rnn)
     if weights.attention:
         layer_weights["additive_attention"] = [("additive_attention/scale:0", weights.att_scale)]
-        order.append("additive_attention")
-    order += ["FF", "softmax"]
+    graph = config["config"] if "config" in config else config
+    order = [entry["name"] for entry in graph["layers"]]           # every layer gets a group, as Keras writes them
+    for entry in graph["layers"]:                                     # weights follow the config's layer names
+        cls = entry["class_name"].split(">")[-1]
+        canon = {"GRU": rnn_name, "LSTM": rnn_name, "AdditiveAttention": "additive_attention", "Dense": "FF"}.get(cls)
+        if canon and canon in layer_weights and entry["name"] != canon:
+            layer_weights[entry["name"]] = [(entry["name"] + w[len(canon):], a) for w, a in layer_weights.pop(canon)]
 
     def build(tree: dict, attrs=None):
         children = {}
@@ -501,8 +593,8 @@ def save_keras_model(path: str, weights) -> None:
         layer_groups[lname] = build(tree, {"weight_names": [n.encode() for n in names]})[0]
     mw = b.group(layer_groups, {"layer_names": [n.encode() for n in order], "backend": "tensorflow",
                                 "keras_version": "2.5.0"})
-    config = keras_model_config(weights.vecsize, weights.units, weights.attention, weights.n_classes,
-                                weights.rnn)
+    if "class_name" not in config:
+        config = {"class_name": "Functional", "config": config}
     root = b.group({"model_weights": mw[0]}, {"model_config": json.dumps(config), "backend": "tensorflow",
                                               "keras_version": "2.5.0"})
     with open(path, "wb") as fh:
@@ -526,15 +618,11 @@ def load_keras_model(path: str):
     if "model_config" not in f.attrs:
         raise HDF5Error("%s has no model_config attribute (not a Keras model file)" % path)
     config = json.loads(_as_str(f.attrs["model_config"]))
+    rnn, vecsize, units, _ = check_keras_topology(config)
     layers = config["config"]["layers"]
     by_class: Dict[str, dict] = {}
     for layer in layers:
-        by_class.setdefault(layer["class_name"], layer)
-    vecsize = int(by_class["InputLayer"]["config"]["batch_input_shape"][1])
-    rnn = "GRU" if "GRU" in by_class else ("LSTM" if "LSTM" in by_class else None)
-    if rnn is None:
-        raise HDF5Error("model has neither a GRU nor an LSTM layer")
-    units = int(by_class[rnn]["config"]["units"])
+        by_class.setdefault(layer["class_name"].split(">")[-1], layer)
     mw = f["model_weights"]
     found: Dict[str, np.ndarray] = {}
     for lname in [_as_str(n) for n in np.atleast_1d(mw.attrs["layer_names"])]:
@@ -553,7 +641,7 @@ def load_keras_model(path: str):
     kernel = pick("/kernel:0", rnn_layer + "/")
     recurrent = pick("recurrent_kernel:0", rnn_layer + "/")
     bias = pick("bias:0", rnn_layer + "/")
-    scale = pick("scale:0", "attention") if "AdditiveAttention" in by_class and rnn == "GRU" else None
+    scale = pick("scale:0", by_class["AdditiveAttention"]["config"]["name"] + "/") if "AdditiveAttention" in by_class else None
     dense = by_class["Dense"]["config"]["name"]
     ffk, ffb = pick("kernel:0", dense + "/"), pick("bias:0", dense + "/")
     for name, v in (("kernel", kernel), ("recurrent_kernel", recurrent), ("bias", bias),
