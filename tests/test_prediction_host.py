@@ -1,0 +1,76 @@
+"""deepgrp_b200.prediction, the parts that need no GPU: the wiring of predict_complete (the reference tests it by
+substituting every collaborator, tests/test_prediction.py:95-152) and the metrics arithmetic
+(tests/test_prediction.py:155-172 checks it against pycm; scikit-learn is what this image has)."""
+import numpy as np
+import pytest
+
+from deepgrp_b200 import model, prediction, preprocessing
+
+
+@pytest.mark.parametrize("step_size", (10, 20))
+@pytest.mark.parametrize("use_mss", (True, False))
+def test_predict_complete_wiring(monkeypatch, tmp_path, step_size, use_mss):
+    opt = model.Options()
+    fwd = np.zeros((100, 10))
+    data = preprocessing.Data(fwd, np.random.rand(100, 4))
+    calls = []
+
+    def fake_setup(options, logdir):
+        assert options is opt and logdir == tmp_path
+        calls.append("setup")
+        return "MODEL"
+
+    def fake_fetch(array, steps, batch_size, vecsize):
+        assert array is fwd and steps == step_size
+        assert (batch_size, vecsize) == (opt.batch_size, opt.vecsize)
+        calls.append("fetch")
+        return "DATA"
+
+    def fake_predict(mdl, iterator, output_shape, steps):
+        assert (mdl, iterator, output_shape, steps) == ("MODEL", "DATA", (4, 100), step_size)   # truelbl.shape[::-1]
+        calls.append("predict")
+        return "PREDICTIONS"
+
+    def fake_mss(pred, options):
+        assert pred == "PREDICTIONS" and options is opt
+        return "MSS"
+
+    def fake_softmax(pred):
+        assert pred == "PREDICTIONS"
+        return "SOFTMAX"
+
+    monkeypatch.setattr(prediction, "setup_prediction_from_options_checkpoint", fake_setup)
+    monkeypatch.setattr(prediction, "fetch_validation_batch", fake_fetch)
+    monkeypatch.setattr(prediction, "predict", fake_predict)
+    monkeypatch.setattr(prediction, "apply_mss", fake_mss)
+    monkeypatch.setattr(prediction, "softmax", fake_softmax)
+    got = prediction.predict_complete(step_size=step_size, options=opt, logdir=tmp_path, data=data, use_mss=use_mss)
+    assert got == ("MSS" if use_mss else "SOFTMAX")
+    assert calls == ["setup", "fetch", "predict"]
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_metrics_against_scikit_learn(oracle, seed):
+    from sklearn import metrics as skm
+    rng = np.random.default_rng(seed)
+    truth = rng.choice([0, 1, 2, 3], size=400, p=[0.55, 0.2, 0.15, 0.1])
+    pred = np.where(rng.random(400) < 0.7, truth, rng.choice([0, 1, 2, 3], size=400))
+    cnf = oracle.confusion_matrix(truth, pred)                   # rows = truth, columns = prediction
+    assert np.array_equal(cnf, skm.confusion_matrix(truth, pred, labels=[0, 1, 2, 3]))
+    m = prediction._calculate_metrics(cnf)
+    prec, rec, f1, _ = skm.precision_recall_fscore_support(truth, pred, labels=[0, 1, 2, 3], zero_division=0)
+    assert np.allclose(m["TPR"], rec) and np.allclose(m["PPV"], prec) and np.allclose(m["F1"], f1)
+    assert np.allclose(m["FNR"], 1 - rec) and np.allclose(m["FDR"], 1 - prec)
+    for k in range(4):                                           # one-vs-rest rates
+        t, p = truth == k, pred == k
+        tn, fp, fn, tp = skm.confusion_matrix(t, p, labels=[False, True]).ravel()
+        assert np.isclose(m["TNR"][k], tn / (tn + fp)) and np.isclose(m["FPR"][k], fp / (fp + tn))
+        assert np.isclose(m["NPV"][k], tn / (tn + fn)) and np.isclose(m["ACC"][k], (tp + tn) / 400)
+    assert np.isclose(m["MCC"], skm.matthews_corrcoef(truth, pred))
+    assert np.isclose(prediction.calculate_multiclass_matthews_cc(cnf), skm.matthews_corrcoef(truth, pred))
+
+
+def test_matthews_cc_limits():
+    assert np.isclose(prediction.calculate_multiclass_matthews_cc(np.diag([5, 7, 3])), 1.0)
+    assert np.isclose(prediction.calculate_multiclass_matthews_cc(np.array([[0, 5], [5, 0]])), -1.0)
+    assert abs(prediction.calculate_multiclass_matthews_cc(np.array([[25, 25], [25, 25]]))) < 1e-12
