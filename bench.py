@@ -192,10 +192,25 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(args):
+    """Which BASELINE.json configuration the arguments describe (the default run is configs[1])."""
+    shape = (args.vecsize, args.units)
+    if shape == (T_DEFAULT, U_DEFAULT):
+        arch = "defaults.toml architecture"
+        which = "configs[1]" if args.bases == CONFIG2_BASES else ("configs[2]" if args.bases == 248_000_000 else
+                                                                  "configs[1] at another record length")
+    elif shape == (150, 32):
+        arch, which = "tests/test_model.json architecture", "configs[0]"
+    elif shape in ((260, 50), (512, 128)):
+        arch = "hyperopt search-space point 5%s (SURVEY.md section 8d)" % ("a" if shape == (260, 50) else "b")
+        which = "configs[4]"
+    else:
+        return "custom workload, not a BASELINE.json configuration (vecsize %d, units %d, attention)" % shape
+    return "BASELINE.json %s: %s (vecsize %d, units %d, attention)" % (which, arch, args.vecsize, args.units)
+
+
 def workload_config(args, bases):
-    return {"workload": "BASELINE.json configs[1]: defaults.toml architecture (vecsize %d, units %d, "
-                        "attention), random-init weights seed 0, synthetic iid-ACGT single-record FASTA"
-                        % (args.vecsize, args.units),
+    return {"workload": workload_name(args) + ", random-init weights seed 0, synthetic iid-ACGT single-record FASTA",
             "bases_per_record": int(bases), "step_size": STEP, "batch_size": BATCH,
             "min_mss_len": MIN_MSS, "xdrop_len": XDROP, "compat": "reference",
             "l2": "flushed between steps (256 MiB memset); per-step working set (predictions + "
@@ -414,9 +429,8 @@ def run_chunk(args, rank, world, local_rank):
     elapsed_ms, range_ms = (float(x) for x in t.cpu())
     if rank == 0:
         cfg = workload_config(args, L)
-        cfg["workload"] = ("BASELINE.json configs[2]: defaults.toml architecture (vecsize %d, units %d, attention), "
-                           "random-init weights seed 0, ONE synthetic iid-ACGT record split by position ranges "
-                           "over the ranks" % (args.vecsize, args.units))
+        cfg["workload"] = (workload_name(args) + ", random-init weights seed 0, ONE synthetic iid-ACGT record split "
+                           "by position ranges over the ranks")
         cfg["sharding"] = ("position ranges with halo recompute; NCCL gather of label (u8) + score (f32) to rank 0, "
                            "which runs MSS + segments for the whole record")
         line = {
