@@ -87,35 +87,36 @@ class CommandLineParser:
         self.threads = 1
         self.xla = False
         self.verbose = 0
-        subparsers = self.parser.add_subparsers(help="sub-command help", dest="command")
-        self.parser.add_argument("--batch_size", "-b", type=int, default=256,
-                                 help="Batch size (only decides where the reference places the "
-                                      "final short batch)")
-        self.parser.add_argument("--step_size", "-s", type=int, default=50, help="Window step size")
-        self.parser.add_argument("--xdrop_length", "-x", type=int, default=50,
-                                 help="XDrop parameter for MSS algorithm, ignored if "
-                                      "--no_use_mss, disabled with values<0")
-        self.parser.add_argument("--min_mss_length", "-l", type=int, default=50,
-                                 help="Minimal length of maximum scoring segments, ignored if "
-                                      "--no_use_mss")
-        self.parser.add_argument("--threads", "-t", type=int, default=1,
-                                 help="Accepted for compatibility; ignored (GPU path)")
-        self.parser.add_argument("--xla", action="store_true",
-                                 help="Accepted for compatibility; ignored")
-        self.parser.add_argument("-v", "--verbose", action="count", default=0,
-                                 help="Increase verbosity")
-        predict_subparser = subparsers.add_parser(
-            name="predict", formatter_class=argparse.ArgumentDefaultsHelpFormatter,
-            description="predict using a deepgrp model")
-        predict_subparser.add_argument("model", type=str,
-                                       help="Keras model in HDF5 format (or .npz weights)")
-        predict_subparser.add_argument("FASTA", nargs="+", type=str, help="Fasta input files")
-        predict_subparser.add_argument("--output", type=str, default="-", help="Output filename")
-        predict_subparser.add_argument("--no_use_mss", "-m", action="store_true",
-                                       help="Disable maximum scoring segment algorithm")
-        predict_subparser.add_argument("--stepwise", action="store_true",
-                                       help="Run the reference's five Python-level calls per record "
-                                            "instead of the fused whole-record GPU call")
+        # the reference's options (deepgrp/__main__.py:101-207), same flags, defaults and destinations
+        integer_options = [
+            ("--batch_size", "-b", 256, "Batch size (only decides where the reference places the final short batch)"),
+            ("--step_size", "-s", 50, "Window step size"),
+            ("--xdrop_length", "-x", 50, "XDrop parameter for MSS algorithm, ignored if --no_use_mss, "
+                                         "disabled with values<0"),
+            ("--min_mss_length", "-l", 50, "Minimal length of maximum scoring segments, ignored if --no_use_mss"),
+            ("--threads", "-t", 1, "Accepted for compatibility; ignored (GPU path)"),
+        ]
+        for long_flag, short_flag, default, text in integer_options:
+            self.parser.add_argument(long_flag, short_flag, type=int, default=default, help=text)
+        self.parser.add_argument("--xla", action="store_true", help="Accepted for compatibility; ignored")
+        self.parser.add_argument("-v", "--verbose", action="count", default=0, help="Increase verbosity")
+        commands = self.parser.add_subparsers(help="sub-command help", dest="command")
+        sub = {name: commands.add_parser(name=name, description=text,
+                                         formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+               for name, text in (("predict", "predict using a deepgrp model"),
+                                  ("train", "Train a deepgrp model (not part of deepgrp_b200: parsed, then refused)"))}
+        sub["predict"].add_argument("model", type=str, help="Keras model in HDF5 format (or .npz weights)")
+        sub["predict"].add_argument("FASTA", nargs="+", type=str, help="Fasta input files")
+        sub["predict"].add_argument("--output", type=str, default="-", help="Output filename")
+        sub["predict"].add_argument("--no_use_mss", "-m", action="store_true",
+                                    help="Disable maximum scoring segment algorithm")
+        sub["predict"].add_argument("--stepwise", action="store_true",
+                                    help="Run the reference's five Python-level calls per record instead of the "
+                                         "fused whole-record GPU call")
+        for name in ("parameter", "trainfile", "validfile", "bedfile"):
+            sub["train"].add_argument(name, type=str)
+        sub["train"].add_argument("--logdir", type=str, default=".")
+        sub["train"].add_argument("--modelfile", type=str, default="model.hdf5")
 
     def parse_args(self, argv=None) -> "CommandLineParser":
         """Parse command line arguments."""
