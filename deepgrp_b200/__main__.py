@@ -23,23 +23,25 @@ _LOG = logging.getLogger(__name__)
 
 
 def _read_multi_fasta(filestream: TextIO) -> Iterator[Tuple[str, str]]:
-    """Reads a multi FASTA file (reference ``deepgrp/__main__.py:20-43``): every line is stripped,
-    ``>`` starts a record (header = rest of the line), other lines are upper-cased and joined;
-    records with an empty header are dropped; a blank line raises ``IndexError``."""
+    """(header, sequence) of every record of a multi-FASTA stream, as the reference reads it
+    (``deepgrp/__main__.py:20-43``): lines are stripped, ``>`` opens a record whose header is the rest of that
+    line, other lines are upper-cased and concatenated.  Its corner cases are kept: a line that is empty after
+    stripping raises ``IndexError`` (the reference indexes its first character), text in front of the first
+    ``>`` and records whose header is empty are dropped."""
     _LOG.debug("Reading FASTA file.")
-    header = ""
-    sequence: List[str] = []
-    for line in filestream:
-        line = line.strip()
-        if line[0] == ">":
-            if header:
-                yield header, "".join(sequence)
-            header = line[1:]
-            sequence = []
+    name, pieces = "", []                     # name == "": nothing to emit for what is being collected
+    for raw_line in filestream:
+        text = raw_line.strip()
+        if not text:
+            raise IndexError("string index out of range")
+        if text.startswith(">"):
+            if name:
+                yield name, "".join(pieces)
+            name, pieces = text[1:], []
         else:
-            sequence.append(line.upper())
-    if header:
-        yield header, "".join(sequence)
+            pieces.append(text.upper())
+    if name:
+        yield name, "".join(pieces)
 
 
 def _read_raw(filename: str) -> bytes:
@@ -57,22 +59,17 @@ def _read_raw(filename: str) -> bytes:
 
 def _predict(dnasequence: str, model: dgmodel.ModelWeights, options: dgmodel.Options,
              step_size: int, use_mss: bool) -> Tuple[np.ndarray, int]:
-    """Runs a prediction for one sequence (reference ``deepgrp/__main__.py:46-83``): the same five
-    calls in the same order, each through the CUDA path."""
-    _LOG.debug("One hot encoding sequence.")
-    start_pos, inputs = dgsequence.one_hot_encode_dna_sequence(dnasequence)
-    _LOG.debug("Start prediction.")
-    data_iterator = dgpred.fetch_validation_batch(inputs, step_size, options.batch_size,
-                                                  options.vecsize)
-    output_shape = (inputs.shape[1], model.output_shape[2])
-    prediction = dgpred.predict(model, data_iterator, output_shape, step_size)
-    _LOG.debug("Finish prediction.")
-    if use_mss:
-        _LOG.debug("Applying MSS.")
-        prediction = dgpred.apply_mss(prediction, options)
-    else:
-        prediction = dgpred.softmax(prediction)
-    return np.asanyarray(prediction.argmax(axis=1)), start_pos
+    """Labels of one sequence and the position of its first non-N base (reference ``deepgrp/__main__.py:46-83``):
+    encode, enumerate windows, predict with the max-vote, then MSS or softmax, argmax -- the reference's five
+    calls in its order, each through the CUDA path."""
+    start_pos, one_hot = dgsequence.one_hot_encode_dna_sequence(dnasequence)
+    n_bases = one_hot.shape[1]
+    _LOG.debug("Encoded %d bases, first base at %d.", n_bases, start_pos)
+    windows = dgpred.fetch_validation_batch(one_hot, step_size, options.batch_size, options.vecsize)
+    votes = dgpred.predict(model, windows, (n_bases, model.output_shape[2]), step_size)
+    _LOG.debug("Prediction finished, %s.", "applying MSS" if use_mss else "softmax")
+    decided = dgpred.apply_mss(votes, options) if use_mss else dgpred.softmax(votes)
+    return np.asanyarray(decided.argmax(axis=1)), start_pos
 
 
 class CommandLineParser:
