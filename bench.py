@@ -118,6 +118,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Host cores this process may run on (affinity-aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -170,7 +178,7 @@ def run_reference(args, rank, world):
         return
     from deepgrp_b200 import model
     weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sample = args.ref_bases
     codes = synth_codes(sample, [1, 0])
     for _ in range(args.warmup):
@@ -334,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
         "mss_rounds": ctx.get_int("mss_rounds"),
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         sample = min(args.ref_bases, L)
         dt, _ = cpu_reference_step(codes[:sample], weights, args.vecsize, threads)
         line["cpu_baseline"] = {
