@@ -115,3 +115,32 @@ def test_stepwise_predict_writes_the_reference_rows(monkeypatch, oracle, tmp_pat
 def test_train_is_refused():
     with pytest.raises(SystemExit):
         cli.CommandLineParser.train(argparse.Namespace(), dgmodel.Options())
+
+
+def test_stepwise_route_with_the_oracle_in_place_of_the_kernels(monkeypatch, oracle, tmp_path):
+    """The whole stepwise command line on the CPU: real files, real Options / window descriptor / row writer, and
+    the oracle standing in for the five GPU calls.  The text must equal the oracle's own end-to-end restatement
+    of the reference (deepgrp/__main__.py:46-83, 275-292), i.e. the host code between the calls adds nothing."""
+    from conftest import random_dna, write_fasta
+    T, U = 150, 32
+    weights = dgmodel.random_weights(T, U, attention=True, seed=0).scaled(4.0)
+    wd = weights.as_dict()
+    fasta = tmp_path / "in.fa"
+    write_fasta(str(fasta), [("r1 x", "NN" + random_dna(2500, 1, "ACGTacgtN") + "N"), ("r2", random_dna(120, 2)),
+                             ("r3", random_dna(1800, 3))])
+    monkeypatch.setattr(cli.dgmodel, "load_model", lambda path: weights)
+    monkeypatch.setattr(cli.dgsequence, "one_hot_encode_dna_sequence", oracle.one_hot_encode_dna_sequence)
+    monkeypatch.setattr(cli.dgsequence, "yield_segments", oracle.yield_segments)
+
+    def predict(model, data, results_shape, step_size):
+        assert model is weights
+        return oracle.predict(lambda b: oracle.model_forward(b, wd), iter(data), results_shape, step_size)
+    monkeypatch.setattr(cli.dgpred, "predict", predict)
+    monkeypatch.setattr(cli.dgpred, "apply_mss", lambda p, o: oracle.apply_mss(p, o.min_mss_len, o.xdrop_len))
+    monkeypatch.setattr(cli.dgpred, "softmax", oracle.softmax)
+    for extra, use_mss in ((["--stepwise"], True), (["--stepwise", "--no_use_mss"], False)):
+        out = tmp_path / ("out%d.tsv" % use_mss)
+        cli.CommandLineParser().parse_args(["-b", "16", "-s", "50", "predict", "m.hdf5", str(fasta), "--output",
+                                            str(out)] + extra).run()
+        expected = oracle.predict_fasta_tsv(str(fasta), wd, T, 16, 50, use_mss, 50, 50)
+        assert out.read_text() == expected and expected.count("\n") > 3
