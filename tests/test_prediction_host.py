@@ -74,3 +74,24 @@ def test_matthews_cc_limits():
     assert np.isclose(prediction.calculate_multiclass_matthews_cc(np.diag([5, 7, 3])), 1.0)
     assert np.isclose(prediction.calculate_multiclass_matthews_cc(np.array([[0, 5], [5, 0]])), -1.0)
     assert abs(prediction.calculate_multiclass_matthews_cc(np.array([[25, 25], [25, 25]]))) < 1e-12
+
+
+@pytest.mark.parametrize("step_size", (1, 2))
+def test_predict_generic_route_known_answer(monkeypatch, oracle, step_size):
+    """The vector of the reference's test_predict (tests/test_prediction.py:74-93): a model that always answers
+    class 1 at the first position of each of its 4 windows, three equal batches -> twelve rows [0, 1, 0] at
+    multiples of the step.  The generic route of predict (any object with predict_on_batch, any iterable of
+    batches) is the reference's loop; the max-merge it calls is the oracle's here, the kernel's on a GPU box."""
+    answer = np.zeros((4, 10, 3), dtype=np.float32)
+    answer[:, 0, 1] = 1
+
+    class ConstantModel:
+        def predict_on_batch(self, batch):
+            assert batch.shape == (4, 10, 5)
+            return answer
+    monkeypatch.setattr(prediction.dgsequence, "get_max", oracle.get_max)
+    batches = (np.random.rand(4, 10, 5) for _ in range(3))
+    got = prediction.predict(model=ConstantModel(), data=batches, results_shape=(50, 3), step_size=step_size)
+    assert got.dtype == np.float32 and got.shape == (50, 3)
+    assert got.sum(axis=0).tolist() == [0, 12, 0]
+    assert all(got[i * step_size].tolist() == [0, 1, 0] for i in range(12))
