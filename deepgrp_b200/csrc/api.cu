@@ -249,6 +249,8 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
   else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
+  else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
+  else if (!strcmp(key, "forward_slab_mb")) c->forward_slab_bytes = (int64_t)value << 20;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -262,6 +264,8 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
   else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
+  else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
+  else if (!strcmp(key, "forward_slab_mb")) *value = c->forward_slab_bytes >> 20;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
   else { set_error("unknown option %s", key); return DGRP_E_ARG; }
@@ -575,10 +579,15 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
         memcpy(&Bh[(size_t)N * KP + off], &lo, 2);
       }
   }
+  std::vector<uint16_t> Bw_single, Bw_pair;
+  int bw_shift = 0;
+  build_tcw_operands(rnn, U, UP, n_classes, att_scale != nullptr, Rp.data(), P.data(), b1.data(), ff_kernel,
+                     Bw_single, Bw_pair, &bw_shift);
   dgrp_model *m = new dgrp_model();
   m->device = c->device; m->rnn = rnn; m->T = vecsize; m->U = U; m->C = n_classes; m->UP = UP;
   m->attention = att_scale != nullptr;
   m->b16_shift = b16_shift;
+  m->bw_shift = bw_shift;
   const int F = m->attention ? 2 * U : U;
   auto up = [&](float **dst, const float *src, size_t count) -> int {
     DGRP_CUDA(cudaMalloc((void **)dst, count * sizeof(float)));
@@ -595,7 +604,11 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
       (!Bs.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit),
                                reinterpret_cast<const float *>(Bs.data()), Bs.size() / 2))) ||
       (!Bh.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit16),
-                               reinterpret_cast<const float *>(Bh.data()), Bh.size() / 2)))) {
+                               reinterpret_cast<const float *>(Bh.data()), Bh.size() / 2))) ||
+      (!Bw_single.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bw_single),
+                                      reinterpret_cast<const float *>(Bw_single.data()), Bw_single.size() / 2))) ||
+      (!Bw_pair.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bw_pair),
+                                    reinterpret_cast<const float *>(Bw_pair.data()), Bw_pair.size() / 2)))) {
     cudaStreamSynchronize(c->stream);
     dgrp_model_destroy(m);
     return rc;
@@ -614,6 +627,8 @@ int dgrp_model_destroy(dgrp_model *m) {
     if (p) cudaFree(p);
   if (m->d_Bsplit) cudaFree(m->d_Bsplit);
   if (m->d_Bsplit16) cudaFree(m->d_Bsplit16);
+  if (m->d_Bw_single) cudaFree(m->d_Bw_single);
+  if (m->d_Bw_pair) cudaFree(m->d_Bw_pair);
   delete m;
   return DGRP_OK;
 }

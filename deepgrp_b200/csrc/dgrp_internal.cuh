@@ -75,6 +75,10 @@ struct dgrp_model {
   uint16_t *d_Bsplit = nullptr;  // [3][3UP x UP] bf16 hi|mid|lo of recurrent^T, UMMA K-major core matrices
   uint16_t *d_Bsplit16 = nullptr;  // [2][..] fp16 hi|lo of (recurrent^T * 2^b16_shift), same layout
   int b16_shift = 0;
+  // wide tcgen05 form (forward_tcw.cu): fp16 hi|lo pieces of the blocked [R | K/2]^T (+ 16 one-hot K rows), for one
+  // CTA per tile and for a CTA pair ([rank][piece][rows of the rank]); null where the shape has no such form
+  uint16_t *d_Bw_single = nullptr, *d_Bw_pair = nullptr;
+  int bw_shift = 0;
   float *d_scale = nullptr;      // [U] or null
   float *d_ffk = nullptr;        // [F, C]
   float *d_ffb = nullptr;        // [C]
@@ -100,7 +104,11 @@ struct dgrp_ctx {
   int forward_fp16x2 = 1;  // tcgen05 forward: operands as 2 fp16 pieces / 3 products instead of 3 bf16 pieces / 6 products
   int forward_gather = 1;  // tcgen05 forward: write window probabilities and max-merge them in a gather pass
                            // (1) instead of 5 atomicMax per window-step (0); falls back to 0 above 40 GB
-  int forward_used_tc = 0; // what the last forward launch used
+  int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
+                           // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
+  int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
+                           // record run in slabs of at most this many bytes of [windows][T][C] probabilities
+  int forward_used_tc = 0; // what the last forward launch used: 0 fp32 kernel, 1 two-tile tcgen05, 2 wide, 3 wide CTA pair
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
   std::vector<int64_t> fa_hdr_off, fa_hdr_len, fa_startpos, fa_length, fa_tsv_off, fa_tsv_len, fa_owner;
@@ -157,6 +165,9 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
 // dense float windows [B, T, 5] -> probs [B, T, C] (predict_on_batch semantics)
 int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t nbatch,
                       float *d_probs);
+// forward_tcw.cu: host-side packing of the wide tcgen05 kernel's weight operand (empty where the shape has no form)
+void build_tcw_operands(int rnn, int U, int UP, int C, bool att, const float *Rp, const float *P, const float *b1,
+                        const float *ffk, std::vector<uint16_t> &single, std::vector<uint16_t> &pair, int *shift);
 // mss.cu
 int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
                      double xdrop, dgrp_seg_t **d_segs_out, int *n_seg);

@@ -37,7 +37,8 @@ Placement make_placement(int64_t length, int T, int step, int batch_size, int co
 }
 
 
-int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p);   // forward_tc.cu
+int launch_forward_tc(dgrp_ctx *c, dgrp_model *m, FwdParams &p);              // forward_tc.cu
+int launch_forward_tcw(dgrp_ctx *c, dgrp_model *m, FwdParams &p, int which);  // forward_tcw.cu
 
 // RNN: 0 = GRU (reset_after, gates z, r, h), 1 = LSTM (gates i, f, c, o; one bias)
 template <int UP, int RNN = 0>
@@ -312,11 +313,52 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
   p.pred = d_pred; p.pred_row0 = pred_row0; p.pred_rows = pred_rows;
   c->forward_used_tc = 0;
   if (c->forward_tc) {
-    const int rc = launch_forward_tc(c, m, p);
-    if (rc != DGRP_E_UNSUPPORTED) {
-      c->forward_used_tc = 1;
-      return rc;
+    // The tcgen05 kernels leave the window probabilities in a [windows][T][C] buffer that a gather pass
+    // max-merges into pred; the windows run in slabs so that the buffer stays below forward_slab_bytes
+    // (33.9 GB for a chr1-sized record otherwise).  The gather folds pred's current value, so slabs compose.
+    const int64_t per_win = (int64_t)m->T * m->C * (int64_t)sizeof(float);
+    int64_t slab = c->forward_slab_bytes / per_win;
+    slab = slab < 4096 ? 4096 : slab & ~(int64_t)4095;   // whole tiles of 64 windows, pairs of them per SM
+    p.win_probs = nullptr;
+    if (c->forward_gather) {
+      const int64_t nw = w_end - w_begin < slab ? w_end - w_begin : slab;
+      if (nw > 0 && c->winprobs.reserve((size_t)(nw * per_win)) == DGRP_OK) p.win_probs = c->winprobs.as<float>();
+      else cudaGetLastError();   // out of memory: the kernels vote with atomicMax instead
     }
+    if (!p.win_probs) slab = w_end - w_begin;
+    for (int64_t w0 = w_begin; w0 < w_end; w0 += slab) {
+      const int64_t w1 = w0 + slab < w_end ? w0 + slab : w_end;
+      p.w_begin = w0; p.w_end = w1;
+      int rc = DGRP_E_UNSUPPORTED, used = 0;
+      if (c->forward_wide == 0) { rc = launch_forward_tc(c, m, p); used = 1; }
+      if (rc == DGRP_E_UNSUPPORTED && c->forward_wide != 2) { rc = launch_forward_tcw(c, m, p, 1); used = 2; }
+      if (rc == DGRP_E_UNSUPPORTED) { rc = launch_forward_tcw(c, m, p, 2); used = 3; }
+      if (rc == DGRP_E_UNSUPPORTED) {
+        if (w0 != w_begin) { set_error("forward: tcgen05 form lost between slabs"); return DGRP_E_CUDA; }
+        p.w_begin = w_begin; p.w_end = w_end; p.win_probs = nullptr;
+        return launch_fwd<false>(c, m, p);
+      }
+      if (rc != DGRP_OK) return rc;
+      c->forward_used_tc = used;
+      if (p.win_probs) {
+        // rows the slab's placed windows cover (both placement families, prediction.py:105)
+        int64_t lo = INT64_MAX, hi = INT64_MIN;
+        const int64_t f0 = w0, f1 = w1 < pl.full_windows ? w1 : pl.full_windows;
+        if (f0 < f1) { lo = f0 * pl.step; hi = (f1 - 1) * pl.step + m->T; }
+        const int64_t t0 = w0 > pl.full_windows ? w0 : pl.full_windows;
+        if (t0 < w1) {
+          const int64_t a = pl.tail_base + (t0 - pl.full_windows) * pl.step;
+          const int64_t b = pl.tail_base + (w1 - 1 - pl.full_windows) * pl.step + m->T;
+          lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+        }
+        lo = lo > pred_row0 ? lo : pred_row0;
+        hi = hi < pred_row0 + pred_rows ? hi : pred_row0 + pred_rows;
+        if (lo < hi)
+          DGRP_CHECK(launch_vote_gather(c, p.win_probs, w0, w1, m->T, m->C, pl.full_windows, pl.tail_base, pl.step,
+                                        d_pred + (size_t)(lo - pred_row0) * m->C, lo, hi - lo));
+      }
+    }
+    return DGRP_OK;
   }
   return launch_fwd<false>(c, m, p);
 }

@@ -151,9 +151,9 @@ def test_config4_shape_multirecord_softmask_and_n_runs(dg, tmp_path):
 
 
 def test_config5_search_space_points(dg, oracle):
-    """5a (T=260, U=50: tcgen05 path) and 5b (T=512, U=128: fp32 kernel, recurrent weights streamed
-    from L2) against the oracle on a short record."""
-    for (T, U, used_tc) in ((260, 50, 1), (512, 128, 0)):
+    """5a (T=260, U=50: the two-tile tcgen05 kernel) and 5b (T=512, U=128: the CTA-pair tcgen05 kernel,
+    forward_tcw.cu), plus a width in between (U=90 pads to 128), against the oracle on a short record."""
+    for (T, U, used_tc) in ((260, 50, 1), (512, 128, 3), (200, 90, 3)):
         w = dg.model.random_weights(T, U, attention=True, seed=5).scaled(3.0)
         text = random_dna(6000, T + U)
         st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
@@ -165,6 +165,50 @@ def test_config5_search_space_points(dg, oracle):
                              oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
         assert np.abs(got - exp).max() < 2e-5
         assert (got.argmax(axis=1) == exp.argmax(axis=1)).mean() >= 0.9999
+
+
+@pytest.mark.parametrize("wide,T,U,att", [(1, 150, 32, True), (1, 342, 60, True), (2, 342, 60, True),
+                                           (2, 150, 40, False), (1, 100, 60, False)])
+def test_wide_kernel_variants_match_the_two_tile_kernel(dg, oracle, wide, T, U, att):
+    """forward_tcw.cu forced (forward_wide = 1: one CTA per tile, 2: CTA pair with tcgen05.mma.cta_group::2) on
+    shapes the two-tile kernel also serves: both against the oracle and against each other."""
+    w = dg.model.random_weights(T, U, attention=att, seed=21).scaled(3.0)
+    text = random_dna(9_000 + 13 * T, T + U + wide)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    ref = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    assert dg.ctx.get_int("forward_used_tc") == 1
+    dg.ctx.set_int("forward_wide", wide)
+    try:
+        got = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+        used = dg.ctx.get_int("forward_used_tc")
+    finally:
+        dg.ctx.set_int("forward_wide", 0)
+    assert used == 1 + wide
+    assert np.abs(got - ref).max() < 2e-6
+    wd = w.as_dict()
+    exp = oracle.predict(lambda b: oracle.model_forward(b, wd, engine="torch"),
+                         oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
+    assert np.abs(got - exp).max() < 2e-5
+    assert (got.argmax(axis=1) == exp.argmax(axis=1)).mean() >= 0.9999
+
+
+def test_window_slabs_compose(dg):
+    """The window-probability buffer is bounded (forward_slab_mb): a record run in many small slabs gives the
+    bit-identical prediction, including the displaced last batch (prediction.py:105)."""
+    T, U = 150, 32
+    w = dg.model.random_weights(T, U, attention=True, seed=3).scaled(4.0)
+    text = random_dna(700_000, 77)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    ref = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    mb = dg.ctx.get_int("forward_slab_mb")
+    dg.ctx.set_int("forward_slab_mb", 1)   # 4096-window slabs (the minimum)
+    try:
+        got = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+    finally:
+        dg.ctx.set_int("forward_slab_mb", mb)
+    assert np.array_equal(got, ref)
 
 
 def test_no_attention_model_through_the_fused_path(dg, oracle):
@@ -191,7 +235,7 @@ def test_lstm_variant(dg, oracle, tmp_path, T, U):
     assert np.abs(got - exp).max() < 2e-5
     text = "NN" + random_dna(15_000, U) + "N"
     labels, startpos, rows = dg.pred.predict_sequence(w, text.encode(), 50, 256, True, 50, 50)
-    assert dg.ctx.get_int("forward_used_tc") == 0
+    assert dg.ctx.get_int("forward_used_tc") == 2   # the wide tcgen05 kernel, one CTA per tile
     lab_o, st_o = oracle.predict_record(text, w.as_dict(), T, 256, 50, True, engine="torch")
     assert startpos == st_o and (labels == lab_o).mean() >= 0.9999
     check_rows_consistent(rows, labels, startpos)

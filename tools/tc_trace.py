@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "deepgrp_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_trace")
 LIB = os.path.join(OUT, "libdeepgrp_b200_trace.so")
-SOURCES = ["api.cu", "encode.cu", "vote.cu", "forward.cu", "forward_tc.cu", "mss.cu", "segments.cu", "fasta.cu", "tsv.cu", "evaluate.cu"]
+SOURCES = ["api.cu", "encode.cu", "vote.cu", "forward.cu", "forward_tc.cu", "forward_tcw.cu", "mss.cu", "segments.cu", "fasta.cu", "tsv.cu", "evaluate.cu"]
 
 
 def build():
