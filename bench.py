@@ -58,8 +58,20 @@ def fasta_text(codes, header, width=60):
     return b">" + header.encode() + b"\n" + body.tobytes() + (tail + b"\n" if tail else b"")
 
 
-def flops_per_window(T, U):
+def flops_per_window(T, U, rnn="GRU"):
+    """Algorithmic FLOPs of one window: recurrent product of both passes, input
+    projection (dense-equivalent), attention, FF.  LSTM (4 gates, no attention, FF on U features)."""
+    if rnn == "LSTM":
+        return 16 * T * U * U + 80 * T * U + 10 * T * U
     return 12 * T * U * U + 85 * T * U + 3 * T
+
+
+FORWARD_KERNELS = {
+    0: "gru_attention_vote_kernel (fp32 FFMA)",
+    1: "gru_tc_attention_vote_kernel (tcgen05, two tiles per SM, fp16 x2 operand pieces)",
+    2: "rnn_tcw_kernel (tcgen05, one tile per SM, N-split MMAs, fp16 x2 operand pieces)",
+    3: "rnn_tcw_kernel (tcgen05 cta_group::2, one tile per SM of a CTA pair, fp16 x2 operand pieces)",
+}
 
 
 class ClockSampler:
@@ -116,6 +128,14 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)) if load else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def make_weights(args):
+    """Random-init weights of the requested architecture (Keras initialisers, seed 0), optionally scaled
+    (the x4 set has confident outputs, so K6-K8 and the TSV see realistic dynamics)."""
+    from deepgrp_b200 import model
+    w = model.random_weights(args.vecsize, args.units, attention=True, seed=0, rnn=args.rnn)
+    return w.scaled(args.weight_scale) if args.weight_scale != 1.0 else w
 
 
 def host_threads():
@@ -177,7 +197,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from deepgrp_b200 import model
-    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    weights = make_weights(args)
     threads = host_threads()
     sample = args.ref_bases
     codes = synth_codes(sample, [1, 0])
@@ -236,7 +256,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
-    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    weights = make_weights(args)
     handle = weights.device_handle(ctx)
     L = args.bases
     codes = synth_codes(L, [1, rank])
@@ -272,9 +292,12 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         device_step()
     barrier()
+    print("[bench] rank %d: %d warm-up steps in %.2f s" % (rank, args.warmup, time.perf_counter() - t_w),
+          file=sys.stderr, flush=True)
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fwd_ms, stage_ms = [], []
@@ -292,6 +315,8 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     rows_per_step = int(n_rows.value)
 
+    print("[bench] rank %d: %d timed steps, %.1f ms each" % (rank, args.steps, elapsed_ms / args.steps),
+          file=sys.stderr, flush=True)
     # end to end through the public API with host buffers
     e2e_warm = max(1, min(args.warmup, 2))
     for _ in range(e2e_warm):
@@ -316,7 +341,7 @@ def run_ours(args, rank, world, local_rank):
     tflops_peak, hbm_peak, peak_kind = peaks()
     n_windows = len(range(0, L - args.vecsize, STEP))
     kernel_ms = float(np.mean(fwd_ms))
-    achieved = flops_per_window(args.vecsize, args.units) * n_windows / (kernel_ms / 1e3) / 1e12
+    achieved = flops_per_window(args.vecsize, args.units, args.rnn) * n_windows / (kernel_ms / 1e3) / 1e12
     mean_stage = {k: float(np.mean([s[k] for s in stage_ms]))
                   for k in ("forward_ms", "score_ms", "mss_ms", "segments_ms", "total_ms")}
     line = {
@@ -330,9 +355,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
-                     "kernel": (("gru_tc_attention_vote_kernel (tcgen05, %s operand pieces)"
-                                 % ("fp16 x2" if ctx.get_int("forward_fp16x2") else "bf16 x3"))
-                                if ctx.get_int("forward_used_tc") else "gru_attention_vote_kernel (fp32 FFMA)"),
+                     "kernel": FORWARD_KERNELS[ctx.get_int("forward_used_tc")],
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
                      "frac": achieved / tflops_peak, "traffic": ncu_traffic(args),
                      "traffic_unit": "bytes of DRAM read + written per launch (ncu, profiles/r01j_fwd_tc_ncu_raw.csv)",
@@ -368,7 +391,7 @@ def run_chunk(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
-    weights = model.random_weights(args.vecsize, args.units, attention=True, seed=0)
+    weights = make_weights(args)
     handle = weights.device_handle(ctx)
     L = args.bases
     d_codes = torch.from_numpy(synth_codes(L, [1, 0])).cuda()       # the same record on every rank
@@ -469,6 +492,9 @@ def main():
     ap.add_argument("--units", type=int, default=U_DEFAULT)
     ap.add_argument("--ref-bases", type=int, default=750_000,
                     help="bases per CPU-reference step (bounded sample: ~10 s on the 16 host cores of a B200 box)")
+    ap.add_argument("--rnn", default="GRU", choices=["GRU", "LSTM"])
+    ap.add_argument("--weight-scale", type=float, default=1.0,
+                    help="multiply the random-init weights (4 = the confident-output set of SURVEY.md section 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="contig", choices=["contig", "chunk"],
                     help="contig (default): one record per rank, weak scaling; chunk: ONE record split by "
