@@ -205,16 +205,20 @@ def run_reference(args, rank, world):
         cpu_reference_step(codes[:max(args.vecsize * 4, sample // 10)], weights, args.vecsize, threads)
     times = [cpu_reference_step(codes, weights, args.vecsize, threads)[0] for _ in range(args.steps)]
     total = sum(times)
+    per_step = sorted(sample / t / 1e6 for t in times)
     value = sample * args.steps / total / 1e6
     line = {
-        "impl": "reference", "metric": "bases classified/sec end-to-end", "value": value,
+        "impl": "reference", "metric": "bases classified/sec (Mbp/s), FASTA file -> TSV text on the host CPU", "value": value,
         "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, sample),
         "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": threads, "kind": "port",
-                         "sample": "%d-base prefix of the workload per step; reference restated on CPU "
-                                   "(TF absent): oracle port with torch.nn.GRU engine" % sample},
+                         "min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1],
+                         "sample": "%d-base prefix of the workload per step (%d bases over the timed steps; the "
+                                   "path is linear in the record length); reference restated on CPU "
+                                   "(TF absent): oracle port with torch.nn.GRU engine"
+                                   % (sample, sample * args.steps)},
         "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -246,151 +250,265 @@ def workload_config(args, bases):
             "sharding": "one record per rank, no collective"}
 
 
+def numa_bind(local_rank):
+    """Run this rank (and what it allocates: first touch decides where pinned buffers live) on the CPUs local to
+    its GPU, as `numactl --cpunodebind` would.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "%d cpus local to GPU %d" % (len(allowed), local_rank)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return "not bound"
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes
     import torch
     import torch.distributed as dist
-    from deepgrp_b200 import _lib, model, prediction
+    from deepgrp_b200 import _lib, prediction
 
     torch.cuda.set_device(local_rank)
+    binding = numa_bind(local_rank) if args.numa_bind else "not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
-    weights = make_weights(args)
-    handle = weights.device_handle(ctx)
-    L = args.bases
-    codes = synth_codes(L, [1, rank])
-    d_codes = torch.from_numpy(codes).cuda()
-    text = fasta_text(codes, "synthetic_%dbp_rank%d" % (L, rank))
-    pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True)
-    pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
-    raw_view = pinned.numpy()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    n_rows = ctypes.c_int64(0)
-
-    def device_step():
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        _lib.check(_lib.lib().dgrp_predict_codes_dev(
-            ctx.handle, handle, ctypes.c_void_p(d_codes.data_ptr()), L, STEP, BATCH, 1, MIN_MSS, XDROP,
-            _lib.COMPAT_REFERENCE, ctypes.byref(n_rows)))
-        return ctx.timings()
+    devnull = open(os.devnull, "wb")
+    sections = set(args.sections.split(","))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    devnull = open(os.devnull, "wb")
+    def allmax(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
 
-    def e2e_step():
-        view = prediction.predict_fasta_tsv_view(weights, raw_view, "synthetic.fa", STEP, BATCH, True,
-                                                 MIN_MSS, XDROP)
-        devnull.write(view)
-        return len(view)
+    def measure(weights, L, steps, warmup, sample_clocks):
+        """One record of L bases per rank: `value` leg (codes resident in HBM, CUDA events on the library's
+        stream) and `e2e` leg (FASTA text in pinned host memory -> TSV text on the host, through the public
+        streaming API, wall clock)."""
+        handle = weights.device_handle(ctx)
+        codes = synth_codes(L, [1, rank])
+        d_codes = torch.from_numpy(codes).cuda()
+        text = fasta_text(codes, "synthetic_%dbp_rank%d" % (L, rank))
+        pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
+        raw_view = pinned.numpy()
+        n_rows = ctypes.c_int64(0)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_w = time.perf_counter()
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    print("[bench] rank %d: %d warm-up steps in %.2f s" % (rank, args.warmup, time.perf_counter() - t_w),
-          file=sys.stderr, flush=True)
-    launches0 = ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fwd_ms, stage_ms = [], []
-    barrier()
-    sampler.mark_begin()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        t = device_step()
-        fwd_ms.append(t["forward_ms"])
-        stage_ms.append(t)
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.stop()
-    rows_per_step = int(n_rows.value)
+        def device_step():
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            _lib.check(_lib.lib().dgrp_predict_codes_dev(
+                ctx.handle, handle, ctypes.c_void_p(d_codes.data_ptr()), L, STEP, BATCH, 1, MIN_MSS, XDROP,
+                _lib.COMPAT_REFERENCE, ctypes.byref(n_rows)))
+            return ctx.timings()
 
-    print("[bench] rank %d: %d timed steps, %.1f ms each" % (rank, args.steps, elapsed_ms / args.steps),
-          file=sys.stderr, flush=True)
-    # end to end through the public API with host buffers
-    e2e_warm = max(1, min(args.warmup, 2))
-    for _ in range(e2e_warm):
-        tsv_len = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        tsv_len = e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        def e2e_step():
+            return prediction.predict_fasta_tsv_stream(weights, raw_view, "synthetic.fa", devnull, STEP, BATCH,
+                                                       True, MIN_MSS, XDROP)
 
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = (float(x) for x in times.cpu())
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        t_w = time.perf_counter()
+        for _ in range(warmup):
+            device_step()
+        barrier()
+        print("[bench] rank %d: %d warm-up steps in %.2f s" % (rank, warmup, time.perf_counter() - t_w),
+              file=sys.stderr, flush=True)
+        launches0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_ms = []
+        barrier()
+        if sampler:
+            sampler.mark_begin()
+        ev0.record(stream)
+        for _ in range(steps):
+            stage_ms.append(device_step())
+        ev1.record(stream)
+        barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        used_kernel = ctx.get_int("forward_used_tc")
+        for _ in range(max(1, min(warmup, 2))):
+            st = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st = e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        elapsed_ms, e2e_ms = allmax([elapsed_ms, e2e_ms])
+        mean_stage = {k: float(np.mean([x[k] for x in stage_ms]))
+                      for k in ("forward_ms", "score_ms", "mss_ms", "segments_ms", "total_ms")}
+        return {"value": world * L * steps / (elapsed_ms / 1e3) / 1e6, "ms_per_step": elapsed_ms / steps,
+                "e2e_value": world * L * steps / (e2e_ms / 1e3) / 1e6, "e2e_ms_per_step": e2e_ms / steps,
+                "h2d": st["h2d_bytes"], "d2h": st["d2h_bytes"], "rows": int(n_rows.value), "launches": int(launches),
+                "stages_ms": mean_stage, "clocks": clocks, "kernel": used_kernel, "codes": codes,
+                "mss_rounds": ctx.get_int("mss_rounds")}
+
+    weights = make_weights(args)
+    L = args.bases
+    main = measure(weights, L, args.steps, args.warmup, True)
+    tflops_peak, hbm_peak, peak_kind = peaks()
+    n_windows = len(range(0, L - args.vecsize, STEP))
+    kernel_ms = main["stages_ms"]["forward_ms"]
+    achieved = flops_per_window(args.vecsize, args.units, args.rnn) * n_windows / (kernel_ms / 1e3) / 1e12
+    line = {
+        "metric": "bases classified/sec (Mbp/s): value = record resident in HBM (device-timed); e2e = FASTA text in "
+                  "host memory -> TSV text in host memory",
+        "value": main["value"], "unit": "Mbp/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, L),
+        "clocks": main["clocks"],
+        "e2e": {"value": main["e2e_value"], "unit": "Mbp/s", "h2d_bytes_per_step": main["h2d"],
+                "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms_per_step"],
+                "api": "deepgrp_b200.prediction.predict_fasta_tsv_stream (C ABI dgrp_fasta_stream_*)"},
+        "gpu_launches": main["launches"],
+        "roofline": {"bound": "tensor", "kernel": FORWARD_KERNELS[main["kernel"]],
+                     "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
+                     "frac": achieved / tflops_peak, "traffic": ncu_traffic(args),
+                     "traffic_unit": "bytes of DRAM read + written per launch (ncu --set full, profiles/)",
+                     "peak_kind": peak_kind,
+                     "kernel_ms": kernel_ms, "share_of_step": kernel_ms / main["ms_per_step"]},
+        "stages_ms": main["stages_ms"], "rows_per_step": main["rows"], "mss_rounds": main["mss_rounds"],
+        "numa": binding,
+    }
+    # -- the confident-output weight set (SURVEY.md section 8d): same shapes, weights x 4 ------------------------
+    if "x4" in sections and args.weight_scale == 1.0:
+        args4 = argparse.Namespace(**vars(args))
+        args4.weight_scale = 4.0
+        x4 = measure(make_weights(args4), L, min(args.steps, 5), 2, False)
+        line["x4"] = {"weights": "the same random-init weights x 4 (max probability up to 0.9, all classes present)",
+                      "value": x4["value"], "ms_per_step": x4["ms_per_step"], "e2e": x4["e2e_value"],
+                      "e2e_ms_per_step": x4["e2e_ms_per_step"], "rows_per_step": x4["rows"],
+                      "d2h_bytes_per_step": x4["d2h"], "stages_ms": x4["stages_ms"], "unit": "Mbp/s"}
+    # -- BASELINE.json configs[2]: ONE chr1-sized record split by position over the ranks (strong scaling) -------
+    if "strong" in sections:
+        a3 = argparse.Namespace(**vars(args))
+        a3.bases, a3.steps, a3.warmup = args.strong_bases, min(args.steps, 3), 1
+        strong = chunk_sharded(a3, rank, world, local_rank, ctx, stream, flush)
+        if rank == 0:
+            line["strong"] = strong
+    # -- BASELINE.json configs[3]: the multi-FASTA genome, contig-sharded, end to end ------------------------------
+    if "genome" in sections:
+        g = genome_section(args, rank, world, weights, devnull, barrier)
+        if rank == 0:
+            line["genome"] = g
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = world * L * args.steps / (elapsed_ms / 1e3) / 1e6
-    e2e_value = world * L * args.steps / (e2e_ms / 1e3) / 1e6
-    tflops_peak, hbm_peak, peak_kind = peaks()
-    n_windows = len(range(0, L - args.vecsize, STEP))
-    kernel_ms = float(np.mean(fwd_ms))
-    achieved = flops_per_window(args.vecsize, args.units, args.rnn) * n_windows / (kernel_ms / 1e3) / 1e12
-    mean_stage = {k: float(np.mean([s[k] for s in stage_ms]))
-                  for k in ("forward_ms", "score_ms", "mss_ms", "segments_ms", "total_ms")}
-    line = {
-        "metric": "bases classified/sec end-to-end", "value": value, "unit": "Mbp/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, L),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": len(text),
-                "d2h_bytes_per_step": tsv_len + 64, "tsv_bytes_per_step": tsv_len,
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor",
-                     "kernel": FORWARD_KERNELS[ctx.get_int("forward_used_tc")],
-                     "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
-                     "frac": achieved / tflops_peak, "traffic": ncu_traffic(args),
-                     "traffic_unit": "bytes of DRAM read + written per launch (ncu, profiles/r01j_fwd_tc_ncu_raw.csv)",
-                     "peak_kind": peak_kind,
-                     "kernel_ms": kernel_ms, "share_of_step": kernel_ms / (elapsed_ms / args.steps)},
-        "stages_ms": mean_stage, "rows_per_step": rows_per_step,
-        "mss_rounds": ctx.get_int("mss_rounds"),
-    }
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        sample = min(args.ref_bases, L)
-        dt, _ = cpu_reference_step(codes[:sample], weights, args.vecsize, threads)
+        sample = min(args.ref_bases // 3, L)
+        vals = []
+        for k in range(3):
+            dt, _ = cpu_reference_step(main["codes"][k * sample:(k + 1) * sample], weights, args.vecsize, threads)
+            vals.append(sample / dt / 1e6)
         line["cpu_baseline"] = {
-            "value": sample / dt / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
-            "sample": "first %d bases of the workload, once; reference restated on CPU (TF absent): "
+            "value": float(np.median(vals)), "min": min(vals), "max": max(vals), "unit": "Mbp/s", "cores": threads,
+            "kind": "port",
+            "sample": "3 disjoint %d-base pieces of the workload, median; reference restated on CPU (TF absent): "
                       "oracle port with torch.nn.GRU engine" % sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_chunk(args, rank, world, local_rank):
+def genome_section(args, rank, world, weights, devnull, barrier):
+    """BASELINE.json configs[3] in shape, scaled to the number of ranks (world / 8 of the 3.1 Gbp genome, so the
+    work per GPU is that of the 8-GPU target run): rank 0 writes the multi-FASTA into /dev/shm, every rank maps it
+    and streams its own contigs (host header index, largest slice first) through the pipelined public API."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import genome_bench
+    from deepgrp_b200 import prediction
+    scale = args.genome_scale if args.genome_scale > 0 else world / 8.0
+    path = "/dev/shm/dgrp_config4_%d.npy" % os.getpid() if world == 1 else "/dev/shm/dgrp_config4_shared.npy"
+    t_gen = time.perf_counter()
+    if rank == 0:
+        bases = genome_bench.write_fasta(path, scale)
+        json.dump({"bases": bases}, open(path + ".json", "w"))
+    barrier()
+    t_gen = time.perf_counter() - t_gen
+    bases = json.load(open(path + ".json"))["bases"]
+    raw = np.load(path, mmap_mode="r")
+
+    def step():
+        return prediction.predict_fasta_tsv_stream(weights, raw, "genome.fa", devnull, STEP, BATCH, True, MIN_MSS,
+                                                   XDROP, rank=rank, world=world)
+    step()                                    # warm-up: buffers, first touch of the mapped file
+    walls, locals_ = [], []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        st = step()
+        locals_.append(time.perf_counter() - t0)
+        barrier()
+        walls.append(time.perf_counter() - t0)
+    stats = torch.tensor([float(st["d2h_bytes"]), float(st["rows"]), min(locals_), float(st["h2d_bytes"]),
+                          st["forward_ms"] / 1e3, float(st["records"])], dtype=torch.float64, device="cuda")
+    allstats = [torch.zeros_like(stats) for _ in range(world)]
+    wall = torch.tensor([min(walls)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_gather(allstats, stats)
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    else:
+        allstats = [stats]
+    out = None
+    if rank == 0:
+        per = [[float(x) for x in s.cpu()] for s in allstats]
+        w = float(wall.cpu()[0])
+        out = {"workload": "BASELINE.json configs[3] in shape: 24 contigs proportional to the human chromosomes, N runs, "
+                           "soft-masked lower case; %.3f of the 3.1 Gbp genome (n_gpus / 8); defaults.toml architecture, "
+                           "random-init weights; contig sharding; mapped FASTA file -> TSV text in host memory" % scale,
+               "value": bases / w / 1e6, "unit": "Mbp/s", "seconds": w, "bases": bases, "scale": scale,
+               "records": int(sum(p[5] for p in per)), "file_bytes": int(raw.size),
+               "tsv_bytes_total": sum(p[0] for p in per), "rows_total": sum(p[1] for p in per),
+               "h2d_bytes_total": sum(p[3] for p in per), "rank_seconds": [p[2] for p in per],
+               "rank_forward_seconds": [p[4] for p in per], "generate_seconds": t_gen}
+    del raw
+    barrier()
+    if rank == 0:
+        for q in (path, path + ".json"):
+            try:
+                os.unlink(q)
+            except OSError:
+                pass
+    return out
+
+
+def chunk_sharded(args, rank, world, local_rank, ctx, stream, flush):
     """BASELINE.json configs[2]: ONE record split by position ranges over the ranks (halo recompute, no
     max-merge exchange); label (1 B) + score (4 B) per base are gathered to rank 0 over NCCL, which runs
     MSS, gap fill and segment extraction for the whole record.  Strong scaling: `value` = record bases /
-    max-over-ranks time of the whole step."""
+    max-over-ranks time of the whole step.  The process group exists already; returns the result dict on rank 0."""
     import ctypes
     import torch
     import torch.distributed as dist
-    from deepgrp_b200 import _lib, model, sharding
+    from deepgrp_b200 import _lib, sharding
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = _lib.context(local_rank)
     weights = make_weights(args)
     handle = weights.device_handle(ctx)
     L = args.bases
@@ -404,8 +522,6 @@ def run_chunk(args, rank, world, local_rank):
     scs = [torch.empty(pad, dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
     full_lab = torch.empty(L, dtype=torch.uint8, device="cuda") if rank == 0 else None
     full_sc = torch.empty(L, dtype=torch.float32, device="cuda") if rank == 0 else None
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     n_rows = ctypes.c_int64(0)
     lib = _lib.lib()
     stage = {"range_ms": [], "finish_ms": []}
@@ -441,7 +557,8 @@ def run_chunk(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step()
     barrier()
-    stage = {"range_ms": [], "finish_ms": []}
+    stage["range_ms"].clear()
+    stage["finish_ms"].clear()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -458,24 +575,41 @@ def run_chunk(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, range_ms = (float(x) for x in t.cpu())
+    if rank != 0:
+        return None
+    cfg = workload_config(args, L)
+    cfg["workload"] = (workload_name(args) + ", random-init weights seed 0, ONE synthetic iid-ACGT record split "
+                       "by position ranges over the ranks")
+    cfg["sharding"] = ("position ranges with halo recompute; NCCL gather of label (u8) + score (f32) to rank 0, "
+                       "which runs MSS + segments for the whole record")
+    finish_ms = float(np.mean(stage["finish_ms"]))
+    return {
+        "metric": "bases classified/sec (Mbp/s), record resident in HBM (device-timed)",
+        "value": L * args.steps / (elapsed_ms / 1e3) / 1e6,
+        "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+        "gpu_launches": int(launches),
+        "stages_ms": {"range_forward_score_max_over_ranks": range_ms, "finish_mss_segments_rank0": finish_ms,
+                      "gather_and_rest": elapsed_ms / args.steps - range_ms - finish_ms},
+        "gather_bytes_per_step": 5 * (L - (ranges[0][1] - ranges[0][0])) if world > 1 else 0,
+        "rows_per_step": int(n_rows.value), "mss_rounds": ctx.get_int("mss_rounds"),
+    }
+
+
+def run_chunk(args, rank, world, local_rank):
+    """`--shard chunk`: the chunk-sharded run alone, as its own JSON line."""
+    import torch
+    import torch.distributed as dist
+    from deepgrp_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    line = chunk_sharded(args, rank, world, local_rank, ctx, stream, flush)
     if rank == 0:
-        cfg = workload_config(args, L)
-        cfg["workload"] = (workload_name(args) + ", random-init weights seed 0, ONE synthetic iid-ACGT record split "
-                           "by position ranges over the ranks")
-        cfg["sharding"] = ("position ranges with halo recompute; NCCL gather of label (u8) + score (f32) to rank 0, "
-                           "which runs MSS + segments for the whole record")
-        line = {
-            "metric": "bases classified/sec end-to-end", "value": L * args.steps / (elapsed_ms / 1e3) / 1e6,
-            "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "gpu_launches": int(launches),
-            "stages_ms": {"range_forward_score_max_over_ranks": range_ms,
-                          "finish_mss_segments_rank0": float(np.mean(stage["finish_ms"])),
-                          "gather_and_rest": elapsed_ms / args.steps - range_ms - float(np.mean(stage["finish_ms"]))},
-            "gather_bytes_per_step": 5 * (L - (ranges[0][1] - ranges[0][0])) if world > 1 else 0,
-            "rows_per_step": int(n_rows.value), "mss_rounds": ctx.get_int("mss_rounds"),
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -496,6 +630,14 @@ def main():
     ap.add_argument("--weight-scale", type=float, default=1.0,
                     help="multiply the random-init weights (4 = the confident-output set of SURVEY.md section 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sections", default="x4,strong,genome",
+                    help="extra measurements attached to the JSON line: x4 (the confident-output weight set), strong "
+                         "(BASELINE.json configs[2], one chr1-sized record chunk-sharded over the ranks), genome "
+                         "(configs[3] in shape, n_gpus/8 of the 3.1 Gbp multi-FASTA, end to end); '' for none")
+    ap.add_argument("--strong-bases", type=int, default=248_000_000)
+    ap.add_argument("--genome-scale", type=float, default=0.0, help="fraction of the 3.1 Gbp genome (0 = n_gpus / 8)")
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",
+                    help="do not restrict the rank to the CPUs local to its GPU")
     ap.add_argument("--shard", default="contig", choices=["contig", "chunk"],
                     help="contig (default): one record per rank, weak scaling; chunk: ONE record split by "
                          "position ranges over the ranks (BASELINE.json configs[2], strong scaling)")
@@ -503,6 +645,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if (args.vecsize, args.units, args.rnn) != (T_DEFAULT, U_DEFAULT, "GRU") or args.bases != CONFIG2_BASES:
+        # a custom shape: the attached sections describe the default architecture's other configurations
+        if args.sections == ap.get_default("sections"):
+            args.sections = ""
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.shard == "chunk":

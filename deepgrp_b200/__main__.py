@@ -8,7 +8,9 @@ as well as the ``predict`` sub-command.  ``train`` is out of scope.
 from __future__ import annotations
 
 import argparse
+import io
 import logging
+import os
 import sys
 from typing import Iterator, List, TextIO, Tuple
 
@@ -44,17 +46,40 @@ def _read_multi_fasta(filestream: TextIO) -> Iterator[Tuple[str, str]]:
         yield name, "".join(pieces)
 
 
-def _read_raw(filename: str) -> bytes:
+def _read_raw(filename: str):
     """Raw FASTA bytes of `filename` ("-" = stdin; ``.gz`` files are decompressed on the host, as the
-    reference's preprocessing script does, deepgrp/_scripts/preprocess_sequence.py:19-38)."""
+    reference's preprocessing script does, deepgrp/_scripts/preprocess_sequence.py:19-38).  A regular file is
+    memory-mapped, so only the bytes the prediction stream uploads (this rank's records) are ever read."""
     if filename == "-":
         return sys.stdin.buffer.read()
     if filename.endswith(".gz"):
         import gzip
         with gzip.open(filename, "rb") as fh:
             return fh.read()
+    import mmap
     with open(filename, "rb") as fh:
-        return fh.read()
+        if os.fstat(fh.fileno()).st_size == 0:
+            return b""
+        return mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+
+
+class _ByteSink:
+    """Adapter for the TSV pieces (bytes-like views): binary streams take them as they are, text streams through
+    their ``.buffer`` when they have one (``sys.stdout``), otherwise decoded (an ``io.StringIO`` in tests)."""
+
+    def __init__(self, outstream):
+        self.out = outstream
+        self.raw = getattr(outstream, "buffer", None)
+        self.binary = isinstance(outstream, (io.RawIOBase, io.BufferedIOBase))
+
+    def write(self, view) -> None:
+        if self.binary:
+            self.out.write(view)
+        elif self.raw is not None:
+            self.out.flush()
+            self.raw.write(view)
+        else:
+            self.out.write(bytes(view).decode("utf-8", "replace"))
 
 
 def _predict(dnasequence: str, model: dgmodel.ModelWeights, options: dgmodel.Options,
@@ -187,11 +212,13 @@ class CommandLineParser:
                     if filename != "-":
                         filestream.close()
             else:
-                view = dgpred.predict_fasta_tsv_view(
-                    model, _read_raw(filename), filename, args.step_size, options.batch_size, use_mss,
-                    options.min_mss_len, options.xdrop_len)
-                outstream.flush()
-                getattr(outstream, "buffer", outstream).write(view)
+                # records stream through the GPU pipeline; a record's rows are written as soon as it is done,
+                # so an error in a later record leaves the earlier rows in the output, as in the reference
+                stats = dgpred.predict_fasta_tsv_stream(
+                    model, _read_raw(filename), filename, _ByteSink(outstream), args.step_size,
+                    options.batch_size, use_mss, options.min_mss_len, options.xdrop_len)
+                _LOG.info("%s: %d records, %d bases, %d rows", filename, stats["records"], stats["bases"],
+                          stats["rows"])
         if args.output != "-":
             outstream.close()
 

@@ -6,6 +6,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include <cuda_fp16.h>
 #include <cmath>
@@ -227,6 +231,8 @@ int dgrp_ctx_destroy(dgrp_ctx *c) {
   for (auto b : bufs) b->release();
   c->pin_small.release(); c->pin_a.release(); c->pin_b.release(); c->tsv_host.release();
   c->tsv_dev.release(); c->tsv_prefix.release();
+  for (int i = 0; i < 2; ++i) { c->st_raw[i].release(); c->st_text[i].release(); c->st_stage[i].release(); }
+  for (int i = 0; i < 4; ++i) c->st_slot[i].release();
   for (auto &e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1088,6 +1094,428 @@ int dgrp_finish_record_dev(dgrp_ctx *c, const uint8_t *d_labels, const float *d_
   stamp(c, 5);
   finish_timings(c, launches0);
   return rc;
+}
+
+}  // extern "C"
+
+/* ------------------------- streaming whole-file driver (pipelined) ------------------------- */
+// deepgrp/__main__.py:275-295 reads a file record by record and writes a record's rows as soon as the record is
+// done.  dgrp_fasta_stream does the same as a three-stage pipeline with bounded memory:
+//   compute thread  cuts the text into slices at header lines (host memchr index), uploads ONLY this rank's
+//                   slices (pinned staging ring, one cudaMemcpyAsync per chunk, a stream of its own), decodes a
+//                   slice on the GPU and runs encode -> forward -> MSS -> segments -> TSV text per record; the
+//                   text of a record lands in one of two device buffers;
+//   copier thread   moves a finished record's text to the host in pieces through a ring of pinned slots on a
+//                   third stream, while the compute thread is already on the next record;
+//   caller          dgrp_fasta_stream_next() hands out one piece at a time (valid until the next call).
+namespace {
+
+constexpr int kSlots = 4;
+constexpr int64_t kSlotBytes = (int64_t)64 << 20;    // one piece of TSV text
+constexpr int64_t kStageBytes = (int64_t)32 << 20;   // one chunk of the upload
+constexpr int64_t kMinSlice = (int64_t)8 << 20;      // adjacent records are merged into slices of at least this size
+
+struct StreamPiece {
+  int slot;
+  int64_t bytes, slice, ordinal, rows;
+  int last;   // last piece of its record
+};
+struct StreamRecord {
+  int buf;    // device text buffer
+  int64_t bytes, slice, ordinal, rows;
+};
+
+}  // namespace
+
+struct dgrp_fasta_stream {
+  dgrp_ctx *c = nullptr;
+  dgrp_model *m = nullptr;
+  const uint8_t *fasta = nullptr;
+  int64_t nbytes = 0;
+  std::string filename;
+  int step = 0, batch_size = 0, use_mss = 0, min_mss_len = 0, xdrop_len = 0, compat = 0;
+  std::vector<int64_t> cuts;     // slice k = [cuts[k], cuts[k + 1])
+  std::vector<int64_t> mine;     // this rank's slices, in file order
+  DevBuf *raw = nullptr, *text = nullptr;     // [2] each; the buffers live in the context and are reused by the next stream
+  PinBuf *stage = nullptr, *slot = nullptr;   // [2], [kSlots]
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_stage[2] = {}, ev_text[2] = {}, ev_slot[kSlots] = {};
+  bool src_pinned = false;
+  std::thread compute, copier;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<StreamRecord> ready;   // compute -> copier
+  std::deque<StreamPiece> pieces;   // copier -> caller
+  int text_busy[2] = {0, 0};        // device text buffer handed to the copier
+  int slot_state[kSlots] = {};      // 0 free, 1 being filled / queued, 2 held by the caller
+  int held = -1;
+  bool compute_done = false, copier_done = false, cancel = false;
+  int rc = DGRP_OK;
+  std::string err;
+  // totals
+  int64_t rows = 0, records = 0, bases = 0, windows = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  double forward_ms = 0.0, gpu_ms = 0.0;
+};
+
+namespace {
+
+// Header lines start a slice: a '>' that is the first byte of a line.  (A '>' after leading whitespace is a
+// header too, __main__.py:34-35; it simply stays inside the preceding slice, which the GPU parser handles.)
+void stream_index(dgrp_fasta_stream *s) {
+  const uint8_t *f = s->fasta;
+  const int64_t n = s->nbytes;
+  s->cuts.clear();
+  s->cuts.push_back(0);
+  int64_t p = 1;
+  while (p < n) {
+    const void *q = memchr(f + p, '>', (size_t)(n - p));
+    if (!q) break;
+    p = (const uint8_t *)q - f;
+    if ((f[p - 1] == '\n' || f[p - 1] == '\r') && p - s->cuts.back() >= kMinSlice) s->cuts.push_back(p);
+    ++p;
+  }
+  s->cuts.push_back(n);
+  // largest-first assignment of slices to ranks (every rank derives the same table)
+  const int64_t ns = (int64_t)s->cuts.size() - 1;
+  const int world = s->c->shard_world > 0 ? s->c->shard_world : 1;
+  std::vector<int64_t> order(ns);
+  for (int64_t k = 0; k < ns; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return (s->cuts[a + 1] - s->cuts[a]) > (s->cuts[b + 1] - s->cuts[b]);
+  });
+  std::vector<int64_t> load(world, 0);
+  std::vector<int> owner(ns, 0);
+  for (int64_t k : order) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[k] = best;
+    load[best] += s->cuts[k + 1] - s->cuts[k];
+  }
+  s->mine.clear();
+  for (int64_t k = 0; k < ns; ++k)
+    if (owner[k] == s->c->shard_rank && s->cuts[k + 1] > s->cuts[k]) s->mine.push_back(k);
+}
+
+#define STREAM_CUDA(call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      dgrp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return DGRP_E_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+// enqueue the upload of slice `k` into raw[b] on s_in and record ev_in[b]
+int stream_upload(dgrp_fasta_stream *s, int64_t k, int b, int *stage_turn) {
+  const int64_t off = s->cuts[k], n = s->cuts[k + 1] - off;
+  DGRP_CHECK(s->raw[b].reserve((size_t)n + 16));
+  if (s->src_pinned) {
+    STREAM_CUDA(cudaMemcpyAsync(s->raw[b].p, s->fasta + off, (size_t)n, cudaMemcpyHostToDevice, s->s_in));
+  } else {
+    for (int64_t o = 0; o < n; o += kStageBytes) {
+      const int t = (*stage_turn)++ & 1;
+      const int64_t len = std::min<int64_t>(kStageBytes, n - o);
+      STREAM_CUDA(cudaEventSynchronize(s->ev_stage[t]));   // the chunk that used this staging buffer has left
+      memcpy(s->stage[t].p, s->fasta + off + o, (size_t)len);
+      STREAM_CUDA(cudaMemcpyAsync(s->raw[b].as<uint8_t>() + o, s->stage[t].p, (size_t)len, cudaMemcpyHostToDevice, s->s_in));
+      STREAM_CUDA(cudaEventRecord(s->ev_stage[t], s->s_in));
+    }
+  }
+  s->h2d_bytes += n;
+  STREAM_CUDA(cudaEventRecord(s->ev_in[b], s->s_in));
+  return DGRP_OK;
+}
+
+// one slice (already on the device in raw[b]): decode, then every record of it
+int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
+  dgrp_ctx *c = s->c;
+  dgrp_model *m = s->m;
+  const uint8_t *fasta = s->fasta + s->cuts[k];          // host view of the slice (headers)
+  const int64_t nbytes = s->cuts[k + 1] - s->cuts[k];
+  STREAM_CUDA(cudaStreamWaitEvent(c->stream, s->ev_in[b], 0));
+  int64_t n_seq = 0, n_hdr = 0;
+  DGRP_CHECK(run_fasta_decode(c, s->raw[b].as<uint8_t>(), nbytes, &n_seq, &n_hdr));
+  std::vector<int64_t> hpos(n_hdr), hseq(n_hdr + 1);
+  if (n_hdr > 0) {
+    const int64_t *t = c->pin_b.as<int64_t>();
+    for (int64_t i = 0; i < n_hdr; ++i) { hpos[i] = t[i]; hseq[i] = t[(n_hdr + 1) + i]; }
+  }
+  hseq[n_hdr] = n_seq;
+  auto ws = [](uint8_t x) { return (x >= 9 && x <= 13) || (x >= 28 && x <= 32); };
+  int64_t ordinal = 0;
+  for (int64_t i = 0; i < n_hdr; ++i) {
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      if (s->cancel) return DGRP_OK;
+    }
+    int64_t hb = hpos[i] + 1, he = hb;
+    while (he < nbytes && fasta[he] != '\n' && !(fasta[he] == '\r' && !(he + 1 < nbytes && fasta[he + 1] == '\n'))) ++he;
+    while (he > hb && ws(fasta[he - 1])) --he;
+    if (he == hb) continue;                         // empty header: record dropped (__main__.py:36)
+    const uint8_t *d_seq = c->io_b.as<uint8_t>() + hseq[i];
+    const int64_t n = hseq[i + 1] - hseq[i];
+    int64_t startpos = 0, length = 0;
+    stamp(c, 0);
+    DGRP_CHECK(core_encode(c, d_seq, n, 1, &startpos, &length));
+    if (length < 0) {
+      set_error("negative dimensions are not allowed (all-'N' record in slice %lld)", (long long)k);
+      return DGRP_E_ALLN;
+    }
+    stamp(c, 1);
+    DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, s->step, s->batch_size, s->compat));
+    s->windows += c->timings.windows; s->bases += length;
+    stamp(c, 2);
+    DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, s->use_mss, s->min_mss_len,
+                           s->xdrop_len));
+    stamp(c, 4);
+    int64_t cnt = 0, need = 0;
+    int tb = -1;
+    if (length > 0) {
+      int64_t *d_tri = nullptr;
+      DGRP_CHECK(run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt));
+      if (cnt > 0) {
+        std::string prefix(s->filename);
+        prefix.push_back('\t');
+        prefix.append(reinterpret_cast<const char *>(fasta + hb), (size_t)(he - hb));
+        prefix.push_back('\t');
+        DGRP_CHECK(c->tsv_prefix.reserve(prefix.size() + 16));
+        STREAM_CUDA(cudaMemcpyAsync(c->tsv_prefix.p, prefix.data(), prefix.size(), cudaMemcpyHostToDevice, c->stream));
+        DGRP_CHECK(run_tsv_measure(c, d_tri, cnt, (int)prefix.size(), &need));   // syncs: `prefix` may go
+        tb = (*text_turn)++ & 1;
+        {
+          std::unique_lock<std::mutex> lk(s->mu);   // the copier still drains the record before last
+          s->cv.wait(lk, [&] { return s->text_busy[tb] == 0 || s->cancel; });
+          if (s->cancel) return DGRP_OK;
+        }
+        DGRP_CHECK(s->text[tb].reserve((size_t)need + 16));
+        DGRP_CHECK(run_tsv_write(c, d_tri, cnt, c->tsv_prefix.as<uint8_t>(), (int)prefix.size(),
+                                 s->text[tb].as<uint8_t>()));
+        STREAM_CUDA(cudaEventRecord(s->ev_text[tb], c->stream));
+      }
+    }
+    stamp(c, 5);
+    STREAM_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s->forward_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); s->gpu_ms += ms;
+    s->rows += cnt; s->records += 1;
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      if (tb >= 0) s->text_busy[tb] = 1;
+      s->ready.push_back(StreamRecord{tb, need, k, ordinal, cnt});   // records without rows travel as empty pieces
+    }
+    s->cv.notify_all();
+    ++ordinal;
+  }
+  return DGRP_OK;
+}
+
+void stream_compute_main(dgrp_fasta_stream *s) {
+  cudaSetDevice(s->c->device);
+  const int64_t launches0 = s->c->launches;
+  int rc = DGRP_OK, stage_turn = 0, text_turn = 0;
+  if (!s->mine.empty()) rc = stream_upload(s, s->mine[0], 0, &stage_turn);
+  for (size_t i = 0; i < s->mine.size() && rc == DGRP_OK; ++i) {
+    if (i + 1 < s->mine.size()) rc = stream_upload(s, s->mine[i + 1], (int)((i + 1) & 1), &stage_turn);
+    if (rc == DGRP_OK) rc = stream_slice(s, s->mine[i], (int)(i & 1), &text_turn);
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->cancel) break;
+  }
+  s->launches = s->c->launches - launches0;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (rc != DGRP_OK) { s->rc = rc; s->err = dgrp_last_error(); }
+    s->compute_done = true;
+  }
+  s->cv.notify_all();
+}
+
+void stream_copier_main(dgrp_fasta_stream *s) {
+  cudaSetDevice(s->c->device);
+  std::deque<StreamPiece> inflight;
+  auto publish_oldest = [&]() {
+    StreamPiece p = inflight.front();
+    inflight.pop_front();
+    if (p.slot >= 0) cudaEventSynchronize(s->ev_slot[p.slot]);
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->pieces.push_back(p);
+    }
+    s->cv.notify_all();
+  };
+  for (;;) {
+    StreamRecord r;
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv.wait(lk, [&] { return !s->ready.empty() || s->compute_done || s->cancel; });
+      if (s->cancel) break;
+      if (s->ready.empty()) break;   // compute finished and everything is copied
+      r = s->ready.front();
+      s->ready.pop_front();
+    }
+    if (r.buf < 0 || r.bytes == 0) {   // a record without rows
+      inflight.push_back(StreamPiece{-1, 0, r.slice, r.ordinal, r.rows, 1});
+      while (!inflight.empty()) publish_oldest();
+      continue;
+    }
+    cudaStreamWaitEvent(s->s_out, s->ev_text[r.buf], 0);
+    bool stop = false;
+    for (int64_t off = 0; off < r.bytes && !stop; off += kSlotBytes) {
+      const int64_t len = std::min<int64_t>(kSlotBytes, r.bytes - off);
+      int slot = -1;
+      for (;;) {
+        {
+          std::lock_guard<std::mutex> lk(s->mu);
+          if (s->cancel) { stop = true; break; }
+          for (int q = 0; q < kSlots; ++q)
+            if (s->slot_state[q] == 0) { slot = q; s->slot_state[q] = 1; break; }
+        }
+        if (slot >= 0) break;
+        if (!inflight.empty()) { publish_oldest(); continue; }   // the caller needs something to release
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->cv.wait(lk, [&] {
+          if (s->cancel) return true;
+          for (int q = 0; q < kSlots; ++q) if (s->slot_state[q] == 0) return true;
+          return false;
+        });
+      }
+      if (stop) break;
+      cudaMemcpyAsync(s->slot[slot].p, s->text[r.buf].as<uint8_t>() + off, (size_t)len, cudaMemcpyDeviceToHost, s->s_out);
+      cudaEventRecord(s->ev_slot[slot], s->s_out);
+      s->d2h_bytes += len;
+      inflight.push_back(StreamPiece{slot, len, r.slice, r.ordinal, off + len >= r.bytes ? r.rows : 0,
+                                     off + len >= r.bytes ? 1 : 0});
+      if ((int)inflight.size() >= kSlots - 1) publish_oldest();
+    }
+    while (!inflight.empty()) publish_oldest();   // the record's last copy has completed: its device buffer is free
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->text_busy[r.buf] = 0;
+    }
+    s->cv.notify_all();
+    if (stop) break;
+  }
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->copier_done = true;
+  }
+  s->cv.notify_all();
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, const char *filename,
+                           int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,
+                           dgrp_fasta_stream **out) {
+  Use use(c->device);
+  *out = nullptr;
+  DGRP_REQUIRE(nbytes >= 0 && filename != nullptr, "bad arguments");
+  DGRP_REQUIRE(step > 0, "step_size must be positive");
+  dgrp_fasta_stream *s = new dgrp_fasta_stream();
+  s->c = c; s->m = m; s->fasta = fasta; s->nbytes = nbytes; s->filename = filename;
+  s->step = step; s->batch_size = batch_size; s->use_mss = use_mss; s->min_mss_len = min_mss_len;
+  s->xdrop_len = xdrop_len; s->compat = compat;
+  s->raw = c->st_raw; s->text = c->st_text; s->stage = c->st_stage; s->slot = c->st_slot;
+  stream_index(s);
+  cudaPointerAttributes attr;
+  if (nbytes > 0 && cudaPointerGetAttributes(&attr, fasta) == cudaSuccess) s->src_pinned = attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  int rc = DGRP_OK;
+  auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == DGRP_OK) { set_error("stream setup: %s", cudaGetErrorString(e)); rc = DGRP_E_CUDA; } };
+  ck(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+  ck(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    ck(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+    ck(cudaEventCreateWithFlags(&s->ev_stage[i], cudaEventDisableTiming));
+    ck(cudaEventCreateWithFlags(&s->ev_text[i], cudaEventDisableTiming));
+    if (!s->src_pinned && rc == DGRP_OK) rc = s->stage[i].reserve((size_t)kStageBytes);
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    ck(cudaEventCreateWithFlags(&s->ev_slot[i], cudaEventDisableTiming));
+    if (rc == DGRP_OK) rc = s->slot[i].reserve((size_t)kSlotBytes);
+  }
+  if (rc != DGRP_OK) { dgrp_fasta_stream_close(s); return rc; }
+  s->compute = std::thread(stream_compute_main, s);
+  s->copier = std::thread(stream_copier_main, s);
+  *out = s;
+  return DGRP_OK;
+}
+
+int dgrp_fasta_stream_next(dgrp_fasta_stream *s, const uint8_t **tsv, int64_t *tsv_len, int64_t *slice,
+                           int64_t *ordinal, int64_t *n_rows, int *last_of_record, int *done) {
+  *tsv = nullptr; *tsv_len = 0; *done = 0;
+  if (slice) *slice = -1;
+  if (ordinal) *ordinal = -1;
+  if (n_rows) *n_rows = 0;
+  if (last_of_record) *last_of_record = 0;
+  std::unique_lock<std::mutex> lk(s->mu);
+  if (s->held >= 0) { s->slot_state[s->held] = 0; s->held = -1; s->cv.notify_all(); }
+  s->cv.wait(lk, [&] { return !s->pieces.empty() || s->copier_done; });
+  if (s->pieces.empty()) {
+    // everything that was produced has been handed out; an error of the compute thread surfaces now, after the
+    // rows of the records before it (the reference has written those when it raises)
+    *done = 1;
+    if (s->rc != DGRP_OK) { set_error("%s", s->err.c_str()); return s->rc; }
+    return DGRP_OK;
+  }
+  const StreamPiece p = s->pieces.front();
+  s->pieces.pop_front();
+  if (p.slot >= 0) { s->slot_state[p.slot] = 2; s->held = p.slot; *tsv = s->slot[p.slot].as<uint8_t>(); }
+  *tsv_len = p.bytes;
+  if (slice) *slice = p.slice;
+  if (ordinal) *ordinal = p.ordinal;
+  if (n_rows) *n_rows = p.rows;
+  if (last_of_record) *last_of_record = p.last;
+  return DGRP_OK;
+}
+
+int dgrp_fasta_stream_stats(dgrp_fasta_stream *s, int64_t *rows, int64_t *records, int64_t *bases, int64_t *windows,
+                            int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes, double *forward_ms,
+                            double *gpu_ms) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (rows) *rows = s->rows;
+  if (records) *records = s->records;
+  if (bases) *bases = s->bases;
+  if (windows) *windows = s->windows;
+  if (launches) *launches = s->launches;
+  if (h2d_bytes) *h2d_bytes = s->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = s->d2h_bytes;
+  if (forward_ms) *forward_ms = s->forward_ms;
+  if (gpu_ms) *gpu_ms = s->gpu_ms;
+  return DGRP_OK;
+}
+
+int dgrp_fasta_stream_close(dgrp_fasta_stream *s) {
+  if (!s) return DGRP_OK;
+  Use use(s->c->device);
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->cancel = true;
+    if (s->held >= 0) { s->slot_state[s->held] = 0; s->held = -1; }
+  }
+  s->cv.notify_all();
+  if (s->compute.joinable()) s->compute.join();
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->compute_done = true;
+  }
+  s->cv.notify_all();
+  if (s->copier.joinable()) s->copier.join();
+  cudaStreamSynchronize(s->c->stream);
+  if (s->s_in) { cudaStreamSynchronize(s->s_in); cudaStreamDestroy(s->s_in); }
+  if (s->s_out) { cudaStreamSynchronize(s->s_out); cudaStreamDestroy(s->s_out); }
+  for (int i = 0; i < 2; ++i) {
+    if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+    if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]);
+    if (s->ev_text[i]) cudaEventDestroy(s->ev_text[i]);
+  }
+  for (int i = 0; i < kSlots; ++i)
+    if (s->ev_slot[i]) cudaEventDestroy(s->ev_slot[i]);
+  delete s;
+  return DGRP_OK;
 }
 
 }  // extern "C"

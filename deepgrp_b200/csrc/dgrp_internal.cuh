@@ -116,6 +116,10 @@ struct dgrp_ctx {
   dgrp::PinBuf tsv_host;     // finished TSV text of the last dgrp_predict_fasta_tsv
   int64_t tsv_len = 0;
   dgrp::DevBuf tsv_dev, tsv_prefix;
+  // buffers of dgrp_fasta_stream (kept across streams): uploaded slices, finished record text, upload staging,
+  // host pieces
+  dgrp::DevBuf st_raw[2], st_text[2];
+  dgrp::PinBuf st_stage[2], st_slot[4];
   // staged one-hot state (dgrp_one_hot_stage -> dgrp_one_hot_fetch)
   int64_t staged_n = 0, staged_start = 0, staged_len = -1;
 };

@@ -277,6 +277,100 @@ def predict_fasta_tsv_view(model: ModelWeights, raw, filename: str, step_size: i
                            xdrop_len, compat)[0]
 
 
+class FastaTsvStream:
+    """Pipelined whole-file prediction (C ABI ``dgrp_fasta_stream_*``; reference ``deepgrp/__main__.py:275-295``
+    writes a record's rows as soon as the record is done).  Iterating yields ``(slice, ordinal, n_rows, last,
+    view)`` per piece of TSV text, in file order of this rank's records; ``view`` is a read-only memoryview of
+    pinned host memory that is valid until the next iteration -- write it out or copy it.  A blank line
+    (``IndexError``) or an all-``N`` record (``ValueError``) is raised after the text of the records before it.
+    ``raw`` must stay alive while the stream is open (a reference is kept)."""
+
+    def __init__(self, model: ModelWeights, raw, filename: str, step_size: int, batch_size: int, use_mss: bool,
+                 min_mss_len: int, xdrop_len: int, compat: str = "reference", rank: int = 0, world: int = 1):
+        self._ctx = _lib.context()
+        self._raw = raw
+        n = len(raw)
+        self._buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+        self._handle = ctypes.c_void_p()
+        self._ctx.set_int("shard_rank", rank)
+        self._ctx.set_int("shard_world", world)
+        try:
+            _lib.check(_lib.lib().dgrp_fasta_stream_open(
+                self._ctx.handle, model.device_handle(self._ctx), _lib.ptr(self._buf), n, os.fsencode(filename),
+                int(step_size), int(batch_size), int(use_mss), int(min_mss_len), int(xdrop_len), _COMPAT[compat],
+                ctypes.byref(self._handle)))
+        finally:
+            self._ctx.set_int("shard_rank", 0)
+            self._ctx.set_int("shard_world", 1)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self._handle:
+            raise StopIteration
+        tsv, tsv_len = ctypes.c_void_p(), ctypes.c_int64(0)
+        sl, od, nr = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        last, done = ctypes.c_int(0), ctypes.c_int(0)
+        rc = _lib.lib().dgrp_fasta_stream_next(self._handle, ctypes.byref(tsv), ctypes.byref(tsv_len),
+                                               ctypes.byref(sl), ctypes.byref(od), ctypes.byref(nr),
+                                               ctypes.byref(last), ctypes.byref(done))
+        if rc != 0 or done.value:
+            self.stats = self._stats()
+            self.close()
+            if rc == _lib.E_FASTA:
+                raise IndexError("string index out of range")
+            if rc == _lib.E_ALLN:
+                raise ValueError("negative dimensions are not allowed")
+            _lib.check(rc)
+            raise StopIteration
+        if tsv_len.value == 0:
+            view = memoryview(b"")
+        else:
+            view = memoryview((ctypes.c_ubyte * tsv_len.value).from_address(tsv.value)).cast("B").toreadonly()
+        return int(sl.value), int(od.value), int(nr.value), bool(last.value), view
+
+    def _stats(self) -> dict:
+        v = [ctypes.c_int64(0) for _ in range(7)]
+        f, g = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        _lib.check(_lib.lib().dgrp_fasta_stream_stats(self._handle, *[ctypes.byref(x) for x in v],
+                                                      ctypes.byref(f), ctypes.byref(g)))
+        names = ("rows", "records", "bases", "windows", "launches", "h2d_bytes", "d2h_bytes")
+        out = {k: int(x.value) for k, x in zip(names, v)}
+        out["forward_ms"], out["gpu_ms"] = float(f.value), float(g.value)
+        return out
+
+    def close(self) -> None:
+        if self._handle:
+            _lib.lib().dgrp_fasta_stream_close(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
+
+
+def predict_fasta_tsv_stream(model: ModelWeights, raw, filename: str, outstream, step_size: int, batch_size: int,
+                             use_mss: bool, min_mss_len: int, xdrop_len: int, compat: str = "reference",
+                             rank: int = 0, world: int = 1) -> dict:
+    """Write the TSV text of ``raw`` (one FASTA file) to the binary stream ``outstream`` piece by piece as the
+    records finish; returns the stream's totals (rows, records, bases, ...)."""
+    with FastaTsvStream(model, raw, filename, step_size, batch_size, use_mss, min_mss_len, xdrop_len, compat,
+                        rank, world) as st:
+        for _, _, _, _, view in st:
+            if len(view):
+                outstream.write(view)
+        return st.stats
+
+
 def predict_fasta_tsv_sharded(model: ModelWeights, raw, filename: str, step_size: int, batch_size: int,
                               use_mss: bool, min_mss_len: int, xdrop_len: int, rank: int, world: int,
                               compat: str = "reference"):

@@ -233,6 +233,31 @@ int dgrp_fasta_records(dgrp_ctx *ctx, int64_t *hdr_off, int64_t *hdr_len, int64_
 int dgrp_fasta_record_tsv(dgrp_ctx *ctx, int64_t *owner, int64_t *tsv_off, int64_t *tsv_len,
                           int64_t cap);
 
+/* Streaming, pipelined form of the whole-file driver.  deepgrp/__main__.py:275-295 writes the rows of a record as
+ * soon as the record is done; this does the same with bounded memory and with the copies off the critical path:
+ * the text is cut into slices at header lines on the host ('>' at a line start), a rank uploads ONLY its own slices
+ * ("shard_rank" / "shard_world": largest slice first to the least loaded rank) through a pinned staging ring, and a
+ * record's finished TSV text travels to the host in pieces of <= 64 MiB on a second stream while the next record is
+ * being computed.  `fasta` must stay valid until _close.  _next returns the next piece of text in file order of this
+ * rank's records (*tsv valid until the following call): (*slice, *ordinal) identify the record (slice number in the
+ * file, record number within the slice), *last_of_record marks its final piece and carries *n_rows; a record without
+ * rows yields one empty piece.  *done = 1 when everything has been handed out -- an error met on the way (blank line,
+ * all-'N' record, CUDA) is returned by that last call, after the text of the records before it, as the reference
+ * has written those rows when it raises.  One stream per context at a time; the context must not be used for
+ * other calls while a stream is open. */
+typedef struct dgrp_fasta_stream dgrp_fasta_stream;
+int dgrp_fasta_stream_open(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
+                           const char *filename, int step, int batch_size, int use_mss, int min_mss_len,
+                           int xdrop_len, int compat, dgrp_fasta_stream **out);
+int dgrp_fasta_stream_next(dgrp_fasta_stream *stream, const uint8_t **tsv, int64_t *tsv_len, int64_t *slice,
+                           int64_t *ordinal, int64_t *n_rows, int *last_of_record, int *done);
+/* totals so far (any pointer may be NULL): rows, records, trimmed bases, windows, kernel launches, bytes uploaded /
+ * copied back, forward-kernel and whole-GPU milliseconds (CUDA events, summed over records) */
+int dgrp_fasta_stream_stats(dgrp_fasta_stream *stream, int64_t *rows, int64_t *records, int64_t *bases,
+                            int64_t *windows, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes,
+                            double *forward_ms, double *gpu_ms);
+int dgrp_fasta_stream_close(dgrp_fasta_stream *stream);
+
 /* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),
  * runs forward + vote + score + MSS + segment extraction entirely on the device and leaves the
  * row count in *n_rows (rows stay on the device).  No host copies except the 8-byte count. */

@@ -334,3 +334,69 @@ def test_predict_complete_from_files_on_disk(dg, oracle, tmp_path):
     cnf = dg.pred.confusion_matrix(true_cls, got.argmax(axis=1))
     assert np.array_equal(cnf, oracle.confusion_matrix(true_cls, got.argmax(axis=1)))
     assert int(np.asarray(cnf).sum()) == true_cls.size
+
+
+def _multi_fasta(tmp_path, n_rec=5, seed=3, with_n=True):
+    rng = np.random.default_rng(seed)
+    recs = []
+    for k in range(n_rec):
+        n = int(rng.integers(3_000, 40_000))
+        seq = random_dna(n, 100 + k)
+        if with_n:
+            seq = "N" * int(rng.integers(0, 30)) + seq + "N" * int(rng.integers(0, 30))
+        recs.append(("rec%d description %d" % (k, n), seq))
+    p = tmp_path / "multi.fa"
+    write_fasta(str(p), recs)
+    return open(p, "rb").read()
+
+
+def test_fasta_stream_equals_one_shot(dg, tmp_path):
+    """dgrp_fasta_stream_* (pipelined: host header index, per-slice upload, text copied back in pieces on a second
+    stream) writes byte for byte what the one-shot dgrp_predict_fasta_tsv returns; sharded streams partition it."""
+    import io
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    raw = _multi_fasta(tmp_path)
+    ref = bytes(dg.pred.predict_fasta_tsv_view(w, raw, "m.fa", 50, 256, True, 50, 50))
+    out = io.BytesIO()
+    stats = dg.pred.predict_fasta_tsv_stream(w, raw, "m.fa", out, 50, 256, True, 50, 50)
+    assert out.getvalue() == ref and len(ref) > 1000
+    assert stats["records"] == 5 and stats["rows"] == ref.count(b"\n")
+    # pinned source memory takes the direct-upload route
+    import torch
+    pinned = torch.empty(len(raw), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(raw, dtype=np.uint8)
+    out2 = io.BytesIO()
+    dg.pred.predict_fasta_tsv_stream(w, pinned.numpy(), "m.fa", out2, 50, 256, True, 50, 50)
+    assert out2.getvalue() == ref
+    # all records are below the slice minimum here: one slice, rank 0 owns it
+    parts = []
+    for r in range(3):
+        o = io.BytesIO()
+        dg.pred.predict_fasta_tsv_stream(w, raw, "m.fa", o, 50, 256, True, 50, 50, rank=r, world=3)
+        parts.append(o.getvalue())
+    assert b"".join(parts) == ref
+
+
+def test_fasta_stream_slices_and_errors(dg, tmp_path):
+    """Records above the 8 MiB slice minimum are cut into slices and shared largest-first; an error (blank line)
+    surfaces after the text of the records before it."""
+    import io
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    recs = [("big%d" % k, random_dna(9_000_000 + 1000 * k, 50 + k)) for k in range(3)]
+    p = tmp_path / "big.fa"
+    write_fasta(str(p), recs)
+    raw = open(p, "rb").read()
+    ref = bytes(dg.pred.predict_fasta_tsv_view(w, raw, "b.fa", 50, 256, True, 50, 50))
+    pieces = {}
+    for r in range(2):
+        with dg.pred.FastaTsvStream(w, raw, "b.fa", 50, 256, True, 50, 50, rank=r, world=2) as st:
+            for sl, od, nr, last, view in st:
+                pieces.setdefault((sl, od), []).append(bytes(view))
+    assert sorted(pieces) == [(0, 0), (1, 0), (2, 0)]
+    assert b"".join(b"".join(pieces[k]) for k in sorted(pieces)) == ref
+    bad = raw[:len(raw) // 2] + b"\n\n" + raw[len(raw) // 2:]
+    out = io.BytesIO()
+    with pytest.raises(IndexError):
+        dg.pred.predict_fasta_tsv_stream(w, bad, "b.fa", out, 50, 256, True, 50, 50)
+    first = ref[:ref.index(b"b.fa\tbig1\t")]
+    assert out.getvalue() == first          # record 0's rows were written before the error
