@@ -1141,7 +1141,10 @@ struct dgrp_fasta_stream {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_stage[2] = {}, ev_text[2] = {}, ev_slot[kSlots] = {};
   bool src_pinned = false;
-  std::thread compute, copier;
+  std::thread compute, copier, uploader;
+  int up_done = 0, dec_done = 0;    // slices (of `mine`) whose upload has been enqueued / that have been decoded
+  int up_rc = DGRP_OK;
+  std::string up_err;
   std::mutex mu;
   std::condition_variable cv;
   std::deque<StreamRecord> ready;   // compute -> copier
@@ -1149,7 +1152,7 @@ struct dgrp_fasta_stream {
   int text_busy[2] = {0, 0};        // device text buffer handed to the copier
   int slot_state[kSlots] = {};      // 0 free, 1 being filled / queued, 2 held by the caller
   int held = -1;
-  bool compute_done = false, copier_done = false, cancel = false;
+  bool compute_done = false, copier_done = false, cancel = false, cancel_upload = false;
   int rc = DGRP_OK;
   std::string err;
   // totals
@@ -1235,7 +1238,13 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
   const int64_t nbytes = s->cuts[k + 1] - s->cuts[k];
   STREAM_CUDA(cudaStreamWaitEvent(c->stream, s->ev_in[b], 0));
   int64_t n_seq = 0, n_hdr = 0;
-  DGRP_CHECK(run_fasta_decode(c, s->raw[b].as<uint8_t>(), nbytes, &n_seq, &n_hdr));
+  const int drc = run_fasta_decode(c, s->raw[b].as<uint8_t>(), nbytes, &n_seq, &n_hdr);
+  {
+    std::lock_guard<std::mutex> lk(s->mu);   // the raw bytes have been consumed (the decode synchronises)
+    s->dec_done += 1;
+  }
+  s->cv.notify_all();
+  DGRP_CHECK(drc);
   std::vector<int64_t> hpos(n_hdr), hseq(n_hdr + 1);
   if (n_hdr > 0) {
     const int64_t *t = c->pin_b.as<int64_t>();
@@ -1311,21 +1320,46 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
   return DGRP_OK;
 }
 
+// The upload runs ahead of the compute thread by one slice: the staging memcpy (page faults of a mapped file
+// included) overlaps the GPU work on the slice before.
+void stream_uploader_main(dgrp_fasta_stream *s) {
+  cudaSetDevice(s->c->device);
+  int stage_turn = 0, rc = DGRP_OK;
+  for (size_t i = 0; i < s->mine.size() && rc == DGRP_OK; ++i) {
+    {
+      std::unique_lock<std::mutex> lk(s->mu);   // raw[i & 1] is free once slice i - 2 has been decoded
+      s->cv.wait(lk, [&] { return (int)i < s->dec_done + 2 || s->cancel || s->cancel_upload; });
+      if (s->cancel || s->cancel_upload) break;
+    }
+    rc = stream_upload(s, s->mine[i], (int)(i & 1), &stage_turn);
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      if (rc != DGRP_OK) { s->up_rc = rc; s->up_err = dgrp_last_error(); }
+      s->up_done = (int)i + 1;
+    }
+    s->cv.notify_all();
+  }
+}
+
 void stream_compute_main(dgrp_fasta_stream *s) {
   cudaSetDevice(s->c->device);
   const int64_t launches0 = s->c->launches;
-  int rc = DGRP_OK, stage_turn = 0, text_turn = 0;
-  if (!s->mine.empty()) rc = stream_upload(s, s->mine[0], 0, &stage_turn);
+  int rc = DGRP_OK, text_turn = 0;
   for (size_t i = 0; i < s->mine.size() && rc == DGRP_OK; ++i) {
-    if (i + 1 < s->mine.size()) rc = stream_upload(s, s->mine[i + 1], (int)((i + 1) & 1), &stage_turn);
-    if (rc == DGRP_OK) rc = stream_slice(s, s->mine[i], (int)(i & 1), &text_turn);
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv.wait(lk, [&] { return s->up_done > (int)i || s->cancel; });
+      if (s->cancel) break;
+      if (s->up_rc != DGRP_OK) { rc = s->up_rc; set_error("%s", s->up_err.c_str()); break; }
+    }
+    rc = stream_slice(s, s->mine[i], (int)(i & 1), &text_turn);
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->cancel) break;
   }
   s->launches = s->c->launches - launches0;
   {
     std::lock_guard<std::mutex> lk(s->mu);
-    if (rc != DGRP_OK) { s->rc = rc; s->err = dgrp_last_error(); }
+    if (rc != DGRP_OK) { s->rc = rc; s->err = dgrp_last_error(); s->cancel_upload = true; }
     s->compute_done = true;
   }
   s->cv.notify_all();
@@ -1438,6 +1472,7 @@ int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int
     if (rc == DGRP_OK) rc = s->slot[i].reserve((size_t)kSlotBytes);
   }
   if (rc != DGRP_OK) { dgrp_fasta_stream_close(s); return rc; }
+  s->uploader = std::thread(stream_uploader_main, s);
   s->compute = std::thread(stream_compute_main, s);
   s->copier = std::thread(stream_copier_main, s);
   *out = s;
@@ -1497,6 +1532,7 @@ int dgrp_fasta_stream_close(dgrp_fasta_stream *s) {
     if (s->held >= 0) { s->slot_state[s->held] = 0; s->held = -1; }
   }
   s->cv.notify_all();
+  if (s->uploader.joinable()) s->uploader.join();
   if (s->compute.joinable()) s->compute.join();
   {
     std::lock_guard<std::mutex> lk(s->mu);

@@ -130,16 +130,64 @@ DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt) {
   s.run_st = -1; s.run_ord = -1; s.run_L0 = 0.0;
 }
 
-// What a chunk did to (max, bottom) after its last x-drop reset, in shift-invariant form.
-struct ChunkSummary {
+// What a chunk did to (max, bottom) after its last x-drop reset, in shift-invariant form: the values the
+// running sum L had at the points that matter (trajectory samples).
+struct Samples {
+  double outL;      // L at the chunk end
+  double runL0;     // L before the run in progress at the chunk end, if that run started inside the chunk
   double carryR;    // R of the run carried in from the previous chunk, if it ended in this chunk
   double minT;      // min t.L over runs that started AND ended in the chunk (latest on ties)
   double maxAfter;  // max R from that run on
   double maxIn;     // max R over runs that started and ended in the chunk
+};
+// Shift invariance under rounding.  While L is small every addition is exact and a chunk executed from
+// L0 + d is the execution from L0 shifted by d.  Once |L| is large (a record of 10^7..10^8 bases whose scores
+// drift upwards: no x-drop reset ever fires, L reaches 2^28) the sums round to the grid g = ulp(L) of L's
+// binade, and rn(x + d) = rn(x) + d still holds for every d that is an EVEN multiple of g -- but for an odd
+// multiple the ties (x exactly between two grid points: a float32 score whose last set bit is g/2, several per
+// cent of all scores) resolve the other way, once, after which the two trajectories are an even multiple
+// apart.  So the chunk's effect is a function of the PARITY of the start value on its grid: every chunk is
+// therefore executed on two trajectories, the main one from the given start state and a shadow one from
+// L + ulp(L) that follows the main one's decisions, and a prediction for start value L0 + m g uses the main
+// samples for even m and the shadow samples (shifted by (m - 1) g) for odd m.  Without this the predicted
+// start states are off by one ulp after every other chunk and the fixed point is only reached chunk by chunk.
+struct ChunkSummary {
+  Samples m, s;     // main / shadow trajectory
   int min_st;       // st of the minT run
   int flags;        // 1: a reset happened, 2: carried run ended here, 4: minT.. valid,
                     // 8: the run in progress at the chunk end started inside the chunk
 };
+
+// spacing of the doubles at |x|; 0 for values so small that every sum of scores is exact
+DGRP_HD double ulp_of(double x) {
+  union V { double d; unsigned long long u; } v;
+  v.d = x;
+  const int e = (int)((v.u >> 52) & 0x7ffu);
+  if (e <= 64 || e == 0x7ff) return 0.0;
+  v.u = (unsigned long long)(e - 52) << 52;
+  return v.d;
+}
+// is d an odd multiple of the grid spacing g (a power of two, so d / g is exact)?
+DGRP_HD bool odd_multiple(double d, double g) {
+  if (g == 0.0 || d == 0.0) return false;
+  const double m = d / g;
+  if (!(m > -9007199254740992.0 && m < 9007199254740992.0)) return false;
+  const double h = m * 0.5;
+  return m == (double)(long long)m && h != (double)(long long)h;
+}
+// the trajectory of `sum` (recorded from start value x_inL) that predicts the execution from yL, and the
+// shift to apply to its samples
+struct Pick {
+  const Samples *p;
+  double dd;
+};
+DGRP_HD Pick pick_trajectory(const ChunkSummary &sum, double x_inL, double yL) {
+  const double d = yL - x_inL, g = ulp_of(x_inL);
+  Pick r;
+  if (odd_multiple(d, g)) { r.p = &sum.s; r.dd = d - g; }
+  else { r.p = &sum.m; r.dd = d; }
+  return r;
+}
 
 // Reduced scan over elements [b, e) of S (e <= n) from state `s`.  `first_ord` is the ordinal of
 // the first run that STARTS in [b, e).  Writes the run records and the chunk summary.
@@ -147,7 +195,11 @@ template <typename ScoreT>
 DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
                         ScanState &s, const RunTable &rt, ChunkSummary &sum) {
   int next_ord = first_ord;
-  sum.carryR = 0.0; sum.minT = 0.0; sum.maxAfter = 0.0; sum.maxIn = 0.0; sum.min_st = -1; sum.flags = 0;
+  sum.m.outL = sum.m.runL0 = sum.m.carryR = sum.m.minT = sum.m.maxAfter = sum.m.maxIn = 0.0;
+  sum.s = sum.m;
+  sum.min_st = -1; sum.flags = 0;
+  double Lb = s.L + ulp_of(s.L);           // the shadow trajectory (see ChunkSummary)
+  double runb = 0.0;                       // its L before the run in progress, for a run that started in the chunk
   bool carried = (s.flags & 2) != 0;       // the run in progress came from before the chunk
   // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
   // a block are independent of the sequential state machine and overlap each other.
@@ -169,7 +221,7 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
       if (v > 0) {
         if (!(s.flags & 2)) {
           s.flags |= 2;
-          s.run_st = i; s.run_L0 = s.L;
+          s.run_st = i; s.run_L0 = s.L; runb = Lb;
           // a "run" that begins at a speculative chunk start in the middle of a true run has no
           // ordinal; it only shapes the (to be discarded) speculative state
           const bool true_start = !prev_pos;
@@ -177,17 +229,19 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
           carried = !true_start;
         }
         s.L += v;                                   // R = L + S[i]; R += S[k]  (mss.c:61-63)
+        Lb += v;
         if (i + 1 == n || !(blk[j + 1] > 0)) {
           const double tL = s.run_L0;
           const int st = s.run_st;
           finish_run(s, i + 1, rt);
           const double R = s.L;
           if (carried) {
-            sum.flags |= 2; sum.carryR = R;
+            sum.flags |= 2; sum.m.carryR = R; sum.s.carryR = Lb;
           } else {
-            if (!(sum.flags & 4) || !(sum.minT < tL)) { sum.minT = tL; sum.min_st = st; sum.maxAfter = R; }
-            else if (R > sum.maxAfter) sum.maxAfter = R;
-            if (!(sum.flags & 4) || R > sum.maxIn) sum.maxIn = R;
+            if (!(sum.flags & 4) || !(sum.m.minT < tL)) {
+              sum.m.minT = tL; sum.s.minT = runb; sum.min_st = st; sum.m.maxAfter = R; sum.s.maxAfter = Lb;
+            } else if (R > sum.m.maxAfter) { sum.m.maxAfter = R; sum.s.maxAfter = Lb; }
+            if (!(sum.flags & 4) || R > sum.m.maxIn) { sum.m.maxIn = R; sum.s.maxIn = Lb; }
             sum.flags |= 4;
           }
           carried = false;
@@ -197,27 +251,35 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
         if (xdrop > 0.0 && s.L + v + xdrop < s.maxv) {  // mss.c:89
           s.L = 0.0; s.maxv = kNegInf;              // mss.c:91 (the flush happens at the next run)
           s.botL = 0.0; s.bot_st = -1; s.flags |= 1;
+          Lb = 0.0;                                 // from here on the frame is absolute: both trajectories agree
           sum.flags = 1;                            // summary restarts after a reset
         }
         s.L += v;                                   // mss.c:93
+        Lb += v;
         prev_pos = false;
       }
     }
   }
   if ((s.flags & 2) && !carried) sum.flags |= 8;
+  sum.m.outL = s.L; sum.s.outL = Lb;
+  sum.m.runL0 = s.run_L0; sum.s.runL0 = runb;
 }
 
 // Predict the end state of a chunk for start state `y` from one known execution x_in -> x_out with
-// summary `sum`.  Exact when all additions involved are exact; otherwise only a guess that the
-// bitwise verification will reject.
+// summary `sum`.  Exact when the additions involved are exact or round the same way on the trajectory
+// picked by the parity of the shift (see ChunkSummary); otherwise only a guess that the bitwise
+// verification will reject.
 DGRP_HD ScanState apply_summary(const ChunkSummary &sum, const ScanState &x_in,
                                 const ScanState &x_out, const ScanState &y) {
   if (sum.flags & 1) return x_out;                  // after a reset the frame is absolute
   const double d = y.L - x_in.L;
+  const Pick pk = pick_trajectory(sum, x_in.L, y.L);
+  const Samples &t = *pk.p;
+  const double dd = pk.dd;
   ScanState o = x_out;
-  o.L = x_out.L + d;
+  o.L = t.outL + dd;
   if (x_out.flags & 2) {
-    if (sum.flags & 8) o.run_L0 = x_out.run_L0 + d;
+    if (sum.flags & 8) o.run_L0 = t.runL0 + dd;
     else if (y.flags & 2) { o.run_L0 = y.run_L0; o.run_st = y.run_st; o.run_ord = y.run_ord; }
     else o.run_L0 = x_out.run_L0 + d;
   }
@@ -227,14 +289,14 @@ DGRP_HD ScanState apply_summary(const ChunkSummary &sum, const ScanState &x_in,
   if (sum.flags & 2) {                              // the carried run ended here
     const double tL = (y.flags & 2) ? y.run_L0 : x_in.run_L0 + d;
     const int st = (y.flags & 2) ? y.run_st : x_in.run_st;
-    const double R = sum.carryR + d;
+    const double R = t.carryR + dd;
     if (empty || !(bot < tL)) { bot = tL; bst = st; mx = R; empty = false; }
     else if (R > mx) mx = R;
   }
   if (sum.flags & 4) {
-    const double mT = sum.minT + d;
-    if (empty || !(bot < mT)) { bot = mT; bst = sum.min_st; mx = sum.maxAfter + d; empty = false; }
-    else if (sum.maxIn + d > mx) mx = sum.maxIn + d;
+    const double mT = t.minT + dd;
+    if (empty || !(bot < mT)) { bot = mT; bst = sum.min_st; mx = t.maxAfter + dd; empty = false; }
+    else if (t.maxIn + dd > mx) mx = t.maxIn + dd;
   }
   o.botL = empty ? 0.0 : bot;
   o.bot_st = empty ? -1 : bst;
@@ -249,18 +311,21 @@ DGRP_HD ScanState apply_summary(const ChunkSummary &sum, const ScanState &x_in,
 // that started and ended inside either chunk, plus the run that crosses the boundary, fold into one
 // (latest minimum t.L, maximum R from there on, maximum R overall) triple -- the fold the state machine
 // itself applies run by run (finish_run: a run whose t.L is not above the bottom replaces the bottom).
-// Like apply_summary this is exact in exact arithmetic and only a prediction otherwise; every
-// predicted start state is verified bitwise by the caller.
+// Both trajectories are composed: A's main (shadow) end value picks, by the parity of its distance from
+// B's recorded start, which of B's trajectories continues it.  Like apply_summary this is a prediction;
+// every predicted start state is verified bitwise by the caller.
 struct Composite {
   ChunkSummary sum;
   ScanState x_in, x_out;
 };
 
-// append the summary (minT, min_st, maxAfter, maxIn) of a later run list to p's
-DGRP_HD void fold_runs(ChunkSummary &p, double minT, int min_st, double maxAfter, double maxIn) {
-  if (!(p.flags & 4) || !(p.minT < minT)) { p.minT = minT; p.min_st = min_st; p.maxAfter = maxAfter; }
-  else if (maxIn > p.maxAfter) p.maxAfter = maxIn;
-  if (!(p.flags & 4) || maxIn > p.maxIn) p.maxIn = maxIn;
+// append the summary (minT, min_st, maxAfter, maxIn) of a later run list to p's (decisions on the main values)
+DGRP_HD void fold_runs(ChunkSummary &p, double minT, double minTs, int min_st, double maxAfter, double maxAfters,
+                       double maxIn, double maxIns) {
+  if (!(p.flags & 4) || !(p.m.minT < minT)) {
+    p.m.minT = minT; p.s.minT = minTs; p.min_st = min_st; p.m.maxAfter = maxAfter; p.s.maxAfter = maxAfters;
+  } else if (maxIn > p.m.maxAfter) { p.m.maxAfter = maxIn; p.s.maxAfter = maxIns; }
+  if (!(p.flags & 4) || maxIn > p.m.maxIn) { p.m.maxIn = maxIn; p.s.maxIn = maxIns; }
   p.flags |= 4;
 }
 
@@ -268,30 +333,37 @@ DGRP_HD Composite compose(const Composite &A, const Composite &B) {
   Composite C;
   C.x_in = A.x_in;
   C.x_out = apply_summary(B.sum, B.x_in, B.x_out, A.x_out);
-  ChunkSummary c;
-  c.carryR = 0.0; c.minT = 0.0; c.maxAfter = 0.0; c.maxIn = 0.0; c.min_st = -1; c.flags = 0;
+  ChunkSummary c = A.sum;
   if ((A.sum.flags & 1) || (B.sum.flags & 1)) {   // a reset inside: the end state is absolute
     c.flags = 1;
+    c.m.outL = c.s.outL = C.x_out.L;
     C.sum = c;
     return C;
   }
-  const double dB = A.x_out.L - B.x_in.L;         // B's recorded frame -> the frame of A's execution
-  c = A.sum;
+  // B's recorded frame -> the frames of A's two trajectories
+  const Pick pm = pick_trajectory(B.sum, B.x_in.L, A.sum.m.outL);
+  const Pick ps = pick_trajectory(B.sum, B.x_in.L, A.sum.s.outL);
   c.flags = A.sum.flags & (2 | 4);
   const bool a_in_run = (A.x_out.flags & 2) != 0, a_run_inside = (A.sum.flags & 8) != 0;
   bool open_inside = false;                       // run in progress at the end started inside A+B
   if (a_in_run) {
     if (B.sum.flags & 2) {                        // the run crossing the boundary ends in B
-      const double R = B.sum.carryR + dB;
-      if (a_run_inside) fold_runs(c, A.x_out.run_L0, A.x_out.run_st, R, R);
-      else { c.flags |= 2; c.carryR = R; }        // it was carried into A as well
+      const double R = pm.p->carryR + pm.dd, Rs = ps.p->carryR + ps.dd;
+      if (a_run_inside) fold_runs(c, A.sum.m.runL0, A.sum.s.runL0, A.x_out.run_st, R, Rs, R, Rs);
+      else { c.flags |= 2; c.m.carryR = R; c.s.carryR = Rs; }   // it was carried into A as well
     } else if (a_run_inside) {
-      open_inside = true;                         // still running at the end of B
+      open_inside = true;                         // still running at the end of B: runL0 stays A's
     }
   }
-  if (B.sum.flags & 4) fold_runs(c, B.sum.minT + dB, B.sum.min_st, B.sum.maxAfter + dB, B.sum.maxIn + dB);
-  if (B.sum.flags & 8) open_inside = true;
+  if (B.sum.flags & 4)
+    fold_runs(c, pm.p->minT + pm.dd, ps.p->minT + ps.dd, B.sum.min_st, pm.p->maxAfter + pm.dd,
+              ps.p->maxAfter + ps.dd, pm.p->maxIn + pm.dd, ps.p->maxIn + ps.dd);
+  if (B.sum.flags & 8) {
+    open_inside = true;
+    c.m.runL0 = pm.p->runL0 + pm.dd; c.s.runL0 = ps.p->runL0 + ps.dd;
+  }
   if (open_inside) c.flags |= 8;
+  c.m.outL = pm.p->outL + pm.dd; c.s.outL = ps.p->outL + ps.dd;
   C.sum = c;
   return C;
 }

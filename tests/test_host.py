@@ -172,6 +172,25 @@ def test_chunked_mss_converges_in_few_rounds(host_mss, oracle):
         assert got_g == ref and rounds_g == rounds and mism == 0, (name, rounds_g, mism)
 
 
+def test_chunked_mss_in_the_rounding_regime(host_mss, oracle):
+    """Scores that drift upwards (a confident random-weight network: 70-90 % of the positions score positive, no
+    x-drop reset ever fires) push the running sum to 2^20..2^30, where the double additions round.  The shadow
+    trajectory (mss_core.cuh, ChunkSummary) keeps the predicted chunk start states exact up to binade crossings:
+    a few rounds, never the sequential completion -- and bit-identical segments."""
+    rng = np.random.default_rng(7)
+    n = 4_000_000
+    xdrop, min_sc = np.log(99) * 500, np.log(99) * 50
+    pos = rng.random(n) < 0.8
+    S = np.where(pos, rng.random(n) * 9.0 + 0.01, -(rng.random(n) * 2.0)).astype(np.float32)
+    ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+    assert len(ref) == 1 and ref[0][2] > 2 ** 23          # one maximal segment, sums far beyond exactness
+    for ch in (512, 1024):
+        got, rounds, _ = host_mss.grouped(S, min_sc, xdrop, ch, 32, 16)
+        assert got == ref and 0 < rounds <= 10, (ch, rounds)
+    got, rounds = host_mss(S, min_sc, xdrop, 1024, 16)    # the sequential chain (float64 route) as well
+    assert got == ref and 0 < rounds <= 10, rounds
+
+
 # ---- Options / weights / CLI ---------------------------------------------------------------------
 def test_options_defaults_aliases_and_toml_roundtrip():
     from deepgrp_b200.model import Options
