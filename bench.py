@@ -487,7 +487,8 @@ def genome_section(args, rank, world, weights, devnull, barrier):
                "records": int(sum(p[5] for p in per)), "file_bytes": int(raw.size),
                "tsv_bytes_total": sum(p[0] for p in per), "rows_total": sum(p[1] for p in per),
                "h2d_bytes_total": sum(p[3] for p in per), "rank_seconds": [p[2] for p in per],
-               "rank_forward_seconds": [p[4] for p in per], "generate_seconds": t_gen}
+               "rank_forward_seconds": [p[4] for p in per], "generate_seconds": t_gen,
+               "rank0_gpu_seconds": st["gpu_ms"] / 1e3, "rank0_waits_ms": st["waits_ms"]}
     del raw
     barrier()
     if rank == 0:

@@ -96,6 +96,7 @@ SIGNATURES = {
     "dgrp_fasta_stream_open": (_I, [_P, _P, _P, _L, ctypes.c_char_p, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P)]),
     "dgrp_fasta_stream_next": (_I, [_P, ctypes.POINTER(_P), _PL, _PL, _PL, _PL, _PI, _PI]),
     "dgrp_fasta_stream_stats": (_I, [_P, _PL, _PL, _PL, _PL, _PL, _PL, _PL, ctypes.POINTER(_D), ctypes.POINTER(_D)]),
+    "dgrp_fasta_stream_waits": (_I, [_P, ctypes.POINTER(_D)]),
     "dgrp_fasta_stream_close": (_I, [_P]),
     "dgrp_predict_codes_dev": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _PL]),
     "dgrp_predict_range_dev": (_I, [_P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _P, _P]),

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -256,6 +257,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
   else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
   else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
+  else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
   else if (!strcmp(key, "forward_slab_mb")) c->forward_slab_bytes = (int64_t)value << 20;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
@@ -271,6 +273,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
   else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
   else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
+  else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;
   else if (!strcmp(key, "forward_slab_mb")) *value = c->forward_slab_bytes >> 20;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
@@ -1158,9 +1161,20 @@ struct dgrp_fasta_stream {
   // totals
   int64_t rows = 0, records = 0, bases = 0, windows = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   double forward_ms = 0.0, gpu_ms = 0.0;
+  // where the threads waited, ms: [0] compute for the upload, [1] compute for a free text buffer, [2] copier for a
+  // finished record, [3] copier for a free slot, [4] copier in event waits (the copies), [5] uploader for a free raw
+  // buffer, [6] uploader in memcpy + enqueue, [7] compute thread total
+  double waits[8] = {};
 };
 
 namespace {
+
+struct WaitClock {   // adds the scope's wall time to a counter
+  double &acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit WaitClock(double &a) : acc(a) {}
+  ~WaitClock() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // Header lines start a slice: a '>' that is the first byte of a line.  (A '>' after leading whitespace is a
 // header too, __main__.py:34-35; it simply stays inside the preceding slice, which the GPU parser handles.)
@@ -1293,6 +1307,7 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
         DGRP_CHECK(run_tsv_measure(c, d_tri, cnt, (int)prefix.size(), &need));   // syncs: `prefix` may go
         tb = (*text_turn)++ & 1;
         {
+          WaitClock wc(s->waits[1]);
           std::unique_lock<std::mutex> lk(s->mu);   // the copier still drains the record before last
           s->cv.wait(lk, [&] { return s->text_busy[tb] == 0 || s->cancel; });
           if (s->cancel) return DGRP_OK;
@@ -1327,11 +1342,15 @@ void stream_uploader_main(dgrp_fasta_stream *s) {
   int stage_turn = 0, rc = DGRP_OK;
   for (size_t i = 0; i < s->mine.size() && rc == DGRP_OK; ++i) {
     {
+      WaitClock wc(s->waits[5]);
       std::unique_lock<std::mutex> lk(s->mu);   // raw[i & 1] is free once slice i - 2 has been decoded
       s->cv.wait(lk, [&] { return (int)i < s->dec_done + 2 || s->cancel || s->cancel_upload; });
       if (s->cancel || s->cancel_upload) break;
     }
-    rc = stream_upload(s, s->mine[i], (int)(i & 1), &stage_turn);
+    {
+      WaitClock wc(s->waits[6]);
+      rc = stream_upload(s, s->mine[i], (int)(i & 1), &stage_turn);
+    }
     {
       std::lock_guard<std::mutex> lk(s->mu);
       if (rc != DGRP_OK) { s->up_rc = rc; s->up_err = dgrp_last_error(); }
@@ -1345,8 +1364,10 @@ void stream_compute_main(dgrp_fasta_stream *s) {
   cudaSetDevice(s->c->device);
   const int64_t launches0 = s->c->launches;
   int rc = DGRP_OK, text_turn = 0;
+  WaitClock total(s->waits[7]);
   for (size_t i = 0; i < s->mine.size() && rc == DGRP_OK; ++i) {
     {
+      WaitClock wc(s->waits[0]);
       std::unique_lock<std::mutex> lk(s->mu);
       s->cv.wait(lk, [&] { return s->up_done > (int)i || s->cancel; });
       if (s->cancel) break;
@@ -1371,7 +1392,7 @@ void stream_copier_main(dgrp_fasta_stream *s) {
   auto publish_oldest = [&]() {
     StreamPiece p = inflight.front();
     inflight.pop_front();
-    if (p.slot >= 0) cudaEventSynchronize(s->ev_slot[p.slot]);
+    if (p.slot >= 0) { WaitClock wc(s->waits[4]); cudaEventSynchronize(s->ev_slot[p.slot]); }
     {
       std::lock_guard<std::mutex> lk(s->mu);
       s->pieces.push_back(p);
@@ -1381,6 +1402,7 @@ void stream_copier_main(dgrp_fasta_stream *s) {
   for (;;) {
     StreamRecord r;
     {
+      WaitClock wc(s->waits[2]);
       std::unique_lock<std::mutex> lk(s->mu);
       s->cv.wait(lk, [&] { return !s->ready.empty() || s->compute_done || s->cancel; });
       if (s->cancel) break;
@@ -1407,6 +1429,7 @@ void stream_copier_main(dgrp_fasta_stream *s) {
         }
         if (slot >= 0) break;
         if (!inflight.empty()) { publish_oldest(); continue; }   // the caller needs something to release
+        WaitClock wc(s->waits[3]);
         std::unique_lock<std::mutex> lk(s->mu);
         s->cv.wait(lk, [&] {
           if (s->cancel) return true;
@@ -1520,6 +1543,12 @@ int dgrp_fasta_stream_stats(dgrp_fasta_stream *s, int64_t *rows, int64_t *record
   if (d2h_bytes) *d2h_bytes = s->d2h_bytes;
   if (forward_ms) *forward_ms = s->forward_ms;
   if (gpu_ms) *gpu_ms = s->gpu_ms;
+  return DGRP_OK;
+}
+
+int dgrp_fasta_stream_waits(dgrp_fasta_stream *s, double *out8) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int i = 0; i < 8; ++i) out8[i] = s->waits[i];
   return DGRP_OK;
 }
 

@@ -125,11 +125,20 @@ __device__ __forceinline__ void lstm_cell4(const float *ai, const float *af, con
   h23 = make_float2(h[2], h[3]);
 }
 
-template <int UP, int RNN, bool PAIR>
+// OVL (two column blocks X, Y only): the MMAs of a round are issued block by block so that the tensor core works
+// while the gate warps do:   XX(t+1) [block X's columns from block X's units] runs during gates Y(t),
+// YX(t+1) and YY(t+1) during gates X(t+1); only XY(t+1) -- a quarter of the products -- is exposed.
+//   issuer, round t:  wait readyX -> XX | wait readyY -> XY, commit doneX; YX, commit freeX; YY, commit doneY
+//   gates,  step  t:  wait doneX -> gates X (new state pieces kept in registers) -> wait freeX (the MMAs that read
+//                     the old A columns of block X are done) -> write them, arrive readyX
+//                     wait doneY -> gates Y -> write, arrive readyY
+template <int UP, int RNN, bool PAIR, bool OVL>
 __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams p) {
   using K = WCfg<UP, RNN, PAIR>;
   using ST = __half;
   constexpr int G = K::G;
+  static_assert(!OVL || K::NBLK == 2, "the overlapped protocol is written for two column blocks");
+  constexpr int NBAR = OVL ? 2 : 1;     // ready / done barriers: one per column block when overlapped
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                                        // [2 pieces][B_BYTES]  this CTA's weight rows
   unsigned char *s_A = s_B + 2 * K::B_BYTES;                            // [2 pieces][A_BYTES]  this CTA's tile
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   float *s_scale = s_P + (RNN ? 0 : 10 * K::PSTRIDE);                   // [UP] attention scale
   float *s_score = s_scale + UP;                                        // [wpp][T]
   uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_score + (size_t)p.wpp * p.T);   // [fwd | rc][code_span]
-  __shared__ __align__(8) unsigned long long s_ready, s_done;
+  __shared__ __align__(8) unsigned long long s_ready[2], s_done[2], s_free;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,9 +184,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   }
   if (tid == 0) {
     // "ready": one arrival per gate warp of every CTA of the pair (lane 0, after the warp's fences);
-    // "done": one arrival, the MMA commit
-    mbar_init(smem_u32(&s_ready), TC_GATE_WARPS * K::NCTA);
-    mbar_init(smem_u32(&s_done), 1);
+    // "done" / "free": one arrival, an MMA commit
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_ready[i]), TC_GATE_WARPS * K::NCTA);
+      mbar_init(smem_u32(&s_done[i]), 1);
+    }
+    mbar_init(smem_u32(&s_free), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   const uint32_t tmem_base = s_tmem;
 
   const bool is_gate = warp < TC_GATE_WARPS;
-  const uint32_t bar_ready = smem_u32(&s_ready), bar_done = smem_u32(&s_done);
+  const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]), bar_free = smem_u32(&s_free);
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   // a unit of work = NCTA tiles (one per CTA of the pair); the pair owns a contiguous range of units
@@ -201,41 +213,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
     if (rank == 0) {
       // ===================== MMA issuer (leader CTA): T + 1 rounds per unit (round 0 = priming on h = 0) =====
       const uint32_t a0 = smem_u32(s_A), b0 = smem_u32(s_B);
+      // the products of column block nb with the state units of block kb (all of them when kb < 0):
+      // (A piece, B piece), smallest first: lo.hi, hi.lo, hi.hi; the one-hot K chunk (only in A's hi piece)
+      // belongs to unit block 0
+      auto issue = [&](int nb, int kb, uint32_t acc) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(K::cw(nb) >> 3) << 17) |
+                               ((uint32_t)((K::ROWS * K::NCTA) >> 4) << 24);   // D fp32, A/B fp16 K-major, N, M
+        const uint32_t d = tmem_base + (uint32_t)K::coff(nb);
+        const uint32_t brow = b0 + (uint32_t)((K::coff(nb) / K::NCTA) / 8) * K::SBO;   // this block's rows of B
+        const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+        const int kc0 = kb < 0 ? 0 : kb * (K::UB / 16), kc1 = kb < 0 ? UP / 16 : (kb + 1) * (K::UB / 16);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+          for (int kc = 0; kc < UP / 16 + 1; ++kc) {
+            const bool onehot = kc == UP / 16;
+            if (onehot ? !(pa[q] == 0 && kb <= 0) : (kc < kc0 || kc >= kc1)) continue;
+            const uint64_t ad = umma_desc(a0 + pa[q] * K::A_BYTES + kc * 256, 128, K::SBO);
+            const uint64_t bd = umma_desc(brow + pb[q] * K::B_BYTES + kc * 256, 128, K::SBO);
+            if (PAIR) umma_f16_pair(d, ad, bd, idesc, acc);
+            else umma_bf16(d, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+      };
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      auto wait_ready = [&](int b, uint32_t parity) {
+        if (PAIR) mbar_wait_cluster_backoff(bar_ready + 8 * b, parity);
+        else mbar_wait_backoff(bar_ready + 8 * b, parity);
+        tc_fence_after();
+      };
       uint32_t rnd = 0;
       for (int64_t unit = unit_lo; unit < unit_hi; ++unit) {
         for (int k = 0; k <= T; ++k, ++rnd) {
-          if (PAIR) mbar_wait_cluster_backoff(bar_ready, rnd & 1u);
-          else mbar_wait_backoff(bar_ready, rnd & 1u);
-          tc_fence_after();
-          if (lane == 0) {
-#pragma unroll
-            for (int b = 0; b < K::NBLK; ++b) {
-              // instruction descriptor: D fp32, A/B fp16, both K-major, N = the block's columns, M = 128 per CTA
-              const uint32_t idesc = (1u << 4) | ((uint32_t)(K::cw(b) >> 3) << 17) |
-                                     ((uint32_t)((K::ROWS * K::NCTA) >> 4) << 24);
-              const uint32_t d = tmem_base + (uint32_t)K::coff(b);
-              const uint32_t brow = b0 + (uint32_t)((K::coff(b) / K::NCTA) / 8) * K::SBO;   // this block's rows of B
-              // (A piece, B piece), smallest products first: lo.hi, hi.lo, hi.hi
-              const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-              uint32_t acc = 0;
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const int nkc = UP / 16 + (pa[q] == 0 ? 1 : 0);   // the one-hot K chunk only exists in A's hi piece
-#pragma unroll
-                for (int kc = 0; kc < UP / 16 + 1; ++kc) {
-                  if (kc >= nkc) break;
-                  const uint64_t ad = umma_desc(a0 + pa[q] * K::A_BYTES + kc * 256, 128, K::SBO);
-                  const uint64_t bd = umma_desc(brow + pb[q] * K::B_BYTES + kc * 256, 128, K::SBO);
-                  if (PAIR) umma_f16_pair(d, ad, bd, idesc, acc);
-                  else umma_bf16(d, ad, bd, idesc, acc);
-                  acc = 1;
-                }
-              }
+          if (OVL) {
+            wait_ready(0, rnd & 1u);
+            if (lane == 0) issue(0, 0, 0u);                                   // XX
+            __syncwarp();
+            wait_ready(1, rnd & 1u);
+            if (lane == 0) {
+              issue(0, 1, 1u); commit(bar_done);                              // XY: block X's columns complete
+              issue(1, 0, 0u); commit(bar_free);                              // YX: A's block-X columns are free again
+              issue(1, 1, 1u); commit(bar_done + 8);                          // YY: block Y's columns complete
             }
-            if (PAIR) umma_commit_pair(bar_done);
-            else umma_commit(bar_done);
+            __syncwarp();
+          } else {
+            wait_ready(0, rnd & 1u);
+            if (lane == 0) {
+#pragma unroll
+              for (int b = 0; b < K::NBLK; ++b) issue(b, -1, 0u);
+              commit(bar_done);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -257,9 +290,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   const size_t sum_thr = ((size_t)(wl / p.wpp) * T * (UP / 8) * p.wpp + (size_t)(wl % p.wpp)) * 8 + (dir ? 4 : 0);
   const int full_span = (K::WT - 1) * p.step + T;
   const int cbase = dir * p.code_span + (dir ? full_span - wl * p.step - T : wl * p.step);
-  // every gate warp's lane 0 arrives on the leader's "ready" barrier
+  // every gate warp's lane 0 arrives on the leader's "ready" barriers
   const uint32_t ready_remote = PAIR ? map_to_rank(bar_ready, 0u) : bar_ready;
-  uint32_t rnd = 0;   // rounds waited for on "done"
+  auto arrive_ready = [&](int b) {
+    tc_fence_before();
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_remote + 8 * b); else mbar_arrive(bar_ready + 8 * b); }
+  };
+  uint32_t rnd = 0;   // rounds waited for
 
   for (int64_t unit = unit_lo; unit < unit_hi; ++unit) {
     const int64_t tile = unit * K::NCTA + rank;
@@ -294,21 +333,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
         *reinterpret_cast<uint4 *>(s_A + K::A_BYTES + off) = make_uint4(0u, 0u, 0u, 0u);
       }
     if (uq == 0) *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase]);
-    tc_fence_before();
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_remote); else mbar_arrive(bar_ready); }
+    arrive_ready(0);
+    if (OVL) arrive_ready(1);
 
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const int trow = s_codes[cbase + t];   // input-table row of this step's base
-      mbar_wait(bar_done, rnd & 1u);
-      ++rnd;
-      tc_fence_after();
-      float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter)
-      tmem_ld4(t_lane + (uint32_t)(G * K::UB + 4 * uq), pj);
+      float pj[4];   // projection of h[t-1] (4 of the 16 extra columns per unit quarter; they sit in block 0)
 #pragma unroll
       for (int b = 0; b < K::NBLK; ++b) {
+        if (b < NBAR) {
+          mbar_wait(bar_done + 8 * b, rnd & 1u);
+          tc_fence_after();
+        }
+        if (b == 0) tmem_ld4(t_lane + (uint32_t)(G * K::UB + 4 * uq), pj);
+        uint32_t hi[K::CB][4], lo[K::CB][4];   // the block's new state as operand pieces
 #pragma unroll
         for (int cc = 0; cc < K::CB; ++cc) {
           const int ci = b * K::CB + cc;                       // this thread's chunk number
@@ -333,23 +372,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
                                     &st[ci * 8 + 4 * j4], us, hn2[2 * j4], hn2[2 * j4 + 1]);
             }
           }
-          // new state -> operand pieces in A (one 16-byte core-matrix row per piece)
-          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split2h(hn2[j], hi[j], lo[j]);
-          const uint32_t off = a_row + (uint32_t)((b * K::UB + ub) >> 3) * 128;
-          *reinterpret_cast<uint4 *>(s_A + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4 *>(s_A + K::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 4; ++j) split2h(hn2[j], hi[cc][j], lo[cc][j]);
         }
+        // new state -> operand pieces in A (one 16-byte core-matrix row per piece and chunk).  Overlapped: the MMAs
+        // that still read block X's old columns (YX of this round) must have completed first.
+        if (OVL && b == 0) mbar_wait(bar_free, rnd & 1u);
+#pragma unroll
+        for (int cc = 0; cc < K::CB; ++cc) {
+          const uint32_t off = a_row + (uint32_t)((b * K::UB + uq * K::UBT + cc * 8) >> 3) * 128;
+          *reinterpret_cast<uint4 *>(s_A + off) = make_uint4(hi[cc][0], hi[cc][1], hi[cc][2], hi[cc][3]);
+          *reinterpret_cast<uint4 *>(s_A + K::A_BYTES + off) = make_uint4(lo[cc][0], lo[cc][1], lo[cc][2], lo[cc][3]);
+        }
+        if (b == 0 && uq == 0 && t + 1 < T)   // the next step's base for the MMA's one-hot K columns
+          *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase + t + 1]);
+        // hand the block's new columns of A to the tensor core (the last step's MMA only feeds the projection);
+        // the scratch stores of this step come after the release
+        if (OVL || b == K::NBLK - 1) arrive_ready(OVL ? b : 0);
       }
-      if (uq == 0 && t + 1 < T)   // the next step's base for the MMA's one-hot K columns
-        *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase + t + 1]);
-      // hand the new A operand to the tensor core (the last step's MMA only feeds the projection);
-      // the scratch stores of this step come after the release
-      tc_fence_before();
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_remote); else mbar_arrive(bar_ready); }
+      ++rnd;
       {
         // avg[t-1].K = h_fwd.(K/2) + h_rc.(K/2), stored by the fwd lane
         float4 o;
@@ -386,10 +427,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
         }
       }
     }
-    // projection of the last state h[T-1] (round T)
+    // projection of the last state h[T-1] (round T; every barrier of the round is waited for, so that the
+    // parities stay in step)
     {
       mbar_wait(bar_done, rnd & 1u);
-      ++rnd;
       tc_fence_after();
       float pj[4];
       tmem_ld4(t_lane + (uint32_t)(G * K::UB + 4 * uq), pj);
@@ -400,6 +441,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
       o.z = (pj[2] + __shfl_xor_sync(0xffffffffu, pj[2], 1)) * us.x;
       o.w = (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1)) * us.x;
       if (dir == 0) *reinterpret_cast<float4 *>(proj0 + ((size_t)wl * T + (T - 1)) * 16 + 4 * uq) = o;
+      if (OVL) {
+        mbar_wait(bar_free, rnd & 1u);
+        mbar_wait(bar_done + 8, rnd & 1u);
+      }
+      ++rnd;
       tc_fence_before();
     }
     // ---- attention + FF + softmax + vote for the CTA's tile ---------------------------------------
@@ -429,8 +475,8 @@ static size_t tcw_smem_bytes(int T, int wpp, int code_span) {
          sizeof(float) * ((size_t)(RNN ? 0 : 10 * K::PSTRIDE) + UP + (size_t)wpp * T) + 2 * (size_t)code_span + 128;
 }
 
-template <int UP, int RNN, bool PAIR>
-static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+template <int UP, int RNN, bool PAIR, bool OVL>
+static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = WCfg<UP, RNN, PAIR>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
@@ -442,7 +488,7 @@ static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   const size_t smem = tcw_smem_bytes<UP, RNN, PAIR>(p.T, wpp, p.code_span);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
   p.wpp = wpp;
-  auto kern = rnn_tcw_kernel<UP, RNN, PAIR>;
+  auto kern = rnn_tcw_kernel<UP, RNN, PAIR, OVL>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_units = (n_tiles + K::NCTA - 1) / K::NCTA;
@@ -469,6 +515,14 @@ static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   DGRP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   c->launches++;
   return DGRP_OK;
+}
+
+template <int UP, int RNN, bool PAIR>
+static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
+  // two column blocks: the MMAs of one block overlap the gate work on the other ("forward_overlap", default on)
+  if (WCfg<UP, RNN, PAIR>::NBLK == 2 && c->forward_overlap)
+    return launch_tcw_o<UP, RNN, PAIR, WCfg<UP, RNN, PAIR>::NBLK == 2>(c, m, p);
+  return launch_tcw_o<UP, RNN, PAIR, false>(c, m, p);
 }
 
 // which = 1: single CTA, 2: CTA pair.  Returns DGRP_E_UNSUPPORTED when the shape has no wide form.

@@ -256,6 +256,10 @@ int dgrp_fasta_stream_next(dgrp_fasta_stream *stream, const uint8_t **tsv, int64
 int dgrp_fasta_stream_stats(dgrp_fasta_stream *stream, int64_t *rows, int64_t *records, int64_t *bases,
                             int64_t *windows, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes,
                             double *forward_ms, double *gpu_ms);
+/* diagnostics: milliseconds the pipeline's threads spent waiting -- [0] compute for the upload, [1] compute for a
+ * free device text buffer, [2] copier for a finished record, [3] copier for a free host slot, [4] copier for its
+ * copies, [5] uploader for a free device buffer, [6] uploader copying, [7] the compute thread in total */
+int dgrp_fasta_stream_waits(dgrp_fasta_stream *stream, double *out8);
 int dgrp_fasta_stream_close(dgrp_fasta_stream *stream);
 
 /* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),
