@@ -54,6 +54,20 @@ void PinBuf::release() {
   p = nullptr; cap = 0;
 }
 
+__global__ void fetch_small_kernel(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+int fetch_small(dgrp_ctx *c, void *pinned_dst, const void *d_src, size_t bytes) {
+  if (bytes == 0) return DGRP_OK;
+  void *mapped = nullptr;
+  DGRP_CUDA(cudaHostGetDevicePointer(&mapped, pinned_dst, 0));
+  fetch_small_kernel<<<1, 128, 0, c->stream>>>(static_cast<unsigned char *>(mapped),
+                                               static_cast<const unsigned char *>(d_src), (int)bytes);
+  c->launches++;
+  DGRP_CUDA(cudaGetLastError());
+  return DGRP_OK;
+}
+
 // s0 = ln(0.99/0.01) and the two thresholds of pymss.pyx:46-53
 static void mss_thresholds(int min_mss_len, int xdrop_len, double *min_sc, double *xdrop) {
   const double s0 = log(0.99 / (1.0 - 0.99));
@@ -159,7 +173,7 @@ static int core_encode(dgrp_ctx *c, const uint8_t *d_seq, int64_t n, int fold_ca
   int64_t *d_fl = c->small.as<int64_t>() + 16;
   DGRP_CHECK(launch_trim(c, d_seq, n, fold_case, d_fl));
   int64_t *h = c->pin_small.as<int64_t>() + 8;
-  DGRP_CUDA(cudaMemcpyAsync(h, d_fl, 16, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, d_fl, 16));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   *startpos = h[0];           // first non-'N' (n when there is none)
   *length = h[1] - h[0];      // (last non-'N' + 1) - startpos: -n for an all-'N' record
@@ -258,6 +272,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
   else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
   else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
+  else if (!strcmp(key, "forward_ub")) c->forward_ub = (int)value;
   else if (!strcmp(key, "forward_slab_mb")) c->forward_slab_bytes = (int64_t)value << 20;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
@@ -274,6 +289,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
   else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
   else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;
+  else if (!strcmp(key, "forward_ub")) *value = c->forward_ub;
   else if (!strcmp(key, "forward_slab_mb")) *value = c->forward_slab_bytes >> 20;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
@@ -588,10 +604,10 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
         memcpy(&Bh[(size_t)N * KP + off], &lo, 2);
       }
   }
-  std::vector<uint16_t> Bw_single, Bw_pair;
+  std::vector<uint16_t> Bw[2][2];
   int bw_shift = 0;
-  build_tcw_operands(rnn, U, UP, n_classes, att_scale != nullptr, Rp.data(), P.data(), b1.data(), ff_kernel,
-                     Bw_single, Bw_pair, &bw_shift);
+  build_tcw_operands(rnn, U, UP, n_classes, att_scale != nullptr, Rp.data(), P.data(), b1.data(), ff_kernel, Bw,
+                     &bw_shift);
   dgrp_model *m = new dgrp_model();
   m->device = c->device; m->rnn = rnn; m->T = vecsize; m->U = U; m->C = n_classes; m->UP = UP;
   m->attention = att_scale != nullptr;
@@ -614,10 +630,17 @@ int dgrp_model_create(dgrp_ctx *c, int rnn, int vecsize, int units, int n_classe
                                reinterpret_cast<const float *>(Bs.data()), Bs.size() / 2))) ||
       (!Bh.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bsplit16),
                                reinterpret_cast<const float *>(Bh.data()), Bh.size() / 2))) ||
-      (!Bw_single.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bw_single),
-                                      reinterpret_cast<const float *>(Bw_single.data()), Bw_single.size() / 2))) ||
-      (!Bw_pair.empty() && (rc = up(reinterpret_cast<float **>(&m->d_Bw_pair),
-                                    reinterpret_cast<const float *>(Bw_pair.data()), Bw_pair.size() / 2)))) {
+      (!Bh.empty() && false)) {
+    cudaStreamSynchronize(c->stream);
+    dgrp_model_destroy(m);
+    return rc;
+  }
+  for (int a = 0; a < 2 && rc == DGRP_OK; ++a)
+    for (int b = 0; b < 2 && rc == DGRP_OK; ++b)
+      if (!Bw[a][b].empty())
+        rc = up(reinterpret_cast<float **>(&m->d_Bw[a][b]), reinterpret_cast<const float *>(Bw[a][b].data()),
+                Bw[a][b].size() / 2);
+  if (rc != DGRP_OK) {
     cudaStreamSynchronize(c->stream);
     dgrp_model_destroy(m);
     return rc;
@@ -636,8 +659,9 @@ int dgrp_model_destroy(dgrp_model *m) {
     if (p) cudaFree(p);
   if (m->d_Bsplit) cudaFree(m->d_Bsplit);
   if (m->d_Bsplit16) cudaFree(m->d_Bsplit16);
-  if (m->d_Bw_single) cudaFree(m->d_Bw_single);
-  if (m->d_Bw_pair) cudaFree(m->d_Bw_pair);
+  for (auto &a : m->d_Bw)
+    for (uint16_t *q : a)
+      if (q) cudaFree(q);
   delete m;
   return DGRP_OK;
 }
@@ -1164,7 +1188,7 @@ struct dgrp_fasta_stream {
   // where the threads waited, ms: [0] compute for the upload, [1] compute for a free text buffer, [2] copier for a
   // finished record, [3] copier for a free slot, [4] copier in event waits (the copies), [5] uploader for a free raw
   // buffer, [6] uploader in memcpy + enqueue, [7] compute thread total
-  double waits[8] = {};
+  double waits[12] = {};   // [8] slice decode, [9] records (host wall), [10] TSV measure + write enqueue, [11] encode
 };
 
 namespace {
@@ -1252,7 +1276,11 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
   const int64_t nbytes = s->cuts[k + 1] - s->cuts[k];
   STREAM_CUDA(cudaStreamWaitEvent(c->stream, s->ev_in[b], 0));
   int64_t n_seq = 0, n_hdr = 0;
-  const int drc = run_fasta_decode(c, s->raw[b].as<uint8_t>(), nbytes, &n_seq, &n_hdr);
+  int drc;
+  {
+    WaitClock wc(s->waits[8]);
+    drc = run_fasta_decode(c, s->raw[b].as<uint8_t>(), nbytes, &n_seq, &n_hdr);
+  }
   {
     std::lock_guard<std::mutex> lk(s->mu);   // the raw bytes have been consumed (the decode synchronises)
     s->dec_done += 1;
@@ -1279,8 +1307,12 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
     const uint8_t *d_seq = c->io_b.as<uint8_t>() + hseq[i];
     const int64_t n = hseq[i + 1] - hseq[i];
     int64_t startpos = 0, length = 0;
+    WaitClock wrec(s->waits[9]);
     stamp(c, 0);
-    DGRP_CHECK(core_encode(c, d_seq, n, 1, &startpos, &length));
+    {
+      WaitClock wc(s->waits[11]);
+      DGRP_CHECK(core_encode(c, d_seq, n, 1, &startpos, &length));
+    }
     if (length < 0) {
       set_error("negative dimensions are not allowed (all-'N' record in slice %lld)", (long long)k);
       return DGRP_E_ALLN;
@@ -1298,6 +1330,7 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
       int64_t *d_tri = nullptr;
       DGRP_CHECK(run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt));
       if (cnt > 0) {
+        WaitClock wc(s->waits[10]);
         std::string prefix(s->filename);
         prefix.push_back('\t');
         prefix.append(reinterpret_cast<const char *>(fasta + hb), (size_t)(he - hb));
@@ -1546,9 +1579,9 @@ int dgrp_fasta_stream_stats(dgrp_fasta_stream *s, int64_t *rows, int64_t *record
   return DGRP_OK;
 }
 
-int dgrp_fasta_stream_waits(dgrp_fasta_stream *s, double *out8) {
+int dgrp_fasta_stream_waits(dgrp_fasta_stream *s, double *out12) {
   std::lock_guard<std::mutex> lk(s->mu);
-  for (int i = 0; i < 8; ++i) out8[i] = s->waits[i];
+  for (int i = 0; i < 12; ++i) out12[i] = s->waits[i];
   return DGRP_OK;
 }
 

@@ -77,7 +77,7 @@ struct dgrp_model {
   int b16_shift = 0;
   // wide tcgen05 form (forward_tcw.cu): fp16 hi|lo pieces of the blocked [R | K/2]^T (+ 16 one-hot K rows), for one
   // CTA per tile and for a CTA pair ([rank][piece][rows of the rank]); null where the shape has no such form
-  uint16_t *d_Bw_single = nullptr, *d_Bw_pair = nullptr;
+  uint16_t *d_Bw[2][2] = {};   // [0 one CTA | 1 CTA pair][0 default column blocks | 1 the GRU's 32-unit blocks]
   int bw_shift = 0;
   float *d_scale = nullptr;      // [U] or null
   float *d_ffk = nullptr;        // [F, C]
@@ -106,6 +106,7 @@ struct dgrp_ctx {
                            // (1) instead of 5 atomicMax per window-step (0); falls back to 0 above 40 GB
   int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
                            // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
+  int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 32 at 128 units, else 64)
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
                            // record run in slabs of at most this many bytes of [windows][T][C] probabilities
@@ -138,6 +139,12 @@ struct Use {  // RAII: make the context's device current
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
+
+// A few bytes (counts, flags, sizes) from the device into PINNED host memory, written by a one-block kernel
+// through the mapped address instead of a D2H memcpy: a copy would queue on the copy engine behind the multi-MB
+// pieces of TSV text that dgrp_fasta_stream moves on its own stream (measured: ~8 ms per FASTA slice decode
+// instead of 0.3).  Visible to the host after the stream has been synchronised.
+int fetch_small(dgrp_ctx *c, void *pinned_dst, const void *d_src, size_t bytes);
 
 // ---- kernel launchers (device pointers, enqueue on ctx->stream) ------------------------------
 // encode.cu
@@ -172,7 +179,7 @@ int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t 
                       float *d_probs);
 // forward_tcw.cu: host-side packing of the wide tcgen05 kernel's weight operand (empty where the shape has no form)
 void build_tcw_operands(int rnn, int U, int UP, int C, bool att, const float *Rp, const float *P, const float *b1,
-                        const float *ffk, std::vector<uint16_t> &single, std::vector<uint16_t> &pair, int *shift);
+                        const float *ffk, std::vector<uint16_t> (&out)[2][2], int *shift);
 // mss.cu
 int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
                      double xdrop, dgrp_seg_t **d_segs_out, int *n_seg);

@@ -220,9 +220,9 @@ int run_fasta_decode(dgrp_ctx *c, const uint8_t *d_raw, int64_t n, int64_t *n_se
   c->launches += 5;
   DGRP_CHECK(c->pin_small.reserve(256));
   unsigned long long *h = c->pin_small.as<unsigned long long>() + 12;   // bytes 96..
-  DGRP_CUDA(cudaMemcpyAsync(h, pb + 4 * a, 136, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, pb + 4 * a, 136));
   uint8_t *h_last = reinterpret_cast<uint8_t *>(c->pin_small.as<unsigned char>() + 240);
-  DGRP_CUDA(cudaMemcpyAsync(h_last, d_raw + (n - 1), 1, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h_last, d_raw + (n - 1), 1));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   const int64_t total_seq = (int64_t)h[0], total_hdr = (int64_t)h[1];
   const unsigned fin = *reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(h) + 64);
@@ -244,7 +244,8 @@ int run_fasta_decode(dgrp_ctx *c, const uint8_t *d_raw, int64_t n, int64_t *n_se
   }
   DGRP_CHECK(c->pin_b.reserve((size_t)(total_hdr + 1) * 16));
   if (total_hdr > 0) {
-    DGRP_CUDA(cudaMemcpyAsync(c->pin_b.p, hdr_pos, (size_t)(total_hdr + 1) * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (total_hdr < 256) DGRP_CHECK(fetch_small(c, c->pin_b.p, hdr_pos, (size_t)(total_hdr + 1) * 16));
+    else DGRP_CUDA(cudaMemcpyAsync(c->pin_b.p, hdr_pos, (size_t)(total_hdr + 1) * 16, cudaMemcpyDeviceToHost, c->stream));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
   }
   DGRP_CUDA(cudaGetLastError());

@@ -26,14 +26,15 @@
 
 namespace dgrp {
 
-template <int UP_, int RNN_, bool PAIR_>
+// UB_ = units per column block: G * UB + 16 <= 256 (GRU: 64 or 32, LSTM: 32)
+template <int UP_, int RNN_, bool PAIR_, int UB_ = (RNN_ ? 32 : 64)>
 struct WCfg {
   static constexpr int UP = UP_, RNN = RNN_;
   static constexpr bool PAIR = PAIR_;
   static constexpr int G = RNN ? 4 : 3;             // gates: GRU z, r, h; LSTM i, f, c, o
-  static constexpr int UBMAX = RNN ? 32 : 64;       // units per column block (G * UB + 16 <= 256)
-  static constexpr int UB = UP < UBMAX ? UP : UBMAX;
+  static constexpr int UB = UP < UB_ ? UP : UB_;
   static constexpr int NBLK = UP / UB;
+  static_assert(G * UB + 16 <= 256, "a column block is one MMA: at most 256 columns");
   static constexpr int NW0 = G * UB + 16, NW = G * UB;   // columns of block 0 (with the projection) / of the others
   static constexpr int N = G * UP + 16;
   static constexpr int KP = UP + 16, KC = KP / 8, SBO = KC * 128;
@@ -67,14 +68,19 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Remote arrive with the default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does
+// for the same hand-over in its 2-SM kernels: the data handed over is shared memory written by this thread and
+// already made visible to the async proxy by fence.proxy.async, and TMEM reads ordered by
+// tcgen05.fence::before_thread_sync.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, which
+// waits for every outstanding global scratch store of the warp: 13 % of the kernel's stall samples.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster_backoff(uint32_t bar, uint32_t parity) {
   uint32_t done;
   for (;;) {
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         " selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -125,20 +131,25 @@ __device__ __forceinline__ void lstm_cell4(const float *ai, const float *af, con
   h23 = make_float2(h[2], h[3]);
 }
 
-// OVL (two column blocks X, Y only): the MMAs of a round are issued block by block so that the tensor core works
-// while the gate warps do:   XX(t+1) [block X's columns from block X's units] runs during gates Y(t),
-// YX(t+1) and YY(t+1) during gates X(t+1); only XY(t+1) -- a quarter of the products -- is exposed.
-//   issuer, round t:  wait readyX -> XX | wait readyY -> XY, commit doneX; YX, commit freeX; YY, commit doneY
-//   gates,  step  t:  wait doneX -> gates X (new state pieces kept in registers) -> wait freeX (the MMAs that read
-//                     the old A columns of block X are done) -> write them, arrive readyX
-//                     wait doneY -> gates Y -> write, arrive readyY
-template <int UP, int RNN, bool PAIR, bool OVL>
+// OVL (two or four column blocks): the MMAs of a round are issued block by block, as soon as the state columns they
+// read have been written, so that the tensor core works while the gate warps do.  With blocks 0..n-1 (the gate warps
+// go through them in this order, all 16 warps on one block at a time) and P(i, j) = "columns of block i from the
+// state units of block j":
+//   issuer, round t+1:  wait ready[j](t) -> P(i, j) for i < j and P(j, i) for i <= j      (j = 0 .. n-2)
+//                       wait ready[n-1](t) -> P(i, n-1), commit done[i]                    (i = 0 .. n-2)
+//                                             P(n-1, i), commit free[i] (i < n-1), commit done[n-1]
+//   gates,  step  t+1:  wait done[j] -> gates of block j, the new state pieces kept in registers -> wait free[j] (the
+//                       MMAs that read block j's old columns of A are done) -> write them, arrive ready[j]
+// Only P(0, n-1) -- 1/n^2 of the products -- is exposed between two steps; a D block is overwritten (first product,
+// no accumulate) only after the gate warps have read it (ready[j] is arrived on after the TMEM loads of block j).
+template <int UP, int RNN, bool PAIR, int UB, bool OVL>
 __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams p) {
-  using K = WCfg<UP, RNN, PAIR>;
+  using K = WCfg<UP, RNN, PAIR, UB>;
   using ST = __half;
   constexpr int G = K::G;
-  static_assert(!OVL || K::NBLK == 2, "the overlapped protocol is written for two column blocks");
-  constexpr int NBAR = OVL ? 2 : 1;     // ready / done barriers: one per column block when overlapped
+  constexpr int NB = K::NBLK;
+  static_assert(!OVL || (NB >= 2 && NB <= 4), "the overlapped protocol needs 2..4 column blocks");
+  constexpr int NBAR = OVL ? NB : 1;     // ready / done barriers: one per column block when overlapped
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *s_B = smem_raw;                                        // [2 pieces][B_BYTES]  this CTA's weight rows
   unsigned char *s_A = s_B + 2 * K::B_BYTES;                            // [2 pieces][A_BYTES]  this CTA's tile
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   float *s_scale = s_P + (RNN ? 0 : 10 * K::PSTRIDE);                   // [UP] attention scale
   float *s_score = s_scale + UP;                                        // [wpp][T]
   uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_score + (size_t)p.wpp * p.T);   // [fwd | rc][code_span]
-  __shared__ __align__(8) unsigned long long s_ready[2], s_done[2], s_free;
+  __shared__ __align__(8) unsigned long long s_ready[4], s_done[4], s_free[4];
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,11 +196,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   if (tid == 0) {
     // "ready": one arrival per gate warp of every CTA of the pair (lane 0, after the warp's fences);
     // "done" / "free": one arrival, an MMA commit
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&s_ready[i]), TC_GATE_WARPS * K::NCTA);
       mbar_init(smem_u32(&s_done[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 1);
     }
-    mbar_init(smem_u32(&s_free), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   const uint32_t tmem_base = s_tmem;
 
   const bool is_gate = warp < TC_GATE_WARPS;
-  const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]), bar_free = smem_u32(&s_free);
+  const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]), bar_free = smem_u32(&s_free[0]);
   const int64_t n_windows = p.w_end - p.w_begin;
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   // a unit of work = NCTA tiles (one per CTA of the pair); the pair owns a contiguous range of units
@@ -250,16 +261,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
       for (int64_t unit = unit_lo; unit < unit_hi; ++unit) {
         for (int k = 0; k <= T; ++k, ++rnd) {
           if (OVL) {
-            wait_ready(0, rnd & 1u);
-            if (lane == 0) issue(0, 0, 0u);                                   // XX
-            __syncwarp();
-            wait_ready(1, rnd & 1u);
-            if (lane == 0) {
-              issue(0, 1, 1u); commit(bar_done);                              // XY: block X's columns complete
-              issue(1, 0, 0u); commit(bar_free);                              // YX: A's block-X columns are free again
-              issue(1, 1, 1u); commit(bar_done + 8);                          // YY: block Y's columns complete
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              wait_ready(j, rnd & 1u);
+              if (lane == 0) {
+                if (j < NB - 1) {
+#pragma unroll
+                  for (int i = 0; i < j; ++i) issue(i, j, 1u);
+#pragma unroll
+                  for (int i = 0; i <= j; ++i) issue(j, i, i > 0 ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < NB - 1; ++i) { issue(i, j, 1u); commit(bar_done + 8 * i); }
+#pragma unroll
+                  for (int i = 0; i < NB; ++i) {
+                    issue(j, i, i > 0 ? 1u : 0u);
+                    if (i < NB - 1) commit(bar_free + 8 * i);
+                  }
+                  commit(bar_done + 8 * j);
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           } else {
             wait_ready(0, rnd & 1u);
             if (lane == 0) {
@@ -334,7 +357,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
       }
     if (uq == 0) *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase]);
     arrive_ready(0);
-    if (OVL) arrive_ready(1);
+    if (OVL) {
+#pragma unroll
+      for (int b = 1; b < NB; ++b) arrive_ready(b);
+    }
 
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -377,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
         }
         // new state -> operand pieces in A (one 16-byte core-matrix row per piece and chunk).  Overlapped: the MMAs
         // that still read block X's old columns (YX of this round) must have completed first.
-        if (OVL && b == 0) mbar_wait(bar_free, rnd & 1u);
+        if (OVL && b < NB - 1) mbar_wait(bar_free + 8 * b, rnd & 1u);
 #pragma unroll
         for (int cc = 0; cc < K::CB; ++cc) {
           const uint32_t off = a_row + (uint32_t)((b * K::UB + uq * K::UBT + cc * 8) >> 3) * 128;
@@ -442,8 +468,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
       o.w = (pj[3] + __shfl_xor_sync(0xffffffffu, pj[3], 1)) * us.x;
       if (dir == 0) *reinterpret_cast<float4 *>(proj0 + ((size_t)wl * T + (T - 1)) * 16 + 4 * uq) = o;
       if (OVL) {
-        mbar_wait(bar_free, rnd & 1u);
-        mbar_wait(bar_done + 8, rnd & 1u);
+#pragma unroll
+        for (int b = 0; b < NB - 1; ++b) mbar_wait(bar_free + 8 * b, rnd & 1u);
+#pragma unroll
+        for (int b = 1; b < NB; ++b) mbar_wait(bar_done + 8 * b, rnd & 1u);
       }
       ++rnd;
       tc_fence_before();
@@ -468,27 +496,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
   }
 }
 
-template <int UP, int RNN, bool PAIR>
+template <int UP, int RNN, bool PAIR, int UB>
 static size_t tcw_smem_bytes(int T, int wpp, int code_span) {
-  using K = WCfg<UP, RNN, PAIR>;
+  using K = WCfg<UP, RNN, PAIR, UB>;
   return (size_t)2 * K::B_BYTES + 2 * K::A_BYTES +
          sizeof(float) * ((size_t)(RNN ? 0 : 10 * K::PSTRIDE) + UP + (size_t)wpp * T) + 2 * (size_t)code_span + 128;
 }
 
-template <int UP, int RNN, bool PAIR, bool OVL>
+template <int UP, int RNN, bool PAIR, int UB, bool OVL>
 static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
-  using K = WCfg<UP, RNN, PAIR>;
+  using K = WCfg<UP, RNN, PAIR, UB>;
   const int64_t n_windows = p.w_end - p.w_begin;
   if (n_windows <= 0) return DGRP_OK;
   const int64_t span = (int64_t)(K::WT - 1) * p.step + p.T;
   if (span > 16384) return DGRP_E_UNSUPPORTED;
   p.code_span = (int)((span + 15) & ~(int64_t)15);
   int wpp = K::WT;
-  while (wpp > 8 && tcw_smem_bytes<UP, RNN, PAIR>(p.T, wpp, p.code_span) > 227 * 1024) wpp >>= 1;
-  const size_t smem = tcw_smem_bytes<UP, RNN, PAIR>(p.T, wpp, p.code_span);
+  while (wpp > 8 && tcw_smem_bytes<UP, RNN, PAIR, UB>(p.T, wpp, p.code_span) > 227 * 1024) wpp >>= 1;
+  const size_t smem = tcw_smem_bytes<UP, RNN, PAIR, UB>(p.T, wpp, p.code_span);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
   p.wpp = wpp;
-  auto kern = rnn_tcw_kernel<UP, RNN, PAIR, OVL>;
+  auto kern = rnn_tcw_kernel<UP, RNN, PAIR, UB, OVL>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_units = (n_tiles + K::NCTA - 1) / K::NCTA;
@@ -517,27 +545,32 @@ static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   return DGRP_OK;
 }
 
-template <int UP, int RNN, bool PAIR>
+template <int UP, int RNN, bool PAIR, int UB>
 static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
-  // two column blocks: the MMAs of one block overlap the gate work on the other ("forward_overlap", default on)
-  if (WCfg<UP, RNN, PAIR>::NBLK == 2 && c->forward_overlap)
-    return launch_tcw_o<UP, RNN, PAIR, WCfg<UP, RNN, PAIR>::NBLK == 2>(c, m, p);
-  return launch_tcw_o<UP, RNN, PAIR, false>(c, m, p);
+  // several column blocks: the MMAs of one block overlap the gate work on another ("forward_overlap", default on)
+  constexpr bool CAN = WCfg<UP, RNN, PAIR, UB>::NBLK >= 2;
+  if (CAN && c->forward_overlap) return launch_tcw_o<UP, RNN, PAIR, UB, CAN>(c, m, p);
+  return launch_tcw_o<UP, RNN, PAIR, UB, false>(c, m, p);
 }
 
 // which = 1: single CTA, 2: CTA pair.  Returns DGRP_E_UNSUPPORTED when the shape has no wide form.
+// "forward_ub" (GRU): units per column block, 64 (two blocks at 128 units) or 32 (four blocks; 0 = default).
 int launch_forward_tcw(dgrp_ctx *c, dgrp_model *m, FwdParams &p, int which) {
   const bool pair = which == 2;
-  p.Bsplit = pair ? m->d_Bw_pair : m->d_Bw_single;
+  const bool fine = m->rnn == 0 && (c->forward_ub == 32 || (c->forward_ub == 0 && m->UP == 128));
+  p.Bsplit = m->d_Bw[pair ? 1 : 0][fine ? 1 : 0];
   if (!p.Bsplit) return DGRP_E_UNSUPPORTED;
   p.b_unscale = ldexpf(1.0f, -(8 + m->bw_shift));
   if (m->rnn == 0) {
-    if (m->UP == 32) return pair ? DGRP_E_UNSUPPORTED : launch_tcw_t<32, 0, false>(c, m, p);
-    if (m->UP == 64) return pair ? launch_tcw_t<64, 0, true>(c, m, p) : launch_tcw_t<64, 0, false>(c, m, p);
-    if (m->UP == 128) return pair ? launch_tcw_t<128, 0, true>(c, m, p) : DGRP_E_UNSUPPORTED;
+    if (m->UP == 32) return pair ? DGRP_E_UNSUPPORTED : launch_tcw_t<32, 0, false, 32>(c, m, p);
+    if (m->UP == 64) {
+      if (fine) return pair ? launch_tcw_t<64, 0, true, 32>(c, m, p) : launch_tcw_t<64, 0, false, 32>(c, m, p);
+      return pair ? launch_tcw_t<64, 0, true, 64>(c, m, p) : launch_tcw_t<64, 0, false, 64>(c, m, p);
+    }
+    if (m->UP == 128 && pair) return fine ? launch_tcw_t<128, 0, true, 32>(c, m, p) : launch_tcw_t<128, 0, true, 64>(c, m, p);
   } else {
-    if (m->UP == 32) return pair ? DGRP_E_UNSUPPORTED : launch_tcw_t<32, 1, false>(c, m, p);
-    if (m->UP == 64) return pair ? launch_tcw_t<64, 1, true>(c, m, p) : launch_tcw_t<64, 1, false>(c, m, p);
+    if (m->UP == 32) return pair ? DGRP_E_UNSUPPORTED : launch_tcw_t<32, 1, false, 32>(c, m, p);
+    if (m->UP == 64) return pair ? launch_tcw_t<64, 1, true, 32>(c, m, p) : launch_tcw_t<64, 1, false, 32>(c, m, p);
   }
   return DGRP_E_UNSUPPORTED;
 }
@@ -547,10 +580,10 @@ int launch_forward_tcw(dgrp_ctx *c, dgrp_model *m, FwdParams &p, int which) {
 // end of block 0) against K row k (units, then 16 rows for the one-hot input columns).  Gate columns are
 // pre-scaled (sigmoid gates by -log2 e, tanh gates by 2 log2 e), projection columns are the halved FF kernel.
 // Rp [UP][G][UP], P [5][G][UP] (kernel + input bias), b1 [G][UP] (GRU recurrent bias; zero for LSTM).
-template <int UP, int RNN>
+template <int UP, int RNN, int UB>
 static void tcw_fill(int U, int C, bool att, const float *Rp, const float *P, const float *b1, const float *ffk,
                      std::vector<float> &dense) {
-  using K = WCfg<UP, RNN, false>;
+  using K = WCfg<UP, RNN, false, UB>;
   constexpr int G = K::G;
   dense.assign((size_t)K::N * K::KP, 0.f);
   for (int b = 0; b < K::NBLK; ++b)
@@ -579,9 +612,9 @@ static void tcw_fill(int U, int C, bool att, const float *Rp, const float *P, co
     }
 }
 
-template <int UP, int RNN, bool PAIR>
+template <int UP, int RNN, bool PAIR, int UB>
 static void tcw_pack(const std::vector<float> &dense, int shift, std::vector<uint16_t> &out) {
-  using K = WCfg<UP, RNN, PAIR>;
+  using K = WCfg<UP, RNN, PAIR, UB>;
   // [rank][piece][B_ROWS x KP] in the UMMA K-major core-matrix layout; CTA `rank` holds, for every column
   // block, rows [rank * cw/NCTA, (rank + 1) * cw/NCTA) of the block at local rows coff/NCTA ...
   out.assign((size_t)K::NCTA * 2 * K::B_ROWS * K::KP, 0);
@@ -603,12 +636,12 @@ static void tcw_pack(const std::vector<float> &dense, int shift, std::vector<uin
     }
 }
 
-template <int UP, int RNN>
+template <int UP, int RNN, int UB>
 static void tcw_build_t(int U, int C, bool att, const float *Rp, const float *P, const float *b1, const float *ffk,
                         bool want_single, bool want_pair, std::vector<uint16_t> &single, std::vector<uint16_t> &pair,
                         int *shift) {
   std::vector<float> dense;
-  tcw_fill<UP, RNN>(U, C, att, Rp, P, b1, ffk, dense);
+  tcw_fill<UP, RNN, UB>(U, C, att, Rp, P, b1, ffk, dense);
   float bmax = 0.f;
   for (float v : dense) bmax = std::fmax(bmax, std::fabs(v));
   int s = 0;
@@ -617,24 +650,30 @@ static void tcw_build_t(int U, int C, bool att, const float *Rp, const float *P,
     std::frexp(bmax, &e);   // the largest entry lands just below 2^14: the low pieces stay normal numbers
     s = std::min(24, std::max(-24, 14 - e));
   }
-  *shift = s;
-  if (want_single) tcw_pack<UP, RNN, false>(dense, s, single);
-  if (want_pair) tcw_pack<UP, RNN, true>(dense, s, pair);
+  *shift = s;   // the same for every block layout of a model (the entries are the same numbers)
+  if (want_single) tcw_pack<UP, RNN, false, UB>(dense, s, single);
+  if (want_pair) tcw_pack<UP, RNN, true, UB>(dense, s, pair);
 }
 
-// Builds the operands for the shapes launch_forward_tcw serves (empty vectors otherwise).
+// Builds the operands for the shapes launch_forward_tcw serves (empty vectors otherwise): out[pair][fine], fine =
+// the GRU's 32-unit column blocks.
 void build_tcw_operands(int rnn, int U, int UP, int C, bool att, const float *Rp, const float *P, const float *b1,
-                        const float *ffk, std::vector<uint16_t> &single, std::vector<uint16_t> &pair, int *shift) {
-  single.clear();
-  pair.clear();
+                        const float *ffk, std::vector<uint16_t> (&out)[2][2], int *shift) {
+  for (auto &a : out)
+    for (auto &v : a) v.clear();
   *shift = 0;
   if (rnn == 0) {
-    if (UP == 32) tcw_build_t<32, 0>(U, C, att, Rp, P, b1, ffk, true, false, single, pair, shift);
-    else if (UP == 64) tcw_build_t<64, 0>(U, C, att, Rp, P, b1, ffk, true, true, single, pair, shift);
-    else if (UP == 128) tcw_build_t<128, 0>(U, C, att, Rp, P, b1, ffk, false, true, single, pair, shift);
+    if (UP == 32) tcw_build_t<32, 0, 32>(U, C, att, Rp, P, b1, ffk, true, false, out[0][0], out[1][0], shift);
+    else if (UP == 64) {
+      tcw_build_t<64, 0, 64>(U, C, att, Rp, P, b1, ffk, true, true, out[0][0], out[1][0], shift);
+      tcw_build_t<64, 0, 32>(U, C, att, Rp, P, b1, ffk, true, true, out[0][1], out[1][1], shift);
+    } else if (UP == 128) {
+      tcw_build_t<128, 0, 64>(U, C, att, Rp, P, b1, ffk, false, true, out[0][0], out[1][0], shift);
+      tcw_build_t<128, 0, 32>(U, C, att, Rp, P, b1, ffk, false, true, out[0][1], out[1][1], shift);
+    }
   } else {
-    if (UP == 32) tcw_build_t<32, 1>(U, C, att, Rp, P, b1, ffk, true, false, single, pair, shift);
-    else if (UP == 64) tcw_build_t<64, 1>(U, C, att, Rp, P, b1, ffk, true, true, single, pair, shift);
+    if (UP == 32) tcw_build_t<32, 1, 32>(U, C, att, Rp, P, b1, ffk, true, false, out[0][0], out[1][0], shift);
+    else if (UP == 64) tcw_build_t<64, 1, 32>(U, C, att, Rp, P, b1, ffk, true, true, out[0][0], out[1][0], shift);
   }
 }
 

@@ -63,7 +63,7 @@ static int compact(dgrp_ctx *c, int64_t n, Pred pred, Emit emit, int64_t *count)
   cp_scan_kernel<<<1, 1024, 0, c->stream>>>(tiles, ntiles, total);
   c->launches += 2;
   unsigned long long *h = c->pin_small.as<unsigned long long>();
-  DGRP_CUDA(cudaMemcpyAsync(h, total, 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, total, 8));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   *count = (int64_t)h[0];
   if (*count > 0) {
@@ -327,7 +327,7 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   cp_scan_kernel<<<1, 1024, 0, c->stream>>>(base, NC, d_total);
   c->launches++;
   unsigned long long *h = c->pin_small.as<unsigned long long>();
-  DGRP_CUDA(cudaMemcpyAsync(h, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, d_total, 8));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   const int NR = (int)h[0];
   if (NR == 0) return DGRP_OK;   // no positive score anywhere: no segments
@@ -410,7 +410,7 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
       mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);
       c->launches++;
     }
-    DGRP_CUDA(cudaMemcpyAsync(h_dirty, sb.n_dirty, 4, cudaMemcpyDeviceToHost, c->stream));
+    DGRP_CHECK(fetch_small(c, h_dirty, sb.n_dirty, 4));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
     if (*h_dirty == 0) { converged = true; break; }
     if (rounds >= max_rounds) break;
@@ -422,7 +422,7 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
     DGRP_CUDA(cudaMemsetAsync(sb.n_dirty, 0, 4, c->stream));
     mss_verify_kernel<<<blocks, threads, 0, c->stream>>>(NC, sb);
     c->launches++;
-    DGRP_CUDA(cudaMemcpyAsync(h_dirty, sb.n_dirty, 4, cudaMemcpyDeviceToHost, c->stream));
+    DGRP_CHECK(fetch_small(c, h_dirty, sb.n_dirty, 4));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
     if (*h_dirty == 0) { converged = true; break; }
   }

@@ -144,9 +144,9 @@ static int run_segments_t(dgrp_ctx *c, const L *d_lab, int64_t n, int64_t offset
   c->launches += 2;
   // host needs the count (and the last label for the reference's trailing zero segment)
   unsigned long long *h = c->pin_small.as<unsigned long long>();
-  DGRP_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, totals, 16));
   L *h_last = reinterpret_cast<L *>(h + 2);
-  DGRP_CUDA(cudaMemcpyAsync(h_last, d_lab + (n - 1), sizeof(L), cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h_last, d_lab + (n - 1), sizeof(L)));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   const int64_t nrun = (int64_t)h[0];
   const bool tail_zero = keep_zero && (*h_last == 0);

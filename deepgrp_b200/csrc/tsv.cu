@@ -143,7 +143,7 @@ int run_tsv_measure(dgrp_ctx *c, const int64_t *d_tri, int64_t n, int prefix_len
   tsv_scan_kernel<<<1, 1024, 0, c->stream>>>(tile, ntiles, total);
   c->launches += 2;
   unsigned long long *h = c->pin_small.as<unsigned long long>();
-  DGRP_CUDA(cudaMemcpyAsync(h, total, 8, cudaMemcpyDeviceToHost, c->stream));
+  DGRP_CHECK(fetch_small(c, h, total, 8));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
   *need = (int64_t)h[0];
   return DGRP_OK;

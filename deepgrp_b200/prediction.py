@@ -338,11 +338,12 @@ class FastaTsvStream:
         names = ("rows", "records", "bases", "windows", "launches", "h2d_bytes", "d2h_bytes")
         out = {k: int(x.value) for k, x in zip(names, v)}
         out["forward_ms"], out["gpu_ms"] = float(f.value), float(g.value)
-        w = (ctypes.c_double * 8)()
+        w = (ctypes.c_double * 12)()
         _lib.check(_lib.lib().dgrp_fasta_stream_waits(self._handle, w))
         out["waits_ms"] = dict(zip(("compute_for_upload", "compute_for_text_buffer", "copier_for_record",
                                     "copier_for_slot", "copier_copies", "uploader_for_buffer", "uploader_copying",
-                                    "compute_total"), (float(x) for x in w)))
+                                    "compute_total", "decode", "records_host", "tsv", "encode"),
+                                   (float(x) for x in w)))
         return out
 
     def close(self) -> None:

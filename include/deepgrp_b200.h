@@ -258,8 +258,9 @@ int dgrp_fasta_stream_stats(dgrp_fasta_stream *stream, int64_t *rows, int64_t *r
                             double *forward_ms, double *gpu_ms);
 /* diagnostics: milliseconds the pipeline's threads spent waiting -- [0] compute for the upload, [1] compute for a
  * free device text buffer, [2] copier for a finished record, [3] copier for a free host slot, [4] copier for its
- * copies, [5] uploader for a free device buffer, [6] uploader copying, [7] the compute thread in total */
-int dgrp_fasta_stream_waits(dgrp_fasta_stream *stream, double *out8);
+ * copies, [5] uploader for a free device buffer, [6] uploader copying, [7] the compute thread in total, [8] slice
+ * decodes, [9] records (host wall clock), [10] TSV measure + write, [11] trim + encode */
+int dgrp_fasta_stream_waits(dgrp_fasta_stream *stream, double *out12);
 int dgrp_fasta_stream_close(dgrp_fasta_stream *stream);
 
 /* Device-resident step used by bench.py's `value` leg: codes already in HBM (d_codes, length L),

@@ -193,6 +193,40 @@ def test_wide_kernel_variants_match_the_two_tile_kernel(dg, oracle, wide, T, U, 
     assert (got.argmax(axis=1) == exp.argmax(axis=1)).mean() >= 0.9999
 
 
+@pytest.mark.parametrize("T,U,wide", [(200, 128, 0), (120, 100, 0), (150, 60, 1), (150, 60, 2)])
+def test_wide_kernel_block_schedules_agree(dg, oracle, T, U, wide):
+    """The wide kernel's column-block layouts (forward_ub 64 / 32: two / four blocks at 128 units) and issue
+    schedules (forward_overlap 1: MMAs block by block under the gate work; 0: one round of MMAs between two
+    steps) compute the same products in different orders: results agree to accumulation-order noise and
+    with the oracle."""
+    w = dg.model.random_weights(T, U, attention=True, seed=31).scaled(3.0)
+    text = random_dna(9_000 + 20 * T, T + U)
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    outs = {}
+    try:
+        dg.ctx.set_int("forward_wide", wide)
+        for ub in (64, 32):
+            for ov in (1, 0):
+                dg.ctx.set_int("forward_ub", ub)
+                dg.ctx.set_int("forward_overlap", ov)
+                outs[(ub, ov)] = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+                assert dg.ctx.get_int("forward_used_tc") == (3 if U > 64 else 1 + wide)
+    finally:
+        dg.ctx.set_int("forward_wide", 0)
+        dg.ctx.set_int("forward_ub", 0)
+        dg.ctx.set_int("forward_overlap", 1)
+    ref = outs[(64, 0)]
+    for key, got in outs.items():
+        assert np.abs(got - ref).max() < 2e-6, key
+    wd = w.as_dict()
+    exp = oracle.predict(lambda b: oracle.model_forward(b, wd, engine="torch"),
+                         oracle.fetch_validation_batch(fwd, 50, 256, T), (fwd.shape[1], 5), 50)
+    for key, got in outs.items():
+        assert np.abs(got - exp).max() < 2e-5, key
+        assert (got.argmax(axis=1) == exp.argmax(axis=1)).mean() >= 0.9999, key
+
+
 def test_window_slabs_compose(dg):
     """The window-probability buffer is bounded (forward_slab_mb): a record run in many small slabs gives the
     bit-identical prediction, including the displaced last batch (prediction.py:105)."""
