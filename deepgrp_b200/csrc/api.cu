@@ -1205,16 +1205,32 @@ struct WaitClock {   // adds the scope's wall time to a counter
 void stream_index(dgrp_fasta_stream *s) {
   const uint8_t *f = s->fasta;
   const int64_t n = s->nbytes;
+  // candidate header positions: '>' right after a line terminator; found by memchr, in parallel for large inputs
+  // (a 3 GB genome is 0.15 s of single-threaded scanning per rank otherwise)
+  const int nt = n > ((int64_t)64 << 20) ? 8 : (n > ((int64_t)8 << 20) ? 4 : 1);
+  std::vector<std::vector<int64_t>> found(nt);
+  auto scan = [&](int t) {
+    int64_t p = std::max<int64_t>(1, n * t / nt);
+    const int64_t end = n * (t + 1) / nt;
+    while (p < end) {
+      const void *q = memchr(f + p, '>', (size_t)(end - p));
+      if (!q) break;
+      p = (const uint8_t *)q - f;
+      if (f[p - 1] == '\n' || f[p - 1] == '\r') found[t].push_back(p);
+      ++p;
+    }
+  };
+  if (nt == 1) scan(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(scan, t);
+    for (auto &x : th) x.join();
+  }
   s->cuts.clear();
   s->cuts.push_back(0);
-  int64_t p = 1;
-  while (p < n) {
-    const void *q = memchr(f + p, '>', (size_t)(n - p));
-    if (!q) break;
-    p = (const uint8_t *)q - f;
-    if ((f[p - 1] == '\n' || f[p - 1] == '\r') && p - s->cuts.back() >= kMinSlice) s->cuts.push_back(p);
-    ++p;
-  }
+  for (int t = 0; t < nt; ++t)
+    for (int64_t p : found[t])
+      if (p - s->cuts.back() >= kMinSlice) s->cuts.push_back(p);
   s->cuts.push_back(n);
   // largest-first assignment of slices to ranks (every rank derives the same table)
   const int64_t ns = (int64_t)s->cuts.size() - 1;

@@ -106,7 +106,7 @@ struct dgrp_ctx {
                            // (1) instead of 5 atomicMax per window-step (0); falls back to 0 above 40 GB
   int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
                            // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
-  int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 32 at 128 units, else 64)
+  int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 64)
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
                            // record run in slabs of at most this many bytes of [windows][T][C] probabilities

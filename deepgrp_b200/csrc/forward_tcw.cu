@@ -554,10 +554,10 @@ static int launch_tcw_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
 }
 
 // which = 1: single CTA, 2: CTA pair.  Returns DGRP_E_UNSUPPORTED when the shape has no wide form.
-// "forward_ub" (GRU): units per column block, 64 (two blocks at 128 units) or 32 (four blocks; 0 = default).
+// "forward_ub" (GRU): units per column block, 64 (two blocks at 128 units; the default) or 32 (four blocks).
 int launch_forward_tcw(dgrp_ctx *c, dgrp_model *m, FwdParams &p, int which) {
   const bool pair = which == 2;
-  const bool fine = m->rnn == 0 && (c->forward_ub == 32 || (c->forward_ub == 0 && m->UP == 128));
+  const bool fine = m->rnn == 0 && c->forward_ub == 32;   // measured at 128 units: 64-unit blocks 147 Mbp/s, 32-unit 144
   p.Bsplit = m->d_Bw[pair ? 1 : 0][fine ? 1 : 0];
   if (!p.Bsplit) return DGRP_E_UNSUPPORTED;
   p.b_unscale = ldexpf(1.0f, -(8 + m->bw_shift));

@@ -7,9 +7,9 @@ memory -- with the contigs sharded over the ranks (largest first, no collective 
     python -m torch.distributed.run --nproc-per-node 8 ... tools/genome_bench.py --scale 0.25
 
 --scale 1.0 is the 3.1 Gbp genome.  With random-init weights almost every base lands in a TSV row
-(~25 bytes of text per base), and the one-shot C-ABI call keeps a rank's whole TSV in pinned host
-memory, so the full scale needs ~10 GB of pinned memory per rank at 8 ranks; 0.25 is the default.
-Rank 0 generates the file into /dev/shm, every rank maps it."""
+(~25 bytes of text per base); the text streams through 4 x 64 MiB of pinned host memory per rank
+(dgrp_fasta_stream_*).  Rank 0 generates the file into /dev/shm, every rank maps it and uploads only its own
+contigs.  `bench.py` runs the same measurement as its "genome" section (write_fasta is imported from here)."""
 import argparse
 import json
 import os
@@ -107,15 +107,12 @@ def main():
     raw = np.load(args.path, mmap_mode="r")
     ctx = _lib.context(local_rank)
     weights = model.random_weights(342, 60, attention=True, seed=0)
-    ctx.set_int("shard_rank", rank)
-    ctx.set_int("shard_world", world)
     devnull = open(os.devnull, "wb")
 
     def step():
-        view, n_rows, n_rec = prediction._fasta_tsv_call(weights, raw, "genome.fa", 50, 256, True, 50, 50,
-                                                         "reference")
-        devnull.write(view)
-        return len(view), n_rows, n_rec
+        st = prediction.predict_fasta_tsv_stream(weights, raw, "genome.fa", devnull, 50, 256, True, 50, 50,
+                                                 rank=rank, world=world)
+        return st["d2h_bytes"], st["rows"], st["records"]
 
     def barrier():
         if world > 1:
