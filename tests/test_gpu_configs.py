@@ -4,6 +4,8 @@ config 1 (tests/test_model.json model T=150, U=32, 1 Mbp) is checked in full aga
 the larger configurations are checked through size-independent properties (sharded == whole,
 lower-case invariance, MSS only fills gaps, segments sorted/disjoint/consistent with labels, TSV row
 count, idempotence of the label -> segments -> labels round trip)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -434,3 +436,63 @@ def test_fasta_stream_slices_and_errors(dg, tmp_path):
         dg.pred.predict_fasta_tsv_stream(w, bad, "b.fa", out, 50, 256, True, 50, 50)
     first = ref[:ref.index(b"b.fa\tbig1\t")]
     assert out.getvalue() == first          # record 0's rows were written before the error
+
+
+@pytest.mark.parametrize("scale", (1.0, 4.0))
+def test_config2_shape_vs_oracle_1mbp(dg, oracle, scale):
+    """defaults.toml architecture (T = 342, U = 60, attention) on a 1 Mbp record against the oracle (torch engine,
+    float32), with the random-init weight set and with the x4 (confident-output) set: probabilities within 1e-3
+    (north_star; measured ~1e-6), labels >= 99.99 % identical, before and after MSS."""
+    T, U, L = 342, 60, 1_000_000
+    w = dg.model.random_weights(T, U, attention=True, seed=0)
+    if scale != 1.0:
+        w = w.scaled(scale)
+    text = synth(L, 2).decode()
+    st, fwd = dg.seq.one_hot_encode_dna_sequence(text)
+    ds = dg.pred.fetch_validation_batch(fwd, 50, 256, T)
+    got = dg.pred.predict(w, ds, (L, 5), 50)
+    assert dg.ctx.get_int("forward_used_tc") == 1
+    wd = w.as_dict()
+    exp = oracle.predict(lambda b: oracle.model_forward(b, wd, engine="torch"),
+                         oracle.fetch_validation_batch(fwd, 50, 256, T), (L, 5), 50)
+    dp = float(np.abs(got - exp).max())
+    agree = float((got.argmax(axis=1) == exp.argmax(axis=1)).mean())
+    print("config-2 shape, weights x%g: max |dp| %.3g, argmax agreement %.6f" % (scale, dp, agree))
+    assert dp < (1e-5 if scale == 1.0 else 1e-4)
+    assert agree >= 0.9999
+    lab_g = dg.pred.apply_mss(got, dg.model.Options(min_mss_len=50, xdrop_len=50)).argmax(axis=1)
+    lab_o = oracle.apply_mss(exp, 50, 50).argmax(axis=1)
+    assert (lab_g == lab_o).mean() >= 0.9999
+
+
+def test_config1_tsv_row_diff(dg, oracle, tmp_path):
+    """BASELINE.json configs[0] end to end as text: the TSV the GPU pipeline writes for the 1 Mbp record against the
+    oracle's restatement of the reference CLI, diffed row by row (tools/tsv_diff.py): the rows are the same up to
+    the <= 1e-4 of the bases whose label sits on a near-tie of the probabilities."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import io
+    import json
+    import tsv_diff
+    T, U, L = 150, 32, 1_000_000
+    rows = {}
+    for scale in (1.0, 4.0):
+        w = dg.model.random_weights(T, U, attention=True, seed=0)
+        if scale != 1.0:
+            w = w.scaled(scale)
+        p = tmp_path / "config1.fa"
+        write_fasta(str(p), [("synthetic_1Mbp", synth(L, 1).decode())])
+        out = io.BytesIO()
+        dg.pred.predict_fasta_tsv_stream(w, open(p, "rb").read(), str(p), out, 50, 256, True, 50, 50)
+        exp = oracle.predict_fasta_tsv(str(p), w.as_dict(), T, 256, 50, True, 50, 50, engine="torch")
+        d = tsv_diff.diff_tsv(out.getvalue().decode(), exp)["total"]
+        rows["weights_x%g" % scale] = d
+        print("config 1, weights x%g:" % scale, json.dumps(d))
+        assert d["rows_b"] > 1000
+        assert d["bases_differ"] <= 1e-4 * L
+        assert d["rows_only_a"] + d["rows_only_b"] <= 4 * max(1, d["bases_differ"])
+    report = os.environ.get("DGRP_TSV_DIFF_REPORT")
+    if report:
+        json.dump({"workload": "BASELINE.json configs[0]: T=150, U=32, 1 Mbp, step 50, batch 256, MSS 50/50; "
+                               "A = GPU pipeline (dgrp_fasta_stream), B = oracle restatement of the reference CLI",
+                   "diff": rows}, open(report, "w"), indent=1)

@@ -195,3 +195,73 @@ def test_oracle_confusion_matrix_vs_histogram(oracle):
     p = rng.integers(0, 4, size=100)
     got = oracle.confusion_matrix(t, p)
     np.testing.assert_equal(got, np.bincount(t * 4 + p, minlength=16).reshape(4, 4))
+
+
+# ---- pins for the floating-point half of the oracle (GRU / AdditiveAttention), beyond the two engines ---------
+def test_gru_known_answer_by_hand():
+    """A 2-unit, 3-step GRU with non-zero input AND recurrent biases, written out scalar by scalar from the Keras
+    equations the reference's layer config selects (tests/test_model.json: reset_after=true, sigmoid / tanh;
+    deepgrp/model.py:225-229): gate order z, r, h;  mx = x.W + b[0];  mh = h.R + b[1];
+    z = sig(mx_z + mh_z);  r = sig(mx_r + mh_r);  hh = tanh(mx_h + r * mh_h);  h' = z h + (1 - z) hh.
+    Step 1 from h = 0 with base A:  mx = (0.6, -0.45 | 0.175, 0.9 | -0.6, 0.45),  mh = b[1] = (-0.05, 0.1 | 0.2, -0.1 |
+    0.15, -0.25);  z = sig(0.55), sig(-0.35);  r = sig(0.375), sig(0.8);  hh = tanh(-0.6 + r0 0.15), tanh(0.45 - r1 0.25);
+    h1 = (1 - z) hh = (-0.172249633362514, 0.158736142330264).  The literals below were produced by exactly this
+    scalar recipe (python floats, no matrix code) and pin both engines of the oracle."""
+    from oracle import oracle as orc
+    kernel = np.array([[0.5, -0.25, 0.125, 0.75, -0.5, 0.25], [0] * 6, [-0.75, 0.5, 0.25, -0.125, 0.375, -0.625],
+                       [0.25, 0.25, -0.5, 0.5, 0.125, 0.875], [0] * 6], np.float64)
+    rec = np.array([[0.5, -0.5, 0.25, 0.75, -0.25, 0.5], [-0.125, 0.375, 0.5, -0.25, 0.625, -0.375]], np.float64)
+    bias = np.array([[0.1, -0.2, 0.05, 0.15, -0.1, 0.2], [-0.05, 0.1, 0.2, -0.1, 0.15, -0.25]], np.float64)
+    # step 1 by hand, as in the docstring
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    z0, z1, r0, r1 = sig(0.55), sig(-0.35), sig(0.375), sig(0.8)
+    h1 = [(1 - z0) * np.tanh(-0.6 + r0 * 0.15), (1 - z1) * np.tanh(0.45 - r1 * 0.25)]
+    expected = np.array([[-0.17224963336251403, 0.15873614233026442],
+                         [0.2437808425306526, -0.09622192184760324],
+                         [0.16276491434039037, 0.3369773730450849]])
+    assert np.allclose(h1, expected[0], rtol=0, atol=1e-15)
+    x = np.eye(5)[[0, 2, 3]][None]                                    # bases A, G, T
+    w = {"kernel": kernel, "recurrent_kernel": rec, "bias": bias}
+    seq, last = orc.gru_sequence(x, w, dtype=np.float64)
+    assert np.allclose(seq[0], expected, rtol=0, atol=1e-15) and np.allclose(last[0], expected[2], atol=1e-15)
+    w32 = {k: v.astype(np.float32) for k, v in w.items()}
+    seq_t, last_t = orc.gru_sequence_torch(x.astype(np.float32), w32)
+    assert np.abs(seq_t[0] - expected).max() < 2e-7 and np.abs(last_t[0] - expected[2]).max() < 2e-7
+
+
+def test_additive_attention_literal_broadcast_form():
+    """Third, independently structured restatement of the attention block: Keras 2.5 AdditiveAttention
+    ._calculate_scores literally -- reduce_sum(scale * tanh(q[:, :, None, :] + k[:, None, :, :]), -1) with
+    q = reshape(hidden) [B, 1, U] and k = v = avg [B, T, U] -- then softmax over the value axis, matmul(weights, value),
+    Flatten / RepeatVector / Concatenate([attention, avg]) / Dense / Softmax(axis=2) (deepgrp/model.py:311-329;
+    layer configs in tests/test_model.json: use_scale=true, causal=false).  Must equal oracle.model_forward."""
+    from oracle import oracle as orc
+    import deepgrp_b200.model as dgmodel
+    rng = np.random.default_rng(11)
+    for T, U in ((7, 4), (23, 10)):
+        w = dgmodel.random_weights(T, U, attention=True, seed=T).scaled(2.5).as_dict()
+        w = {k: (v.astype(np.float64) if v is not None else None) for k, v in w.items()}
+        w["bias"] = rng.normal(scale=0.3, size=w["bias"].shape)          # non-zero biases
+        w["ff_bias"] = rng.normal(scale=0.3, size=w["ff_bias"].shape)
+        x = np.eye(5)[rng.integers(0, 5, size=(3, T))]
+        got = orc.model_forward(x, w, dtype=np.float64)
+        fwd, hf = orc.gru_sequence(x, w, dtype=np.float64)
+        rev, hr = orc.gru_sequence(orc.reverse_complement(x), w, dtype=np.float64)
+        hidden = ((hf + hr) / 2).reshape(3, 1, U)                        # Average + Reshape((1, units))
+        avg = (fwd + rev) / 2                                            # Average
+        q, k, v = hidden, avg, avg
+        q_r, k_r = q[:, :, None, :], k[:, None, :, :]                    # [B, Tq, 1, U], [B, 1, Tv, U]
+        scores = np.sum(w["att_scale"] * np.tanh(q_r + k_r), axis=-1)    # [B, Tq = 1, Tv]
+        e = np.exp(scores - scores.max(axis=-1, keepdims=True))
+        weights = e / e.sum(axis=-1, keepdims=True)
+        ctx = np.matmul(weights, v)                                      # [B, 1, U]
+        rep = np.repeat(ctx.reshape(3, U)[:, None, :], T, axis=1)        # Flatten + RepeatVector(T)
+        feat = np.concatenate([rep, avg], axis=-1)                       # Concatenate([attention, avg])
+        logits = feat @ w["ff_kernel"] + w["ff_bias"]
+        el = np.exp(logits - logits.max(axis=2, keepdims=True))
+        exp = el / el.sum(axis=2, keepdims=True)
+        assert np.abs(got - exp).max() < 1e-13, (T, U)
+        # the torch-engine route (what the GPU parity tests compare against) agrees in float32
+        w32 = {kk: (vv.astype(np.float32) if vv is not None else None) for kk, vv in w.items()}
+        got32 = orc.model_forward(x.astype(np.float32), w32, engine="torch")
+        assert np.abs(got32 - exp).max() < 5e-6, (T, U)
