@@ -146,9 +146,14 @@ def predict(model, data, results_shape: Tuple[int, int], step_size: int,
             compat: str = "reference") -> np.ndarray:
     """Predict for a complete sequence (reference ``deepgrp/prediction.py:89-111``): every window's
     class probabilities are merged into ``float32[L, C]`` by elementwise maximum."""
+    # The fused route enumerates AND places windows with one step, so it only applies when the dataset was
+    # built with the step `predict` is called with (the reference enumerates with the dataset's step and places
+    # with predict's), on an integer one-hot matrix; anything else takes the reference's literal loop below.
     if isinstance(model, ModelWeights) and isinstance(data, WindowDataset) \
             and data.vecsize == model.vecsize and data.data.shape[0] == 5 \
-            and tuple(results_shape) == (data.length, model.n_classes):
+            and tuple(results_shape) == (data.length, model.n_classes) \
+            and int(step_size) == step_size and data.step_size == int(step_size) \
+            and np.issubdtype(np.asarray(data.data).dtype, np.integer):
         fwd = np.ascontiguousarray(data.data, dtype=np.int8)
         predictions = np.zeros(results_shape, dtype=np.float32)
         if data.length:

@@ -95,3 +95,29 @@ def test_predict_generic_route_known_answer(monkeypatch, oracle, step_size):
     assert got.dtype == np.float32 and got.shape == (50, 3)
     assert got.sum(axis=0).tolist() == [0, 12, 0]
     assert all(got[i * step_size].tolist() == [0, 1, 0] for i in range(12))
+
+
+def test_predict_takes_the_literal_loop_when_the_steps_differ(monkeypatch, oracle):
+    """The reference enumerates windows with the dataset's step and places them with predict's (deepgrp/prediction.py:
+    28-37, 103-111).  The fused GPU route uses one step for both, so a mismatch -- or a non-integer matrix -- must go
+    through the reference's literal loop (here with the oracle's vote standing in for the GPU call)."""
+    import deepgrp_b200.sequence as dgsequence
+    T, U = 20, 4
+    w = model.random_weights(T, U, attention=True, seed=0)
+    rng = np.random.default_rng(0)
+    fwd = np.eye(5, dtype=np.int8)[rng.integers(0, 5, size=300)].T.copy()
+
+    def no_gpu(*a, **k):
+        raise AssertionError("the fused route must not be taken")
+    monkeypatch.setattr(prediction._lib, "context", no_gpu)
+    monkeypatch.setattr(dgsequence, "get_max", oracle.get_max)
+    monkeypatch.setattr(model.ModelWeights, "predict_on_batch",
+                        lambda self, b: oracle.model_forward(b, self.as_dict()))
+    ds = prediction.fetch_validation_batch(fwd, 10, 8, T)
+    got = prediction.predict(w, ds, (300, 5), 5)                   # placed with step 5, enumerated with 10
+    exp = oracle.predict(lambda b: oracle.model_forward(b, w.as_dict()),
+                         oracle.fetch_validation_batch(fwd, 10, 8, T), (300, 5), 5)
+    assert np.array_equal(got, exp)
+    ds_f = prediction.fetch_validation_batch(fwd.astype(np.float32) * 0.5, 10, 8, T)
+    got_f = prediction.predict(w, ds_f, (300, 5), 10)              # a float matrix that is not one-hot
+    assert got_f.shape == (300, 5) and np.isfinite(got_f).all()
