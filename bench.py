@@ -321,6 +321,11 @@ def run_ours(args, rank, world, local_rank):
             return ctx.timings()
 
         def e2e_step():
+            if args.e2e_api == "oneshot":   # the one-call form (whole TSV in one pinned buffer, one D2H copy)
+                view = prediction.predict_fasta_tsv_view(weights, raw_view, "synthetic.fa", STEP, BATCH, True,
+                                                         MIN_MSS, XDROP)
+                devnull.write(view)
+                return {"h2d_bytes": len(text), "d2h_bytes": len(view)}
             return prediction.predict_fasta_tsv_stream(weights, raw_view, "synthetic.fa", devnull, STEP, BATCH,
                                                        True, MIN_MSS, XDROP)
 
@@ -635,6 +640,7 @@ def main():
                     help="extra measurements attached to the JSON line: x4 (the confident-output weight set), strong "
                          "(BASELINE.json configs[2], one chr1-sized record chunk-sharded over the ranks), genome "
                          "(configs[3] in shape, n_gpus/8 of the 3.1 Gbp multi-FASTA, end to end); '' for none")
+    ap.add_argument("--e2e-api", default="stream", choices=["stream", "oneshot"])
     ap.add_argument("--strong-bases", type=int, default=248_000_000)
     ap.add_argument("--genome-scale", type=float, default=0.0, help="fraction of the 3.1 Gbp genome (0 = n_gpus / 8)")
     ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",

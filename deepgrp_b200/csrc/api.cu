@@ -266,6 +266,7 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *c) { return c->launches; }
 int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
+  else if (!strcmp(key, "mss_tiled")) c->mss_tiled = (int)value;
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
@@ -273,6 +274,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
   else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
   else if (!strcmp(key, "forward_ub")) c->forward_ub = (int)value;
+  else if (!strcmp(key, "stream_slot_mb")) c->stream_slot_mb = (int)value;
   else if (!strcmp(key, "forward_slab_mb")) c->forward_slab_bytes = (int64_t)value << 20;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
@@ -283,6 +285,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   if (!strcmp(key, "mss_chunk")) *value = c->mss_chunk;
   else if (!strcmp(key, "mss_max_rounds")) *value = c->mss_max_rounds;
   else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
+  else if (!strcmp(key, "mss_tiled")) *value = c->mss_tiled;
   else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
@@ -290,6 +293,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
   else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;
   else if (!strcmp(key, "forward_ub")) *value = c->forward_ub;
+  else if (!strcmp(key, "stream_slot_mb")) *value = c->stream_slot_mb;
   else if (!strcmp(key, "forward_slab_mb")) *value = c->forward_slab_bytes >> 20;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
@@ -1138,7 +1142,7 @@ int dgrp_finish_record_dev(dgrp_ctx *c, const uint8_t *d_labels, const float *d_
 namespace {
 
 constexpr int kSlots = 4;
-constexpr int64_t kSlotBytes = (int64_t)64 << 20;    // one piece of TSV text
+constexpr int64_t kSlotBytesDefault = (int64_t)64 << 20;    // one piece of TSV text ("stream_slot_mb")
 constexpr int64_t kStageBytes = (int64_t)32 << 20;   // one chunk of the upload
 constexpr int64_t kMinSlice = (int64_t)8 << 20;      // adjacent records are merged into slices of at least this size
 
@@ -1168,6 +1172,7 @@ struct dgrp_fasta_stream {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_stage[2] = {}, ev_text[2] = {}, ev_slot[kSlots] = {};
   bool src_pinned = false;
+  int64_t slot_bytes = kSlotBytesDefault;
   std::thread compute, copier, uploader;
   int up_done = 0, dec_done = 0;    // slices (of `mine`) whose upload has been enqueued / that have been decoded
   int up_rc = DGRP_OK;
@@ -1466,8 +1471,8 @@ void stream_copier_main(dgrp_fasta_stream *s) {
     }
     cudaStreamWaitEvent(s->s_out, s->ev_text[r.buf], 0);
     bool stop = false;
-    for (int64_t off = 0; off < r.bytes && !stop; off += kSlotBytes) {
-      const int64_t len = std::min<int64_t>(kSlotBytes, r.bytes - off);
+    for (int64_t off = 0; off < r.bytes && !stop; off += s->slot_bytes) {
+      const int64_t len = std::min<int64_t>(s->slot_bytes, r.bytes - off);
       int slot = -1;
       for (;;) {
         {
@@ -1525,6 +1530,7 @@ int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int
   s->step = step; s->batch_size = batch_size; s->use_mss = use_mss; s->min_mss_len = min_mss_len;
   s->xdrop_len = xdrop_len; s->compat = compat;
   s->raw = c->st_raw; s->text = c->st_text; s->stage = c->st_stage; s->slot = c->st_slot;
+  if (c->stream_slot_mb > 0) s->slot_bytes = (int64_t)c->stream_slot_mb << 20;
   stream_index(s);
   cudaPointerAttributes attr;
   if (nbytes > 0 && cudaPointerGetAttributes(&attr, fasta) == cudaSuccess) s->src_pinned = attr.type == cudaMemoryTypeHost;
@@ -1540,8 +1546,8 @@ int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int
     if (!s->src_pinned && rc == DGRP_OK) rc = s->stage[i].reserve((size_t)kStageBytes);
   }
   for (int i = 0; i < kSlots; ++i) {
-    ck(cudaEventCreateWithFlags(&s->ev_slot[i], cudaEventDisableTiming));
-    if (rc == DGRP_OK) rc = s->slot[i].reserve((size_t)kSlotBytes);
+    ck(cudaEventCreateWithFlags(&s->ev_slot[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    if (rc == DGRP_OK) rc = s->slot[i].reserve((size_t)s->slot_bytes);
   }
   if (rc != DGRP_OK) { dgrp_fasta_stream_close(s); return rc; }
   s->uploader = std::thread(stream_uploader_main, s);

@@ -98,6 +98,7 @@ struct dgrp_ctx {
   // tuning knobs / diagnostics (dgrp_ctx_set_int / dgrp_ctx_get_int)
   int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)
   int mss_max_rounds = 0;  // Jacobi rounds before the sequential completion (0 = default)
+  int mss_tiled = 1;       // float32 scores: chunk scan with the scores staged through shared memory (0: one thread reads its chunk)
   int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
   int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
   int forward_sum16 = 1;   // tcgen05 forward: keep h_fwd + h_rc (attention scores only) in half precision
@@ -106,6 +107,7 @@ struct dgrp_ctx {
                            // (1) instead of 5 atomicMax per window-step (0); falls back to 0 above 40 GB
   int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
                            // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
+  int stream_slot_mb = 0;  // dgrp_fasta_stream: size of one host piece of TSV text, MiB (0 = 64)
   int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 64)
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a

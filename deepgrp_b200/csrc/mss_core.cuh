@@ -189,32 +189,38 @@ DGRP_HD Pick pick_trajectory(const ChunkSummary &sum, double x_inL, double yL) {
   return r;
 }
 
-// Reduced scan over elements [b, e) of S (e <= n) from state `s`.  `first_ord` is the ordinal of
-// the first run that STARTS in [b, e).  Writes the run records and the chunk summary.
-template <typename ScoreT>
-DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
-                        ScanState &s, const RunTable &rt, ChunkSummary &sum) {
-  int next_ord = first_ord;
-  sum.m.outL = sum.m.runL0 = sum.m.carryR = sum.m.minT = sum.m.maxAfter = sum.m.maxIn = 0.0;
-  sum.s = sum.m;
-  sum.min_st = -1; sum.flags = 0;
-  double Lb = s.L + ulp_of(s.L);           // the shadow trajectory (see ChunkSummary)
-  double runb = 0.0;                       // its L before the run in progress, for a run that started in the chunk
-  bool carried = (s.flags & 2) != 0;       // the run in progress came from before the chunk
-  // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
-  // a block are independent of the sequential state machine and overlap each other.
-  constexpr int BL = 8;
-  bool prev_pos = b > 0 && ((double)S[b - 1] > 0);
-  for (int i0 = b; i0 < e; i0 += BL) {
-    const int m = e - i0 < BL ? e - i0 : BL;
-    double blk[BL + 1];
+// Reduced scan over elements [b, e) of S (e <= n) from state `s`, as an object so that the caller decides where the
+// scores come from (global memory directly, or a shared-memory tile loaded cooperatively: mss.cu): begin(), then
+// block() for consecutive groups of up to BL scores (+1 look-ahead value), then end().  `first_ord` is the ordinal
+// of the first run that STARTS in [b, e).  Writes the run records and the chunk summary.
+constexpr int SCAN_BL = 8;
+
+struct ChunkScan {
+  ScanState &s;
+  const RunTable &rt;
+  ChunkSummary &sum;
+  double xdrop;
+  int n, next_ord;
+  double Lb;      // the shadow trajectory (see ChunkSummary)
+  double runb;    // its L before the run in progress, for a run that started in the chunk
+  bool carried;   // the run in progress came from before the chunk
+  bool prev_pos;
+
+  DGRP_HD ChunkScan(ScanState &s_, const RunTable &rt_, ChunkSummary &sum_, double xdrop_, int n_, int first_ord,
+                    bool prev_positive)
+      : s(s_), rt(rt_), sum(sum_), xdrop(xdrop_), n(n_), next_ord(first_ord), prev_pos(prev_positive) {
+    sum.m.outL = sum.m.runL0 = sum.m.carryR = sum.m.minT = sum.m.maxAfter = sum.m.maxIn = 0.0;
+    sum.s = sum.m;
+    sum.min_st = -1; sum.flags = 0;
+    Lb = s.L + ulp_of(s.L);
+    runb = 0.0;
+    carried = (s.flags & 2) != 0;
+  }
+
+  // scores blk[0..m) are elements i0.. of S; blk[m] is the look-ahead value S[i0 + m] (anything when i0 + m >= n)
+  DGRP_HD void block(int i0, int m, const double *blk) {
     DGRP_UNROLL
-    for (int j = 0; j <= BL; ++j) {
-      const int idx = i0 + j;
-      blk[j] = (j <= m && idx < n) ? (double)S[idx] : 0.0;
-    }
-    DGRP_UNROLL
-    for (int j = 0; j < BL; ++j) {
+    for (int j = 0; j < SCAN_BL; ++j) {
       if (j >= m) break;
       const int i = i0 + j;
       const double v = blk[j];
@@ -260,9 +266,32 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
       }
     }
   }
-  if ((s.flags & 2) && !carried) sum.flags |= 8;
-  sum.m.outL = s.L; sum.s.outL = Lb;
-  sum.m.runL0 = s.run_L0; sum.s.runL0 = runb;
+
+  DGRP_HD void end() {
+    if ((s.flags & 2) && !carried) sum.flags |= 8;
+    sum.m.outL = s.L; sum.s.outL = Lb;
+    sum.m.runL0 = s.run_L0; sum.s.runL0 = runb;
+  }
+};
+
+template <typename ScoreT>
+DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
+                        ScanState &s, const RunTable &rt, ChunkSummary &sum) {
+  ChunkScan sc(s, rt, sum, xdrop, n, first_ord, b > 0 && ((double)S[b - 1] > 0));
+  // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
+  // a block are independent of the sequential state machine and overlap each other.
+  constexpr int BL = SCAN_BL;
+  for (int i0 = b; i0 < e; i0 += BL) {
+    const int m = e - i0 < BL ? e - i0 : BL;
+    double blk[BL + 1];
+    DGRP_UNROLL
+    for (int j = 0; j <= BL; ++j) {
+      const int idx = i0 + j;
+      blk[j] = (j <= m && idx < n) ? (double)S[idx] : 0.0;
+    }
+    sc.block(i0, m, blk);
+  }
+  sc.end();
 }
 
 // Predict the end state of a chunk for start state `y` from one known execution x_in -> x_out with
