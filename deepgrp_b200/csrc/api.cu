@@ -266,7 +266,6 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *c) { return c->launches; }
 int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "mss_chunk")) c->mss_chunk = (int)value;
   else if (!strcmp(key, "mss_max_rounds")) c->mss_max_rounds = (int)value;
-  else if (!strcmp(key, "mss_tiled")) c->mss_tiled = (int)value;
   else if (!strcmp(key, "forward_tc")) c->forward_tc = (int)value;
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
@@ -285,7 +284,6 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   if (!strcmp(key, "mss_chunk")) *value = c->mss_chunk;
   else if (!strcmp(key, "mss_max_rounds")) *value = c->mss_max_rounds;
   else if (!strcmp(key, "mss_rounds")) *value = c->mss_rounds;
-  else if (!strcmp(key, "mss_tiled")) *value = c->mss_tiled;
   else if (!strcmp(key, "forward_tc")) *value = c->forward_tc;
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;

@@ -98,7 +98,6 @@ struct dgrp_ctx {
   // tuning knobs / diagnostics (dgrp_ctx_set_int / dgrp_ctx_get_int)
   int mss_chunk = 0;       // elements per MSS scan chunk (0 = automatic)
   int mss_max_rounds = 0;  // Jacobi rounds before the sequential completion (0 = default)
-  int mss_tiled = 1;       // float32 scores: chunk scan with the scores staged through shared memory (0: one thread reads its chunk)
   int mss_rounds = 0;      // rounds used by the last MSS call (negative: completed sequentially)
   int forward_tc = 1;      // 1: tcgen05 recurrence where available, 0: fp32 FFMA kernel
   int forward_sum16 = 1;   // tcgen05 forward: keep h_fwd + h_rc (attention scores only) in half precision

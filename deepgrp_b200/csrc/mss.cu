@@ -118,87 +118,6 @@ __global__ void mss_scan_kernel(const T *__restrict__ S, int n, double xdrop, in
   b.sum[c] = sum;
 }
 
-// The same scan with the scores staged through shared memory (float32 scores, the fused path).  One thread per
-// chunk reading its own 4 kB of scores touches 32 different lines per warp load and keeps ~10 warps per SM in
-// flight: 0.66 TB/s.  Here a block of SCAN_THREADS chunks loads tiles of SCAN_TE scores per chunk cooperatively
-// (a warp instruction = one chunk's 128 contiguous bytes, cp.async, three tiles in flight) and every thread then
-// runs the state machine on its own row of the tile (row stride 33 floats: conflict-free).
-constexpr int SCAN_THREADS = 96, SCAN_TE = 32, SCAN_STRIDE = SCAN_TE + 1, SCAN_STAGES = 3;
-
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int bytes = valid ? 4 : 0;   // 0: zero-fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) mss_scan_tiled_kernel(const float *__restrict__ S, int n, double xdrop,
-                                                                      int CH, int NC, int mode, ScanBufs b, RunTable rt) {
-  __shared__ float tile[SCAN_STAGES][SCAN_THREADS * SCAN_STRIDE];
-  const int c0 = blockIdx.x * SCAN_THREADS, c = c0 + (int)threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool active = c < NC && (mode == 0 || b.dirty[c]);
-  if (!__syncthreads_or(active)) return;
-  ScanState s;
-  mss::state_canonical(s);
-  if (active && mode != 0) s = b.pred[c];
-  if (active) b.used[c] = s;
-  const int lo = active ? c * CH : 0, hi = active ? (lo + CH < n ? lo + CH : n) : 0;
-  ChunkSummary sum;
-  mss::ChunkScan sc(s, rt, sum, xdrop, n, active ? (int)b.base[c] : 0, active && lo > 0 && S[lo - 1] > 0.f);
-  const float la_end = (active && hi < n) ? S[hi] : 0.f;   // the look-ahead of the chunk's last score
-  const int ntiles = CH / SCAN_TE;                          // CH is a multiple of 32
-  // warp w loads rows w*32 .. w*32+31 of a tile: row r = chunk c0 + r, element (c0 + r) * CH + k * TE + lane
-  auto load = [&](int k) {
-    float *dst = tile[k % SCAN_STAGES];
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = warp * 32 + rr;
-      const long long idx = (long long)(c0 + r) * CH + (long long)k * SCAN_TE + lane;
-      const bool ok = c0 + r < NC && idx < n;
-      cp_async4(dst + r * SCAN_STRIDE + lane, S + (ok ? idx : 0), ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  load(0);
-  if (ntiles > 1) load(1);
-  for (int k = 0; k < ntiles; ++k) {
-    if (k + 2 < ntiles) {
-      load(k + 2);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");   // tiles <= k + 1 have landed
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    if (active) {
-      const float *row = tile[k % SCAN_STAGES] + threadIdx.x * SCAN_STRIDE;
-      const float *nxt = tile[(k + 1) % SCAN_STAGES] + threadIdx.x * SCAN_STRIDE;
-      const int t0 = lo + k * SCAN_TE;
-#pragma unroll
-      for (int q = 0; q < SCAN_TE / mss::SCAN_BL; ++q) {
-        const int i0 = t0 + q * mss::SCAN_BL;
-        if (i0 >= hi) break;
-        const int m = hi - i0 < mss::SCAN_BL ? hi - i0 : mss::SCAN_BL;
-        double blk[mss::SCAN_BL + 1];
-#pragma unroll
-        for (int j = 0; j < mss::SCAN_BL; ++j) blk[j] = (double)row[q * mss::SCAN_BL + j];
-        // look-ahead: the next score of this row, the first score of the next tile, or of the next chunk
-        const int jn = (q + 1) * mss::SCAN_BL;
-        float la = jn < SCAN_TE ? row[jn] : (k + 1 < ntiles ? nxt[0] : la_end);
-        if (i0 + mss::SCAN_BL >= hi) la = (i0 + m == hi) ? la_end : la;
-        blk[mss::SCAN_BL] = (double)la;
-        if (m < mss::SCAN_BL) blk[m] = (double)la_end;   // partial block at the end of the record
-        sc.block(i0, m, blk);
-      }
-    }
-    __syncthreads();   // the stage is overwritten by the load of tile k + 3
-  }
-  if (active) {
-    sc.end();
-    b.out[c] = s;
-    b.sum[c] = sum;
-  }
-}
-
 // One warp walks the chunk summaries: predicts every chunk's start state and marks the chunks whose
 // last execution started from something else.  Lanes stage 32 chunks at a time in shared memory,
 // lane 0 does the (inherently sequential, O(1) per chunk) chain.
@@ -457,12 +376,11 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   // ---- stage 1
   const int threads = 128;
   const int blocks = (NC + threads - 1) / threads;
+  // (Staging the scores through shared memory -- coalesced cp.async tiles, a block in lock step -- was measured
+  // SLOWER: 12.2 instead of 7.8 ms for the 248 Mbp finish.  The scan is bound by the instructions of the state
+  // machine, a run ending every 2-4 scores with random-init weights, not by its uncoalesced loads.)
   auto launch_scan = [&](int mode) {
-    if (sizeof(T) == 4 && CH % SCAN_TE == 0 && c->mss_tiled)
-      mss_scan_tiled_kernel<<<(NC + SCAN_THREADS - 1) / SCAN_THREADS, SCAN_THREADS, 0, c->stream>>>(
-          reinterpret_cast<const float *>(d_S), n, xdrop, CH, NC, mode, sb, rt);
-    else
-      mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, mode, sb, rt);
+    mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, mode, sb, rt);
     c->launches++;
   };
   launch_scan(0);
