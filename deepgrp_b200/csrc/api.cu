@@ -77,16 +77,38 @@ static void mss_thresholds(int min_mss_len, int xdrop_len, double *min_sc, doubl
 
 static void stamp(dgrp_ctx *c, int i) { cudaEventRecord(c->ev[i], c->stream); }
 
-// codes (device, trimmed record of length L) -> predictions f32[L, C] in c->pred
+// codes (device, trimmed record of length L) -> predictions f32[L, C] in c->pred, or -- want_scores, when the vote
+// and the score transform could be fused (c->fused_last) -- label u8[L] in c->labels and score f32[L] in
+// c->scores32 with the predictions never materialised
 static int core_predict(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t L, int step,
-                        int batch_size, int compat) {
+                        int batch_size, int compat, bool want_scores = false) {
   DGRP_REQUIRE(step > 0, "step_size must be positive");
+  c->fused_last = 0;
   DGRP_CHECK(c->pred.reserve((size_t)(L > 0 ? L : 1) * m->C * sizeof(float)));
-  if (L > 0) DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)L * m->C * sizeof(float), c->stream));
   const Placement pl = make_placement(L, m->T, step, batch_size, compat);
   c->timings.windows = pl.n_windows;
   c->timings.bases = L;
+  if (want_scores && L > 0) {
+    DGRP_CHECK(c->labels.reserve((size_t)L));
+    DGRP_CHECK(c->scores32.reserve((size_t)L * 4));
+    bool fused = false;
+    DGRP_CHECK(run_forward_vote(c, m, d_codes, 0, 0, pl.n_windows, pl, c->pred.as<float>(), 0, L,
+                                c->labels.as<uint8_t>(), c->scores32.as<float>(), &fused));
+    c->fused_last = fused ? 1 : 0;
+    return DGRP_OK;
+  }
+  if (L > 0) DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)L * m->C * sizeof(float), c->stream));
   return run_forward_vote(c, m, d_codes, 0, 0, pl.n_windows, pl, c->pred.as<float>(), 0, L);
+}
+
+// core_labels on what core_predict left: fused label + score, or the predictions
+static int core_labels(dgrp_ctx *c, const float *d_pred, const uint8_t *d_lab_in, const float *d_score_in, int64_t L,
+                       int C, int use_mss, int min_mss_len, int xdrop_len);
+static int core_labels_after_predict(dgrp_ctx *c, int64_t L, int C, int use_mss, int min_mss_len, int xdrop_len) {
+  if (c->fused_last)
+    return core_labels(c, nullptr, c->labels.as<uint8_t>(), c->scores32.as<float>(), L, C, use_mss, min_mss_len,
+                       xdrop_len);
+  return core_labels(c, c->pred.as<float>(), nullptr, nullptr, L, C, use_mss, min_mss_len, xdrop_len);
 }
 
 // predictions (device f32[L, C]) or ready (label, score) -> final labels in c->labels2
@@ -270,6 +292,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_sum16")) c->forward_sum16 = (int)value;
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
   else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
+  else if (!strcmp(key, "forward_fuse_score")) c->forward_fuse_score = (int)value;
   else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
   else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
   else if (!strcmp(key, "forward_ub")) c->forward_ub = (int)value;
@@ -288,6 +311,8 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_sum16")) *value = c->forward_sum16;
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
   else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
+  else if (!strcmp(key, "forward_fuse_score")) *value = c->forward_fuse_score;
+  else if (!strcmp(key, "fused_last")) *value = c->fused_last;
   else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
   else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;
   else if (!strcmp(key, "forward_ub")) *value = c->forward_ub;
@@ -767,9 +792,9 @@ int dgrp_predict_sequence(dgrp_ctx *c, dgrp_model *m, const uint8_t *seq, int64_
   }
   stamp(c, 1);
   const int64_t L = *length;
-  DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), L, step, batch_size, compat));
+  DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), L, step, batch_size, compat, use_mss != 0));
   stamp(c, 2);
-  DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, L, m->C, use_mss, min_mss_len, xdrop_len));
+  DGRP_CHECK(core_labels_after_predict(c, L, m->C, use_mss, min_mss_len, xdrop_len));
   stamp(c, 4);
   if (labels && L > 0)
     DGRP_CUDA(cudaMemcpyAsync(labels, c->labels2.p, (size_t)L, cudaMemcpyDeviceToHost, c->stream));
@@ -866,10 +891,10 @@ static int predict_fasta_impl(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, 
     c->fa_startpos.push_back(startpos); c->fa_length.push_back(length);
     c->fa_tsv_off.push_back(c->tsv_len); c->fa_tsv_len.push_back(0); c->fa_owner.push_back(owner_of[k]);
     stamp(c, 1);
-    if ((rc = core_predict(c, m, c->codes.as<uint8_t>(), length, step, batch_size, compat))) break;
+    if ((rc = core_predict(c, m, c->codes.as<uint8_t>(), length, step, batch_size, compat, use_mss != 0))) break;
     windows += c->timings.windows; bases += length;
     stamp(c, 2);
-    if ((rc = core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, use_mss, min_mss_len, xdrop_len))) break;
+    if ((rc = core_labels_after_predict(c, length, m->C, use_mss, min_mss_len, xdrop_len))) break;
     stamp(c, 4);
     if (length > 0) {
       int64_t *d_tri = nullptr;
@@ -1000,9 +1025,9 @@ int dgrp_predict_codes_dev(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, i
   *n_rows = 0;
   stamp(c, 0);
   stamp(c, 1);
-  DGRP_CHECK(core_predict(c, m, d_codes, length, step, batch_size, compat));
+  DGRP_CHECK(core_predict(c, m, d_codes, length, step, batch_size, compat, use_mss != 0));
   stamp(c, 2);
-  DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, use_mss, min_mss_len, xdrop_len));
+  DGRP_CHECK(core_labels_after_predict(c, length, m->C, use_mss, min_mss_len, xdrop_len));
   stamp(c, 4);
   int rc = DGRP_OK;
   if (length > 0) rc = core_rows(c, length, 0, 0, false, nullptr, 0, n_rows);
@@ -1337,11 +1362,10 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
       return DGRP_E_ALLN;
     }
     stamp(c, 1);
-    DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, s->step, s->batch_size, s->compat));
+    DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, s->step, s->batch_size, s->compat, s->use_mss != 0));
     s->windows += c->timings.windows; s->bases += length;
     stamp(c, 2);
-    DGRP_CHECK(core_labels(c, c->pred.as<float>(), nullptr, nullptr, length, m->C, s->use_mss, s->min_mss_len,
-                           s->xdrop_len));
+    DGRP_CHECK(core_labels_after_predict(c, length, m->C, s->use_mss, s->min_mss_len, s->xdrop_len));
     stamp(c, 4);
     int64_t cnt = 0, need = 0;
     int tb = -1;

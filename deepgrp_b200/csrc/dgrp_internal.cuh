@@ -111,6 +111,8 @@ struct dgrp_ctx {
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
                            // record run in slabs of at most this many bytes of [windows][T][C] probabilities
+  int forward_fuse_score = 1;   // whole-record calls: fuse vote + score transform when the windows fit one slab
+  int fused_last = 0;      // the last core_predict produced label + score directly (no predictions in HBM)
   int forward_used_tc = 0; // what the last forward launch used: 0 fp32 kernel, 1 two-tile tcgen05, 2 wide, 3 wide CTA pair
   // results of the last dgrp_predict_fasta (fetched with dgrp_fasta_rows / dgrp_fasta_records)
   std::vector<dgrp_row_t> fa_rows;
@@ -156,7 +158,7 @@ int launch_onehot_to_codes(dgrp_ctx *c, const int8_t *d_fwd, int64_t len, uint8_
 // vote.cu
 int launch_vote_gather(dgrp_ctx *c, const float *d_win, int64_t w_begin, int64_t w_end, int T, int C,
                        int64_t full_windows, int64_t tail_base, int step, float *d_pred, int64_t pred_row0,
-                       int64_t pred_rows);
+                       int64_t pred_rows, uint8_t *d_label = nullptr, float *d_score = nullptr);
 int launch_get_max(dgrp_ctx *c, float *d_out, const float *d_in, int64_t batch, int64_t dim0,
                    int64_t dim1, int64_t stride);
 int launch_score(dgrp_ctx *c, const float *d_pred, int64_t n, int C, uint8_t *d_label,
@@ -172,9 +174,13 @@ struct Placement {  // where window w is max-merged (prediction.py:105 compatibi
 Placement make_placement(int64_t length, int T, int step, int batch_size, int compat);
 // Run GRU + attention + FF + softmax for windows [w_begin, w_end) of the code array and
 // max-merge into d_pred (rows relative to pred_row0; rows outside [0, pred_rows) are dropped).
+// With d_label / d_score (whole record, pred_row0 = 0): when the windows fit one slab of the tcgen05 path the vote
+// and the score transform are fused (*fused = true: label + score written, d_pred untouched and NOT zero-filled by
+// the caller beforehand); otherwise *fused = false and d_pred (zero-initialised by the caller) holds the votes.
 int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
                      int64_t w_begin, int64_t w_end, const Placement &pl, float *d_pred,
-                     int64_t pred_row0, int64_t pred_rows);
+                     int64_t pred_row0, int64_t pred_rows, uint8_t *d_label = nullptr, float *d_score = nullptr,
+                     bool *fused = nullptr);
 // dense float windows [B, T, 5] -> probs [B, T, C] (predict_on_batch semantics)
 int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t nbatch,
                       float *d_probs);

@@ -304,7 +304,8 @@ static void fill_model(FwdParams &p, const dgrp_model *m) {
 
 int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
                      int64_t w_begin, int64_t w_end, const Placement &pl, float *d_pred,
-                     int64_t pred_row0, int64_t pred_rows) {
+                     int64_t pred_row0, int64_t pred_rows, uint8_t *d_label, float *d_score, bool *fused) {
+  if (fused) *fused = false;
   FwdParams p = {};
   fill_model(p, m);
   p.codes = d_codes; p.codes_base = codes_base;
@@ -326,6 +327,18 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
       else cudaGetLastError();   // out of memory: the kernels vote with atomicMax instead
     }
     if (!p.win_probs) slab = w_end - w_begin;
+    // one slab holds every window of the record: the gather pass sees each row's final vote and can apply the
+    // score transform at once (label + score out, the predictions never written)
+    const bool fuse = fused && d_label && d_score && p.win_probs && w_end - w_begin <= slab && pred_row0 == 0 &&
+                      c->forward_fuse_score;
+    if (fuse && w_end <= w_begin) {   // no window at all (L <= T): every row is a never-covered row
+      DGRP_CHECK(launch_vote_gather(c, p.win_probs, 0, 0, m->T, m->C, pl.full_windows, pl.tail_base, pl.step, d_pred, 0,
+                                    pred_rows, d_label, d_score));
+      *fused = true;
+      return DGRP_OK;
+    }
+    if (!fuse && fused && pred_rows > 0)   // the caller left the zero-fill to us
+      DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
     for (int64_t w0 = w_begin; w0 < w_end; w0 += slab) {
       const int64_t w1 = w0 + slab < w_end ? w0 + slab : w_end;
       p.w_begin = w0; p.w_end = w1;
@@ -336,11 +349,17 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
       if (rc == DGRP_E_UNSUPPORTED) {
         if (w0 != w_begin) { set_error("forward: tcgen05 form lost between slabs"); return DGRP_E_CUDA; }
         p.w_begin = w_begin; p.w_end = w_end; p.win_probs = nullptr;
+        if (fuse && pred_rows > 0)
+          DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
         return launch_fwd<false>(c, m, p);
       }
       if (rc != DGRP_OK) return rc;
       c->forward_used_tc = used;
-      if (p.win_probs) {
+      if (fuse) {
+        DGRP_CHECK(launch_vote_gather(c, p.win_probs, w0, w1, m->T, m->C, pl.full_windows, pl.tail_base, pl.step, d_pred,
+                                      0, pred_rows, d_label, d_score));
+        *fused = true;
+      } else if (p.win_probs) {
         // rows the slab's placed windows cover (both placement families, prediction.py:105)
         int64_t lo = INT64_MAX, hi = INT64_MIN;
         const int64_t f0 = w0, f1 = w1 < pl.full_windows ? w1 : pl.full_windows;
@@ -360,6 +379,8 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
     }
     return DGRP_OK;
   }
+  if (fused && pred_rows > 0)
+    DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
   return launch_fwd<false>(c, m, p);
 }
 

@@ -46,21 +46,44 @@ int launch_get_max(dgrp_ctx *c, float *d_out, const float *d_in, int64_t batch, 
   return DGRP_OK;
 }
 
+// prediction.py:51-57 (float32 arithmetic, then widened):
+//   cls = argmax(p) (first maximum); m = max(p) + 1e-6f; m > 0.99f -> 0.99f;
+//   t = logf(m / (1 - m)); score = cls > 0 ? t : -10 * t.
+// An all-zero (never covered) row gives cls 0, t = log(1e-6/(1-1e-6)) -> score +138.155.
+template <int C>
+__device__ __forceinline__ void score_row(const float *__restrict__ p, int &cls, float &score) {
+  float best = p[0];
+  cls = 0;
+#pragma unroll
+  for (int k = 1; k < C; ++k) {
+    float v = p[k];
+    if (v > best) { best = v; cls = k; }
+  }
+  float m = best + 1e-6f;
+  if (m > 0.99f) m = 0.99f;
+  float t = logf(m / (1.0f - m));
+  score = cls > 0 ? t : -10.0f * t;
+}
+
 // Max-merge of window probabilities into the prediction rows (the vote of prediction.py:103-111 /
 // maxcalc.c:10-24 in gather form): row r takes the maximum over the windows of [w_begin, w_end) whose
 // PLACED rows cover it -- windows of complete batches sit at w * step, those of the short last batch
 // at tail_base + (w - full_windows) * step (prediction.py:105).  `win` is [w - w_begin][T][C].  One
 // thread per row; consecutive rows read consecutive 4C-byte records of the same window.  The row's
 // current value takes part in the maximum (zero-initialised, or the other window family's result).
+// FUSED form (label != null; all windows of the record are in `win`): the row's vote is final here, so the score
+// transform of prediction.py:51-57 is applied at once and `pred` is neither read nor written -- the float32[L, C]
+// predictions never touch HBM (K6 of SURVEY.md section 2.3: "emits label u8 + score").
 __global__ void vote_gather_kernel(const float *__restrict__ win, int64_t w_begin, int64_t w_end, int T, int C,
                                    int64_t full_windows, int64_t tail_base, int step,
-                                   float *__restrict__ pred, int64_t pred_row0, int64_t pred_rows) {
+                                   float *__restrict__ pred, int64_t pred_row0, int64_t pred_rows,
+                                   uint8_t *__restrict__ label, float *__restrict__ score) {
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < pred_rows; r += gs) {
     const int64_t g = r + pred_row0;   // record position
     float acc[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) acc[k] = k < C ? pred[r * C + k] : 0.f;
+    for (int k = 0; k < 5; ++k) acc[k] = (k < C && !label) ? pred[r * C + k] : 0.f;
     bool any = false;
 #pragma unroll
     for (int fam = 0; fam < 2; ++fam) {
@@ -83,7 +106,18 @@ __global__ void vote_gather_kernel(const float *__restrict__ win, int64_t w_begi
         any = true;
       }
     }
-    if (any) {
+    if (label) {
+      int cls = 0;
+      float best = acc[0];
+#pragma unroll
+      for (int k = 1; k < 5; ++k)
+        if (k < C && acc[k] > best) { best = acc[k]; cls = k; }
+      float m = best + 1e-6f;
+      if (m > 0.99f) m = 0.99f;
+      const float t = logf(m / (1.0f - m));
+      label[r] = (uint8_t)cls;
+      score[r] = cls > 0 ? t : -10.0f * t;
+    } else if (any) {
 #pragma unroll
       for (int k = 0; k < 5; ++k)
         if (k < C) pred[r * C + k] = acc[k];
@@ -93,35 +127,16 @@ __global__ void vote_gather_kernel(const float *__restrict__ win, int64_t w_begi
 
 int launch_vote_gather(dgrp_ctx *c, const float *d_win, int64_t w_begin, int64_t w_end, int T, int C,
                        int64_t full_windows, int64_t tail_base, int step, float *d_pred, int64_t pred_row0,
-                       int64_t pred_rows) {
-  if (pred_rows <= 0 || w_end <= w_begin) return DGRP_OK;
+                       int64_t pred_rows, uint8_t *d_label, float *d_score) {
+  if (pred_rows <= 0 || (w_end <= w_begin && !d_label)) return DGRP_OK;
   const int threads = 256;
   const int64_t want = (pred_rows + threads - 1) / threads;
   const int64_t cap = (int64_t)c->sm_count * 16;
   vote_gather_kernel<<<(unsigned)(want < cap ? want : cap), threads, 0, c->stream>>>(
-      d_win, w_begin, w_end, T, C, full_windows, tail_base, step, d_pred, pred_row0, pred_rows);
+      d_win, w_begin, w_end, T, C, full_windows, tail_base, step, d_pred, pred_row0, pred_rows, d_label, d_score);
   c->launches++;
   DGRP_CUDA(cudaGetLastError());
   return DGRP_OK;
-}
-
-// prediction.py:51-57 (float32 arithmetic, then widened):
-//   cls = argmax(p) (first maximum); m = max(p) + 1e-6f; m > 0.99f -> 0.99f;
-//   t = logf(m / (1 - m)); score = cls > 0 ? t : -10 * t.
-// An all-zero (never covered) row gives cls 0, t = log(1e-6/(1-1e-6)) -> score +138.155.
-template <int C>
-__device__ __forceinline__ void score_row(const float *__restrict__ p, int &cls, float &score) {
-  float best = p[0];
-  cls = 0;
-#pragma unroll
-  for (int k = 1; k < C; ++k) {
-    float v = p[k];
-    if (v > best) { best = v; cls = k; }
-  }
-  float m = best + 1e-6f;
-  if (m > 0.99f) m = 0.99f;
-  float t = logf(m / (1.0f - m));
-  score = cls > 0 ? t : -10.0f * t;
 }
 
 __global__ void score_kernel(const float *__restrict__ pred, int64_t n, int C,

@@ -496,3 +496,32 @@ def test_config1_tsv_row_diff(dg, oracle, tmp_path):
         json.dump({"workload": "BASELINE.json configs[0]: T=150, U=32, 1 Mbp, step 50, batch 256, MSS 50/50; "
                                "A = GPU pipeline (dgrp_fasta_stream), B = oracle restatement of the reference CLI",
                    "diff": rows}, open(report, "w"), indent=1)
+
+
+@pytest.mark.parametrize("scale", (1.0, 4.0))
+def test_fused_vote_and_score_equals_the_two_pass_form(dg, scale):
+    """Whole-record calls fuse the max-vote with the score transform when every window fits one slab (label u8 + score
+    f32 out of the gather pass, the float32[L, C] predictions never written); with the fusion off, or with the
+    windows in several slabs, the predictions are materialised and scored by a second kernel.  Same labels, same
+    rows -- bit for bit, the vote being order-independent and the score transform the same instructions."""
+    w = dg.model.random_weights(150, 32, attention=True, seed=5)
+    if scale != 1.0:
+        w = w.scaled(scale)
+    text = ("NNN" + random_dna(400_000, 9) + "N").encode()
+    out = {}
+    try:
+        for fuse, slab_mb in ((1, 8192), (0, 8192), (1, 1)):
+            dg.ctx.set_int("forward_fuse_score", fuse)
+            dg.ctx.set_int("forward_slab_mb", slab_mb)
+            labels, startpos, rows = dg.pred.predict_sequence(w, text, 50, 256, True, 50, 50)
+            out[(fuse, slab_mb)] = (labels.copy(), startpos, rows.copy(), dg.ctx.get_int("fused_last"))
+    finally:
+        dg.ctx.set_int("forward_fuse_score", 1)
+        dg.ctx.set_int("forward_slab_mb", 8192)
+    assert out[(1, 8192)][3] == 1 and out[(0, 8192)][3] == 0 and out[(1, 1)][3] == 0
+    ref = out[(0, 8192)]
+    for key, (labels, startpos, rows, _) in out.items():
+        assert startpos == ref[1] and np.array_equal(labels, ref[0]) and np.array_equal(rows, ref[2]), key
+    # a record shorter than the window: no window at all, every row scores +138.155 (class 0)
+    short = dg.pred.predict_sequence(w, b"ACGTACGTAC" * 10, 50, 256, True, 50, 50)
+    assert short[0].size == 100
