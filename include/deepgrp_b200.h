@@ -85,7 +85,12 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
  * products [+15 % forward time, same measured accuracy]), "shard_rank" / "shard_world" (contig sharding of
  * dgrp_predict_fasta*: records are assigned largest-first to the least loaded rank; a rank
  * computes only its own records), and read-only "mss_rounds" (rounds the last MSS call used;
- * negative = completed sequentially), "forward_used_tc", "sm_count". */
+ * negative = completed sequentially), "forward_used_tc" (what the last forward used: 0 fp32 kernel, 1 two-tile tcgen05, 2 wide tcgen05 with one CTA per
+ * tile, 3 wide tcgen05 CTA pair), "fused_last", "sm_count".  Round 2: "forward_wide" (0 auto, 1 / 2 force the wide
+ * kernel's one-CTA / CTA-pair variant where it exists), "forward_ub" (GRU column blocks of 64 or 32 units),
+ * "forward_overlap" (issue the wide kernel's MMAs block by block under the gate work), "forward_slab_mb" (bound of the
+ * window-probability buffer), "forward_fuse_score" (fuse vote + score transform for whole-record calls),
+ * "stream_slot_mb" (host piece size of dgrp_fasta_stream). */
 int dgrp_ctx_set_int(dgrp_ctx *ctx, const char *key, int64_t value);
 int dgrp_ctx_get_int(dgrp_ctx *ctx, const char *key, int64_t *value);
 
@@ -133,7 +138,8 @@ int dgrp_find_mss_labels(dgrp_ctx *ctx, const double *scores, const int64_t *lab
  *      1 = LSTM (gate order i,f,c,o): kernel[5,4U], recurrent[U,4U], bias[4U]; att_scale is ignored
  *          (the reference builds no attention for LSTM, deepgrp/model.py:308) and ff_kernel is [U,C].
  * att_scale[U] or NULL (no attention), ff_kernel[F,C] (F = 2U with attention else U), ff_bias[C].
- * The tcgen05 recurrence covers GRU with units <= 64; LSTM and wider GRUs run the fp32 kernel. */
+ * tcgen05 recurrence: GRU with units <= 64 on the two-tile kernel, 65..128 on a CTA pair (cta_group::2), LSTM with
+ * units <= 64 on the one-tile kernel; LSTM with 65..128 units runs the fp32 kernel; units > 128 are refused. */
 int dgrp_model_create(dgrp_ctx *ctx, int rnn, int vecsize, int units, int n_classes,
                       const float *kernel, const float *recurrent, const float *bias,
                       const float *att_scale, const float *ff_kernel, const float *ff_bias,
