@@ -1230,9 +1230,8 @@ struct WaitClock {   // adds the scope's wall time to a counter
 
 // Header lines start a slice: a '>' that is the first byte of a line.  (A '>' after leading whitespace is a
 // header too, __main__.py:34-35; it simply stays inside the preceding slice, which the GPU parser handles.)
-void stream_index(dgrp_fasta_stream *s) {
-  const uint8_t *f = s->fasta;
-  const int64_t n = s->nbytes;
+// slices [cuts[k], cuts[k+1]) of the text and their owners; pure host code (also exported as dgrp_fasta_index)
+void index_slices(const uint8_t *f, int64_t n, int world, std::vector<int64_t> &cuts, std::vector<int> &owner) {
   // candidate header positions: '>' right after a line terminator; found by memchr, in parallel for large inputs
   // (a 3 GB genome is 0.15 s of single-threaded scanning per rank otherwise)
   const int nt = n > ((int64_t)64 << 20) ? 8 : (n > ((int64_t)8 << 20) ? 4 : 1);
@@ -1254,31 +1253,36 @@ void stream_index(dgrp_fasta_stream *s) {
     for (int t = 0; t < nt; ++t) th.emplace_back(scan, t);
     for (auto &x : th) x.join();
   }
-  s->cuts.clear();
-  s->cuts.push_back(0);
+  cuts.clear();
+  cuts.push_back(0);
   for (int t = 0; t < nt; ++t)
     for (int64_t p : found[t])
-      if (p - s->cuts.back() >= kMinSlice) s->cuts.push_back(p);
-  s->cuts.push_back(n);
+      if (p - cuts.back() >= kMinSlice) cuts.push_back(p);
+  cuts.push_back(n);
   // largest-first assignment of slices to ranks (every rank derives the same table)
-  const int64_t ns = (int64_t)s->cuts.size() - 1;
-  const int world = s->c->shard_world > 0 ? s->c->shard_world : 1;
+  const int64_t ns = (int64_t)cuts.size() - 1;
+  if (world < 1) world = 1;
   std::vector<int64_t> order(ns);
   for (int64_t k = 0; k < ns; ++k) order[k] = k;
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-    return (s->cuts[a + 1] - s->cuts[a]) > (s->cuts[b + 1] - s->cuts[b]);
+    return (cuts[a + 1] - cuts[a]) > (cuts[b + 1] - cuts[b]);
   });
   std::vector<int64_t> load(world, 0);
-  std::vector<int> owner(ns, 0);
+  owner.assign(ns, 0);
   for (int64_t k : order) {
     int best = 0;
     for (int r = 1; r < world; ++r)
       if (load[r] < load[best]) best = r;
     owner[k] = best;
-    load[best] += s->cuts[k + 1] - s->cuts[k];
+    load[best] += cuts[k + 1] - cuts[k];
   }
+}
+
+void stream_index(dgrp_fasta_stream *s) {
+  std::vector<int> owner;
+  index_slices(s->fasta, s->nbytes, s->c->shard_world, s->cuts, owner);
   s->mine.clear();
-  for (int64_t k = 0; k < ns; ++k)
+  for (int64_t k = 0; k + 1 < (int64_t)s->cuts.size(); ++k)
     if (owner[k] == s->c->shard_rank && s->cuts[k + 1] > s->cuts[k]) s->mine.push_back(k);
 }
 
@@ -1539,6 +1543,19 @@ void stream_copier_main(dgrp_fasta_stream *s) {
 }  // namespace
 
 extern "C" {
+
+int dgrp_fasta_index(const uint8_t *fasta, int64_t nbytes, int world, int64_t *cuts, int32_t *owner, int64_t cap,
+                     int64_t *n_slices) {
+  std::vector<int64_t> cv;
+  std::vector<int> ov;
+  if (nbytes < 0 || !n_slices) { set_error("bad arguments"); return DGRP_E_ARG; }
+  index_slices(fasta, nbytes, world, cv, ov);
+  *n_slices = (int64_t)ov.size();
+  if ((int64_t)ov.size() > cap) { set_error("slice table too small: %lld needed", (long long)ov.size()); return DGRP_E_CAPACITY; }
+  for (size_t k = 0; k < ov.size(); ++k) { if (cuts) cuts[k] = cv[k]; if (owner) owner[k] = ov[k]; }
+  if (cuts) cuts[ov.size()] = cv[ov.size()];
+  return DGRP_OK;
+}
 
 int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, const char *filename,
                            int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,

@@ -127,3 +127,19 @@ def merge_record_texts(pieces: Sequence[Sequence[Tuple[int, bytes]]]) -> bytes:
     """Rank 0: per-rank lists of (record index, TSV bytes) -> the file's TSV in record order."""
     allp = sorted((p for rank_list in pieces for p in rank_list), key=lambda t: t[0])
     return b"".join(t[1] for t in allp)
+
+
+def fasta_slices(raw, world: int = 1):
+    """The host index of the streaming driver (C ABI ``dgrp_fasta_index``; no GPU needed): ``(cuts, owner)`` --
+    ``cuts[k]:cuts[k+1]`` is slice ``k`` of the FASTA text (whole records, >= 8 MiB unless the file ends) and
+    ``owner[k]`` the rank it goes to, largest slice first to the least loaded rank."""
+    import ctypes
+    from . import _lib
+    n = len(raw)
+    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    cap = max(1, n // (8 << 20) + 2)
+    cuts, owner = np.zeros(cap + 1, np.int64), np.zeros(cap, np.int32)
+    ns = ctypes.c_int64(0)
+    _lib.check(_lib.lib().dgrp_fasta_index(_lib.ptr(buf), n, int(world), _lib.ptr(cuts), _lib.ptr(owner), cap,
+                                           ctypes.byref(ns)))
+    return cuts[:ns.value + 1].copy(), owner[:ns.value].copy()

@@ -252,6 +252,11 @@ int dgrp_fasta_record_tsv(dgrp_ctx *ctx, int64_t *owner, int64_t *tsv_off, int64
  * has written those rows when it raises.  One stream per context at a time; the context must not be used for
  * other calls while a stream is open. */
 typedef struct dgrp_fasta_stream dgrp_fasta_stream;
+/* The stream's host index alone (no GPU needed): the text is cut at header lines into slices of >= 8 MiB,
+ * cuts[0 .. n_slices] (cap + 1 entries) are their byte offsets and owner[k] the rank slice k goes to among `world`
+ * ranks (largest slice first to the least loaded rank).  DGRP_E_CAPACITY with *n_slices = required if cap is too small. */
+int dgrp_fasta_index(const uint8_t *fasta, int64_t nbytes, int world, int64_t *cuts, int32_t *owner, int64_t cap,
+                     int64_t *n_slices);
 int dgrp_fasta_stream_open(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,
                            const char *filename, int step, int batch_size, int use_mss, int min_mss_len,
                            int xdrop_len, int compat, dgrp_fasta_stream **out);

@@ -73,3 +73,27 @@ def test_gather_ranges_gloo_world2(tmp_path):
     pos = np.arange(length, dtype=np.int64)
     assert np.array_equal(np.load(tmp_path / "labels.npy"), (pos % 5).astype(np.uint8))
     assert np.array_equal(np.load(tmp_path / "scores.npy"), (np.sin(pos * 0.001) * 10).astype(np.float32))
+
+
+def test_fasta_slices_partition_the_text_at_headers():
+    """dgrp_fasta_index (the streaming driver's host index, no GPU): slices are whole records of >= 8 MiB, they
+    partition the text, and the largest-first assignment is balanced and the same for every rank."""
+    from deepgrp_b200 import sharding
+    rng = np.random.default_rng(4)
+    sizes = [9_500_000, 300, 12_000_000, 40_000, 8_400_000, 20_000_000, 1_000]
+    parts = []
+    for k, n in enumerate(sizes):
+        body = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, size=n)].tobytes()
+        lines = b"\n".join(body[i:i + 60] for i in range(0, n, 60))
+        parts.append(b">rec%d with > inside\n" % k + lines + b"\n")
+    raw = b"".join(parts)
+    cuts, owner = sharding.fasta_slices(raw, 3)
+    assert cuts[0] == 0 and cuts[-1] == len(raw) and (np.diff(cuts) > 0).all()
+    for c in cuts[1:-1]:
+        assert raw[c:c + 4] == b">rec" and raw[c - 1:c] == b"\n"           # cut points are header lines
+    assert (np.diff(cuts)[:-1] >= 8 << 20).all()                             # small records ride with a neighbour
+    load = np.bincount(owner, weights=np.diff(cuts), minlength=3)
+    assert load.max() <= 1.6 * load.mean()
+    cuts1, owner1 = sharding.fasta_slices(raw, 1)
+    assert np.array_equal(cuts1, cuts) and (owner1 == 0).all()
+    assert sharding.fasta_slices(b"", 2)[0].tolist() == [0, 0]
