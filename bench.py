@@ -414,6 +414,18 @@ def run_ours(args, rank, world, local_rank):
         strong = chunk_sharded(a3, rank, world, local_rank, ctx, stream, flush)
         if rank == 0:
             line["strong"] = strong
+    # -- BASELINE.json configs[4]: the widest search-space point (T = 512, U = 128) on a 248 Mbp record, chunk-sharded ------
+    if "config5b" in sections:
+        a5 = argparse.Namespace(**vars(args))
+        a5.bases, a5.vecsize, a5.units, a5.steps, a5.warmup = args.strong_bases, 512, 128, min(args.steps, 2), 1
+        c5 = chunk_sharded(a5, rank, world, local_rank, ctx, stream, flush)
+        if rank == 0:
+            nw = len(range(0, a5.bases - a5.vecsize, STEP))
+            tf = flops_per_window(a5.vecsize, a5.units) * nw / world / (c5["stages_ms"]["range_forward_score_max_over_ranks"] / 1e3) / 1e12
+            c5["roofline"] = {"bound": "tensor", "kernel": FORWARD_KERNELS[ctx.get_int("forward_used_tc")],
+                              "achieved_per_gpu": tf, "peak": tflops_peak, "unit": "TFLOP/s", "frac": tf / tflops_peak,
+                              "note": "forward + vote + score time of the slowest rank; algorithmic FLOPs of its share"}
+            line["config5b"] = c5
     # -- BASELINE.json configs[3]: the multi-FASTA genome, contig-sharded, end to end ------------------------------
     if "genome" in sections:
         g = genome_section(args, rank, world, weights, devnull, barrier)
@@ -636,9 +648,10 @@ def main():
     ap.add_argument("--weight-scale", type=float, default=1.0,
                     help="multiply the random-init weights (4 = the confident-output set of SURVEY.md section 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sections", default="x4,strong,genome",
+    ap.add_argument("--sections", default="x4,strong,config5b,genome",
                     help="extra measurements attached to the JSON line: x4 (the confident-output weight set), strong "
-                         "(BASELINE.json configs[2], one chr1-sized record chunk-sharded over the ranks), genome "
+                         "(BASELINE.json configs[2], one chr1-sized record chunk-sharded over the ranks), config5b (configs[4]: "
+                         "T = 512, U = 128 on the same record length, chunk-sharded), genome "
                          "(configs[3] in shape, n_gpus/8 of the 3.1 Gbp multi-FASTA, end to end); '' for none")
     ap.add_argument("--e2e-api", default="stream", choices=["stream", "oneshot"])
     ap.add_argument("--strong-bases", type=int, default=248_000_000)
