@@ -293,6 +293,7 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_fp16x2")) c->forward_fp16x2 = (int)value;
   else if (!strcmp(key, "forward_gather")) c->forward_gather = (int)value;
   else if (!strcmp(key, "forward_fuse_score")) c->forward_fuse_score = (int)value;
+  else if (!strcmp(key, "forward_smem_vote")) c->forward_smem_vote = (int)value;
   else if (!strcmp(key, "forward_wide")) c->forward_wide = (int)value;
   else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
   else if (!strcmp(key, "forward_ub")) c->forward_ub = (int)value;
@@ -312,6 +313,7 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_fp16x2")) *value = c->forward_fp16x2;
   else if (!strcmp(key, "forward_gather")) *value = c->forward_gather;
   else if (!strcmp(key, "forward_fuse_score")) *value = c->forward_fuse_score;
+  else if (!strcmp(key, "forward_smem_vote")) *value = c->forward_smem_vote;
   else if (!strcmp(key, "fused_last")) *value = c->fused_last;
   else if (!strcmp(key, "forward_wide")) *value = c->forward_wide;
   else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;

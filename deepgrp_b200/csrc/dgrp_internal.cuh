@@ -111,6 +111,7 @@ struct dgrp_ctx {
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
                            // record run in slabs of at most this many bytes of [windows][T][C] probabilities
+  int forward_smem_vote = 1;    // tcgen05 forward: max-merge a tile's windows in shared memory (no window probabilities in HBM)
   int forward_fuse_score = 1;   // whole-record calls: fuse vote + score transform when the windows fit one slab
   int fused_last = 0;      // the last core_predict produced label + score directly (no predictions in HBM)
   int forward_used_tc = 0; // what the last forward launch used: 0 fp32 kernel, 1 two-tile tcgen05, 2 wide, 3 wide CTA pair

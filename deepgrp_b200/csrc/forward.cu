@@ -317,11 +317,27 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
     // The tcgen05 kernels leave the window probabilities in a [windows][T][C] buffer that a gather pass
     // max-merges into pred; the windows run in slabs so that the buffer stays below forward_slab_bytes
     // (33.9 GB for a chr1-sized record otherwise).  The gather folds pred's current value, so slabs compose.
+    auto dispatch = [&](FwdParams &q, int *used) -> int {
+      int rc = DGRP_E_UNSUPPORTED;
+      if (c->forward_wide == 0) { rc = launch_forward_tc(c, m, q); *used = 1; }
+      if (rc == DGRP_E_UNSUPPORTED && c->forward_wide != 2) { rc = launch_forward_tcw(c, m, q, 1); *used = 2; }
+      if (rc == DGRP_E_UNSUPPORTED) { rc = launch_forward_tcw(c, m, q, 2); *used = 3; }
+      return rc;
+    };
+    // Will the kernel max-merge a tile's windows in shared memory (the usual case)?  Then no window probabilities
+    // exist in HBM: one launch over all windows, the tile spans go straight into the zero-initialised pred.
+    bool smem_vote = false;
+    if (w_end > w_begin) {
+      FwdParams q = p;
+      q.query = 1;
+      int used = 0;
+      smem_vote = dispatch(q, &used) == DGRP_OK && q.smem_vote;
+    }
     const int64_t per_win = (int64_t)m->T * m->C * (int64_t)sizeof(float);
     int64_t slab = c->forward_slab_bytes / per_win;
     slab = slab < 4096 ? 4096 : slab & ~(int64_t)4095;   // whole tiles of 64 windows, pairs of them per SM
     p.win_probs = nullptr;
-    if (c->forward_gather) {
+    if (c->forward_gather && !smem_vote) {
       const int64_t nw = w_end - w_begin < slab ? w_end - w_begin : slab;
       if (nw > 0 && c->winprobs.reserve((size_t)(nw * per_win)) == DGRP_OK) p.win_probs = c->winprobs.as<float>();
       else cudaGetLastError();   // out of memory: the kernels vote with atomicMax instead
@@ -342,10 +358,8 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
     for (int64_t w0 = w_begin; w0 < w_end; w0 += slab) {
       const int64_t w1 = w0 + slab < w_end ? w0 + slab : w_end;
       p.w_begin = w0; p.w_end = w1;
-      int rc = DGRP_E_UNSUPPORTED, used = 0;
-      if (c->forward_wide == 0) { rc = launch_forward_tc(c, m, p); used = 1; }
-      if (rc == DGRP_E_UNSUPPORTED && c->forward_wide != 2) { rc = launch_forward_tcw(c, m, p, 1); used = 2; }
-      if (rc == DGRP_E_UNSUPPORTED) { rc = launch_forward_tcw(c, m, p, 2); used = 3; }
+      int used = 0;
+      int rc = dispatch(p, &used);
       if (rc == DGRP_E_UNSUPPORTED) {
         if (w0 != w_begin) { set_error("forward: tcgen05 form lost between slabs"); return DGRP_E_CUDA; }
         p.w_begin = w_begin; p.w_end = w_end; p.win_probs = nullptr;

@@ -23,6 +23,9 @@ struct FwdParams {
   float *scratch, *ff2, *qbuf;
   float *pred;
   int64_t pred_row0, pred_rows;
+  int smem_vote;          // tcgen05 form: max-merge a tile's windows in shared memory (the idle A operand) and write
+                          // every row of the tile's span once; set by the launcher when the span fits
+  int query;              // launcher: only decide (smem_vote, support) and return, do not launch
   float *win_probs;       // tcgen05 form: [w - w_begin][T][C] window probabilities instead of the vote
                           // (merged afterwards by vote_gather_kernel), or null: atomicMax into pred
 };

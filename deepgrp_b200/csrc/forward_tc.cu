@@ -429,7 +429,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     for (int s = 0; s < nt; ++s)
       attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(
           p, sum0 + (size_t)s * K::WT * T * UP, q0 + (size_t)s * K::WT * UP,
-          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, p.wpp, s_scale, s_score);
+          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, p.wpp, s_scale, s_score,
+          p.smem_vote == 1 ? reinterpret_cast<float *>(s_A)            // A is idle: every MMA of the unit has completed
+                           : (p.smem_vote == 2 ? reinterpret_cast<float *>(s_codes + 4 * (size_t)p.code_span) : nullptr));
     tile += nt;
   }
 
@@ -469,8 +471,20 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   const size_t smem = tc_smem_bytes<UP, NP>(p.T, wpp, p.code_span);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
   p.wpp = wpp;
+  // the tile's span of rows, max-merged in the A operand's shared memory during the second phase
+  // (1: in the A operand, idle in the second phase; 2: small models, whose A is smaller than the span -- a region of
+  // its own behind the staged codes)
+  const size_t vote_bytes = (size_t)span * p.C * sizeof(float);
+  size_t smem_total = smem;
+  p.smem_vote = 0;
+  if (c->forward_smem_vote) {
+    if (vote_bytes <= (size_t)2 * NP * K::A_BYTES) p.smem_vote = 1;
+    else if (smem + vote_bytes <= 227 * 1024) { p.smem_vote = 2; smem_total = smem + vote_bytes; }
+  }
+  if (p.query) return DGRP_OK;
+  if (p.smem_vote) p.win_probs = nullptr;
   auto kern = gru_tc_attention_vote_kernel<UP, ST, NP>;
-  DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < c->sm_count ? n_pairs : c->sm_count);
@@ -481,7 +495,7 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   p.qbuf = reinterpret_cast<float *>(c->avg.as<unsigned char>() + rows * p.T * UP * sizeof(ST));
   p.ff2 = c->io_c.as<float>();
   // p.win_probs (window probabilities, max-merged by the caller's gather pass) or the atomic vote: forward.cu
-  kern<<<grid, TC_THREADS, smem, c->stream>>>(p);
+  kern<<<grid, TC_THREADS, smem_total, c->stream>>>(p);
   c->launches++;
   DGRP_CUDA(cudaGetLastError());
   return DGRP_OK;

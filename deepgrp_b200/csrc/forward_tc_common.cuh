@@ -272,9 +272,19 @@ __device__ __forceinline__ float inv4_dot(const float *d, const float *sc) {
 template <int UP, int WT, int NWARPS, typename ST>
 __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, const ST *sum, const float *qbuf,
                                                         const float *proj, int64_t w_tile0, int wpp,
-                                                        const float *s_scale, float *s_score) {
+                                                        const float *s_scale, float *s_score, float *s_vote = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.T, C = p.C;
+  // Shared-memory vote (s_vote: float[(WT - 1) * step + T][C], the idle A operand): the tile's windows overlap each
+  // other, so their probabilities are max-merged on chip (shared-memory atomicMax on the int view, probabilities
+  // are > 0) and every row of the tile's span leaves the SM once -- a plain store for the rows only this tile's
+  // windows cover, a global atomicMax for the T - step rows at either end that the neighbouring tiles share and
+  // for rows the displaced last batch (prediction.py:105) may land on.  The [windows][T][C] probabilities never
+  // touch HBM.
+  const int vspan = (WT - 1) * p.step + T;
+  if (s_vote) {
+    for (int i = tid; i < vspan * C; i += NWARPS * 32) s_vote[i] = 0.f;   // ordered before the votes by the pass barrier
+  }
   constexpr int NCH = UP / 8;          // 8-unit chunks per avg row
   constexpr int CPL = NCH / 4;         // chunks per lane: cj, cj + 4, ...
   constexpr int CH = CPL > 2 ? 2 : CPL;   // chunks per lane and sweep
@@ -457,7 +467,14 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
 #pragma unroll
           for (int c = 0; c < 5; ++c) { lg[c] = c < C ? exp_fast(lg[c] - mx) : 0.f; sum_e += lg[c]; }
           const float inv = 1.0f / sum_e;
-          if (p.win_probs) {
+          if (s_vote && w < p.full_windows) {
+            if (t < T) {
+              int *dst = reinterpret_cast<int *>(s_vote) + ((int)(w - w_tile0) * p.step + t) * C;
+#pragma unroll
+              for (int c = 0; c < 5; ++c)
+                if (c < C) atomicMax(dst + c, __float_as_int(lg[c] * inv));
+            }
+          } else if (p.win_probs) {
             // plain stores of the window's probabilities; vote_gather_kernel max-merges them
             if (t < T) {
               float *dst = p.win_probs + ((size_t)(w - p.w_begin) * T + t) * C;
@@ -480,6 +497,37 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
     TC_TRACE2(3);
     asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");   // s_score is rewritten by the next pass
     TC_TRACE2(4);
+  }
+  if (s_vote) {
+    // the tile's merged rows -> pred.  Row r of the span is record row w_tile0 * step + r.
+    const int64_t row0 = w_tile0 * (int64_t)p.step - p.pred_row0;
+    const int64_t tail_lo = p.tail_base - p.pred_row0;                      // rows the displaced batch can touch
+    const int64_t tail_hi = tail_lo + (p.w_end > p.full_windows ? (p.w_end - p.full_windows - 1) * (int64_t)p.step + T : 0);
+    const bool first = w_tile0 == p.w_begin;
+    const bool last = w_tile0 + WT >= (p.full_windows < p.w_end ? p.full_windows : p.w_end);
+    const int own_lo = first ? 0 : T - p.step;                             // below: shared with the previous tile
+    const int own_hi = last ? vspan : WT * p.step;                         // from here on: shared with the next tile
+    for (int r = tid; r < vspan; r += NWARPS * 32) {
+      const int64_t g = row0 + r;
+      if (g < 0 || g >= p.pred_rows) continue;
+      float v[5];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { v[c] = c < C ? s_vote[r * C + c] : 0.f; any |= v[c] != 0.f; }
+      if (!any) continue;                                                   // no window of this tile covers the row
+      float *dst = p.pred + (size_t)g * C;
+      const bool shared_row = r < own_lo || r >= own_hi || (g >= tail_lo && g < tail_hi);
+      if (shared_row) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+          if (c < C) atomicMax(reinterpret_cast<int *>(dst) + c, __float_as_int(v[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+          if (c < C) dst[c] = v[c];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");   // the next tile zeroes s_vote
   }
 }
 

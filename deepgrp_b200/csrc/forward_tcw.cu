@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
         *reinterpret_cast<uint4 *>(s_A + off) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4 *>(s_A + K::A_BYTES + off) = make_uint4(0u, 0u, 0u, 0u);
       }
-    if (uq == 0) *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase]);
+    if (uq == 0) {
+      *reinterpret_cast<uint4 *>(s_A + oh_off) = onehot_row(s_codes[cbase]);
+      *reinterpret_cast<uint4 *>(s_A + oh_off + 128) = make_uint4(0u, 0u, 0u, 0u);   // (A doubles as the vote buffer)
+    }
     arrive_ready(0);
     if (OVL) {
 #pragma unroll
@@ -481,7 +484,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
     gate_bar_sync();
     if (live)
       attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(p, sum0, q0, proj0, p.w_begin + tile * K::WT, p.wpp,
-                                                            s_scale, s_score);
+                                                            s_scale, s_score,
+                                                            p.smem_vote == 1 ? reinterpret_cast<float *>(s_A)
+                                                            : (p.smem_vote == 2 ? reinterpret_cast<float *>(s_codes + 2 * (size_t)p.code_span) : nullptr));
   }
 
   // ---- teardown: every MMA of the pair has completed (each CTA saw its last "done"); the pair's CTAs
@@ -516,8 +521,17 @@ static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   const size_t smem = tcw_smem_bytes<UP, RNN, PAIR, UB>(p.T, wpp, p.code_span);
   if (smem > 227 * 1024) return DGRP_E_UNSUPPORTED;   // caller falls back to the fp32 kernel
   p.wpp = wpp;
+  const size_t vote_bytes = (size_t)span * p.C * sizeof(float);
+  size_t smem_total = smem;
+  p.smem_vote = 0;
+  if (c->forward_smem_vote) {
+    if (vote_bytes <= (size_t)2 * K::A_BYTES) p.smem_vote = 1;          // in the A operand, idle in the second phase
+    else if (smem + vote_bytes <= 227 * 1024) { p.smem_vote = 2; smem_total = smem + vote_bytes; }   // a region of its own
+  }
+  if (p.query) return DGRP_OK;
+  if (p.smem_vote) p.win_probs = nullptr;
   auto kern = rnn_tcw_kernel<UP, RNN, PAIR, UB, OVL>;
-  DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
   const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
   const int64_t n_units = (n_tiles + K::NCTA - 1) / K::NCTA;
   const int64_t max_groups = c->sm_count / K::NCTA;
@@ -531,7 +545,7 @@ static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = smem_total;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -240,11 +240,15 @@ def test_window_slabs_compose(dg):
     ref = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
     mb = dg.ctx.get_int("forward_slab_mb")
     dg.ctx.set_int("forward_slab_mb", 1)   # 4096-window slabs (the minimum)
+    dg.ctx.set_int("forward_smem_vote", 0)  # the route with the window probabilities in HBM
     try:
         got = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
+        dg.ctx.set_int("forward_slab_mb", mb)
+        one = dg.pred.predict(w, ds, (fwd.shape[1], 5), 50)
     finally:
         dg.ctx.set_int("forward_slab_mb", mb)
-    assert np.array_equal(got, ref)
+        dg.ctx.set_int("forward_smem_vote", 1)
+    assert np.array_equal(got, ref) and np.array_equal(one, ref)   # ref: the shared-memory vote (default)
 
 
 def test_no_attention_model_through_the_fused_path(dg, oracle):
@@ -499,27 +503,32 @@ def test_config1_tsv_row_diff(dg, oracle, tmp_path):
 
 
 @pytest.mark.parametrize("scale", (1.0, 4.0))
-def test_fused_vote_and_score_equals_the_two_pass_form(dg, scale):
-    """Whole-record calls fuse the max-vote with the score transform when every window fits one slab (label u8 + score
-    f32 out of the gather pass, the float32[L, C] predictions never written); with the fusion off, or with the
-    windows in several slabs, the predictions are materialised and scored by a second kernel.  Same labels, same
-    rows -- bit for bit, the vote being order-independent and the score transform the same instructions."""
+def test_vote_forms_agree_bit_for_bit(dg, scale):
+    """The max-vote in its forms: (default) a tile's windows merged in shared memory and every row of the tile's span
+    written once, shared rows by atomicMax; window probabilities in HBM + a gather pass fused with the score
+    transform (label u8 + score f32 out, the float32[L, C] predictions never written); the same with a separate
+    score kernel; the same with the windows in several slabs.  Same labels, same rows -- bit for bit, the vote
+    being order-independent and the score transform the same instructions."""
     w = dg.model.random_weights(150, 32, attention=True, seed=5)
     if scale != 1.0:
         w = w.scaled(scale)
     text = ("NNN" + random_dna(400_000, 9) + "N").encode()
     out = {}
     try:
-        for fuse, slab_mb in ((1, 8192), (0, 8192), (1, 1)):
+        # (shared-memory vote, fuse, slab MiB): the default; window probabilities in HBM + fused gather; the same
+        # with a separate score pass; the same in several slabs
+        for smem, fuse, slab_mb in ((1, 1, 8192), (0, 1, 8192), (0, 0, 8192), (0, 1, 1)):
+            dg.ctx.set_int("forward_smem_vote", smem)
             dg.ctx.set_int("forward_fuse_score", fuse)
             dg.ctx.set_int("forward_slab_mb", slab_mb)
             labels, startpos, rows = dg.pred.predict_sequence(w, text, 50, 256, True, 50, 50)
-            out[(fuse, slab_mb)] = (labels.copy(), startpos, rows.copy(), dg.ctx.get_int("fused_last"))
+            out[(smem, fuse, slab_mb)] = (labels.copy(), startpos, rows.copy(), dg.ctx.get_int("fused_last"))
     finally:
+        dg.ctx.set_int("forward_smem_vote", 1)
         dg.ctx.set_int("forward_fuse_score", 1)
         dg.ctx.set_int("forward_slab_mb", 8192)
-    assert out[(1, 8192)][3] == 1 and out[(0, 8192)][3] == 0 and out[(1, 1)][3] == 0
-    ref = out[(0, 8192)]
+    assert [out[k][3] for k in ((1, 1, 8192), (0, 1, 8192), (0, 0, 8192), (0, 1, 1))] == [0, 1, 0, 0]   # "fused_last"
+    ref = out[(0, 0, 8192)]
     for key, (labels, startpos, rows, _) in out.items():
         assert startpos == ref[1] and np.array_equal(labels, ref[0]) and np.array_equal(rows, ref[2]), key
     # a record shorter than the window: no window at all, every row scores +138.155 (class 0)
