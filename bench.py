@@ -156,12 +156,12 @@ def peaks():
 
 def ncu_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the forward kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r02d_*); None for any other workload."""
+    `ncu --set full` capture of this same workload (profiles/r02v_*); None for any other workload."""
     if (args.bases, args.vecsize, args.units) != (CONFIG2_BASES, T_DEFAULT, U_DEFAULT):
         return None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02d_fwd_tc_ncu_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02v_fwd_tc_ncu_raw.csv"))))
         col = {name: (unit, val) for name, unit, val in zip(rows[0], rows[1], rows[2])}
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         total = 0.0
