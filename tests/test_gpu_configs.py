@@ -534,3 +534,24 @@ def test_vote_forms_agree_bit_for_bit(dg, scale):
     # a record shorter than the window: no window at all, every row scores +138.155 (class 0)
     short = dg.pred.predict_sequence(w, b"ACGTACGTAC" * 10, 50, 256, True, 50, 50)
     assert short[0].size == 100
+
+
+def test_fasta_stream_can_be_abandoned(dg, tmp_path):
+    """Closing a stream before it is exhausted (the caller broke out of its loop, or raised) stops the pipeline's
+    threads without a hang and leaves the context usable."""
+    import io
+    import time
+    w = dg.model.random_weights(150, 32, attention=True, seed=0).scaled(4.0)
+    recs = [("r%d" % k, random_dna(9_000_000, 70 + k)) for k in range(3)]
+    p = tmp_path / "three.fa"
+    write_fasta(str(p), recs)
+    raw = open(p, "rb").read()
+    t0 = time.time()
+    st = dg.pred.FastaTsvStream(w, raw, "t.fa", 50, 256, True, 50, 50)
+    first = next(st)
+    assert len(first[4]) > 0
+    st.close()
+    assert time.time() - t0 < 60
+    out = io.BytesIO()
+    stats = dg.pred.predict_fasta_tsv_stream(w, raw, "t.fa", out, 50, 256, True, 50, 50)   # the context still works
+    assert stats["records"] == 3 and out.getvalue().count(b"\n") == stats["rows"]
