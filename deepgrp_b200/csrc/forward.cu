@@ -312,6 +312,11 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
   p.w_begin = w_begin; p.w_end = w_end;
   p.step = pl.step; p.full_windows = pl.full_windows; p.tail_base = pl.tail_base;
   p.pred = d_pred; p.pred_row0 = pred_row0; p.pred_rows = pred_rows;
+  if (w_end <= w_begin) {   // no window in this range (a record no longer than the window; an empty placement family)
+    if (fused && pred_rows > 0)   // the caller left the zero-fill to us
+      DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
+    return DGRP_OK;               // (forward_used_tc keeps what the last real launch used)
+  }
   c->forward_used_tc = 0;
   if (c->forward_tc) {
     // The tcgen05 kernels leave the window probabilities in a [windows][T][C] buffer that a gather pass
