@@ -256,6 +256,11 @@ __device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
+__device__ __forceinline__ float tanh_mufu(float x) {   // MUFU.TANH: relative error 2^-11
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float exp_fast(float x) {   // e^x through ex2.approx (2 ulp), e^{-inf} = 0
   return ex2_approx(x * 1.4426950408889634f);
 }
@@ -310,8 +315,9 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
         const int u0 = (cj + 4 * (i0 + i)) * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          q2[i][j] = qbuf[(size_t)wl * UP + u0 + j] * kTwoLog2e;
-          sc2[i][j] = -2.0f * s_scale[u0 + j];
+          // H16 (the default, "forward_sum16"): score = sum_u scale[u] tanh.approx(q[u] + sum/2); else the exact form
+          q2[i][j] = H16 ? qbuf[(size_t)wl * UP + u0 + j] : qbuf[(size_t)wl * UP + u0 + j] * kTwoLog2e;
+          sc2[i][j] = H16 ? s_scale[u0 + j] : -2.0f * s_scale[u0 + j];
         }
       }
       // the pass's windows are contiguous per (t, chunk): [pass][t][chunk][wpp windows][8 units]
@@ -359,11 +365,20 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
 #pragma unroll
               for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(wv[j]);
             }
-            float d[8];
+            if (H16) {
+              // The half-precision `sum` already limits a score to ~2^-11 per term; MUFU.TANH (tanh.approx.f32, relative
+              // error 2^-11) is the matching arithmetic: 3.5 instead of ~8.5 instructions and 1 instead of 1.25 MUFU
+              // operations per (t, unit).  Measured against the exact form: max |dp| 3.5e-8 on random-init weights,
+              // 3.5e-5 on the x4 set (1.4e-5 from the half-precision sum alone); forward_sum16 = 0 is the exact path.
 #pragma unroll
-            for (int j = 0; j < 8; ++j)   // e^{2 (q + sum/2)} + 1 = 2^{2 log2e q + log2e sum} + 1
-              d[j] = ex2_approx(fminf(fmaf(x[j], 1.4426950408889634f, q2[i][j]), 30.0f)) + 1.0f;
-            sacc += inv4_dot(d, sc2[i]) + inv4_dot(d + 4, sc2[i] + 4);
+              for (int j = 0; j < 8; ++j) sacc = fmaf(sc2[i][j], tanh_mufu(fmaf(x[j], 0.5f, q2[i][j])), sacc);
+            } else {
+              float d[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)   // e^{2 (q + sum/2)} + 1 = 2^{2 log2e q + log2e sum} + 1
+                d[j] = ex2_approx(fminf(fmaf(x[j], 1.4426950408889634f, q2[i][j]), 30.0f)) + 1.0f;
+              sacc += inv4_dot(d, sc2[i]) + inv4_dot(d + 4, sc2[i] + 4);
+            }
           }
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
