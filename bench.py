@@ -283,6 +283,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
+    ctx.set_int("stream_early_rows", args.early_rows)
+    ctx.set_int("stream_early_slabs", args.early_slabs)
+    ctx.set_int("stream_early_ratio", args.early_ratio)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     devnull = open(os.devnull, "wb")
@@ -368,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e_value": world * L * steps / (e2e_ms / 1e3) / 1e6, "e2e_ms_per_step": e2e_ms / steps,
                 "h2d": st["h2d_bytes"], "d2h": st["d2h_bytes"], "rows": int(n_rows.value), "launches": int(launches),
                 "stages_ms": mean_stage, "clocks": clocks, "kernel": used_kernel, "codes": codes,
-                "mss_rounds": ctx.get_int("mss_rounds")}
+                "mss_rounds": ctx.get_int("mss_rounds"), "early_parts": ctx.get_int("stream_early_parts")}
 
     weights = make_weights(args)
     L = args.bases
@@ -387,7 +390,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": main["clocks"],
         "e2e": {"value": main["e2e_value"], "unit": "Mbp/s", "h2d_bytes_per_step": main["h2d"],
                 "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms_per_step"],
-                "api": "deepgrp_b200.prediction.predict_fasta_tsv_stream (C ABI dgrp_fasta_stream_*)"},
+                "api": "deepgrp_b200.prediction.predict_fasta_tsv_stream (C ABI dgrp_fasta_stream_*)",
+                "early_parts": main["early_parts"]},
         "gpu_launches": main["launches"],
         "roofline": {"bound": "tensor", "kernel": FORWARD_KERNELS[main["kernel"]],
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
@@ -405,7 +409,8 @@ def run_ours(args, rank, world, local_rank):
         x4 = measure(make_weights(args4), L, min(args.steps, 5), 2, False)
         line["x4"] = {"weights": "the same random-init weights x 4 (max probability up to 0.9, all classes present)",
                       "value": x4["value"], "ms_per_step": x4["ms_per_step"], "e2e": x4["e2e_value"],
-                      "e2e_ms_per_step": x4["e2e_ms_per_step"], "rows_per_step": x4["rows"],
+                      "e2e_ms_per_step": x4["e2e_ms_per_step"], "e2e_early_parts": x4["early_parts"],
+                      "rows_per_step": x4["rows"],
                       "d2h_bytes_per_step": x4["d2h"], "stages_ms": x4["stages_ms"], "unit": "Mbp/s"}
     # -- BASELINE.json configs[2]: ONE chr1-sized record split by position over the ranks (strong scaling) -------
     if "strong" in sections:
@@ -654,6 +659,11 @@ def main():
                          "T = 512, U = 128 on the same record length, chunk-sharded), genome "
                          "(configs[3] in shape, n_gpus/8 of the 3.1 Gbp multi-FASTA, end to end); '' for none")
     ap.add_argument("--e2e-api", default="stream", choices=["stream", "oneshot"])
+    ap.add_argument("--early-rows", type=int, default=1,
+                    help="e2e leg: 1 = a long record's rows leave slab by slab while it is still being computed "
+                         "(dgrp_fasta_stream, DESIGN.md section 7), 0 = after the record's last window")
+    ap.add_argument("--early-slabs", type=int, default=0, help="position slabs of a long record (0 = library default)")
+    ap.add_argument("--early-ratio", type=int, default=0, help="slab size relative to the one before, per cent (0 = library default)")
     ap.add_argument("--strong-bases", type=int, default=248_000_000)
     ap.add_argument("--genome-scale", type=float, default=0.0, help="fraction of the 3.1 Gbp genome (0 = n_gpus / 8)")
     ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",

@@ -298,6 +298,10 @@ int dgrp_ctx_set_int(dgrp_ctx *c, const char *key, int64_t value) {
   else if (!strcmp(key, "forward_overlap")) c->forward_overlap = (int)value;
   else if (!strcmp(key, "forward_ub")) c->forward_ub = (int)value;
   else if (!strcmp(key, "stream_slot_mb")) c->stream_slot_mb = (int)value;
+  else if (!strcmp(key, "stream_early_rows")) c->stream_early_rows = (int)value;
+  else if (!strcmp(key, "stream_early_slabs")) c->stream_early_slabs = (int)value;
+  else if (!strcmp(key, "stream_early_unit")) c->stream_early_unit = (int)value;
+  else if (!strcmp(key, "stream_early_ratio")) c->stream_early_ratio = (int)value;
   else if (!strcmp(key, "forward_slab_mb")) c->forward_slab_bytes = (int64_t)value << 20;
   else if (!strcmp(key, "shard_rank")) c->shard_rank = (int)value;
   else if (!strcmp(key, "shard_world")) c->shard_world = (int)value;
@@ -319,6 +323,11 @@ int dgrp_ctx_get_int(dgrp_ctx *c, const char *key, int64_t *value) {
   else if (!strcmp(key, "forward_overlap")) *value = c->forward_overlap;
   else if (!strcmp(key, "forward_ub")) *value = c->forward_ub;
   else if (!strcmp(key, "stream_slot_mb")) *value = c->stream_slot_mb;
+  else if (!strcmp(key, "stream_early_rows")) *value = c->stream_early_rows;
+  else if (!strcmp(key, "stream_early_slabs")) *value = c->stream_early_slabs;
+  else if (!strcmp(key, "stream_early_unit")) *value = c->stream_early_unit;
+  else if (!strcmp(key, "stream_early_ratio")) *value = c->stream_early_ratio;
+  else if (!strcmp(key, "stream_early_parts")) *value = c->stream_early_parts;
   else if (!strcmp(key, "forward_slab_mb")) *value = c->forward_slab_bytes >> 20;
   else if (!strcmp(key, "forward_used_tc")) *value = c->forward_used_tc;
   else if (!strcmp(key, "sm_count")) *value = c->sm_count;
@@ -1179,6 +1188,7 @@ struct StreamPiece {
 struct StreamRecord {
   int buf;    // device text buffer
   int64_t bytes, slice, ordinal, rows;
+  int final_part;   // 0: rows of a record that is still being computed ("early rows"), more text follows
 };
 
 }  // namespace
@@ -1318,6 +1328,44 @@ int stream_upload(dgrp_fasta_stream *s, int64_t k, int b, int *stage_turn) {
   return DGRP_OK;
 }
 
+// Slab ends (positions) of a long record for the early-rows route; fewer than two = not worth it.  A slab is a
+// whole number of forward "units" (unit_w windows = one round of two tiles on every SM) minus the halo windows a
+// position range recomputes, so that the persistent kernel's CTAs get equal tile counts.  The first slab is a
+// PROBE of one unit: it tells whether the record's scores flush at all (if not, the rest runs as one call).
+// The n_slabs slabs after it shrink geometrically (ratio_pct per cent each) because only the LAST slab's text
+// cannot overlap any compute.
+void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, int ratio_pct,
+                std::vector<int64_t> &ends) {
+  ends.clear();
+  if (step <= 0 || unit_w <= 0) return;
+  const double K = (double)(length / step) / (double)unit_w - 1.0;   // units in the record behind the probe
+  int n = n_slabs;
+  if ((double)n > K / 2.0) n = (int)(K / 2.0);
+  if (n < 2) return;
+  const double ratio = (ratio_pct > 0 && ratio_pct <= 100 ? ratio_pct : 55) / 100.0;
+  double wsum = 0.0, w = 1.0;
+  for (int i = 0; i < n; ++i) { wsum += w; w *= ratio; }
+  const int64_t halo = (T + step - 1) / step + 8;
+  auto rows_of = [&](int64_t k) {
+    int64_t rows = (k * unit_w - halo) * step;
+    if (rows <= 0) rows = k * unit_w * step;
+    if (rows > 64) rows &= ~(int64_t)63;
+    return rows;
+  };
+  int64_t pos = rows_of(1);
+  ends.push_back(pos);
+  w = 1.0;
+  for (int i = 0; i + 1 < n; ++i, w *= ratio) {
+    int64_t k = (int64_t)(w / wsum * K + 0.5);
+    if (k < 1) k = 1;
+    const int64_t rows = rows_of(k);
+    if (pos + rows + unit_w * step >= length) break;
+    pos += rows;
+    ends.push_back(pos);
+  }
+  ends.push_back(length);
+}
+
 // one slice (already on the device in raw[b]): decode, then every record of it
 int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
   dgrp_ctx *c = s->c;
@@ -1367,51 +1415,135 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
       set_error("negative dimensions are not allowed (all-'N' record in slice %lld)", (long long)k);
       return DGRP_E_ALLN;
     }
-    stamp(c, 1);
-    DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, s->step, s->batch_size, s->compat, s->use_mss != 0));
-    s->windows += c->timings.windows; s->bases += length;
-    stamp(c, 2);
-    DGRP_CHECK(core_labels_after_predict(c, length, m->C, s->use_mss, s->min_mss_len, s->xdrop_len));
-    stamp(c, 4);
-    int64_t cnt = 0, need = 0;
-    int tb = -1;
-    if (length > 0) {
-      int64_t *d_tri = nullptr;
-      DGRP_CHECK(run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt));
+    s->bases += length;
+    std::string prefix(s->filename);
+    prefix.push_back('\t');
+    prefix.append(reinterpret_cast<const char *>(fasta + hb), (size_t)(he - hb));
+    prefix.push_back('\t');
+    bool prefix_up = false;
+    bool cancelled = false;
+    // rows (device triples) -> TSV text in one of the two device text buffers -> the copier.  final_part = 0: rows of
+    // a record whose later positions are still being computed; its text travels like a record's, without the
+    // end-of-record mark.  Synchronises the stream.
+    auto emit = [&](const int64_t *d_tri, int64_t cnt, int final_part) -> int {
+      int64_t need = 0;
+      int tb = -1;
       if (cnt > 0) {
         WaitClock wc(s->waits[10]);
-        std::string prefix(s->filename);
-        prefix.push_back('\t');
-        prefix.append(reinterpret_cast<const char *>(fasta + hb), (size_t)(he - hb));
-        prefix.push_back('\t');
-        DGRP_CHECK(c->tsv_prefix.reserve(prefix.size() + 16));
-        STREAM_CUDA(cudaMemcpyAsync(c->tsv_prefix.p, prefix.data(), prefix.size(), cudaMemcpyHostToDevice, c->stream));
-        DGRP_CHECK(run_tsv_measure(c, d_tri, cnt, (int)prefix.size(), &need));   // syncs: `prefix` may go
+        if (!prefix_up) {
+          DGRP_CHECK(c->tsv_prefix.reserve(prefix.size() + 16));
+          STREAM_CUDA(cudaMemcpyAsync(c->tsv_prefix.p, prefix.data(), prefix.size(), cudaMemcpyHostToDevice, c->stream));
+          prefix_up = true;
+        }
+        DGRP_CHECK(run_tsv_measure(c, d_tri, cnt, (int)prefix.size(), &need));   // syncs
         tb = (*text_turn)++ & 1;
         {
-          WaitClock wc(s->waits[1]);
-          std::unique_lock<std::mutex> lk(s->mu);   // the copier still drains the record before last
+          WaitClock wc1(s->waits[1]);
+          std::unique_lock<std::mutex> lk(s->mu);   // the copier still drains the text before last
           s->cv.wait(lk, [&] { return s->text_busy[tb] == 0 || s->cancel; });
-          if (s->cancel) return DGRP_OK;
+          if (s->cancel) { cancelled = true; return DGRP_OK; }
         }
         DGRP_CHECK(s->text[tb].reserve((size_t)need + 16));
         DGRP_CHECK(run_tsv_write(c, d_tri, cnt, c->tsv_prefix.as<uint8_t>(), (int)prefix.size(),
                                  s->text[tb].as<uint8_t>()));
         STREAM_CUDA(cudaEventRecord(s->ev_text[tb], c->stream));
       }
-    }
-    stamp(c, 5);
-    STREAM_CUDA(cudaStreamSynchronize(c->stream));
+      if (final_part) stamp(c, 5);
+      STREAM_CUDA(cudaStreamSynchronize(c->stream));
+      s->rows += cnt;
+      if (cnt > 0 || final_part) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (tb >= 0) s->text_busy[tb] = 1;
+        s->ready.push_back(StreamRecord{tb, need, k, ordinal, cnt, final_part});   // records without rows travel as empty pieces
+      }
+      s->cv.notify_all();
+      return DGRP_OK;
+    };
+    // Long records with MSS: positions in slabs, see stream_record_slabs
+    std::vector<int64_t> slab_end;
+    if (s->use_mss && c->stream_early_rows && length > 0)
+      plan_slabs(length, m->T, s->step, c->stream_early_unit > 0 ? c->stream_early_unit : (int64_t)c->sm_count * 128,
+                 c->stream_early_slabs > 0 ? c->stream_early_slabs : 4, c->stream_early_ratio, slab_end);
+    c->stream_early_parts = 0;
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s->forward_ms += ms;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); s->gpu_ms += ms;
-    s->rows += cnt; s->records += 1;
-    {
-      std::lock_guard<std::mutex> lk(s->mu);
-      if (tb >= 0) s->text_busy[tb] = 1;
-      s->ready.push_back(StreamRecord{tb, need, k, ordinal, cnt});   // records without rows travel as empty pieces
+    if (slab_end.size() >= 2) {
+      // "Early rows".  MSS needs the whole record before the LAST candidate is final, but not before the first:
+      // whenever a run of positive scores finds no candidate with a smaller running sum the reference flushes its
+      // stack (mss.c:78-81) and nothing before that run can change any more.  The record is computed in position
+      // slabs (halo recompute, as for chunk sharding); after each slab MSS runs over [restart, slab end) from the
+      // carried running sum, the part before the last flush is gap-filled, cut into rows and formatted, and its
+      // text crosses PCIe while the next slab's forward runs.  Scores that drift upwards never flush: the first
+      // slab that makes little progress ends the probing and the record finishes as a whole.  Identical rows
+      // either way (tests/test_gpu_stream.py; the resumed scan is pinned on the CPU in tests/test_host.py).
+      DGRP_CHECK(c->labels.reserve((size_t)length));
+      DGRP_CHECK(c->scores32.reserve((size_t)length * 4));
+      DGRP_CHECK(c->labels2.reserve((size_t)length));
+      DGRP_REQUIRE(length < 2147483647LL, "record longer than 2^31-1 bases (int indices in mss.h:16)");
+      uint8_t *lab = c->labels.as<uint8_t>(), *lab2 = c->labels2.as<uint8_t>();
+      float *sc = c->scores32.as<float>();
+      double min_sc, xdrop;
+      mss_thresholds(s->min_mss_len, s->xdrop_len, &min_sc, &xdrop);
+      int64_t p0 = 0, r = 0, e = 0;   // slab start; MSS resumes at r (running sum L0); rows are out up to e
+      double L0 = 0.0;
+      bool probing = true;
+      for (size_t q = 0; q < slab_end.size() && !cancelled; ++q) {
+        const int64_t p1 = slab_end[q];
+        const bool last = q + 1 == slab_end.size();
+        stamp(c, 1);
+        DGRP_CHECK(core_predict_range(c, m, c->codes.as<uint8_t>(), 0, length, length, p0, p1, s->step, s->batch_size,
+                                      s->compat, lab + p0, sc + p0));
+        stamp(c, 2);
+        s->windows += c->timings.windows;
+        p0 = p1;
+        dgrp_seg_t *d_segs = nullptr;
+        int n_seg = 0;
+        int64_t *d_tri = nullptr;
+        int64_t cnt = 0;
+        if (last) {
+          DGRP_CHECK(run_mss_segments(c, nullptr, sc + r, (int)(length - r), min_sc, xdrop, &d_segs, &n_seg, L0, nullptr));
+          DGRP_CHECK(run_gap_fill(c, d_segs, n_seg, lab + r, nullptr, (int)(length - r), m->C, lab2 + r));
+          stamp(c, 4);
+          DGRP_CHECK(run_segments(c, lab2 + e, nullptr, length - e, startpos + e, false, &d_tri, &cnt));
+          DGRP_CHECK(emit(d_tri, cnt, 1));
+        } else if (probing) {
+          MssResume rs;
+          DGRP_CHECK(run_mss_segments(c, nullptr, sc + r, (int)(p1 - r), min_sc, xdrop, &d_segs, &n_seg, L0, &rs));
+          if (rs.restart > 0) {
+            DGRP_CHECK(run_gap_fill(c, d_segs, n_seg, lab + r, nullptr, rs.restart, m->C, lab2 + r));
+            if (rs.restart < (p1 - r) / 2) probing = false;
+            r += rs.restart;
+            L0 = rs.L0;
+            int64_t tail = 0;
+            DGRP_CHECK(run_segments(c, lab2 + e, nullptr, r - e, startpos + e, false, &d_tri, &cnt, &tail));
+            e += tail;
+            DGRP_CHECK(emit(d_tri, cnt, 0));
+            if (cnt > 0) c->stream_early_parts += 1;
+          } else {
+            probing = false;
+          }
+        }
+        STREAM_CUDA(cudaEventSynchronize(c->ev[2]));
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s->forward_ms += ms;
+        // nothing (more) to gain from slabs: the rest of the record in one call
+        if (!probing && q + 2 < slab_end.size()) slab_end.erase(slab_end.begin() + (q + 1), slab_end.end() - 1);
+      }
+      if (cancelled) return DGRP_OK;
+    } else {
+      stamp(c, 1);
+      DGRP_CHECK(core_predict(c, m, c->codes.as<uint8_t>(), length, s->step, s->batch_size, s->compat, s->use_mss != 0));
+      s->windows += c->timings.windows;
+      stamp(c, 2);
+      DGRP_CHECK(core_labels_after_predict(c, length, m->C, s->use_mss, s->min_mss_len, s->xdrop_len));
+      stamp(c, 4);
+      int64_t cnt = 0;
+      int64_t *d_tri = nullptr;
+      if (length > 0) DGRP_CHECK(run_segments(c, c->labels2.as<uint8_t>(), nullptr, length, startpos, false, &d_tri, &cnt));
+      DGRP_CHECK(emit(d_tri, cnt, 1));
+      if (cancelled) return DGRP_OK;
+      cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s->forward_ms += ms;
     }
-    s->cv.notify_all();
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); s->gpu_ms += ms;
+    s->records += 1;
     ++ordinal;
   }
   return DGRP_OK;
@@ -1493,7 +1625,7 @@ void stream_copier_main(dgrp_fasta_stream *s) {
       s->ready.pop_front();
     }
     if (r.buf < 0 || r.bytes == 0) {   // a record without rows
-      inflight.push_back(StreamPiece{-1, 0, r.slice, r.ordinal, r.rows, 1});
+      inflight.push_back(StreamPiece{-1, 0, r.slice, r.ordinal, r.rows, r.final_part});
       while (!inflight.empty()) publish_oldest();
       continue;
     }
@@ -1524,7 +1656,7 @@ void stream_copier_main(dgrp_fasta_stream *s) {
       cudaEventRecord(s->ev_slot[slot], s->s_out);
       s->d2h_bytes += len;
       inflight.push_back(StreamPiece{slot, len, r.slice, r.ordinal, off + len >= r.bytes ? r.rows : 0,
-                                     off + len >= r.bytes ? 1 : 0});
+                                     (off + len >= r.bytes && r.final_part) ? 1 : 0});
       if ((int)inflight.size() >= kSlots - 1) publish_oldest();
     }
     while (!inflight.empty()) publish_oldest();   // the record's last copy has completed: its device buffer is free

@@ -107,6 +107,12 @@ struct dgrp_ctx {
   int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
                            // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
   int stream_slot_mb = 0;  // dgrp_fasta_stream: size of one host piece of TSV text, MiB (0 = 64)
+  int stream_early_rows = 1;   // dgrp_fasta_stream: long records are computed in position slabs and the rows that are
+                               // final after a slab (everything before the last MSS flush) leave while the next slab runs
+  int stream_early_slabs = 0;  // number of slabs of a long record behind the one-unit probe slab (0 = default: 4)
+  int stream_early_unit = 0;   // windows per unit of a slab (0 = one wave of the forward kernel: 128 x SM count)
+  int stream_early_ratio = 0;  // size of a slab relative to the one before it, per cent (0 = default: 55)
+  int stream_early_parts = 0;  // diagnostic: parts of the last record's text that left before its last slab
   int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 64)
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates
   int64_t forward_slab_bytes = (int64_t)8 << 30;   // bound of the window-probability buffer: the windows of a
@@ -189,8 +195,17 @@ int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t 
 void build_tcw_operands(int rnn, int U, int UP, int C, bool att, const float *Rp, const float *P, const float *b1,
                         const float *ffk, std::vector<uint16_t> (&out)[2][2], int *shift);
 // mss.cu
+// L0: the running sum the scan starts from (0 at the start of a record).  resume != nullptr: the scores are a
+// PREFIX of a record ("open end"): only the segments that are final whatever follows are returned -- those the
+// last FLUSH run (mss.c:78-81) or an earlier event flushed -- and *resume receives where and with which running
+// sum the record can be resumed (restart = -1: nowhere yet; the caller then passes the same prefix start again).
+struct MssResume {
+  int restart;   // index of the first element of the last FLUSH run
+  double L0;     // running sum before it
+};
 int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
-                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg);
+                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg, double L0 = 0.0,
+                     MssResume *resume = nullptr);
 int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t *d_label_in,
                  const int64_t *d_label64_in, int n, int nof_labels, uint8_t *d_label_out);
 int launch_labels_to_onehot(dgrp_ctx *c, const uint8_t *d_label, int64_t n, int C, double *d_out);
@@ -205,8 +220,12 @@ int launch_filter_segments(dgrp_ctx *c, const uint8_t *d_in, uint8_t *d_out, int
 int launch_confusion(dgrp_ctx *c, const uint8_t *d_truth, const uint8_t *d_pred, int64_t n,
                      unsigned long long *d_cnf, int *d_bad);
 // segments.cu
+// open_tail != nullptr: the labels are a prefix of a record whose continuation is not known yet.  The
+// reference's special case of the record's last element does not apply, and a run that reaches the end of
+// the prefix is NOT emitted: *open_tail receives its first index (n when the prefix ends on a zero).
 int run_segments(dgrp_ctx *c, const uint8_t *d_label, const int64_t *d_label64, int64_t n,
-                 int64_t offset, bool keep_zero, int64_t **d_triples, int64_t *n_out);
+                 int64_t offset, bool keep_zero, int64_t **d_triples, int64_t *n_out,
+                 int64_t *open_tail = nullptr);
 int launch_get_segments(dgrp_ctx *c, const int64_t *d_classes, int64_t size, int64_t startpos,
                         int64_t *d_out3);
 

@@ -1,6 +1,8 @@
 // K7: chunked maximal-scoring-segment scan + majority gap fill.
 // Replaces deepgrp/_mss/mss.c:50-101 (mss_find_all) and deepgrp/_mss/pymss.pyx:31-80
 // (_find_mss_labels).  The algorithm and why it is bit-exact are described in mss_core.cuh.
+#include <algorithm>
+
 #include "dgrp_internal.cuh"
 #include "mss_core.cuh"
 #include "scan_util.cuh"
@@ -98,22 +100,26 @@ struct ScanBufs {
   int *n_dirty;
 };
 
-// mode 0: every chunk from the canonical state; mode 1: stale chunks from their predicted state.
+// mode 0: chunk 0 from the initial state (running sum L0), every other chunk from the canonical state;
+// mode 1: stale chunks from their predicted state.  store = 0: a speculative first round that leaves the run
+// records to the second one (which then re-runs every chunk): its 25 bytes per run were the larger part of
+// the round's memory traffic.
 template <typename T>
 __global__ void mss_scan_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
-                                int mode, ScanBufs b, RunTable rt) {
+                                int mode, double L0, int store, ScanBufs b, RunTable rt) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
   ScanState s;
-  if (mode == 0) mss::state_canonical(s);
-  else {
+  if (mode == 0) {
+    if (c == 0) mss::state_initial(s, L0); else mss::state_canonical(s);
+  } else {
     if (!b.dirty[c]) return;
     s = b.pred[c];
   }
   b.used[c] = s;
   const int lo = c * CH, hi = lo + CH < n ? lo + CH : n;
   ChunkSummary sum;
-  mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, rt, sum);
+  mss::scan_chunk(S, n, xdrop, lo, hi, (int)b.base[c], s, rt, sum, store != 0);
   b.out[c] = s;
   b.sum[c] = sum;
 }
@@ -121,13 +127,13 @@ __global__ void mss_scan_kernel(const T *__restrict__ S, int n, double xdrop, in
 // One warp walks the chunk summaries: predicts every chunk's start state and marks the chunks whose
 // last execution started from something else.  Lanes stage 32 chunks at a time in shared memory,
 // lane 0 does the (inherently sequential, O(1) per chunk) chain.
-__global__ void mss_chain_kernel(int NC, ScanBufs b) {
+__global__ void mss_chain_kernel(int NC, ScanBufs b, double L0, int force) {
   __shared__ ScanState s_used[32], s_out[32], s_pred[32];
   __shared__ ChunkSummary s_sum[32];
   __shared__ uint8_t s_dirty[32];
   const int lane = threadIdx.x;
   ScanState s;
-  mss::state_canonical(s);
+  mss::state_initial(s, L0);
   int n_dirty = 0;
   for (int base = 0; base < NC; base += 32) {
     const int c = base + lane;
@@ -137,8 +143,9 @@ __global__ void mss_chain_kernel(int NC, ScanBufs b) {
       const int m = NC - base < 32 ? NC - base : 32;
       for (int k = 0; k < m; ++k) {
         s_pred[k] = s;
-        if (mss::state_equal(s_used[k], s)) { s_dirty[k] = 0; s = s_out[k]; }
-        else { s_dirty[k] = 1; ++n_dirty; s = mss::apply_summary(s_sum[k], s_used[k], s_out[k], s); }
+        const bool same = mss::state_equal(s_used[k], s);
+        if (same && !force) s_dirty[k] = 0; else { s_dirty[k] = 1; ++n_dirty; }   // force: nothing has been stored yet
+        s = same ? s_out[k] : mss::apply_summary(s_sum[k], s_used[k], s_out[k], s);
       }
     }
     __syncwarp();
@@ -170,10 +177,11 @@ __global__ void mss_group_compose_kernel(int NC, ScanBufs b, mss::Composite *com
   comp[g] = acc;
 }
 
-__global__ void mss_group_chain_kernel(int NG, const mss::Composite *comp, ScanState *gstart, int *n_dirty) {
+__global__ void mss_group_chain_kernel(int NG, const mss::Composite *comp, ScanState *gstart, int *n_dirty,
+                                       double L0) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ScanState s;
-  mss::state_canonical(s);
+  mss::state_initial(s, L0);
   for (int g = 0; g < NG; ++g) {
     gstart[g] = s;
     const mss::Composite k = comp[g];
@@ -207,7 +215,7 @@ __global__ void mss_super_fill_kernel(int NG, const mss::Composite *comp, const 
   }
 }
 
-__global__ void mss_group_fill_kernel(int NC, ScanBufs b, const ScanState *gstart) {
+__global__ void mss_group_fill_kernel(int NC, ScanBufs b, const ScanState *gstart, int force) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = g * MSS_GROUP;
   if (c0 >= NC) return;
@@ -217,19 +225,20 @@ __global__ void mss_group_fill_kernel(int NC, ScanBufs b, const ScanState *gstar
   for (int c = c0; c < c1; ++c) {
     b.pred[c] = s;
     const ScanState used = b.used[c], out = b.out[c];
-    if (mss::state_equal(used, s)) { b.dirty[c] = 0; s = out; }
-    else { b.dirty[c] = 1; ++n_dirty; s = mss::apply_summary(b.sum[c], used, out, s); }
+    const bool same = mss::state_equal(used, s);
+    if (same && !force) b.dirty[c] = 0; else { b.dirty[c] = 1; ++n_dirty; }
+    s = same ? out : mss::apply_summary(b.sum[c], used, out, s);
   }
   if (n_dirty) atomicAdd(b.n_dirty, n_dirty);
 }
 
 // Parallel verification of the fixed point: every chunk must have started from exactly the state its
 // predecessor ended in (chunk 0 from the canonical state).  Counts the chunks for which that fails.
-__global__ void mss_verify_kernel(int NC, ScanBufs b) {
+__global__ void mss_verify_kernel(int NC, ScanBufs b, double L0) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
   ScanState expect;
-  if (c == 0) mss::state_canonical(expect);
+  if (c == 0) mss::state_initial(expect, L0);
   else expect = b.out[c - 1];
   if (!mss::state_equal(b.used[c], expect)) atomicAdd(b.n_dirty, 1);
 }
@@ -238,10 +247,10 @@ __global__ void mss_verify_kernel(int NC, ScanBufs b) {
 // sums round in every chunk): walk the chain, re-running every chunk that is stale.
 template <typename T>
 __global__ void mss_complete_kernel(const T *__restrict__ S, int n, double xdrop, int CH, int NC,
-                                    ScanBufs b, RunTable rt) {
+                                    double L0, ScanBufs b, RunTable rt) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   ScanState s;
-  mss::state_canonical(s);
+  mss::state_initial(s, L0);
   for (int c = 0; c < NC; ++c) {
     if (mss::state_equal(b.used[c], s)) { s = b.out[c]; continue; }
     b.used[c] = s;
@@ -290,13 +299,38 @@ struct EmitSeg {
   }
 };
 
+// ---- open end (a prefix of a record) ---------------------------------------------------------------
+// The last FLUSH run of the table: there the reference empties its stack whatever follows (mss.c:78-81), so the
+// candidates flushed up to it are final although the record goes on, and the record can be resumed at the
+// run's first element with the running sum before it.
+struct MssLast {
+  int k;       // ordinal of the last FLUSH run, -1: none
+  int st;      // its first element
+  double L;    // the running sum before it
+};
+__global__ void mss_last_flush_kernel(const uint8_t *__restrict__ kind, int NR, int *last) {
+  int best = -1;
+  const int gs = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < NR; k += gs)
+    if (kind[k] == mss::RUN_FLUSH) best = k;   // k grows along the loop
+  for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(last, best);
+}
+__global__ void mss_last_record_kernel(const int *last, RunTable rt, MssLast *out) {
+  const int k = *last;
+  out->k = k;
+  out->st = k >= 0 ? rt.st[k] : 0;
+  out->L = k >= 0 ? rt.L[k] : 0.0;
+}
+
 static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 template <typename T>
 static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdrop,
-                     dgrp_seg_t **d_segs_out, int *n_seg) {
+                     dgrp_seg_t **d_segs_out, int *n_seg, double L0, MssResume *resume) {
   *n_seg = 0;
   *d_segs_out = nullptr;
+  if (resume) { resume->restart = -1; resume->L0 = L0; }
   if (n <= 0) return DGRP_OK;
   int CH = c->mss_chunk;
   if (CH <= 0) {
@@ -329,8 +363,8 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   unsigned long long *h = c->pin_small.as<unsigned long long>();
   DGRP_CHECK(fetch_small(c, h, d_total, 8));
   DGRP_CUDA(cudaStreamSynchronize(c->stream));
-  const int NR = (int)h[0];
-  if (NR == 0) return DGRP_OK;   // no positive score anywhere: no segments
+  int NR = (int)h[0];
+  if (NR == 0) return DGRP_OK;   // no positive score anywhere: no segments (and nowhere to resume)
 
   // ---- buffers
   const size_t nr1 = (size_t)NR + 1;
@@ -379,16 +413,20 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   // (Staging the scores through shared memory -- coalesced cp.async tiles, a block in lock step -- was measured
   // SLOWER: 12.2 instead of 7.8 ms for the 248 Mbp finish.  The scan is bound by the instructions of the state
   // machine, a run ending every 2-4 scores with random-init weights, not by its uncoalesced loads.)
-  auto launch_scan = [&](int mode) {
-    mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, mode, sb, rt);
+  const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 32;   // a round costs ~1 ms per 50 M scores, the sequential completion seconds
+  // With more than one chunk nearly every chunk of the first round starts from a guess and is run again: the
+  // first round then only produces the summaries ("lean") and the first chain pass marks every chunk stale.
+  const bool lean = NC > 1 && max_rounds >= 2;
+  auto launch_scan = [&](int mode, int store) {
+    mss_scan_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, xdrop, CH, NC, mode, L0, store, sb, rt);
     c->launches++;
   };
-  launch_scan(0);
+  launch_scan(0, lean ? 0 : 1);
   int *h_dirty = reinterpret_cast<int *>(h + 2);
   int rounds = 1;
-  const int max_rounds = c->mss_max_rounds > 0 ? c->mss_max_rounds : 32;   // a round costs ~1 ms per 50 M scores, the sequential completion seconds
   bool converged = NC == 1;
   while (!converged) {
+    const int force = (lean && rounds == 1) ? 1 : 0;
     // predict all start states from the chunk summaries ...
     if (sizeof(T) == 4 && NC > 4 * MSS_GROUP) {
       // ... float32 scores: composed per group in parallel, a sequential pass over the groups only
@@ -407,13 +445,13 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
       const int gb = (NG + 63) / 64, sbk = (NS + 63) / 64;
       mss_group_compose_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, comp);
       mss_super_compose_kernel<<<sbk, 64, 0, c->stream>>>(NG, comp, super);
-      mss_group_chain_kernel<<<1, 32, 0, c->stream>>>(NS, super, sstart, sb.n_dirty);
+      mss_group_chain_kernel<<<1, 32, 0, c->stream>>>(NS, super, sstart, sb.n_dirty, L0);
       mss_super_fill_kernel<<<sbk, 64, 0, c->stream>>>(NG, comp, sstart, gstart);
-      mss_group_fill_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, gstart);
+      mss_group_fill_kernel<<<gb, 64, 0, c->stream>>>(NC, sb, gstart, force);
       c->launches += 5;
     } else {
       // ... sequential over chunks, O(1) each (float64 scores: sums round, composed shifts would miss)
-      mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb);
+      mss_chain_kernel<<<1, 32, 0, c->stream>>>(NC, sb, L0, force);
       c->launches++;
     }
     DGRP_CHECK(fetch_small(c, h_dirty, sb.n_dirty, 4));
@@ -421,21 +459,40 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
     if (*h_dirty == 0) { converged = true; break; }
     if (rounds >= max_rounds) break;
     // ... re-run the stale chunks in parallel ...
-    launch_scan(1);
+    launch_scan(1, 1);
     ++rounds;
     // ... and verify the chain in parallel; only a failed check needs another sequential pass
     DGRP_CUDA(cudaMemsetAsync(sb.n_dirty, 0, 4, c->stream));
-    mss_verify_kernel<<<blocks, threads, 0, c->stream>>>(NC, sb);
+    mss_verify_kernel<<<blocks, threads, 0, c->stream>>>(NC, sb, L0);
     c->launches++;
     DGRP_CHECK(fetch_small(c, h_dirty, sb.n_dirty, 4));
     DGRP_CUDA(cudaStreamSynchronize(c->stream));
     if (*h_dirty == 0) { converged = true; break; }
   }
   if (!converged) {
-    mss_complete_kernel<T><<<1, 32, 0, c->stream>>>(d_S, n, xdrop, CH, NC, sb, rt);
+    mss_complete_kernel<T><<<1, 32, 0, c->stream>>>(d_S, n, xdrop, CH, NC, L0, sb, rt);
     c->launches++;
   }
   c->mss_rounds = converged ? rounds : -rounds;
+
+  if (resume) {
+    // open end: everything from the last FLUSH run on is left to the next call (see MssLast)
+    int *d_last = reinterpret_cast<int *>(c->small.as<unsigned char>() + 128);
+    MssLast *d_rec = reinterpret_cast<MssLast *>(c->small.as<unsigned char>() + 144);
+    DGRP_CUDA(cudaMemsetAsync(d_last, 0xff, 4, c->stream));
+    const int lb = (int)std::min<int64_t>(((int64_t)NR + 255) / 256, (int64_t)c->sm_count * 8);
+    mss_last_flush_kernel<<<lb, 256, 0, c->stream>>>(rt.kind, NR, d_last);
+    mss_last_record_kernel<<<1, 1, 0, c->stream>>>(d_last, rt, d_rec);
+    c->launches += 2;
+    MssLast *h_rec = reinterpret_cast<MssLast *>(h + 4);
+    DGRP_CHECK(fetch_small(c, h_rec, d_rec, sizeof(MssLast)));
+    DGRP_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_rec->k < 0) return DGRP_OK;
+    resume->restart = h_rec->st;
+    resume->L0 = h_rec->L;
+    NR = h_rec->k;               // the runs before it: their last region ends at a FLUSH event
+    if (NR == 0) return DGRP_OK;
+  }
 
   // ---- stage 2
   int64_t n_ev = 0;
@@ -461,9 +518,9 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
 }
 
 int run_mss_segments(dgrp_ctx *c, const double *d_s64, const float *d_s32, int n, double min_sc,
-                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg) {
-  if (d_s64) return run_mss_t<double>(c, d_s64, n, min_sc, xdrop, d_segs_out, n_seg);
-  return run_mss_t<float>(c, d_s32, n, min_sc, xdrop, d_segs_out, n_seg);
+                     double xdrop, dgrp_seg_t **d_segs_out, int *n_seg, double L0, MssResume *resume) {
+  if (d_s64) return run_mss_t<double>(c, d_s64, n, min_sc, xdrop, d_segs_out, n_seg, L0, resume);
+  return run_mss_t<float>(c, d_s32, n, min_sc, xdrop, d_segs_out, n_seg, L0, resume);
 }
 
 // ---- gap fill (pymss.pyx:59-77) -------------------------------------------------------------------

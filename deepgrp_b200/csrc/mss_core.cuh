@@ -80,6 +80,15 @@ DGRP_HD void state_canonical(ScanState &s) {
   s.bot_st = -1; s.run_st = -1; s.run_ord = -1; s.flags = 1;
 }
 
+// The state a scan STARTS from: nothing on the stack, running sum L0.  L0 = 0 is the start of a record
+// (mss.c:59); a non-zero L0 resumes a record at the first element of a FLUSH run (see run_mss_segments in
+// mss.cu, "open end"): there the reference's stack has just been emptied and everything the machine still
+// reads is the running sum, so the run classifies as FLUSH again and every later double is the same.
+DGRP_HD void state_initial(ScanState &s, double L0) {
+  state_canonical(s);
+  s.L = L0;
+}
+
 DGRP_HD bool state_equal(const ScanState &a, const ScanState &b) {
   // compare bit patterns of the doubles through integer views (so that -0.0 != 0.0, NaN == NaN)
   union V { double d; long long i; };
@@ -101,7 +110,8 @@ struct RunTable {
 };
 
 // Close the run in progress at index k (exclusive end); mss.c:64-87 reduced to (L, max, bottom).
-DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt) {
+// `store` = false only computes the state (a speculative first round whose records would be rewritten anyway).
+DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt, bool store = true) {
   const double R = s.L, tL = s.run_L0;
   const double old_max = s.maxv;
   if (R > s.maxv) s.maxv = R;                       // mss.c:64
@@ -121,7 +131,7 @@ DGRP_HD void finish_run(ScanState &s, int k, const RunTable &rt) {
     kind = RUN_PLAIN;
     rec_st = s.run_st; rec_L = tL;
   }
-  if (s.run_ord >= 0) {
+  if (store && s.run_ord >= 0) {
     rt.st[s.run_ord] = rec_st; rt.en[s.run_ord] = k;
     rt.L[s.run_ord] = rec_L; rt.R[s.run_ord] = R;
     rt.kind[s.run_ord] = kind;
@@ -205,10 +215,11 @@ struct ChunkScan {
   double runb;    // its L before the run in progress, for a run that started in the chunk
   bool carried;   // the run in progress came from before the chunk
   bool prev_pos;
+  bool store;     // write the run records (false: a speculative round that only wants the summary)
 
   DGRP_HD ChunkScan(ScanState &s_, const RunTable &rt_, ChunkSummary &sum_, double xdrop_, int n_, int first_ord,
-                    bool prev_positive)
-      : s(s_), rt(rt_), sum(sum_), xdrop(xdrop_), n(n_), next_ord(first_ord), prev_pos(prev_positive) {
+                    bool prev_positive, bool store_ = true)
+      : s(s_), rt(rt_), sum(sum_), xdrop(xdrop_), n(n_), next_ord(first_ord), prev_pos(prev_positive), store(store_) {
     sum.m.outL = sum.m.runL0 = sum.m.carryR = sum.m.minT = sum.m.maxAfter = sum.m.maxIn = 0.0;
     sum.s = sum.m;
     sum.min_st = -1; sum.flags = 0;
@@ -239,7 +250,7 @@ struct ChunkScan {
         if (i + 1 == n || !(blk[j + 1] > 0)) {
           const double tL = s.run_L0;
           const int st = s.run_st;
-          finish_run(s, i + 1, rt);
+          finish_run(s, i + 1, rt, store);
           const double R = s.L;
           if (carried) {
             sum.flags |= 2; sum.m.carryR = R; sum.s.carryR = Lb;
@@ -276,8 +287,8 @@ struct ChunkScan {
 
 template <typename ScoreT>
 DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int first_ord,
-                        ScanState &s, const RunTable &rt, ChunkSummary &sum) {
-  ChunkScan sc(s, rt, sum, xdrop, n, first_ord, b > 0 && ((double)S[b - 1] > 0));
+                        ScanState &s, const RunTable &rt, ChunkSummary &sum, bool store = true) {
+  ChunkScan sc(s, rt, sum, xdrop, n, first_ord, b > 0 && ((double)S[b - 1] > 0), store);
   // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
   // a block are independent of the sequential state machine and overlap each other.
   constexpr int BL = SCAN_BL;

@@ -82,7 +82,20 @@ def host_mss():
         m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
                CH, group, out, cap, ctypes.byref(rounds), max_rounds, ctypes.byref(mism))
         return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value, mism.value
+    def run_open(S, min_sc, xdrop, CH, group, L0, open_end, max_rounds=0):
+        """Prefix of a record: (segments, rounds, restart index or -1, running sum before the restart run)."""
+        S = np.ascontiguousarray(S)
+        cap = S.size // 2 + 2
+        out = (_Seg * cap)()
+        rounds, restart, restart_l = ctypes.c_int(0), ctypes.c_int(-1), ctypes.c_double(0.0)
+        fn = lib.host_mss_open_f64 if S.dtype == np.float64 else lib.host_mss_open_f32
+        fn.restype = ctypes.c_int
+        m = fn(S.size, ctypes.c_void_p(S.ctypes.data), ctypes.c_double(min_sc), ctypes.c_double(xdrop),
+               CH, group, ctypes.c_double(L0), int(open_end), out, cap, ctypes.byref(rounds), max_rounds,
+               ctypes.byref(restart), ctypes.byref(restart_l))
+        return [(out[i].st, out[i].en, out[i].sc) for i in range(m)], rounds.value, restart.value, restart_l.value
     run.grouped = run_grouped
+    run.open = run_open
     return run
 
 
@@ -113,6 +126,55 @@ def test_chunked_mss_logic_bit_exact(host_mss, oracle):
                     for max_rounds in (0, 2):      # 2: forces the sequential completion path
                         got, _ = host_mss(S, min_sc, xdrop, CH, max_rounds)
                         assert got == ref, (trial, xdrop, min_sc, CH, max_rounds)
+
+
+def _mss_in_slabs(host_mss, S, min_sc, xdrop, cuts, CH, group, max_rounds=0):
+    """What dgrp_fasta_stream does with a long record (api.cu, "early rows"): after every slab of scores the
+    scan runs over [restart, slab end) from the carried running sum, keeps what the last FLUSH run made final
+    and resumes at that run; the last pass runs to the true end."""
+    r, L0, out = 0, 0.0, []
+    for p in list(cuts) + [None]:
+        sub = S[r:p] if p is not None else S[r:]
+        segs, _, restart, restart_l = host_mss.open(sub, min_sc, xdrop, CH, group, L0, p is not None, max_rounds)
+        out += [(a + r, b + r, sc) for a, b, sc in segs]
+        if p is not None and restart >= 0:
+            r, L0 = r + restart, restart_l
+    return out
+
+
+def test_resumable_mss_equals_the_whole_record(host_mss, oracle):
+    """mss.c:50-101 has no entry point that resumes; the claim checked here is that restarting at the first
+    element of a run that found no candidate with a smaller L (mss.c:78-81: the stack is flushed, the run becomes
+    the bottom) with the running sum carried over reproduces every later segment bit for bit -- in the exact
+    regime, with x-drop resets, with upward drift (no flush: nothing is final before the end) and with sums
+    that round."""
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        n = int(rng.integers(20, 3000))
+        kind = trial % 6
+        base = rng.normal(size=n)
+        if kind == 0:
+            S = base - 0.3
+        elif kind == 1:
+            S = base + 0.3
+        elif kind == 2:
+            S = base * 5 - 1
+        elif kind == 3:
+            S = (base - 0.1) * 1e3 + 1e9 * (rng.random(n) < 0.002)
+        elif kind == 4:
+            S = np.where(rng.random(n) < 0.5, base, -np.abs(base) * 3)
+        else:
+            S = np.where(rng.random(n) < 0.1, 138.0, -4.6) * (1 + 1e-3 * base)
+        S = S.astype(np.float32)
+        if trial % 3 == 0:
+            S = S.astype(np.float64) * (1 + 1e-9 * rng.normal(size=n))     # true doubles: sums round
+        min_sc = float(rng.choice([0.0, 1.0, 5.0, 229.7]))
+        xdrop = float(rng.choice([-1.0, 3.0, 20.0, 100.0, 2297.0]))
+        ref = [(int(a), int(b), float(c)) for a, b, c in oracle.mss_find_all(S.astype(np.float64), min_sc, xdrop)]
+        cuts = sorted(set(int(x) for x in rng.integers(1, n, size=int(rng.integers(1, 6)))))
+        for CH, group, max_rounds in ((16, 0, 0), (64, 4, 0), (1000, 0, 0), (32, 0, 2)):
+            got = _mss_in_slabs(host_mss, S, min_sc, xdrop, cuts, CH, group, max_rounds)
+            assert got == ref, (trial, kind, cuts, CH, group, max_rounds)
 
 
 def test_grouped_summary_chain(host_mss, oracle):
