@@ -286,6 +286,8 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_int("stream_early_rows", args.early_rows)
     ctx.set_int("stream_early_slabs", args.early_slabs)
     ctx.set_int("stream_early_ratio", args.early_ratio)
+    if args.mss_chunk:
+        ctx.set_int("mss_chunk", args.mss_chunk)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     devnull = open(os.devnull, "wb")
@@ -371,7 +373,8 @@ def run_ours(args, rank, world, local_rank):
                 "e2e_value": world * L * steps / (e2e_ms / 1e3) / 1e6, "e2e_ms_per_step": e2e_ms / steps,
                 "h2d": st["h2d_bytes"], "d2h": st["d2h_bytes"], "rows": int(n_rows.value), "launches": int(launches),
                 "stages_ms": mean_stage, "clocks": clocks, "kernel": used_kernel, "codes": codes,
-                "mss_rounds": ctx.get_int("mss_rounds"), "early_parts": ctx.get_int("stream_early_parts")}
+                "mss_rounds": ctx.get_int("mss_rounds"), "early_parts": ctx.get_int("stream_early_parts"),
+                "e2e_last": {k: st[k] for k in ("forward_ms", "gpu_ms", "launches", "waits_ms") if k in st}}
 
     weights = make_weights(args)
     L = args.bases
@@ -391,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": main["e2e_value"], "unit": "Mbp/s", "h2d_bytes_per_step": main["h2d"],
                 "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms_per_step"],
                 "api": "deepgrp_b200.prediction.predict_fasta_tsv_stream (C ABI dgrp_fasta_stream_*)",
-                "early_parts": main["early_parts"]},
+                "early_parts": main["early_parts"], "last_step": main["e2e_last"]},
         "gpu_launches": main["launches"],
         "roofline": {"bound": "tensor", "kernel": FORWARD_KERNELS[main["kernel"]],
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
@@ -663,6 +666,7 @@ def main():
                     help="e2e leg: 1 = a long record's rows leave slab by slab while it is still being computed "
                          "(dgrp_fasta_stream, DESIGN.md section 7), 0 = after the record's last window")
     ap.add_argument("--early-slabs", type=int, default=0, help="position slabs of a long record (0 = library default)")
+    ap.add_argument("--mss-chunk", type=int, default=0, help="scores per thread of the MSS scan (0 = automatic)")
     ap.add_argument("--early-ratio", type=int, default=0, help="slab size relative to the one before, per cent (0 = library default)")
     ap.add_argument("--strong-bases", type=int, default=248_000_000)
     ap.add_argument("--genome-scale", type=float, default=0.0, help="fraction of the 3.1 Gbp genome (0 = n_gpus / 8)")

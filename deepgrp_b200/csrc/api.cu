@@ -68,6 +68,15 @@ int fetch_small(dgrp_ctx *c, void *pinned_dst, const void *d_src, size_t bytes) 
   return DGRP_OK;
 }
 
+// sum of n scores (double): the direction the running sum of the MSS scan drifts in
+__global__ void score_drift_kernel(const float *__restrict__ sc, int64_t n, double *out) {
+  double acc = 0.0;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) acc += (double)sc[i];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // s0 = ln(0.99/0.01) and the two thresholds of pymss.pyx:46-53
 static void mss_thresholds(int min_mss_len, int xdrop_len, double *min_sc, double *xdrop) {
   const double s0 = log(0.99 / (1.0 - 0.99));
@@ -1330,15 +1339,13 @@ int stream_upload(dgrp_fasta_stream *s, int64_t k, int b, int *stage_turn) {
 
 // Slab ends (positions) of a long record for the early-rows route; fewer than two = not worth it.  A slab is a
 // whole number of forward "units" (unit_w windows = one round of two tiles on every SM) minus the halo windows a
-// position range recomputes, so that the persistent kernel's CTAs get equal tile counts.  The first slab is a
-// PROBE of one unit: it tells whether the record's scores flush at all (if not, the rest runs as one call).
-// The n_slabs slabs after it shrink geometrically (ratio_pct per cent each) because only the LAST slab's text
-// cannot overlap any compute.
+// position range recomputes, so that the persistent kernel's CTAs get equal tile counts.  The slabs shrink
+// geometrically (ratio_pct per cent each) because only the LAST slab's text cannot overlap any compute.
 void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, int ratio_pct,
                 std::vector<int64_t> &ends) {
   ends.clear();
   if (step <= 0 || unit_w <= 0) return;
-  const double K = (double)(length / step) / (double)unit_w - 1.0;   // units in the record behind the probe
+  const double K = (double)(length / step) / (double)unit_w;   // units in the record
   int n = n_slabs;
   if ((double)n > K / 2.0) n = (int)(K / 2.0);
   if (n < 2) return;
@@ -1352,8 +1359,7 @@ void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, in
     if (rows > 64) rows &= ~(int64_t)63;
     return rows;
   };
-  int64_t pos = rows_of(1);
-  ends.push_back(pos);
+  int64_t pos = 0;
   w = 1.0;
   for (int i = 0; i + 1 < n; ++i, w *= ratio) {
     int64_t k = (int64_t)(w / wsum * K + 0.5);
@@ -1367,7 +1373,7 @@ void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, in
 }
 
 // one slice (already on the device in raw[b]): decode, then every record of it
-int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
+int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn, bool last_slice) {
   dgrp_ctx *c = s->c;
   dgrp_model *m = s->m;
   const uint8_t *fasta = s->fasta + s->cuts[k];          // host view of the slice (headers)
@@ -1461,7 +1467,10 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
     };
     // Long records with MSS: positions in slabs, see stream_record_slabs
     std::vector<int64_t> slab_end;
-    if (s->use_mss && c->stream_early_rows && length > 0)
+    // (by default only for the rank's LAST record: the text of every other record crosses PCIe under the next
+    // record's forward anyway, and the slabs cost a few per cent of kernel efficiency; 2 = every long record)
+    if (s->use_mss && length > 0 &&
+        (c->stream_early_rows >= 2 || (c->stream_early_rows == 1 && last_slice && i + 1 == n_hdr)))
       plan_slabs(length, m->T, s->step, c->stream_early_unit > 0 ? c->stream_early_unit : (int64_t)c->sm_count * 128,
                  c->stream_early_slabs > 0 ? c->stream_early_slabs : 4, c->stream_early_ratio, slab_end);
     c->stream_early_parts = 0;
@@ -1506,6 +1515,24 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn) {
           DGRP_CHECK(run_segments(c, lab2 + e, nullptr, length - e, startpos + e, false, &d_tri, &cnt));
           DGRP_CHECK(emit(d_tri, cnt, 1));
         } else if (probing) {
+          if (q == 0) {
+            // Which way do the scores drift?  Upwards (confident class-0 calls score positive: the x4 weight set,
+            // config 5b) the running sum keeps rising, no run ever finds the stack without a smaller L and
+            // nothing is final before the record ends: the MSS pass over the slab would be wasted (it is the
+            // expensive rounding regime, too), so the rest of the record runs as one call.
+            DGRP_CHECK(c->small.reserve(256));
+            DGRP_CHECK(c->pin_small.reserve(256));
+            double *d_sum = reinterpret_cast<double *>(c->small.as<unsigned char>() + 192);
+            STREAM_CUDA(cudaMemsetAsync(d_sum, 0, 8, c->stream));
+            score_drift_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(sc, p1, d_sum);
+            c->launches++;
+            double *h_sum = reinterpret_cast<double *>(c->pin_small.as<unsigned char>() + 96);
+            DGRP_CHECK(fetch_small(c, h_sum, d_sum, 8));
+            STREAM_CUDA(cudaStreamSynchronize(c->stream));
+            if (*h_sum > 0.0) probing = false;
+          }
+        }
+        if (!last && probing) {
           MssResume rs;
           DGRP_CHECK(run_mss_segments(c, nullptr, sc + r, (int)(p1 - r), min_sc, xdrop, &d_segs, &n_seg, L0, &rs));
           if (rs.restart > 0) {
@@ -1587,7 +1614,7 @@ void stream_compute_main(dgrp_fasta_stream *s) {
       if (s->cancel) break;
       if (s->up_rc != DGRP_OK) { rc = s->up_rc; set_error("%s", s->up_err.c_str()); break; }
     }
-    rc = stream_slice(s, s->mine[i], (int)(i & 1), &text_turn);
+    rc = stream_slice(s, s->mine[i], (int)(i & 1), &text_turn, i + 1 == s->mine.size());
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->cancel) break;
   }

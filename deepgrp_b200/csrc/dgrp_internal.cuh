@@ -107,9 +107,10 @@ struct dgrp_ctx {
   int forward_wide = 0;    // 0: the wide tcgen05 kernel (forward_tcw.cu) only where the two-tile kernel has no form
                            // (units > 64, LSTM); 1 / 2: force its single-CTA / CTA-pair variant where it exists
   int stream_slot_mb = 0;  // dgrp_fasta_stream: size of one host piece of TSV text, MiB (0 = 64)
-  int stream_early_rows = 1;   // dgrp_fasta_stream: long records are computed in position slabs and the rows that are
-                               // final after a slab (everything before the last MSS flush) leave while the next slab runs
-  int stream_early_slabs = 0;  // number of slabs of a long record behind the one-unit probe slab (0 = default: 4)
+  int stream_early_rows = 1;   // dgrp_fasta_stream: a long record is computed in position slabs and the rows that are
+                               // final after a slab (everything before the last MSS flush) leave while the next slab runs:
+                               // 1 = the rank's last record (whose text nothing else would hide), 2 = every long record, 0 = off
+  int stream_early_slabs = 0;  // number of slabs of a long record (0 = default: 4)
   int stream_early_unit = 0;   // windows per unit of a slab (0 = one wave of the forward kernel: 128 x SM count)
   int stream_early_ratio = 0;  // size of a slab relative to the one before it, per cent (0 = default: 55)
   int stream_early_parts = 0;  // diagnostic: parts of the last record's text that left before its last slab

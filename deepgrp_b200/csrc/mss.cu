@@ -88,6 +88,38 @@ __global__ void mss_count_runs_kernel(const T *__restrict__ S, int n, int CH, un
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[(i0 + (int)threadIdx.x) / CH], __popc(m));
   }
 }
+// float scores: four per thread (one 128-bit load when the array is 16-byte aligned), the score before them from
+// the neighbouring lane; a warp covers 128 scores = one chunk when CH is a multiple of 128
+__global__ void mss_count_runs4_kernel(const float *__restrict__ S, int n, int CH, unsigned int *cnt) {
+  const int lane = threadIdx.x & 31;
+  const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15u) == 0;
+  const bool warp_chunk = CH % 128 == 0;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x * 4; b0 < n; b0 += gs) {
+    const int64_t i = b0 + (int64_t)threadIdx.x * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i + 4 <= n && aligned) {
+      const float4 t = *reinterpret_cast<const float4 *>(S + i);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (i + k < n) v[k] = S[i + k];
+    }
+    float before = __shfl_up_sync(0xffffffffu, v[3], 1);
+    if (lane == 0) before = (i > 0 && i - 1 < n) ? S[i - 1] : 0.f;
+    unsigned c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c += (i + k < n && v[k] > 0.f && !((k ? v[k - 1] : before) > 0.f)) ? 1u : 0u;
+    }
+    if (warp_chunk) {
+      for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+      if (lane == 0 && c) atomicAdd(&cnt[(b0 + (int64_t)(threadIdx.x & ~31) * 4) / CH], c);
+    } else if (c) {
+      atomicAdd(&cnt[i / CH], c);   // CH is a multiple of 32, i of 4: the thread's four scores share a chunk
+    }
+  }
+}
 
 // ---- stage 1: reduced scan, chunked (see mss_core.cuh item 4) --------------------------------------
 using mss::ChunkSummary;
@@ -336,8 +368,9 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
   if (CH <= 0) {
     // The scan is sequential inside a chunk (~0.25 us per score, twice); the summary pass is sequential
     // over chunks (~0.25 us each, float64 scores) or over groups of 32 chunks (float32 scores): chunk ~
-    // sqrt(n) / 2 resp. sqrt(n / 64) balances the two (measured optima: 1024 at 46.7 M, 2048 at 248 M).
-    const int64_t per = sizeof(T) == 4 ? 2 * MSS_GROUP : 4;
+    // sqrt(n) / 2 resp. sqrt(n / 256) balances the two (512 at 46.7 M, 1024 at 248 M).
+    // (round 2, with the lean first round: 512 instead of 1024 at 46.7 M is 1.48 instead of 1.66 ms, profiles/r03c_*)
+    const int64_t per = sizeof(T) == 4 ? 8 * MSS_GROUP : 4;
     CH = 64;
     while (CH < 16384 && (int64_t)CH * CH * per < (int64_t)n) CH <<= 1;
   }
@@ -352,7 +385,13 @@ static int run_mss_t(dgrp_ctx *c, const T *d_S, int n, double min_sc, double xdr
     const int threads = 256;
     int64_t want = ((int64_t)n + threads - 1) / threads;
     const int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
-    mss_count_runs_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, CH, base);
+    if (sizeof(T) == 4) {
+      want = ((int64_t)n + threads * 4 - 1) / (threads * 4);
+      const int blocks4 = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
+      mss_count_runs4_kernel<<<blocks4, threads, 0, c->stream>>>(reinterpret_cast<const float *>(d_S), n, CH, base);
+    } else {
+      mss_count_runs_kernel<T><<<blocks, threads, 0, c->stream>>>(d_S, n, CH, base);
+    }
     c->launches++;
   }
   DGRP_CHECK(c->pin_small.reserve(256));
@@ -633,6 +672,18 @@ __global__ void copy_labels_kernel(const LabT *__restrict__ in, int64_t n, uint8
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs)
     out[i] = (uint8_t)in[i];
 }
+// 16 labels per thread where source and destination share their 16-byte phase; the edges byte by byte
+__global__ void copy_labels16_kernel(const uint8_t *__restrict__ in, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t head = (16 - (int64_t)(reinterpret_cast<uintptr_t>(in) & 15u)) & 15;
+  const int64_t h = head < n ? head : n;
+  const int64_t words = (n - h) / 16;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x, t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4 *src = reinterpret_cast<const uint4 *>(in + h);
+  uint4 *dst = reinterpret_cast<uint4 *>(out + h);
+  for (int64_t i = t; i < words; i += gs) dst[i] = src[i];
+  for (int64_t i = t; i < h; i += gs) out[i] = in[i];
+  for (int64_t i = h + words * 16 + t; i < n; i += gs) out[i] = in[i];
+}
 
 int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t *d_label_in,
                  const int64_t *d_label64_in, int n, int nof_labels, uint8_t *d_label_out) {
@@ -642,8 +693,12 @@ int run_gap_fill(dgrp_ctx *c, const dgrp_seg_t *d_segs, int n_seg, const uint8_t
   int64_t want = ((int64_t)n + threads - 1) / threads;
   int blocks = (int)(want < (int64_t)c->sm_count * 16 ? want : (int64_t)c->sm_count * 16);
   if (d_label_in) {
-    if (d_label_in != d_label_out)
-      copy_labels_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_label_in, n, d_label_out);
+    if (d_label_in != d_label_out) {
+      if (((reinterpret_cast<uintptr_t>(d_label_in) ^ reinterpret_cast<uintptr_t>(d_label_out)) & 15u) == 0)
+        copy_labels16_kernel<<<blocks, threads, 0, c->stream>>>(d_label_in, n, d_label_out);
+      else
+        copy_labels_kernel<uint8_t><<<blocks, threads, 0, c->stream>>>(d_label_in, n, d_label_out);
+    }
   } else {
     copy_labels_kernel<int64_t><<<blocks, threads, 0, c->stream>>>(d_label64_in, n, d_label_out);
   }

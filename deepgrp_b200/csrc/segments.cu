@@ -133,8 +133,9 @@ __global__ void seg_scatter_kernel(const L *__restrict__ lab, int64_t n, const u
 // The byte-per-thread kernels above read every label three times and store a triple as three scattered
 // 8-byte writes from two different threads: 4.8 % / 1.3 % of the HBM peak on the 248 Mbp record
 // (profiles/r02n_*).  Here a thread takes 16 consecutive labels with one 128-bit load (the two neighbours
-// come from the adjacent lanes), start / end flags are 16-bit masks, and the tile's rows leave as consecutive
-// 8-byte stores.  The label pointer may be any byte address (a record is processed in position slabs, api.cu):
+// come from the adjacent lanes), compares four labels per 32-bit operation (a byte-by-byte version of the same
+// kernel spent ~25 instructions per label and was no faster than the old one), start / end flags are 16-bit
+// masks, and the tile's rows leave as consecutive 8-byte stores.  The label pointer may be any byte address (a record is processed in position slabs, api.cu):
 // the tile grid is laid over the 16-byte aligned address below it.
 constexpr int SV_THREADS = 256;
 constexpr int SV_PER = 16;
@@ -142,18 +143,25 @@ constexpr int SV_TILE = SV_THREADS * SV_PER;   // 4096 labels
 
 struct SegWord {
   unsigned ms, me;      // bit k: a run starts at / ends after element k of the thread's 16
-  uint8_t b[SV_PER];
+  uint32_t q[4];        // the 16 labels (little endian; 0 outside the array)
 };
+
+// 0x80 in every byte of x that is not zero
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) {
+  return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+// the 0x80 flags of four bytes -> bits 0..3
+__device__ __forceinline__ unsigned flags4(uint32_t f) { return (f * 0x00204081u) >> 28; }
 
 // labels v0 .. v0+15 of the virtual (aligned) array; p = v - mis is the index into lab[0, n)
 __device__ __forceinline__ void seg_word(const uint8_t *__restrict__ lab, int64_t n, int mis, int64_t v0, bool open,
                                          SegWord &w) {
   const int lane = threadIdx.x & 31;
   const int64_t p0 = v0 - mis;
-  const uint8_t *src = lab + p0;                         // 16-byte aligned
   uint32_t q[4] = {0u, 0u, 0u, 0u};
-  if (p0 >= 0 && p0 + SV_PER <= n) {
-    const uint4 t = *reinterpret_cast<const uint4 *>(src);
+  const bool whole = p0 >= 0 && p0 + SV_PER <= n;
+  if (whole) {
+    const uint4 t = *reinterpret_cast<const uint4 *>(lab + p0);   // 16-byte aligned
     q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
   } else if (p0 + SV_PER > 0 && p0 < n) {                // the first / last word of the array: byte by byte
 #pragma unroll
@@ -163,24 +171,39 @@ __device__ __forceinline__ void seg_word(const uint8_t *__restrict__ lab, int64_
     }
   }
 #pragma unroll
-  for (int k = 0; k < SV_PER; ++k) w.b[k] = (uint8_t)(q[k >> 2] >> (8 * (k & 3)));
+  for (int i = 0; i < 4; ++i) w.q[i] = q[i];
   // neighbours across the thread boundary: the adjacent lanes' edge bytes, global loads at the warp's edges
-  unsigned prev = __shfl_up_sync(0xffffffffu, (unsigned)w.b[SV_PER - 1], 1);
-  unsigned next = __shfl_down_sync(0xffffffffu, (unsigned)w.b[0], 1);
+  unsigned prev = __shfl_up_sync(0xffffffffu, q[3] >> 24, 1);
+  unsigned next = __shfl_down_sync(0xffffffffu, q[0] & 0xffu, 1);
   if (lane == 0) prev = (p0 - 1 >= 0 && p0 - 1 < n) ? lab[p0 - 1] : 0u;
   if (lane == 31) next = (p0 + SV_PER >= 0 && p0 + SV_PER < n) ? lab[p0 + SV_PER] : 0u;
   unsigned ms = 0u, me = 0u;
+  if (p0 + SV_PER <= n - 2 || (open && p0 + SV_PER <= n)) {
+    // Four labels per 32-bit operation.  Outside the array the labels read as 0, which makes position 0 a start
+    // and position n - 1 an end by the ordinary rule (label differs from its neighbour); only the reference's
+    // special case of the record's last element (sequence.pyx:43-52: positions n - 2 and n - 1 of a closed
+    // record) needs the byte loop below.
 #pragma unroll
-  for (int k = 0; k < SV_PER; ++k) {
-    const int64_t p = p0 + k;
-    const unsigned cur = w.b[k];
-    const unsigned pv = k ? (unsigned)w.b[k - 1] : prev;
-    const unsigned nx = k + 1 < SV_PER ? (unsigned)w.b[k + 1] : next;
-    const bool in = p >= 0 && p < n && cur != 0u;
-    const bool st = in && (p == 0 || pv != cur || (!open && p == n - 1));
-    const bool en = in && (p + 1 == n || nx != cur || (!open && p + 1 == n - 1));
-    ms |= (unsigned)st << k;
-    me |= (unsigned)en << k;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t before = (q[i] << 8) | (i ? q[i - 1] >> 24 : prev);
+      const uint32_t after = (q[i] >> 8) | ((i < 3 ? q[i + 1] : next) << 24);
+      const uint32_t cur = nz_bytes(q[i]);
+      ms |= flags4(cur & nz_bytes(q[i] ^ before)) << (4 * i);
+      me |= flags4(cur & nz_bytes(q[i] ^ after)) << (4 * i);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SV_PER; ++k) {
+      const int64_t p = p0 + k;
+      const unsigned cur = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
+      const unsigned pv = k ? (q[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xffu : prev;
+      const unsigned nx = k + 1 < SV_PER ? (q[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu : next;
+      const bool in = p >= 0 && p < n && cur != 0u;
+      const bool st = in && (p == 0 || pv != cur || (!open && p == n - 1));
+      const bool en = in && (p + 1 == n || nx != cur || (!open && p + 1 == n - 1));
+      ms |= (unsigned)st << k;
+      me |= (unsigned)en << k;
+    }
   }
   w.ms = ms; w.me = me;
 }
@@ -207,12 +230,13 @@ __global__ void __launch_bounds__(SV_THREADS) segv_scatter_kernel(const uint8_t 
                                                                   const unsigned int *__restrict__ bend,
                                                                   int64_t *__restrict__ triples, int64_t offset) {
   __shared__ unsigned short s_spos[SV_TILE], s_epos[SV_TILE];   // tile-local index of a start / of a run's last element
-  __shared__ uint8_t s_slab[SV_TILE];
+  __shared__ __align__(16) uint8_t s_lab[SV_TILE];              // the tile's labels
   __shared__ unsigned int s_ws[SV_THREADS / 32], s_we[SV_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile_v0 = (int64_t)blockIdx.x * SV_TILE;
   SegWord w;
   seg_word(lab, n, mis, tile_v0 + (int64_t)threadIdx.x * SV_PER, open != 0, w);
+  reinterpret_cast<uint4 *>(s_lab)[threadIdx.x] = make_uint4(w.q[0], w.q[1], w.q[2], w.q[3]);
   // exclusive offsets of this thread's starts / ends inside the tile
   const unsigned cs = __popc(w.ms), ce = __popc(w.me);
   unsigned is = cs, ie = ce;
@@ -228,15 +252,8 @@ __global__ void __launch_bounds__(SV_THREADS) segv_scatter_kernel(const uint8_t 
     if (k < warp) { os += s_ws[k]; oe += s_we[k]; }
     ns += s_ws[k]; ne += s_we[k];
   }
-#pragma unroll
-  for (int k = 0; k < SV_PER; ++k) {   // unrolled: w.b[k] stays in registers
-    if ((w.ms >> k) & 1u) {
-      s_spos[os] = (unsigned short)(threadIdx.x * SV_PER + k);
-      s_slab[os] = w.b[k];
-      ++os;
-    }
-    if ((w.me >> k) & 1u) s_epos[oe++] = (unsigned short)(threadIdx.x * SV_PER + k);
-  }
+  for (unsigned m = w.ms; m; m &= m - 1) s_spos[os++] = (unsigned short)(threadIdx.x * SV_PER + __ffs(m) - 1);
+  for (unsigned m = w.me; m; m &= m - 1) s_epos[oe++] = (unsigned short)(threadIdx.x * SV_PER + __ffs(m) - 1);
   __syncthreads();
   // Starts and ends alternate along the record, so the run ordinal of the tile's first end (E0) is the one of
   // its first start (S0) or one less (a run that is open at the tile's first element).  Rows o = E0 .. : field
@@ -252,7 +269,8 @@ __global__ void __launch_bounds__(SV_THREADS) segv_scatter_kernel(const uint8_t 
     if (fld == 1) {
       if (ei < (int64_t)ne) triples[3 * o + 1] = pos0 + s_epos[ei] + 1;
     } else if (si >= 0 && si < (int64_t)ns) {
-      triples[3 * o + fld] = fld == 0 ? pos0 + s_spos[si] : (int64_t)s_slab[si];
+      const unsigned at = s_spos[si];
+      triples[3 * o + fld] = fld == 0 ? pos0 + at : (int64_t)s_lab[at];
     }
   }
 }

@@ -9,7 +9,15 @@ namespace dgrp {
 
 constexpr int TSV_THREADS = 256;
 
+// Positions are below 2^32 for every record the path accepts (2^31 - 1 bases, mss.h:16): decimal digits with 32-bit
+// arithmetic (a division by the constant 10 is a multiply-high), the 64-bit loop only beyond that.  The 64-bit
+// divisions of the first version were ~4 000 instructions per row and bounded both kernels.
+__device__ __forceinline__ int n_digits32(uint32_t v) {
+  return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
 __device__ __forceinline__ int n_digits(unsigned long long v) {
+  if (v <= 0xffffffffull) return n_digits32((uint32_t)v);
   int d = 1;
   while (v >= 10ull) { v /= 10ull; ++d; }
   return d;
@@ -20,6 +28,12 @@ __device__ __forceinline__ int fmt_len(long long v) {
 __device__ __forceinline__ uint8_t *fmt_put(uint8_t *p, long long v) {
   unsigned long long u = v < 0 ? (unsigned long long)(-v) : (unsigned long long)v;
   if (v < 0) *p++ = '-';
+  if (u <= 0xffffffffull) {
+    uint32_t w = (uint32_t)u;
+    const int d = n_digits32(w);
+    for (int k = d - 1; k >= 0; --k) { const uint32_t q = w / 10u; p[k] = (uint8_t)('0' + (w - q * 10u)); w = q; }
+    return p + d;
+  }
   const int d = n_digits(u);
   for (int k = d - 1; k >= 0; --k) { p[k] = (uint8_t)('0' + (u % 10ull)); u /= 10ull; }
   return p + d;

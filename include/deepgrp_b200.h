@@ -90,7 +90,9 @@ int64_t dgrp_ctx_launch_count(dgrp_ctx *ctx);
  * kernel's one-CTA / CTA-pair variant where it exists), "forward_ub" (GRU column blocks of 64 or 32 units),
  * "forward_overlap" (issue the wide kernel's MMAs block by block under the gate work), "forward_slab_mb" (bound of the
  * window-probability buffer), "forward_fuse_score" (fuse vote + score transform for whole-record calls),
- * "stream_slot_mb" (host piece size of dgrp_fasta_stream). */
+ * "stream_slot_mb" (host piece size of dgrp_fasta_stream), "stream_early_rows" / "stream_early_slabs" /
+ * "stream_early_ratio" / "stream_early_unit" (position slabs of a long record in dgrp_fasta_stream; get-only
+ * "stream_early_parts": parts of the last record's text that left before its last slab). */
 int dgrp_ctx_set_int(dgrp_ctx *ctx, const char *key, int64_t value);
 int dgrp_ctx_get_int(dgrp_ctx *ctx, const char *key, int64_t *value);
 
@@ -246,8 +248,13 @@ int dgrp_fasta_record_tsv(dgrp_ctx *ctx, int64_t *owner, int64_t *tsv_off, int64
  * record's finished TSV text travels to the host in pieces of <= 64 MiB on a second stream while the next record is
  * being computed.  `fasta` must stay valid until _close.  _next returns the next piece of text in file order of this
  * rank's records (*tsv valid until the following call): (*slice, *ordinal) identify the record (slice number in the
- * file, record number within the slice), *last_of_record marks its final piece and carries *n_rows; a record without
- * rows yields one empty piece.  *done = 1 when everything has been handed out -- an error met on the way (blank line,
+ * file, record number within the slice), *last_of_record marks its final piece; *n_rows is the number of rows that
+ * are complete with this piece (the counts of a record's pieces add up to its rows); a record without rows yields
+ * one empty piece.  A long record (>= ~4 waves of the forward kernel) with MSS is computed in position slabs and the
+ * rows that are already final -- everything before the last run at which mss.c:78-81 flushes its candidate stack --
+ * leave as pieces while the later slabs are still being computed ("stream_early_rows": 1, the default, for the last
+ * record of the rank's share -- the only one whose text no later record's compute would hide --, 2 for every long
+ * record, 0 never; the text is the same bytes in the same order either way).  *done = 1 when everything has been handed out -- an error met on the way (blank line,
  * all-'N' record, CUDA) is returned by that last call, after the text of the records before it, as the reference
  * has written those rows when it raises.  One stream per context at a time; the context must not be used for
  * other calls while a stream is open. */

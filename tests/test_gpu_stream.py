@@ -28,10 +28,11 @@ def dg(gpu_ctx):
 
 
 class early:
-    """Context options for the early-rows route; `unit` = windows per slab unit (the default is one wave of the
-    forward kernel, far above a test record)."""
+    """Context options for the early-rows route: rows = 2 every long record (the default, 1, only the stream's last
+    record), 0 off; `unit` = windows per slab unit (the default is one wave of the forward kernel, far above a test
+    record)."""
 
-    def __init__(self, ctx, rows=1, unit=64, slabs=0):
+    def __init__(self, ctx, rows=2, unit=64, slabs=0):
         self.ctx, self.opts = ctx, {"stream_early_rows": rows, "stream_early_unit": unit, "stream_early_slabs": slabs}
 
     def __enter__(self):
@@ -73,7 +74,7 @@ def test_early_rows_equal_the_one_shot_text(dg, T, U, scale):
     assert ref.count(b"\n") > 10
     parts_seen = []
     for slabs in (0, 2, 3, 6):
-        with early(dg.ctx, 1, 64, slabs):
+        with early(dg.ctx, 2, 64, slabs):
             got, stats = stream_text(dg, w, raw, "e.fa")
             parts_seen.append(dg.ctx.get_int("stream_early_parts"))
         assert got == ref, (T, U, scale, slabs)
@@ -93,7 +94,7 @@ def test_early_rows_pieces_and_record_marks(dg):
     w = dg.model.random_weights(342, 60, attention=True, seed=0)
     raw = one_record(50_000, 11) + one_record(4_000, 12).replace(b"chrT", b"chrS") + one_record(45_000, 13).replace(b"chrT", b"chrU")
     ref = bytes(dg.pred.predict_fasta_tsv_view(w, raw, "p.fa", 50, 256, True, 50, 50))
-    with early(dg.ctx, 1, 64, 4):
+    with early(dg.ctx, 2, 64, 4):
         text, marks, rows = {}, {}, 0
         with dg.pred.FastaTsvStream(w, raw, "p.fa", 50, 256, True, 50, 50) as st:
             for sl, od, nr, last, view in st:
@@ -106,6 +107,16 @@ def test_early_rows_pieces_and_record_marks(dg):
     for k, m in marks.items():
         assert m[-1] and not any(m[:-1]), (k, m)
     assert len(marks[(0, 0)]) >= 3          # the long record left in several parts
+    # the default (1): only the stream's last record is computed in slabs -- the text of the others crosses PCIe
+    # under the next record's forward anyway
+    with early(dg.ctx, 1, 64, 4):
+        marks1, text1 = {}, {}
+        with dg.pred.FastaTsvStream(w, raw, "p.fa", 50, 256, True, 50, 50) as st:
+            for sl, od, nr, last, view in st:
+                marks1.setdefault((sl, od), []).append(last)
+                text1.setdefault((sl, od), []).append(bytes(view))
+    assert b"".join(b"".join(text1[k]) for k in sorted(text1)) == ref
+    assert len(marks1[(0, 0)]) == 1 and len(marks1[(0, 1)]) == 1 and len(marks1[(0, 2)]) >= 3
 
 
 @pytest.mark.parametrize("compat", ("reference", "fixed"))
@@ -116,7 +127,7 @@ def test_early_rows_with_n_runs_steps_and_placement(dg, compat):
     for seed, step, n in ((21, 50, 41_234), (22, 37, 30_011), (23, 150, 52_000)):
         raw = one_record(n, seed, n_runs=True)
         ref = bytes(dg.pred.predict_fasta_tsv_view(w, raw, "n.fa", step, 256, True, 50, 50, compat))
-        with early(dg.ctx, 1, 48, 5):
+        with early(dg.ctx, 2, 48, 5):
             got, _ = stream_text(dg, w, raw, "n.fa", compat, step)
         assert got == ref, (seed, step, compat)
 
@@ -128,7 +139,7 @@ def test_early_rows_long_label_runs(dg):
     raw = one_record(80_000, 31)
     ref = bytes(dg.pred.predict_fasta_tsv_view(w, raw, "l.fa", 50, 256, True, 50, 50))
     for unit in (32, 64, 200):
-        with early(dg.ctx, 1, unit, 5):
+        with early(dg.ctx, 2, unit, 5):
             got, _ = stream_text(dg, w, raw, "l.fa")
         assert got == ref, unit
 
