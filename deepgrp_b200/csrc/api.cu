@@ -1094,8 +1094,8 @@ static int core_predict_range(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes
   c->timings.bases = rows;
   DGRP_CHECK(c->pred.reserve((size_t)rows * m->C * 4));
   DGRP_CUDA(cudaMemsetAsync(c->pred.p, 0, (size_t)rows * m->C * 4, c->stream));
-  DGRP_CHECK(run_forward_vote(c, m, d_codes, codes_base, a0, a1, pl, c->pred.as<float>(), pos0, rows));
-  DGRP_CHECK(run_forward_vote(c, m, d_codes, codes_base, t0, t1, pl, c->pred.as<float>(), pos0, rows));
+  DGRP_CHECK(run_forward_vote(c, m, d_codes, codes_base, a0, a1, pl, c->pred.as<float>(), pos0, rows, nullptr, nullptr,
+                              nullptr, t0, t1));
   return launch_score(c, c->pred.as<float>(), rows, m->C, d_labels, d_scores, nullptr, nullptr);
 }
 

@@ -182,13 +182,14 @@ struct Placement {  // where window w is max-merged (prediction.py:105 compatibi
 Placement make_placement(int64_t length, int T, int step, int batch_size, int compat);
 // Run GRU + attention + FF + softmax for windows [w_begin, w_end) of the code array and
 // max-merge into d_pred (rows relative to pred_row0; rows outside [0, pred_rows) are dropped).
+// [w2_begin, w2_end): a second window range voted into the same rows (not with d_label / d_score).
 // With d_label / d_score (whole record, pred_row0 = 0): when the windows fit one slab of the tcgen05 path the vote
 // and the score transform are fused (*fused = true: label + score written, d_pred untouched and NOT zero-filled by
 // the caller beforehand); otherwise *fused = false and d_pred (zero-initialised by the caller) holds the votes.
 int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
                      int64_t w_begin, int64_t w_end, const Placement &pl, float *d_pred,
                      int64_t pred_row0, int64_t pred_rows, uint8_t *d_label = nullptr, float *d_score = nullptr,
-                     bool *fused = nullptr);
+                     bool *fused = nullptr, int64_t w2_begin = 0, int64_t w2_end = 0);
 // dense float windows [B, T, 5] -> probs [B, T, C] (predict_on_batch semantics)
 int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t nbatch,
                       float *d_probs);

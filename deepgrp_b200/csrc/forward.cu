@@ -304,8 +304,16 @@ static void fill_model(FwdParams &p, const dgrp_model *m) {
 
 int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t codes_base,
                      int64_t w_begin, int64_t w_end, const Placement &pl, float *d_pred,
-                     int64_t pred_row0, int64_t pred_rows, uint8_t *d_label, float *d_score, bool *fused) {
+                     int64_t pred_row0, int64_t pred_rows, uint8_t *d_label, float *d_score, bool *fused,
+                     int64_t w2_begin, int64_t w2_end) {
   if (fused) *fused = false;
+  // A second window range (the displaced last batch of a position range, api.cu): the tcgen05 kernels with the
+  // vote in shared memory run it in the same launch; every other route runs it as a call of its own afterwards.
+  bool has2 = w2_end > w2_begin;
+  if (has2 && w_end <= w_begin) { w_begin = w2_begin; w_end = w2_end; has2 = false; }
+  auto second = [&]() -> int {
+    return has2 ? run_forward_vote(c, m, d_codes, codes_base, w2_begin, w2_end, pl, d_pred, pred_row0, pred_rows) : DGRP_OK;
+  };
   FwdParams p = {};
   fill_model(p, m);
   p.codes = d_codes; p.codes_base = codes_base;
@@ -348,6 +356,10 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
       else cudaGetLastError();   // out of memory: the kernels vote with atomicMax instead
     }
     if (!p.win_probs) slab = w_end - w_begin;
+    if (has2 && smem_vote && !fused) {   // one launch for both ranges (4 tiles of their own would hold the GPU for a whole
+      p.w2_begin = w2_begin; p.w2_end = w2_end;   // unit time: 1.3 ms at the defaults)
+      has2 = false;
+    }
     // one slab holds every window of the record: the gather pass sees each row's final vote and can apply the
     // score transform at once (label + score out, the predictions never written)
     const bool fuse = fused && d_label && d_score && p.win_probs && w_end - w_begin <= slab && pred_row0 == 0 &&
@@ -370,7 +382,9 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
         p.w_begin = w_begin; p.w_end = w_end; p.win_probs = nullptr;
         if (fuse && pred_rows > 0)
           DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
-        return launch_fwd<false>(c, m, p);
+        if (p.w2_end > p.w2_begin) { has2 = true; p.w2_begin = p.w2_end = 0; }   // (not reached: the query found a form)
+        DGRP_CHECK(launch_fwd<false>(c, m, p));
+        return second();
       }
       if (rc != DGRP_OK) return rc;
       c->forward_used_tc = used;
@@ -396,11 +410,12 @@ int run_forward_vote(dgrp_ctx *c, dgrp_model *m, const uint8_t *d_codes, int64_t
                                         d_pred + (size_t)(lo - pred_row0) * m->C, lo, hi - lo));
       }
     }
-    return DGRP_OK;
+    return second();
   }
   if (fused && pred_rows > 0)
     DGRP_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)pred_rows * m->C * sizeof(float), c->stream));
-  return launch_fwd<false>(c, m, p);
+  DGRP_CHECK(launch_fwd<false>(c, m, p));
+  return second();
 }
 
 int run_forward_dense(dgrp_ctx *c, dgrp_model *m, const float *d_batch, int64_t nbatch,

@@ -13,6 +13,9 @@ struct FwdParams {
   const float *dense;     // dense mode: [n][T][5] windows (predict_on_batch semantics)
   float *probs_out;       // dense mode: [n][T][C]
   int64_t w_begin, w_end; // window index range
+  int64_t w2_begin, w2_end;   // tcgen05 forms with the vote in shared memory: a second window range run by the same
+                          // launch behind the first (tiles never mix the two) -- the windows of the displaced
+                          // last batch (prediction.py:105) that land in a position range; empty: w2_end <= w2_begin
   int T, U, C, step, attention;
   int64_t full_windows, tail_base;
   const float *P, *Wk, *b0, *Rp, *b1, *scale, *ffk, *ffb;

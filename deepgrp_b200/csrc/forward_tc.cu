@@ -157,8 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
   // function of the step alone (a per-slot parity register was spilled and reloaded inside the step loop).
   const int extra = (T & 1) ? 0 : 1;
   const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]);
-  const int64_t n_windows = p.w_end - p.w_begin;
-  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  const int64_t n_tiles = launch_tiles(p, K::WT);
   // this CTA's contiguous tile range; the first `lead` units are single tiles (phase shift, see top)
   const int64_t tile_lo = n_tiles * blockIdx.x / gridDim.x, tile_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
   const int64_t my_tiles = tile_hi - tile_lo;   // a single-tile unit costs ~3/4 of a period for half the work
@@ -254,9 +253,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     {
       const int nthr = TC_GATE_WARPS * 32;
       for (int s = 0; s < nt; ++s) {
-        const int64_t w_first = p.w_begin + (tile + s) * K::WT;
+        const TileRange tr = tile_range(p, tile + s, K::WT);
+        const int64_t w_first = tr.w0;
         int64_t w_last = w_first + K::WT - 1;
-        w_last = w_last < p.w_end ? w_last : p.w_end - 1;
+        w_last = w_last < tr.hi ? w_last : tr.hi - 1;
         const int span = (int)((w_last - w_first) * p.step) + T;
         const uint8_t *src = p.codes + (w_first * (int64_t)p.step - p.codes_base);
         uint8_t *fwd_copy = s_codes + (size_t)(2 * s) * p.code_span, *rc_copy = fwd_copy + p.code_span;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_tc_attention_vote_kernel(co
     for (int s = 0; s < nt; ++s)
       attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(
           p, sum0 + (size_t)s * K::WT * T * UP, q0 + (size_t)s * K::WT * UP,
-          proj0 + (size_t)s * K::WT * T * 16, p.w_begin + (tile + s) * K::WT, p.wpp, s_scale, s_score,
+          proj0 + (size_t)s * K::WT * T * 16, tile_range(p, tile + s, K::WT), p.wpp, s_scale, s_score,
           p.smem_vote == 1 ? reinterpret_cast<float *>(s_A)            // A is idle: every MMA of the unit has completed
                            : (p.smem_vote == 2 ? reinterpret_cast<float *>(s_codes + 4 * (size_t)p.code_span) : nullptr));
     tile += nt;
@@ -460,7 +460,7 @@ template <int UP, typename ST, int NP>
 static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = TCfg<UP, NP>;
   const int64_t n_windows = p.w_end - p.w_begin;
-  if (n_windows <= 0) return DGRP_OK;
+  if (n_windows <= 0 && p.w2_end <= p.w2_begin) return DGRP_OK;
   // windows per pass of the second phase: as many score rows as shared memory holds
   // staged base codes of a tile: 63 * step + T bytes; very large steps have no tcgen05 form
   const int64_t span = (int64_t)(K::WT - 1) * p.step + p.T;
@@ -485,7 +485,8 @@ static int launch_tc_t(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   if (p.smem_vote) p.win_probs = nullptr;
   auto kern = gru_tc_attention_vote_kernel<UP, ST, NP>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
-  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  const int64_t n_tiles = (n_windows > 0 ? (n_windows + K::WT - 1) / K::WT : 0) +
+                          (p.w2_end > p.w2_begin ? (p.w2_end - p.w2_begin + K::WT - 1) / K::WT : 0);
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < c->sm_count ? n_pairs : c->sm_count);
   const size_t rows = (size_t)grid * 2 * K::WT;   // window slots in flight

@@ -233,6 +233,23 @@ __device__ __forceinline__ void gru_cell4(const float4 xz, const float4 xr, cons
   hp[0] = h01.x; hp[1] = h01.y; hp[2] = h23.x; hp[3] = h23.y;
 }
 
+// Tiles of a launch: those of windows [w_begin, w_end), then those of [w2_begin, w2_end).
+struct TileRange {
+  int64_t w0;       // first window of the tile
+  int64_t lo, hi;   // the window range it belongs to
+};
+__device__ __forceinline__ int64_t range_tiles(int64_t lo, int64_t hi, int WT) { return hi > lo ? (hi - lo + WT - 1) / WT : 0; }
+__device__ __forceinline__ int64_t launch_tiles(const FwdParams &p, int WT) {
+  return range_tiles(p.w_begin, p.w_end, WT) + range_tiles(p.w2_begin, p.w2_end, WT);
+}
+__device__ __forceinline__ TileRange tile_range(const FwdParams &p, int64_t tile, int WT) {
+  const int64_t ta = range_tiles(p.w_begin, p.w_end, WT);
+  TileRange r;
+  if (tile < ta) { r.w0 = p.w_begin + tile * WT; r.lo = p.w_begin; r.hi = p.w_end; }
+  else { r.w0 = p.w2_begin + (tile - ta) * WT; r.lo = p.w2_begin; r.hi = p.w2_end; }
+  return r;
+}
+
 // Second phase for one tile, in passes of WPP windows (WPP * T floats of scores fit in shared memory).
 //   sum   [T][UP/8 chunks][64 windows][8 units]  h_fwd[t] + h_rc[t]; the layout the gate warps can
 //         write with full 128-byte lines (a warp's 32 rows are 16 windows x 2 directions x 4 units)
@@ -277,8 +294,9 @@ __device__ __forceinline__ float inv4_dot(const float *d, const float *sc) {
 
 template <int UP, int WT, int NWARPS, typename ST>
 __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, const ST *sum, const float *qbuf,
-                                                        const float *proj, int64_t w_tile0, int wpp,
+                                                        const float *proj, const TileRange tr, int wpp,
                                                         const float *s_scale, float *s_score, float *s_vote = nullptr) {
+  const int64_t w_tile0 = tr.w0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.T, C = p.C;
   // Shared-memory vote (s_vote: float[(WT - 1) * step + T][C], the idle A operand): the tile's windows overlap each
@@ -300,7 +318,7 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
   constexpr int PU = 11;               // rows in flight per lane (softmax / vote passes): all of T <= 352 at once
   TC_TRACE_DECL;
   for (int w0 = 0; w0 < WT; w0 += wpp) {
-    if (w_tile0 + w0 >= p.w_end) break;
+    if (w_tile0 + w0 >= tr.hi) break;
     if (p.attention) {
       const int ngrp = wpp >> 3, grp = warp % ngrp, sl = warp / ngrp, nsl = NWARPS / ngrp;
       const int wi = lane & 7, cj = lane >> 3;
@@ -400,7 +418,7 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
       if (lane == 0 && wq + NWARPS < wpp)   // the next window of this warp
         l2_prefetch(proj + (size_t)(wl + NWARPS) * T * 16, (uint32_t)T * 64u);
       const int64_t w = w_tile0 + wl;
-      if (w >= p.w_end) break;
+      if (w >= tr.hi) break;
       const float *pr = proj + (size_t)wl * T * 16;
       const float *sc = s_score + (size_t)wq * T;
       float ctxk[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -518,9 +536,10 @@ __device__ __forceinline__ void attention_vote_sum_tile(const FwdParams &p, cons
     // the tile's merged rows -> pred.  Row r of the span is record row w_tile0 * step + r.
     const int64_t row0 = w_tile0 * (int64_t)p.step - p.pred_row0;
     const int64_t tail_lo = p.tail_base - p.pred_row0;                      // rows the displaced batch can touch
-    const int64_t tail_hi = tail_lo + (p.w_end > p.full_windows ? (p.w_end - p.full_windows - 1) * (int64_t)p.step + T : 0);
-    const bool first = w_tile0 == p.w_begin;
-    const bool last = w_tile0 + WT >= (p.full_windows < p.w_end ? p.full_windows : p.w_end);
+    const int64_t w_max = p.w2_end > p.w2_begin && p.w2_end > p.w_end ? p.w2_end : p.w_end;   // the launch's last window
+    const int64_t tail_hi = tail_lo + (w_max > p.full_windows ? (w_max - p.full_windows - 1) * (int64_t)p.step + T : 0);
+    const bool first = w_tile0 == tr.lo;
+    const bool last = w_tile0 + WT >= (p.full_windows < tr.hi ? p.full_windows : tr.hi);
     const int own_lo = first ? 0 : T - p.step;                             // below: shared with the previous tile
     const int own_hi = last ? vspan : WT * p.step;                         // from here on: shared with the next tile
     for (int r = tid; r < vspan; r += NWARPS * 32) {

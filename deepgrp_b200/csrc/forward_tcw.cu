@@ -211,8 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
 
   const bool is_gate = warp < TC_GATE_WARPS;
   const uint32_t bar_ready = smem_u32(&s_ready[0]), bar_done = smem_u32(&s_done[0]), bar_free = smem_u32(&s_free[0]);
-  const int64_t n_windows = p.w_end - p.w_begin;
-  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  const int64_t n_tiles = launch_tiles(p, K::WT);
   // a unit of work = NCTA tiles (one per CTA of the pair); the pair owns a contiguous range of units
   const int64_t n_units = (n_tiles + K::NCTA - 1) / K::NCTA;
   const int64_t n_groups = gridDim.x / K::NCTA, grp = blockIdx.x / K::NCTA;
@@ -329,9 +328,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
     // The bases of the tile (one contiguous span of 63 * step + T codes), translated to input-table rows:
     // a forward copy (rows 0..3, 8 for 'N') and a reversed + complemented one (rows 4..7, 9)
     {
-      const int64_t w_first = p.w_begin + tile * K::WT;
+      const TileRange tr = tile_range(p, tile, K::WT);
+      const int64_t w_first = tr.w0;
       int64_t w_last = w_first + K::WT - 1;
-      w_last = w_last < p.w_end ? w_last : p.w_end - 1;
+      w_last = w_last < tr.hi ? w_last : tr.hi - 1;
       const int span = live ? (int)((w_last - w_first) * p.step) + T : 0;
       const uint8_t *src = p.codes + (w_first * (int64_t)p.step - p.codes_base);
       uint8_t *fwd_copy = s_codes, *rc_copy = s_codes + p.code_span;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rnn_tcw_kernel(const FwdParams 
     __threadfence_block();
     gate_bar_sync();
     if (live)
-      attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(p, sum0, q0, proj0, p.w_begin + tile * K::WT, p.wpp,
+      attention_vote_sum_tile<UP, K::WT, TC_GATE_WARPS, ST>(p, sum0, q0, proj0, tile_range(p, tile, K::WT), p.wpp,
                                                             s_scale, s_score,
                                                             p.smem_vote == 1 ? reinterpret_cast<float *>(s_A)
                                                             : (p.smem_vote == 2 ? reinterpret_cast<float *>(s_codes + 2 * (size_t)p.code_span) : nullptr));
@@ -512,7 +512,7 @@ template <int UP, int RNN, bool PAIR, int UB, bool OVL>
 static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   using K = WCfg<UP, RNN, PAIR, UB>;
   const int64_t n_windows = p.w_end - p.w_begin;
-  if (n_windows <= 0) return DGRP_OK;
+  if (n_windows <= 0 && p.w2_end <= p.w2_begin) return DGRP_OK;
   const int64_t span = (int64_t)(K::WT - 1) * p.step + p.T;
   if (span > 16384) return DGRP_E_UNSUPPORTED;
   p.code_span = (int)((span + 15) & ~(int64_t)15);
@@ -532,7 +532,8 @@ static int launch_tcw_o(dgrp_ctx *c, dgrp_model *m, FwdParams &p) {
   if (p.smem_vote) p.win_probs = nullptr;
   auto kern = rnn_tcw_kernel<UP, RNN, PAIR, UB, OVL>;
   DGRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
-  const int64_t n_tiles = (n_windows + K::WT - 1) / K::WT;
+  const int64_t n_tiles = (n_windows > 0 ? (n_windows + K::WT - 1) / K::WT : 0) +
+                          (p.w2_end > p.w2_begin ? (p.w2_end - p.w2_begin + K::WT - 1) / K::WT : 0);
   const int64_t n_units = (n_tiles + K::NCTA - 1) / K::NCTA;
   const int64_t max_groups = c->sm_count / K::NCTA;
   const int grid = (int)(n_units < max_groups ? n_units : max_groups) * K::NCTA;

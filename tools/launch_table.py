@@ -60,6 +60,10 @@ def main():
         "copy_labels_kernel": (2 * L, "label read + written"),
         "seg_count_kernel": (L, "labels read"),
         "seg_scatter_kernel": (L + 20 * a.rows, "labels read + (start, end, label) per run written"),
+        "mss_count_runs4_kernel": (4 * L, "score read"),
+        "copy_labels16_kernel": (2 * L, "label read + written"),
+        "segv_count_kernel": (L, "labels read"),
+        "segv_scatter_kernel": (L + 24 * a.rows, "labels read + (start, end, label) int64 triples written"),
         "tsv_len_kernel": (20 * a.rows + 4 * a.rows, "triples read + row length written"),
         "tsv_write_kernel": (20 * a.rows + 8 * a.rows + a.tsv, "triples + row offsets read, text written"),
     }
