@@ -18,7 +18,7 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def load(path):
+def load(path, until=None):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[h]
@@ -29,6 +29,8 @@ def load(path):
         if len(r) <= vi:
             continue
         name = r[ki].replace("void ", "").split("(")[0].split("<")[0].replace("dgrp::", "")
+        if until and name == until:      # e.g. the first FASTA decode: only the device-resident steps before it
+            break
         agg.setdefault(name, []).append(float(r[vi].replace(",", "")) * scale[r[ui]])
     return agg
 
@@ -43,6 +45,8 @@ def main():
     ap.add_argument("--classes", type=int, default=5)
     ap.add_argument("--rows", type=int, default=19_352_370, help="TSV rows per step")
     ap.add_argument("--tsv", type=int, default=1_151_928_519, help="TSV bytes per step")
+    ap.add_argument("--until", default=None, help="stop at the first launch of this kernel (fa_tile_fn_kernel: only "
+                                                  "the device-resident steps, whose launches cover the whole record)")
     a = ap.parse_args()
     L, T, C = a.bases, a.vecsize, a.classes
     W = len(range(0, L - T, a.step))
@@ -71,7 +75,7 @@ def main():
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except (OSError, KeyError, ValueError):
         hbm = 6650.0
-    agg = load(a.csv)
+    agg = load(a.csv, a.until)
     total = sum(sum(v) for v in agg.values())
     print("| kernel | launches | mean us | share | algorithmic MB / launch | GB/s | of %.0f GB/s | bytes counted |" % hbm)
     print("|---|---|---|---|---|---|---|---|")
