@@ -94,6 +94,7 @@ SIGNATURES = {
     "dgrp_fasta_records": (_I, [_P, _P, _P, _P, _P, _L]),
     "dgrp_fasta_record_tsv": (_I, [_P, _P, _P, _P, _L]),
     "dgrp_fasta_index": (_I, [_P, _L, _I, _P, _P, _L, _PL]),
+    "dgrp_fasta_stream_plan": (_I, [_L, _I, _I, _L, _I, _I, _P, _I, _PI]),
     "dgrp_fasta_stream_open": (_I, [_P, _P, _P, _L, ctypes.c_char_p, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P)]),
     "dgrp_fasta_stream_next": (_I, [_P, ctypes.POINTER(_P), _PL, _PL, _PL, _PL, _PI, _PI]),
     "dgrp_fasta_stream_stats": (_I, [_P, _PL, _PL, _PL, _PL, _PL, _PL, _PL, ctypes.POINTER(_D), ctypes.POINTER(_D)]),

@@ -1718,6 +1718,19 @@ int dgrp_fasta_index(const uint8_t *fasta, int64_t nbytes, int world, int64_t *c
   return DGRP_OK;
 }
 
+int dgrp_fasta_stream_plan(int64_t length, int vecsize, int step, int64_t unit_windows, int n_slabs, int ratio_pct,
+                           int64_t *ends, int cap, int *n_out) {
+  if (!n_out || length < 0 || vecsize <= 0 || step <= 0) { set_error("bad arguments"); return DGRP_E_ARG; }
+  std::vector<int64_t> e;
+  plan_slabs(length, vecsize, step, unit_windows > 0 ? unit_windows : (int64_t)148 * 128, n_slabs > 0 ? n_slabs : 4,
+             ratio_pct, e);
+  if (e.size() < 2) e.clear();
+  *n_out = (int)e.size();
+  if ((int)e.size() > cap) { set_error("slab table too small: %d needed", (int)e.size()); return DGRP_E_CAPACITY; }
+  for (size_t i = 0; i < e.size(); ++i) ends[i] = e[i];
+  return DGRP_OK;
+}
+
 int dgrp_fasta_stream_open(dgrp_ctx *c, dgrp_model *m, const uint8_t *fasta, int64_t nbytes, const char *filename,
                            int step, int batch_size, int use_mss, int min_mss_len, int xdrop_len, int compat,
                            dgrp_fasta_stream **out) {

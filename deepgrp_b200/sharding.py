@@ -129,6 +129,20 @@ def merge_record_texts(pieces: Sequence[Sequence[Tuple[int, bytes]]]) -> bytes:
     return b"".join(t[1] for t in allp)
 
 
+def stream_slabs(length: int, vecsize: int, step_size: int, unit_windows: int = 0, n_slabs: int = 0,
+                 ratio_pct: int = 0) -> np.ndarray:
+    """The position slabs ``dgrp_fasta_stream_*`` cuts a long record into for its early rows (C ABI
+    ``dgrp_fasta_stream_plan``; host arithmetic, no GPU needed): the slab ends, the last one ``length``; empty when
+    the record is too short for that route."""
+    import ctypes
+    from . import _lib
+    ends = np.zeros(64, np.int64)
+    n = ctypes.c_int(0)
+    _lib.check(_lib.lib().dgrp_fasta_stream_plan(int(length), int(vecsize), int(step_size), int(unit_windows),
+                                                 int(n_slabs), int(ratio_pct), _lib.ptr(ends), 64, ctypes.byref(n)))
+    return ends[:n.value].copy()
+
+
 def fasta_slices(raw, world: int = 1):
     """The host index of the streaming driver (C ABI ``dgrp_fasta_index``; no GPU needed): ``(cuts, owner)`` --
     ``cuts[k]:cuts[k+1]`` is slice ``k`` of the FASTA text (whole records, >= 8 MiB unless the file ends) and

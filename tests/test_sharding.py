@@ -97,3 +97,29 @@ def test_fasta_slices_partition_the_text_at_headers():
     cuts1, owner1 = sharding.fasta_slices(raw, 1)
     assert np.array_equal(cuts1, cuts) and (owner1 == 0).all()
     assert sharding.fasta_slices(b"", 2)[0].tolist() == [0, 0]
+
+
+def test_stream_slab_plan():
+    """dgrp_fasta_stream_plan (host arithmetic of the early-rows route, no GPU): the slabs partition the record,
+    every slab but the last is a whole number of forward waves minus the halo windows a position range recomputes
+    (so the persistent kernel's CTAs get equal tile counts), they shrink, and short records get no plan."""
+    from deepgrp_b200 import sharding
+    T, step, unit = 342, 50, 148 * 128
+    ends = sharding.stream_slabs(46_700_000, T, step)
+    assert ends[-1] == 46_700_000 and len(ends) == 4 and (np.diff(ends) > 0).all()
+    sizes = np.diff(np.concatenate([[0], ends]))
+    assert (sizes[:-2] > sizes[1:-1]).all()                       # geometric: only the last slab's text is exposed
+    assert sizes[-1] < 0.15 * 46_700_000
+    halo = -(-T // step) + 8
+    for n in sizes[:-1]:
+        assert n % 64 == 0
+        windows = n // step + halo                                # what the range recomputes, roughly
+        assert windows % unit < 0.01 * unit or unit - windows % unit < 0.01 * unit
+    assert len(sharding.stream_slabs(3_000_000, T, step)) == 0    # below ~4 waves: one call
+    assert len(sharding.stream_slabs(5_000_000, T, step)) == 2
+    for length in (4_736_000, 10_000_001, 248_000_000, 2_000_000_000):
+        for slabs, ratio in ((0, 0), (2, 30), (6, 90), (3, 100)):
+            e = sharding.stream_slabs(length, T, step, 0, slabs, ratio)
+            assert len(e) == 0 or (e[-1] == length and (np.diff(e) > 0).all() and e[0] > 0 and len(e) <= max(slabs, 4))
+    small = sharding.stream_slabs(60_000, 150, 50, 64, 6)          # the unit the GPU tests use
+    assert 4 <= len(small) <= 6 and small[-1] == 60_000 and (np.diff(small) > 0).all()
