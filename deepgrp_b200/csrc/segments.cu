@@ -2,6 +2,7 @@
 // :79-85 (yield_segments), including the reference's `size - 1` loop bounds: a run that reaches
 // the last element is emitted as [s, n-1) plus [n-1, n).
 #include "dgrp_internal.cuh"
+#include "seg_core.cuh"
 
 namespace dgrp {
 
@@ -138,20 +139,13 @@ __global__ void seg_scatter_kernel(const L *__restrict__ lab, int64_t n, const u
 // masks, and the tile's rows leave as consecutive 8-byte stores.  The label pointer may be any byte address (a record is processed in position slabs, api.cu):
 // the tile grid is laid over the 16-byte aligned address below it.
 constexpr int SV_THREADS = 256;
-constexpr int SV_PER = 16;
+constexpr int SV_PER = seg::PER;
 constexpr int SV_TILE = SV_THREADS * SV_PER;   // 4096 labels
 
 struct SegWord {
   unsigned ms, me;      // bit k: a run starts at / ends after element k of the thread's 16
   uint32_t q[4];        // the 16 labels (little endian; 0 outside the array)
 };
-
-// 0x80 in every byte of x that is not zero
-__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) {
-  return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-}
-// the 0x80 flags of four bytes -> bits 0..3
-__device__ __forceinline__ unsigned flags4(uint32_t f) { return (f * 0x00204081u) >> 28; }
 
 // labels v0 .. v0+15 of the virtual (aligned) array; p = v - mis is the index into lab[0, n)
 __device__ __forceinline__ void seg_word(const uint8_t *__restrict__ lab, int64_t n, int mis, int64_t v0, bool open,
@@ -177,35 +171,7 @@ __device__ __forceinline__ void seg_word(const uint8_t *__restrict__ lab, int64_
   unsigned next = __shfl_down_sync(0xffffffffu, q[0] & 0xffu, 1);
   if (lane == 0) prev = (p0 - 1 >= 0 && p0 - 1 < n) ? lab[p0 - 1] : 0u;
   if (lane == 31) next = (p0 + SV_PER >= 0 && p0 + SV_PER < n) ? lab[p0 + SV_PER] : 0u;
-  unsigned ms = 0u, me = 0u;
-  if (p0 + SV_PER <= n - 2 || (open && p0 + SV_PER <= n)) {
-    // Four labels per 32-bit operation.  Outside the array the labels read as 0, which makes position 0 a start
-    // and position n - 1 an end by the ordinary rule (label differs from its neighbour); only the reference's
-    // special case of the record's last element (sequence.pyx:43-52: positions n - 2 and n - 1 of a closed
-    // record) needs the byte loop below.
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t before = (q[i] << 8) | (i ? q[i - 1] >> 24 : prev);
-      const uint32_t after = (q[i] >> 8) | ((i < 3 ? q[i + 1] : next) << 24);
-      const uint32_t cur = nz_bytes(q[i]);
-      ms |= flags4(cur & nz_bytes(q[i] ^ before)) << (4 * i);
-      me |= flags4(cur & nz_bytes(q[i] ^ after)) << (4 * i);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < SV_PER; ++k) {
-      const int64_t p = p0 + k;
-      const unsigned cur = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
-      const unsigned pv = k ? (q[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xffu : prev;
-      const unsigned nx = k + 1 < SV_PER ? (q[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu : next;
-      const bool in = p >= 0 && p < n && cur != 0u;
-      const bool st = in && (p == 0 || pv != cur || (!open && p == n - 1));
-      const bool en = in && (p + 1 == n || nx != cur || (!open && p + 1 == n - 1));
-      ms |= (unsigned)st << k;
-      me |= (unsigned)en << k;
-    }
-  }
-  w.ms = ms; w.me = me;
+  seg::flags16(q, prev, next, p0, n, open, w.ms, w.me);
 }
 
 __global__ void __launch_bounds__(SV_THREADS) segv_count_kernel(const uint8_t *__restrict__ lab, int64_t n, int mis,

@@ -4,40 +4,15 @@
 // thread at the offset given by a 64-bit exclusive scan of the row lengths, so the host only
 // receives finished bytes.
 #include "dgrp_internal.cuh"
+#include "seg_core.cuh"
 
 namespace dgrp {
 
 constexpr int TSV_THREADS = 256;
 
-// Positions are below 2^32 for every record the path accepts (2^31 - 1 bases, mss.h:16): decimal digits with 32-bit
-// arithmetic (a division by the constant 10 is a multiply-high), the 64-bit loop only beyond that.  The 64-bit
-// divisions of the first version were ~4 000 instructions per row and bounded both kernels.
-__device__ __forceinline__ int n_digits32(uint32_t v) {
-  return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
-         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
-}
-__device__ __forceinline__ int n_digits(unsigned long long v) {
-  if (v <= 0xffffffffull) return n_digits32((uint32_t)v);
-  int d = 1;
-  while (v >= 10ull) { v /= 10ull; ++d; }
-  return d;
-}
-__device__ __forceinline__ int fmt_len(long long v) {
-  return v < 0 ? 1 + n_digits((unsigned long long)(-v)) : n_digits((unsigned long long)v);
-}
-__device__ __forceinline__ uint8_t *fmt_put(uint8_t *p, long long v) {
-  unsigned long long u = v < 0 ? (unsigned long long)(-v) : (unsigned long long)v;
-  if (v < 0) *p++ = '-';
-  if (u <= 0xffffffffull) {
-    uint32_t w = (uint32_t)u;
-    const int d = n_digits32(w);
-    for (int k = d - 1; k >= 0; --k) { const uint32_t q = w / 10u; p[k] = (uint8_t)('0' + (w - q * 10u)); w = q; }
-    return p + d;
-  }
-  const int d = n_digits(u);
-  for (int k = d - 1; k >= 0; --k) { p[k] = (uint8_t)('0' + (u % 10ull)); u /= 10ull; }
-  return p + d;
-}
+using seg::fmt_len;
+using seg::fmt_put;
+
 __device__ __forceinline__ unsigned row_len(const int64_t *tri, int64_t i, int prefix_len) {
   return (unsigned)(prefix_len + fmt_len(tri[3 * i]) + 1 + fmt_len(tri[3 * i + 1]) + 1 +
                     fmt_len(tri[3 * i + 2]) + 1);

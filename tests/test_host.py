@@ -409,3 +409,78 @@ def test_fasta_kernel_logic_edge_cases(host_fasta, text):
             host_fasta(text.encode("latin-1"))
         return
     assert host_fasta(text.encode("latin-1")) == exp
+
+
+# ---- segment kernels and TSV number formatting on the host -------------------------------------------
+@pytest.fixture(scope="module")
+def host_seg():
+    so = os.path.join(HERE, "host", "libseg_host.so")
+    src = os.path.join(HERE, "host", "seg_host.cpp")
+    core = os.path.join(ROOT, "deepgrp_b200", "csrc", "seg_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    lib = ctypes.CDLL(so)
+    lib.seg_host_rows.restype = ctypes.c_int64
+    lib.seg_host_fmt.restype = ctypes.c_int
+
+    def rows(lab, mis=0, open_end=False, offset=0):
+        lab = np.ascontiguousarray(lab, dtype=np.uint8)
+        tri = np.zeros((lab.size + 2, 3), np.int64)
+        m = lib.seg_host_rows(ctypes.c_void_p(lab.ctypes.data), ctypes.c_int64(lab.size), int(mis), int(open_end),
+                              ctypes.c_int64(offset), ctypes.c_void_p(tri.ctypes.data), ctypes.c_int64(lab.size + 2))
+        assert m >= 0, "incomplete row or unpaired start / end"
+        return tri[:m]
+    rows.lib = lib
+    return rows
+
+
+def test_segment_kernel_logic_equals_yield_segments(host_seg, oracle):
+    """seg_core.cuh (four labels per 32-bit operation, tile lists, rows that straddle tiles) against
+    sequence.pyx:40-53, 79-85 restated by the oracle: every alignment of the label pointer, labels with the high
+    bit set, runs longer than a tile, the `size - 1` special case, and the open-ended form of the early rows."""
+    rng = np.random.default_rng(0)
+    for trial in range(160):
+        n = int(rng.integers(1, 20000))
+        kind = trial % 4
+        if kind == 0:
+            lab = rng.choice([0, 1, 2, 3, 4, 127, 128, 255], n)
+        elif kind == 1:
+            lab = np.repeat(rng.integers(0, 3, n // 50 + 1), 50)[:n]
+        elif kind == 2:
+            lab = np.repeat(rng.integers(0, 4, n // 5000 + 1), 5000)[:n]
+        else:
+            lab = np.where(rng.random(n) < 0.02, 0, 1)
+        lab = lab.astype(np.int64)
+        mis, off = int(rng.integers(0, 16)), int(rng.integers(0, 1000))
+        exp = np.array([(s, e, l) for s, e, l in oracle.yield_segments(lab, off) if l > 0], np.int64).reshape(-1, 3)
+        got = host_seg(lab, mis, False, off)
+        assert got.shape == exp.shape and (got == exp).all(), (trial, n, mis)
+        # open end: the rows of a longer record, except that a run reaching the end of the prefix is closed there
+        longer = np.concatenate([lab, [0, 0, 0]])
+        exp_o = np.array([(s, e, l) for s, e, l in oracle.yield_segments(longer, off) if l > 0], np.int64).reshape(-1, 3)
+        got_o = host_seg(lab, mis, True, off)
+        assert got_o.shape == exp_o.shape, (trial, "open")
+        if lab[-1] != 0:
+            assert (got_o[:-1] == exp_o[:-1]).all() and got_o[-1, 0] == exp_o[-1, 0] and got_o[-1, 1] == n + off
+        else:
+            assert (got_o == exp_o).all()
+    for lab in ([7], [0], [3, 3], [3, 0], [0, 3], [5] * 4096, [5] * 4097, [1, 2] * 2049):
+        lab = np.array(lab, np.int64)
+        exp = np.array([(s, e, l) for s, e, l in oracle.yield_segments(lab, 0) if l > 0], np.int64).reshape(-1, 3)
+        for mis in (0, 1, 15):
+            got = host_seg(lab, mis)
+            assert got.shape == exp.shape and (got == exp).all(), (lab[:4], lab.size, mis)
+
+
+def test_tsv_number_text_equals_python(host_seg):
+    """tsv.cu formats a row's numbers with 32-bit arithmetic below 2^32 and a 64-bit loop above; both must be
+    Python's "{}".format (deepgrp/__main__.py:288-292)."""
+    buf = (ctypes.c_ubyte * 32)()
+    rng = np.random.default_rng(1)
+    values = [0, 1, 9, 10, 11, 99, 100, 999_999_999, 1_000_000_000, 2_147_483_647, 4_294_967_295, 4_294_967_296,
+              9_999_999_999, 10**18, 2**63 - 1, -1, -10, -4_294_967_296, -(2**63)]
+    values += [10**k + d for k in range(1, 19) for d in (-1, 0, 1)]
+    values += [int(x) for x in rng.integers(0, 2**31, 300)] + [int(x) for x in rng.integers(-2**62, 2**62, 100)]
+    for v in values:
+        n = host_seg.lib.seg_host_fmt(ctypes.c_longlong(v), buf)
+        assert n > 0 and bytes(buf[:n]) == str(v).encode(), v
