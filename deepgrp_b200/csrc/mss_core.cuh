@@ -292,7 +292,26 @@ DGRP_HD void scan_chunk(const ScoreT *S, int n, double xdrop, int b, int e, int 
   // Scores are consumed in blocks of BL values (+1 look-ahead) held in registers, so that the loads of
   // a block are independent of the sequential state machine and overlap each other.
   constexpr int BL = SCAN_BL;
-  for (int i0 = b; i0 < e; i0 += BL) {
+  int i0 = b;
+#if defined(__CUDA_ARCH__)
+  // Device, float32 scores: a thread reads its own chunk, so every lane of a load instruction touches a different
+  // line -- nine scalar loads per block were 32 sector accesses each and the L1 was the busiest unit of the kernel
+  // (86 % of its peak, profiles/r02s2_hbm_kernels_ncu.md).  Two 128-bit loads per block instead, issued one block
+  // ahead: the next block's first score is this block's look-ahead, so no ninth load is needed.
+  if (sizeof(ScoreT) == 4 && (reinterpret_cast<uintptr_t>(S) & 15u) == 0 && (b & 3) == 0 && b + 2 * BL <= n &&
+      b + BL <= e) {
+    const float4 *F = reinterpret_cast<const float4 *>(S);
+    float4 c0 = F[i0 >> 2], c1 = F[(i0 >> 2) + 1];
+    for (; i0 + BL <= e && i0 + 2 * BL <= n; i0 += BL) {
+      const float4 n0 = F[(i0 >> 2) + 2], n1 = F[(i0 >> 2) + 3];
+      const double blk[BL + 1] = {(double)c0.x, (double)c0.y, (double)c0.z, (double)c0.w, (double)c1.x,
+                                  (double)c1.y, (double)c1.z, (double)c1.w, (double)n0.x};
+      sc.block(i0, BL, blk);
+      c0 = n0; c1 = n1;
+    }
+  }
+#endif
+  for (; i0 < e; i0 += BL) {
     const int m = e - i0 < BL ? e - i0 : BL;
     double blk[BL + 1];
     DGRP_UNROLL
