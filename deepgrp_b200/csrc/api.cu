@@ -1340,7 +1340,10 @@ int stream_upload(dgrp_fasta_stream *s, int64_t k, int b, int *stage_turn) {
 // Slab ends (positions) of a long record for the early-rows route; fewer than two = not worth it.  A slab is a
 // whole number of forward "units" (unit_w windows = one round of two tiles on every SM) minus the halo windows a
 // position range recomputes, so that the persistent kernel's CTAs get equal tile counts.  The slabs shrink
-// geometrically (ratio_pct per cent each) because only the LAST slab's text cannot overlap any compute.
+// geometrically (ratio_pct per cent each) because only the LAST slab's text cannot overlap any compute; the default
+// (6 slabs, 80 %: 27 / 22 / 17 / 14 / 11 / 9 % of the record) also keeps the FIRST slab small, so that the copies
+// start early where several ranks share one host's memory and a rank's text takes as long as its forward
+// (DESIGN.md section 6); on one GPU it measures the same as 4 slabs at 55 % (profiles/r02s2_summary.md).
 void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, int ratio_pct,
                 std::vector<int64_t> &ends) {
   ends.clear();
@@ -1349,7 +1352,7 @@ void plan_slabs(int64_t length, int T, int step, int64_t unit_w, int n_slabs, in
   int n = n_slabs;
   if ((double)n > K / 2.0) n = (int)(K / 2.0);
   if (n < 2) return;
-  const double ratio = (ratio_pct > 0 && ratio_pct <= 100 ? ratio_pct : 55) / 100.0;
+  const double ratio = (ratio_pct > 0 && ratio_pct <= 100 ? ratio_pct : 80) / 100.0;
   double wsum = 0.0, w = 1.0;
   for (int i = 0; i < n; ++i) { wsum += w; w *= ratio; }
   const int64_t halo = (T + step - 1) / step + 8;
@@ -1472,7 +1475,7 @@ int stream_slice(dgrp_fasta_stream *s, int64_t k, int b, int *text_turn, bool la
     if (s->use_mss && length > 0 &&
         (c->stream_early_rows >= 2 || (c->stream_early_rows == 1 && last_slice && i + 1 == n_hdr)))
       plan_slabs(length, m->T, s->step, c->stream_early_unit > 0 ? c->stream_early_unit : (int64_t)c->sm_count * 128,
-                 c->stream_early_slabs > 0 ? c->stream_early_slabs : 4, c->stream_early_ratio, slab_end);
+                 c->stream_early_slabs > 0 ? c->stream_early_slabs : 6, c->stream_early_ratio, slab_end);
     c->stream_early_parts = 0;
     float ms = 0.f;
     if (slab_end.size() >= 2) {
@@ -1722,7 +1725,7 @@ int dgrp_fasta_stream_plan(int64_t length, int vecsize, int step, int64_t unit_w
                            int64_t *ends, int cap, int *n_out) {
   if (!n_out || length < 0 || vecsize <= 0 || step <= 0) { set_error("bad arguments"); return DGRP_E_ARG; }
   std::vector<int64_t> e;
-  plan_slabs(length, vecsize, step, unit_windows > 0 ? unit_windows : (int64_t)148 * 128, n_slabs > 0 ? n_slabs : 4,
+  plan_slabs(length, vecsize, step, unit_windows > 0 ? unit_windows : (int64_t)148 * 128, n_slabs > 0 ? n_slabs : 6,
              ratio_pct, e);
   if (e.size() < 2) e.clear();
   *n_out = (int)e.size();

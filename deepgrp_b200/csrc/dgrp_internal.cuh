@@ -110,9 +110,9 @@ struct dgrp_ctx {
   int stream_early_rows = 1;   // dgrp_fasta_stream: a long record is computed in position slabs and the rows that are
                                // final after a slab (everything before the last MSS flush) leave while the next slab runs:
                                // 1 = the rank's last record (whose text nothing else would hide), 2 = every long record, 0 = off
-  int stream_early_slabs = 0;  // number of slabs of a long record (0 = default: 4)
+  int stream_early_slabs = 0;  // number of slabs of a long record (0 = default: 6)
   int stream_early_unit = 0;   // windows per unit of a slab (0 = one wave of the forward kernel: 128 x SM count)
-  int stream_early_ratio = 0;  // size of a slab relative to the one before it, per cent (0 = default: 55)
+  int stream_early_ratio = 0;  // size of a slab relative to the one before it, per cent (0 = default: 80)
   int stream_early_parts = 0;  // diagnostic: parts of the last record's text that left before its last slab
   int forward_ub = 0;      // wide kernel, GRU: units per column block (64 or 32; 0 = default: 64)
   int forward_overlap = 1; // wide kernel with two column blocks: issue the MMAs block by block so that they overlap the gates

@@ -267,7 +267,7 @@ int dgrp_fasta_index(const uint8_t *fasta, int64_t nbytes, int world, int64_t *c
 /* The position slabs the stream would cut a record of `length` bases into (host arithmetic only, no GPU needed):
  * ends[0 .. *n_slabs) are the slab ends, the last one = length; *n_slabs = 0 when the record is too short for the
  * early-rows route.  unit_windows = windows of one forward wave (0: 128 x 148), n_slabs / ratio_pct = 0: the defaults
- * (4 slabs, each 55 % of the one before).  DGRP_E_CAPACITY when cap is too small. */
+ * (6 slabs, each 80 % of the one before).  DGRP_E_CAPACITY when cap is too small. */
 int dgrp_fasta_stream_plan(int64_t length, int vecsize, int step, int64_t unit_windows, int n_slabs, int ratio_pct,
                            int64_t *ends, int cap, int *n_out);
 int dgrp_fasta_stream_open(dgrp_ctx *ctx, dgrp_model *model, const uint8_t *fasta, int64_t nbytes,

@@ -106,10 +106,10 @@ def test_stream_slab_plan():
     from deepgrp_b200 import sharding
     T, step, unit = 342, 50, 148 * 128
     ends = sharding.stream_slabs(46_700_000, T, step)
-    assert ends[-1] == 46_700_000 and len(ends) == 4 and (np.diff(ends) > 0).all()
+    assert ends[-1] == 46_700_000 and len(ends) == 6 and (np.diff(ends) > 0).all()
     sizes = np.diff(np.concatenate([[0], ends]))
     assert (sizes[:-2] > sizes[1:-1]).all()                       # geometric: only the last slab's text is exposed
-    assert sizes[-1] < 0.15 * 46_700_000
+    assert sizes[-1] < 0.15 * 46_700_000 and sizes[0] < 0.30 * 46_700_000   # the copies start early, the tail is short
     halo = -(-T // step) + 8
     for n in sizes[:-1]:
         assert n % 64 == 0
@@ -120,6 +120,6 @@ def test_stream_slab_plan():
     for length in (4_736_000, 10_000_001, 248_000_000, 2_000_000_000):
         for slabs, ratio in ((0, 0), (2, 30), (6, 90), (3, 100)):
             e = sharding.stream_slabs(length, T, step, 0, slabs, ratio)
-            assert len(e) == 0 or (e[-1] == length and (np.diff(e) > 0).all() and e[0] > 0 and len(e) <= max(slabs, 4))
+            assert len(e) == 0 or (e[-1] == length and (np.diff(e) > 0).all() and e[0] > 0 and len(e) <= max(slabs, 6))
     small = sharding.stream_slabs(60_000, 150, 50, 64, 6)          # the unit the GPU tests use
     assert 4 <= len(small) <= 6 and small[-1] == 60_000 and (np.diff(small) > 0).all()
