@@ -484,3 +484,66 @@ def test_tsv_number_text_equals_python(host_seg):
     for v in values:
         n = host_seg.lib.seg_host_fmt(ctypes.c_longlong(v), buf)
         assert n > 0 and bytes(buf[:n]) == str(v).encode(), v
+
+
+def _gap_fill(lab2, labels, base, segs, nof):
+    """pymss.pyx:59-77 on the segments of one pass (local coordinates + base)."""
+    for st, en, _ in segs:
+        part = labels[base + st:base + en]
+        counts = np.bincount(part, minlength=nof)
+        best, bestv = 1, counts[1]
+        for k in range(2, nof):
+            if bestv < counts[k]:
+                best, bestv = k, counts[k]
+        lab2[base + st:base + en] = np.where(part == 0, best, part)
+
+
+def test_early_rows_scheme_on_the_host(host_mss, host_seg, oracle):
+    """The early rows of dgrp_fasta_stream (api.cu) with the kernels' own scalar logic on the CPU: after every slab
+    the resumable MSS (mss_core.cuh) over [restart, slab end), gap fill of what became final, the open-ended segment
+    pass (seg_core.cuh) over [emitted, restart) with the run that reaches the end held back; the last slab closes
+    both.  The rows must be those of the reference's whole-record sequence find_mss_labels -> argmax ->
+    yield_segments (prediction.py:58, __main__.py:83, 288-292), whatever the cuts."""
+    rng = np.random.default_rng(21)
+    s0 = float(np.log(0.99 / (1.0 - 0.99)))
+    nof = 5
+    early_rows = 0
+    for trial in range(60):
+        n = int(rng.integers(300, 6000))
+        kind = trial % 4
+        # labels with runs, scores as apply_mss makes them: positive for repeats, -10 x for class 0 (prediction.py:51-57)
+        labels = np.repeat(rng.choice([0, 0, 0, 1, 2, 3, 4], n // 7 + 1), rng.integers(1, 15, n // 7 + 1))[:n]
+        if labels.size < n:
+            labels = np.concatenate([labels, np.zeros(n - labels.size, np.int64)])
+        labels = labels.astype(np.int64)
+        conf = {0: 0.9, 1: 0.6, 2: 0.3, 3: 0.52}[kind]
+        m = np.clip(conf + 0.25 * rng.normal(size=n), 0.05, 0.99).astype(np.float32)
+        t = np.log(m / (1 - m)).astype(np.float32)
+        scores = np.where(labels > 0, t, -10 * t).astype(np.float32)
+        min_len, xdrop_len = int(rng.choice([1, 5, 50])), int(rng.choice([0, 5, 50]))
+        min_sc, xdrop = s0 * min_len, (s0 * xdrop_len * 10.0 if xdrop_len > 0 else -1.0)
+        start = int(rng.integers(0, 50))
+        final = oracle.find_mss_relabel(scores.astype(np.float64), labels, nof, min_len, xdrop_len).astype(np.int64)
+        exp = [(s, e, l) for s, e, l in oracle.yield_segments(final, start) if l > 0]
+        cuts = sorted(set(int(x) for x in rng.integers(1, n, size=int(rng.integers(1, 6)))))
+        r = e = 0
+        L0, rows, lab2 = 0.0, [], labels.copy()
+        for p in cuts:
+            segs, _, restart, restart_l = host_mss.open(scores[r:p], min_sc, xdrop, 64, 4, L0, True)
+            if restart > 0:
+                _gap_fill(lab2, labels, r, [sg for sg in segs], nof)
+                r, L0 = r + restart, restart_l
+                tri = host_seg(lab2[e:r].astype(np.uint8), int(rng.integers(0, 16)), True, start + e)
+                tail = r - e
+                if len(tri) and lab2[r - 1] != 0:          # the run that reaches the end of the prefix is held back
+                    tail = int(tri[-1, 0]) - (start + e)
+                    tri = tri[:-1]
+                rows += [tuple(int(x) for x in row) for row in tri]
+                e += tail
+        early_rows += len(rows)
+        segs, _, _, _ = host_mss.open(scores[r:], min_sc, xdrop, 64, 4, L0, False)
+        _gap_fill(lab2, labels, r, segs, nof)
+        rows += [tuple(int(x) for x in row) for row in host_seg(lab2[e:].astype(np.uint8), 3, False, start + e)]
+        assert np.array_equal(lab2, final), (trial, kind)
+        assert rows == exp, (trial, kind, cuts)
+    assert early_rows > 1000          # the scheme was exercised: rows did leave before the last slab
